@@ -1,0 +1,135 @@
+/* radsearch_b200 -- C ABI of the B200-native RadSearch env-step / reset / GAE path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every buffer is owned by
+ * the caller (PyTorch allocates them; pass tensor.data_ptr()); the library allocates nothing persistent, keeps no
+ * mutable global state, never synchronises the host, and every launch is CUDA-graph capturable on `stream`.
+ *
+ * Return convention: 0 ok; <0 argument error (text in rs_last_error(), thread-local); >0 a cudaError_t.
+ * Per-environment soft failures are OR-ed into RsState.status[n] (RS_ST_*), never abort.
+ *
+ * Reference interfaces replaced (R = /root/reference/gym_rad_search/gym_rad_search/envs/rad_search_env.py,
+ * P = /root/reference/algos/multiagent/ppo.py, T = /root/reference/algos/multiagent/train.py):
+ *   rs_step            R:443-728   RadSearch.step (agent_step, take_action R:876-946, is_intersect R:1133-1146,
+ *                                  obstruction_sensors R:1172-1261, correct_coords R:1263-1306) + caller rules T:394-405
+ *   rs_reset           R:730-797   RadSearch.reset (create_obs R:948-1011, sample_source_loc_pos R:1013-1131)
+ *   rs_load_scenarios  R:799-874   RadSearch.refresh_environment
+ *   rs_gae             P:391-423   PPOBuffer.GAE_advantage_and_rewardsToGO (discount_cumsum P:62-85)
+ *   rs_adv_normalize   P:445-446   advantage normalisation in PPOBuffer.get (statistics: mpi_tools.py:71-95)
+ */
+#ifndef RADSEARCH_B200_H
+#define RADSEARCH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_VERSION 1
+#define RS_OBS_DIM 11            /* [count, x/2200, y/2200, 8 proximity sensors]            R:591-593 */
+#define RS_MAX_K 8               /* obstruction slots (env allows 0..7)                     R:317     */
+#define RS_MAX_A 8               /* agents per environment                                            */
+
+/* rs_step / rs_reset flags */
+#define RS_F_AUTO_RESET 1        /* apply T:394-405: timeout at max_ep_len, schedule a reset on done/timeout      */
+#define RS_F_EPOCH_END 2         /* this is the last step of the epoch: schedule every env, new obstructions T:484 */
+#define RS_F_RESET_LIST 4        /* rs_reset: reset the envs rs_step scheduled (RsState.reset_list / reset_count)  */
+#define RS_F_NEW_OBSTACLES 8     /* rs_reset: draw new obstructions for every env being reset (env.epoch_end)      */
+#define RS_F_FAST_POISSON 16     /* Philox path only: fp32 acceptance test in the PTRS sampler (KS-equivalent)     */
+
+/* info[n][a] bits */
+#define RS_I_OOB 1               /* Agent.out_of_bounds     R:919, 931 */
+#define RS_I_BLOCKED 2           /* Agent.obstacle_blocking R:937 (sticky)                   */
+#define RS_I_COLLISION 4         /* Agent.collision         R:909                            */
+#define RS_I_LOS_BLOCKED 8       /* Agent.intersect         R:495                            */
+#define RS_I_MOVED 16            /* take_action returned True                               */
+
+/* ended[n] bits (caller rules T:394-405) */
+#define RS_E_TERMINAL 1          /* any agent reported done this step                       */
+#define RS_E_TIMEOUT 2           /* steps_in_episode == max_ep_len                          */
+#define RS_E_RESET 4             /* a reset was scheduled for this env                      */
+
+/* status[n] bits */
+#define RS_ST_REJECT_CAP 1u      /* a rejection-sampling loop hit its cap (reference: MAX_CREATION_TRIES / hang)   */
+#define RS_ST_LAMBDA_INF 2u      /* detector exactly on the source: intensity/0 (reference raises)                 */
+#define RS_ST_UNIFORMS_OUT 4u    /* injected uniform stream exhausted                                              */
+#define RS_ST_CORRECT_MISS 8u    /* correct_coords would never terminate (reference hangs)                         */
+#define RS_ST_WALL_ASSERT 16u    /* `assert dists[i] == 0.0` in obstruction_sensors would fire                     */
+#define RS_ST_COORD_RANGE 32u    /* |coordinate| > 16383: outside the exact-int32 geometry range                   */
+
+/* Environment constants (dataclass fields R:320-390 that the hot path reads). */
+typedef struct RsConfig {
+    int32_t bbox[4];             /* x0,y0,x1,y1                                default 0,0,2700,2700  R:321-325 */
+    int32_t obs_area[2];         /* observation_area                           default 200,500        R:326     */
+    int32_t enforce;             /* enforce_grid_boundaries                                           R:329     */
+    int32_t n_agents;            /* number_agents                                                     R:353     */
+    int32_t obstruction_count;   /* -1 random 1..5, 0..7 fixed                                        R:328     */
+    int32_t count_law;           /* 0 = reference (intensity/distance + bkg, R:498-502), 1 = inverse square     */
+    int32_t max_ep_len;          /* steps_per_episode                           default 120           T:394     */
+    int32_t k_max;               /* obstruction slots allocated in RsState (>= max num_obs)                     */
+} RsConfig;
+
+/* Structure-of-arrays environment state in HBM; N = envs on this rank, A = n_agents, K = k_max.  All device pointers. */
+typedef struct RsState {
+    int32_t *src;                /* [N][2]    source x,y                                                        */
+    int32_t *rad;                /* [N][2]    intensity, background                                             */
+    int32_t *rects;              /* [K][N][4] x0,y0,x1,y1 (16-byte rows; slot k of env n at (k*N+n)*4)          */
+    int32_t *meta;               /* [N]       num_obs | done<<8 | ep_len<<16                                    */
+    int32_t *det;                /* [A][N][2] detector x,y                                                      */
+    double *best;                /* [A][N]    Agent.prev_det_dist (running minimum of the shortest-path length)  */
+    int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24                       */
+    double *dsrc;                /* [4K][N]   shortest-path length source -> obstruction corner c (inf if none)  */
+    uint32_t *vis;               /* [4K][N]   corner-to-corner visibility bit masks                              */
+    uint32_t *status;            /* [N]       RS_ST_* bits, sticky until cleared by the caller                   */
+    int32_t *reset_list;         /* [N]       envs scheduled for reset by the last rs_step                       */
+    int32_t *reset_count;        /* [1]                                                                          */
+} RsState;
+
+/* One environment step for n_env environments (all agents).  actions[N][A] in 0..8 (8 = idle), or NULL for the
+ * reference's step(None) probe.  Outputs (any may be NULL except obs): obs[N][A][11] f32, reward[N][A] f32,
+ * team_reward[N] f32, done[N][A] u8, info[N][A] u8 (RS_I_*), ended[N] u8 (RS_E_*), final_obs[N][A][11] f32 (written
+ * only for envs that were scheduled for reset).  uniforms: NULL = Philox4x32-10 stream keyed (seed, env_id0+n, agent,
+ * step_ctr); else [N][A][n_uniforms] doubles consumed in order by the Poisson sampler (numpy next_double stream). */
+int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, float *obs, float *reward,
+            float *team_reward, uint8_t *done, uint8_t *info, uint8_t *ended, float *final_obs, int32_t n_env,
+            uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms, int32_t n_uniforms,
+            int32_t flags, void *stream);
+
+/* Reset (re-sample source, detector, intensities; obstructions too where requested) and write the initial
+ * observation.  Which envs: flags&RS_F_RESET_LIST -> those scheduled by rs_step; else reset_mask[N] (NULL = all).
+ * New obstructions: flags&RS_F_NEW_OBSTACLES -> all of them; else new_obstacles_mask[N] (NULL = none). */
+int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, const uint8_t *new_obstacles_mask,
+             float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms,
+             int32_t n_uniforms, int32_t flags, void *stream);
+
+/* Scenario injection: src[N][2], det[N][2], intensity[N], bkg[N], rects[N][k_in][4] (x0,y0,x1,y1), num_obs[N] -- all
+ * int32 device arrays.  Builds the per-episode tables and writes the initial observation (a step(None) probe). */
+int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src, const int32_t *det,
+                      const int32_t *intensity, const int32_t *bkg, const int32_t *rects, int32_t k_in,
+                      const int32_t *num_obs, float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed,
+                      uint64_t step_ctr, const double *uniforms, int32_t n_uniforms, void *stream);
+
+/* GAE-lambda advantages and rewards-to-go over a [T][N] rollout.  path_end[t][n] != 0 where the caller finished a
+ * trajectory after step t; boot[t][n] = bootstrap value passed there (read only where path_end or t == T-1).
+ * stats (nullable): double[2] device accumulators += {sum(adv), sum(adv^2)} (zero them first).
+ * variant: 0 auto, 1 thread-per-column, 2 warp-shuffle scan along T. */
+int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
+           int32_t T, int32_t N, double gamma, double lam, double *stats, int32_t variant, void *stream);
+
+/* stats[0] += sum(x - c), stats[1] += sum((x - c)^2) over n floats, fp64 accumulation; c = *center (device double,
+ * NULL = 0).  Two calls give the reference's two-pass mean / population std (mpi_tools.py:71-95) with an all-reduce
+ * of the two scalars in between when the envs are sharded over ranks. */
+int rs_adv_stats(const float *x, int64_t n, const double *center, double *stats, void *stream);
+
+/* x[i] = (x[i] - *mean) / *std   (device doubles)                                                     P:446 */
+int rs_adv_normalize(float *x, int64_t n, const double *mean, const double *std, void *stream);
+
+const char *rs_last_error(void);
+int rs_version(void);
+/* sizeof checks for the binding */
+int rs_sizeof_config(void);
+int rs_sizeof_state(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,572 @@
+// Per-environment logic of the RadSearch step / reset kernels.  One thread owns one environment; its obstruction
+// rectangles, source-distance table and corner-visibility masks live in a private shared-memory column (Col<T>).
+// R: = /root/reference/gym_rad_search/gym_rad_search/envs/rad_search_env.py, T: = algos/multiagent/train.py
+#pragma once
+#include "rs_device.cuh"
+
+namespace rs {
+
+template <typename T>
+struct Col {
+    T *p;
+    int stride;
+    __device__ __forceinline__ T &operator[](int i) const { return p[i * stride]; }
+};
+
+struct Params {
+    int bx0, by0, bx1, by1;       // bbox
+    int sx0, sy0, sx1, sy1;       // search area R:393-420
+    int lo, hi;                   // observation_area
+    int enforce, n_agents, obstruction_count, count_law, max_ep_len, k_max;
+    double max_dist;              // R:423-425
+    double inv_scale;             // 1 / search_area[2][1]  R:435
+};
+
+__host__ __device__ inline Params make_params(const RsConfig &c) {
+    Params p;
+    p.bx0 = c.bbox[0]; p.by0 = c.bbox[1]; p.bx1 = c.bbox[2]; p.by1 = c.bbox[3];
+    p.lo = c.obs_area[0]; p.hi = c.obs_area[1];
+    p.sx0 = p.bx0 + p.lo; p.sy0 = p.by0 + p.lo; p.sx1 = p.bx1 - p.hi; p.sy1 = p.by1 - p.hi;
+    p.enforce = c.enforce; p.n_agents = c.n_agents; p.obstruction_count = c.obstruction_count;
+    p.count_law = c.count_law; p.max_ep_len = c.max_ep_len; p.k_max = c.k_max;
+    const double dy = (double)(p.sy1 - p.sy0);
+    p.max_dist = sqrt(dy * dy);
+    p.inv_scale = 1.0 / (double)p.sy1;
+    return p;
+}
+
+struct EnvView {
+    Col<int4> rects;
+    Col<double> dsrc;
+    int num_obs;
+    int sx, sy;          // source
+    int intensity, bkg;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// shortest path source -> p around the rectangles (R:491-493) from the per-episode table dsrc[corner]
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx, int qy) {
+    bool hit = false;
+    for (int k = 0; k < e.num_obs; k++) hit = hit || (seg_rect(px, py, qx, qy, e.rects[k]) & 1);
+    return !hit;
+}
+
+__device__ __forceinline__ double dist_int(int dx, int dy) { return sqrt((double)(dx * dx + dy * dy)); }
+
+__device__ __forceinline__ double shortest_path(const EnvView &e, int px, int py) {
+    if (visible(e, px, py, e.sx, e.sy)) return dist_int(px - e.sx, py - e.sy);
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    const int nc = 4 * e.num_obs;
+    for (int c = 0; c < nc; c++) {
+        const double ds = e.dsrc[c];
+        if (!(ds < best)) continue;                     // cannot improve (also skips unreachable corners)
+        const int4 r = e.rects[c >> 2];
+        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+        const double cand = ds + dist_int(px - cx, py - cy);
+        if (cand < best && visible(e, px, py, cx, cy)) best = cand;
+    }
+    return best;
+}
+
+// is_intersect R:1133-1146, including the leftover `not isclose(sqrt(euc_dist), sp_dist, abs_tol=0.1)` clause
+__device__ __forceinline__ bool los_blocked(const EnvView &e, int px, int py, double euc, double sp) {
+    const double a = sqrt(euc), b = sp;
+    const double diff = fabs(a - b), big = fmax(fabs(a), fabs(b));
+    const double tol = fmax(1e-09 * big, 0.1);
+    if (a == b || (isfinite(a) && isfinite(b) && diff <= tol)) return false;
+    bool hit = false;
+    for (int k = 0; k < e.num_obs; k++) hit = hit || los_blocked_rect(px, py, e.sx, e.sy, e.rects[k]);
+    return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// obstruction_sensors R:1172-1261 and correct_coords R:1263-1306
+// ---------------------------------------------------------------------------------------------------------------
+// closed ray [p, p+step(d)] touches the axis-aligned lattice edge; d2 = squared distance p -> edge (clamped projection)
+__device__ __forceinline__ bool ray_hits_vedge(int px, int py, int sx, int sy, int c, int ya, int yb) {
+    // edge x = c, y in [ya, yb]
+    if (sx == 0) {
+        if (px != c) return false;
+        const int lo = min(py, py + sy), hi = max(py, py + sy);
+        return lo <= yb && ya <= hi;
+    }
+    const int t = c - px;                           // need t/sx in [0,1]
+    if (sx > 0 ? (t < 0 || t > sx) : (t > 0 || t < sx)) return false;
+    // y at the crossing: sy is 0 or +-|sx|
+    const int yat = py + (sy == 0 ? 0 : ((sy > 0) == (sx > 0) ? t : -t));
+    return ya <= yat && yat <= yb;
+}
+__device__ __forceinline__ int clampdist(int v, int a, int b) { return v < a ? a - v : (v > b ? v - b : 0); }
+
+__device__ __forceinline__ void correct_coords(int px, int py, int4 r, float out[8], uint32_t &status) {
+    int lo_d[8];
+    int nstar = 0x7fffffff;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int cx = coef_x(d), cy = coef_y(d);
+        int lo = 1, hi = 0x7fffffff;
+        bool ok = true;
+        const int X = 10 * px, Y = 10 * py;
+        if (cx == 0) ok = ok && (10 * r.x <= X && X <= 10 * r.z);
+        else if (cx > 0) { lo = max(lo, 10 * r.x - X); hi = min(hi, 10 * r.z - X); }
+        else { lo = max(lo, X - 10 * r.z); hi = min(hi, X - 10 * r.x); }
+        if (cy == 0) ok = ok && (10 * r.y <= Y && Y <= 10 * r.w);
+        else if (cy > 0) { lo = max(lo, 10 * r.y - Y); hi = min(hi, 10 * r.w - Y); }
+        else { lo = max(lo, Y - 10 * r.w); hi = min(hi, Y - 10 * r.y); }
+        ok = ok && lo <= hi;
+        lo_d[d] = ok ? lo : 0x7fffffff;
+        nstar = min(nstar, lo_d[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 8; d++) out[d] = 0.0f;
+    if (nstar == 0x7fffffff) { status |= RS_ST_CORRECT_MISS; return; }
+    int xc = 0, cnt = 0;
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+        if (lo_d[d] == nstar) { xc |= 1 << d; cnt++; }
+    if (cnt >= 4) {
+#pragma unroll
+        for (int ii = 0; ii <= 6; ii += 2) {
+            const int lo = (ii + 7) & 7, hi = ii + 1;
+            if (((xc >> lo) & 1) && ((xc >> hi) & 1)) { out[ii] = 1.0f; out[lo] = 1.0f; out[hi] = 1.0f; }
+        }
+    }
+}
+
+__device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int px, int py, float out[8],
+                                        uint32_t &status) {
+    // squared distance of the best scored edge per direction; -1 = no hit
+    int best_d2[8];
+#pragma unroll
+    for (int d = 0; d < 8; d++) best_d2[d] = -1;
+    // candidate rectangles: a ray is at most 100 (71 per axis) long
+    int cand = 0;
+    for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        if (r.x - 100 <= px && px <= r.z + 100 && r.y - 100 <= py && py <= r.w + 100) cand |= 1 << k;
+    }
+    if (cand) {
+        int hits_best = -1, best_k = 0;
+        int hits[RS_MAX_K];
+#pragma unroll
+        for (int k = 0; k < RS_MAX_K; k++) hits[k] = 0;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            const int sx = step_dx(d), sy = step_dy(d);
+            int inter = 0;
+            int dmin = -1;
+#pragma unroll
+            for (int k = 0; k < RS_MAX_K; k++) {
+                if (!((cand >> k) & 1)) continue;
+                const int4 r = e.rects[k];
+                // edge order R:1000-1006: (p0,p1) left, (p0,p3) bottom, (p2,p1) top, (p2,p3) right
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    bool hit;
+                    int d2;
+                    if (s == 0 || s == 3) {
+                        const int c = (s == 0) ? r.x : r.z;
+                        hit = ray_hits_vedge(px, py, sx, sy, c, r.y, r.w);
+                        const int ddx = px - c, ddy = clampdist(py, r.y, r.w);
+                        d2 = ddx * ddx + ddy * ddy;
+                    } else {
+                        const int c = (s == 1) ? r.y : r.w;
+                        hit = ray_hits_vedge(py, px, sy, sx, c, r.x, r.z);      // transposed
+                        const int ddy = py - c, ddx = clampdist(px, r.x, r.z);
+                        d2 = ddx * ddx + ddy * ddy;
+                    }
+                    if (inter < 2 && hit) {
+                        dmin = (dmin < 0 || d2 < dmin) ? d2 : dmin;
+                        inter++;
+                        hits[k]++;
+                    }
+                }
+            }
+            best_d2[d] = dmin;
+        }
+        int ones = 0;
+#pragma unroll
+        for (int d = 0; d < 8; d++) ones += (best_d2[d] == 0);
+        if (ones > 3) {
+            // max(zip(obs_idx_ls, self.poly)) R:1222-1226: most hits, ties -> lexicographically largest vertex list
+#pragma unroll
+            for (int k = 0; k < RS_MAX_K; k++) {
+                if (k >= e.num_obs) continue;
+                bool take = hits[k] > hits_best;
+                if (!take && hits[k] == hits_best) {
+                    const int4 a = e.rects[k], b = e.rects[best_k];
+                    take = (a.x != b.x) ? (a.x > b.x) : ((a.y != b.y) ? (a.y > b.y) : ((a.w != b.w) ? (a.w > b.w) : (a.z > b.z)));
+                }
+                if (take) { hits_best = hits[k]; best_k = k; }
+            }
+            correct_coords(px, py, e.rects[best_k], out, status);
+#pragma unroll
+            for (int d = 0; d < 8; d++) best_d2[d] = -2;      // already final
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        if (best_d2[d] == -1) out[d] = 0.0f;
+        else if (best_d2[d] >= 0) out[d] = __fdiv_rn(110.0f - __fsqrt_rn((float)best_d2[d]), 110.0f);
+    }
+    if (P.enforce) {                                           // R:1232-1259
+        if (px - 110 < P.bx0) { if (out[0] != 0.0f) status |= RS_ST_WALL_ASSERT; out[0] = __fdiv_rn(110.0f - fabsf((float)(px - P.bx0)), 110.0f); }
+        if (py - 110 < P.by0) { if (out[6] != 0.0f) status |= RS_ST_WALL_ASSERT; out[6] = __fdiv_rn(110.0f - fabsf((float)(py - P.by0)), 110.0f); }
+        if (P.bx1 <= px + 110) { if (out[4] != 0.0f) status |= RS_ST_WALL_ASSERT; out[4] = __fdiv_rn(110.0f - fabsf((float)(P.bx1 - px)), 110.0f); }
+        if (P.by1 <= py + 110) { if (out[2] != 0.0f) status |= RS_ST_WALL_ASSERT; out[2] = __fdiv_rn(110.0f - fabsf((float)(P.by1 - py)), 110.0f); }
+    }
+}
+
+// in_obstruction R:1148-1170
+__device__ __forceinline__ bool in_obstruction(const EnvView &e, int px, int py) {
+    bool found = false, blocked = false;
+    for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        if (!found && in_rect_closed(px, py, r)) { found = true; blocked = in_rect_open(px, py, r); }
+    }
+    return blocked;
+}
+
+// measurement + sensors + observation row for one agent at (px,py).  R:495-502, 570-593
+template <bool kFast>
+__device__ __forceinline__ bool observe(const Params &P, const EnvView &e, int px, int py, double euc, double sp,
+                                        Rng &g, float *obs_row, uint32_t &status) {
+    const bool blocked_los = los_blocked(e, px, py, euc, sp);
+    double lam;
+    if (blocked_los) lam = (double)e.bkg;
+    else {
+        double d = euc;
+        if (d == 0.0) { status |= RS_ST_LAMBDA_INF; d = 1.0; }
+        lam = (P.count_law == 1) ? (double)e.intensity / (d * d) + (double)e.bkg : (double)e.intensity / d + (double)e.bkg;
+    }
+    const long long cnt = poisson<kFast>(g, lam);
+    status |= g.status;
+    float s[8];
+    if (e.num_obs > 0 || P.enforce) sensors(P, e, px, py, s, status);
+    else {
+#pragma unroll
+        for (int d = 0; d < 8; d++) s[d] = 0.0f;
+    }
+    obs_row[0] = (float)cnt;
+    obs_row[1] = (float)((double)px * P.inv_scale);
+    obs_row[2] = (float)((double)py * P.inv_scale);
+#pragma unroll
+    for (int d = 0; d < 8; d++) obs_row[3 + d] = s[d];
+    return blocked_los;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RadSearch.step R:443-728 for one environment (all agents), plus the caller rules T:394-405 when auto-reset is on
+// ---------------------------------------------------------------------------------------------------------------
+struct StepArgs {
+    const int32_t *actions;
+    float *obs, *reward, *team_reward, *final_obs;
+    uint8_t *done, *info, *ended;
+    int n_env;
+    uint32_t env_id0;
+    uint64_t seed, step_ctr;
+    const double *uniforms;
+    int n_uniforms, flags;
+};
+
+template <bool kFast>
+__device__ __forceinline__ void step_env(const Params &P, const RsState &S, const StepArgs &a, int n, Col<int4> rects,
+                                         Col<double> dsrc) {
+    const int N = a.n_env, A = P.n_agents;
+    const int meta = S.meta[n];
+    EnvView e;
+    e.rects = rects; e.dsrc = dsrc;
+    e.num_obs = meta & 0xff;
+    int done = (meta >> 8) & 1;
+    int ep_len = meta >> 16;
+    const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
+    const int2 rad = reinterpret_cast<const int2 *>(S.rad)[n];
+    e.sx = src.x; e.sy = src.y; e.intensity = rad.x; e.bkg = rad.y;
+    for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = S.dsrc[(size_t)c * N + n];
+    uint32_t status = 0;
+
+    int propx[RS_MAX_A], propy[RS_MAX_A];
+    const bool have_act = a.actions != nullptr;
+    if (have_act && A > 1) {
+        for (int i = 0; i < A; i++) {
+            const int2 d = reinterpret_cast<const int2 *>(S.det)[(size_t)i * N + n];
+            const int act = a.actions[(size_t)n * A + i];
+            propx[i] = d.x + step_dx(act); propy[i] = d.y + step_dy(act);
+        }
+    }
+    bool have_max = false;
+    double max_reward = 0.0;
+    for (int ag = 0; ag < A; ag++) {
+        const size_t ia = (size_t)ag * N + n;
+        int2 det = reinterpret_cast<const int2 *>(S.det)[ia];
+        double best = S.best[ia];
+        int af = S.aflags[ia];
+        const int action = have_act ? a.actions[(size_t)n * A + ag] : -1;
+        int info = 0;
+        bool moved = false;
+        if (action >= 0) {                                              // take_action R:876-946
+            const int tx = det.x + step_dx(action), ty = det.y + step_dy(action);
+            int cnt = 0;
+            if (A > 1) for (int i = 0; i < A; i++) cnt += (propx[i] == tx && propy[i] == ty);
+            if (cnt > 1) info |= RS_I_COLLISION;
+            else {
+                bool roll = false;
+                if (P.enforce) {
+                    if (tx < P.bx0 || ty < P.by0 || P.bx1 <= tx || P.by1 <= ty) { info |= RS_I_OOB; af += 1; roll = true; }
+                } else {
+                    if (det.x < P.sx0 || det.y < P.sy0 || P.sx1 < det.x || P.sy1 < det.y) { info |= RS_I_OOB; af += 1; }
+                }
+                if (in_obstruction(e, tx, ty)) { roll = true; af |= 1 << 24; }
+                if (!roll) { det.x = tx; det.y = ty; moved = true; }
+            }
+        }
+        if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
+        // the reference keeps stale sp/euc when the detector did not move; recomputing them at the unchanged position
+        // gives the same numbers (R:528-567)
+        const double sp = shortest_path(e, det.x, det.y);
+        const double euc = dist_int(det.x - e.sx, det.y - e.sy);
+        Rng g;
+        if (a.uniforms) g.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
+        else g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 0, (uint32_t)ag, a.step_ctr);
+        float *row = a.obs + ((size_t)n * A + ag) * RS_OBS_DIM;
+        if (observe<kFast>(P, e, det.x, det.y, euc, sp, g, row, status)) info |= RS_I_LOS_BLOCKED;
+        double reward;
+        if (moved) {                                                    // R:507-522
+            info |= RS_I_MOVED;
+            if (sp < 110) { reward = 0.1; done = 1; }
+            else if (sp < best) { reward = 0.1; best = sp; }
+            else if (action == 8) reward = -1.0 * sp / P.max_dist;
+            else reward = -0.5 * sp / P.max_dist;
+        } else {
+            reward = -0.5 * sp / P.max_dist;                            // R:549, 567
+        }
+        reward = round2(reward);                                        // R:613
+        if (!have_max || max_reward == 0.0) { max_reward = reward; have_max = true; }   // R:661-665
+        else if (max_reward < reward) max_reward = reward;
+        if (af & (1 << 24)) info |= RS_I_BLOCKED;
+        reinterpret_cast<int2 *>(S.det)[ia] = det;
+        S.best[ia] = best;
+        S.aflags[ia] = af;
+        if (a.reward) a.reward[(size_t)n * A + ag] = (float)reward;
+        if (a.done) a.done[(size_t)n * A + ag] = (uint8_t)done;
+        if (a.info) a.info[(size_t)n * A + ag] = (uint8_t)info;
+    }
+    if (a.team_reward) a.team_reward[n] = (float)max_reward;
+    int ended = done ? RS_E_TERMINAL : 0;
+    if (have_act) ep_len += 1;
+    if (a.flags & RS_F_AUTO_RESET) {                                    // T:394-405, 446-548
+        const bool timeout = ep_len == P.max_ep_len;
+        if (timeout) ended |= RS_E_TIMEOUT;
+        if (done || timeout || (a.flags & RS_F_EPOCH_END)) {
+            ended |= RS_E_RESET;
+            const int slot = atomicAdd(S.reset_count, 1);
+            S.reset_list[slot] = n;
+            if (a.final_obs) {
+                for (int i = 0; i < A * RS_OBS_DIM; i++)
+                    a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = a.obs[(size_t)n * A * RS_OBS_DIM + i];
+            }
+        }
+    }
+    if (a.ended) a.ended[n] = (uint8_t)ended;
+    S.meta[n] = e.num_obs | (done << 8) | (ep_len << 16);
+    if (status) S.status[n] |= status;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset R:730-797: scenario sampling (Philox domain 1), per-episode tables, initial observation (step(None) probe)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rand_point(const Params &P, Rng &g, int &x, int &y) {     // R:1026-1036
+    const uint32_t span = (uint32_t)(P.sx1 - P.sx0);
+    x = P.sx0 + (int)g.below(span);
+    y = P.sx0 + (int)g.below(span);
+}
+
+__device__ __forceinline__ int create_obstructions(const Params &P, Rng &g, Col<int4> rects, uint32_t &status) {
+    const int hx = (int)((double)P.sx1 * 0.9), hy = (int)((double)P.sy1 * 0.9);            // R:961-966
+    int num_obs = 0;
+    for (int attempt = 0; attempt < 256; attempt++) {
+        num_obs = (P.obstruction_count == -1) ? 1 + (int)g.below(5) : P.obstruction_count;  // R:745-750
+        int ii = 0, tries = 0;
+        while (ii < num_obs && tries < 4096) {
+            tries++;
+            const int sx = P.sx0 + (int)g.below((uint32_t)(hx - P.sx0));
+            const int sy = P.sy0 + (int)g.below((uint32_t)(hy - P.sy0));
+            const int ex = P.lo + (int)g.below((uint32_t)(P.hi - P.lo));
+            const int ey = P.lo + (int)g.below((uint32_t)(P.hi - P.lo));
+            const int4 r = make_int4(sx, sy, sx + ex, sy + ey);
+            bool touch = false;
+            for (int kk = 0; kk < ii; kk++) touch = touch || rects_touch(rects[kk], r);       // R:985-992
+            if (!touch) { rects[ii] = r; ii++; }
+        }
+        if (ii < num_obs) { status |= RS_ST_REJECT_CAP; num_obs = ii; }
+        bool nested = false;                                                                // is_valid R:788-791
+        for (int i = 0; i < num_obs; i++)
+            for (int j = i + 1; j < num_obs; j++) nested = nested || rects_nested(rects[i], rects[j]);
+        if (!nested) return num_obs;
+    }
+    status |= RS_ST_REJECT_CAP;
+    return num_obs;
+}
+
+__device__ __forceinline__ void sample_source_loc_pos(const Params &P, Rng &g, const EnvView &e, int &sx, int &sy,
+                                                      int &dx_, int &dy_, uint32_t &status) {
+    int srcx, srcy, detx, dety;
+    rand_point(P, g, srcx, srcy);
+    rand_point(P, g, detx, dety);
+    int tries = 0;
+    for (;;) {                                                                               // R:1057-1076
+        bool inside = false;
+        for (int k = 0; k < e.num_obs; k++) inside = inside || in_rect_closed(detx, dety, e.rects[k]);
+        if (!inside) break;
+        if (++tries > 100000) { status |= RS_ST_REJECT_CAP; break; }
+        rand_point(P, g, detx, dety);
+    }
+    int num_retry = 0;
+    tries = 0;
+    for (;;) {                                                                               // R:1091-1129
+        for (;;) {
+            const int ddx = detx - srcx, ddy = dety - srcy;
+            if (ddx * ddx + ddy * ddy >= 1000000) break;
+            if (++tries > 100000) { status |= RS_ST_REJECT_CAP; break; }
+            rand_point(P, g, srcx, srcy);
+        }
+        bool resamp = false, inter = false;
+        for (int k = 0; k < e.num_obs; k++) {
+            if (resamp) break;
+            const int4 r = e.rects[k];
+            if (in_rect_closed(srcx, srcy, r)) resamp = true;
+            if (!resamp && los_blocked_rect(detx, dety, srcx, srcy, r)) inter = true;
+        }
+        if (e.num_obs == 0 || (num_retry > 20 && !resamp)) break;
+        else if (resamp || !inter) { rand_point(P, g, srcx, srcy); num_retry++; }
+        else break;
+        if (++tries > 100000) { status |= RS_ST_REJECT_CAP; break; }
+    }
+    sx = srcx; sy = srcy; dx_ = detx; dy_ = dety;
+}
+
+// corner-to-corner visibility masks (depends on the obstructions only)
+__device__ __forceinline__ void build_visibility(const EnvView &e, Col<uint32_t> vis) {
+    const int nc = 4 * e.num_obs;
+    for (int c = 0; c < nc; c++) vis[c] = 0u;
+    for (int c = 0; c < nc; c++) {
+        const int4 rc = e.rects[c >> 2];
+        const int cx = corner_x(rc, c & 3), cy = corner_y(rc, c & 3);
+        uint32_t m = vis[c];
+        for (int c2 = c + 1; c2 < nc; c2++) {
+            const int4 r2 = e.rects[c2 >> 2];
+            if (visible(e, cx, cy, corner_x(r2, c2 & 3), corner_y(r2, c2 & 3))) {
+                m |= 1u << c2;
+                vis[c2] = vis[c2] | (1u << c);
+            }
+        }
+        vis[c] = m;
+    }
+}
+
+// dsrc[c] = shortest path length source -> corner c: Dijkstra on the corner visibility graph, sums accumulated from
+// the source outwards (the order Polyline::length() adds them)
+__device__ __forceinline__ void build_dsrc(const EnvView &e, Col<uint32_t> vis) {
+    const int nc = 4 * e.num_obs;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int c = 0; c < nc; c++) {
+        const int4 r = e.rects[c >> 2];
+        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+        e.dsrc[c] = visible(e, e.sx, e.sy, cx, cy) ? dist_int(cx - e.sx, cy - e.sy) : inf;
+    }
+    uint32_t fin = 0;
+    for (int it = 0; it < nc; it++) {
+        int u = -1;
+        double du = inf;
+        for (int c = 0; c < nc; c++) {
+            const double d = e.dsrc[c];
+            if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
+        }
+        if (u < 0) break;
+        fin |= 1u << u;
+        const int4 ru = e.rects[u >> 2];
+        const int ux = corner_x(ru, u & 3), uy = corner_y(ru, u & 3);
+        uint32_t m = vis[u] & ~fin;
+        while (m) {
+            const int w = __ffs(m) - 1;
+            m &= m - 1;
+            const int4 rw = e.rects[w >> 2];
+            const double nd = du + dist_int(ux - corner_x(rw, w & 3), uy - corner_y(rw, w & 3));
+            if (nd < e.dsrc[w]) e.dsrc[w] = nd;
+        }
+    }
+}
+
+struct ResetArgs {
+    float *obs;
+    int n_env;
+    uint32_t env_id0;
+    uint64_t seed, step_ctr;
+    const double *uniforms;
+    int n_uniforms;
+    // scenario injection (all nullptr when sampling)
+    const int32_t *in_src, *in_det, *in_intensity, *in_bkg, *in_rects, *in_num_obs;
+    int k_in;
+};
+
+template <bool kFast>
+__device__ __forceinline__ void reset_env(const Params &P, const RsState &S, const ResetArgs &a, int n,
+                                          bool new_obstacles, Col<int4> rects, Col<double> dsrc, Col<uint32_t> vis) {
+    const int N = a.n_env, A = P.n_agents;
+    uint32_t status = 0;
+    EnvView e;
+    e.rects = rects; e.dsrc = dsrc;
+    Rng g;
+    g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, a.step_ctr);
+    const bool inject = a.in_src != nullptr;
+    int detx, dety;
+    if (inject) {                                                       // refresh_environment R:799-874
+        e.num_obs = min(a.in_num_obs[n], P.k_max);
+        for (int k = 0; k < e.num_obs; k++)
+            rects[k] = reinterpret_cast<const int4 *>(a.in_rects)[(size_t)n * a.k_in + k];
+        new_obstacles = true;
+    } else if (new_obstacles) {
+        e.num_obs = create_obstructions(P, g, rects, status);           // R:744-762
+    } else {
+        e.num_obs = S.meta[n] & 0xff;
+        for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+        for (int c = 0; c < 4 * e.num_obs; c++) vis[c] = S.vis[(size_t)c * N + n];
+    }
+    if (new_obstacles) {
+        build_visibility(e, vis);
+        for (int k = 0; k < e.num_obs; k++) reinterpret_cast<int4 *>(S.rects)[(size_t)k * N + n] = rects[k];
+        for (int c = 0; c < 4 * e.num_obs; c++) S.vis[(size_t)c * N + n] = vis[c];
+    }
+    if (inject) {
+        e.sx = a.in_src[2 * n]; e.sy = a.in_src[2 * n + 1];
+        detx = a.in_det[2 * n]; dety = a.in_det[2 * n + 1];
+        e.intensity = a.in_intensity[n]; e.bkg = a.in_bkg[n];
+    } else {
+        sample_source_loc_pos(P, g, e, e.sx, e.sy, detx, dety, status);  // R:764-769
+        e.intensity = 1000000 + (int)g.below(9000000u);                  // R:778
+        e.bkg = 10 + (int)g.below(41u);                                  // R:779
+    }
+    build_dsrc(e, vis);
+    for (int c = 0; c < 4 * e.num_obs; c++) S.dsrc[(size_t)c * N + n] = dsrc[c];
+    reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
+    reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
+    S.meta[n] = e.num_obs;                                               // done = 0, ep_len = 0   R:739-740
+    const double sp = shortest_path(e, detx, dety);                      // prev_det_dist R:771-776
+    const double euc = dist_int(detx - e.sx, dety - e.sy);
+    for (int ag = 0; ag < A; ag++) {
+        const size_t ia = (size_t)ag * N + n;
+        reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
+        S.best[ia] = sp;
+        S.aflags[ia] = 0;                                                // Agent.reset R:289-300
+        Rng gp;
+        if (a.uniforms) gp.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
+        else gp.init_philox(a.seed, a.env_id0 + (uint32_t)n, 2, (uint32_t)ag, a.step_ctr);
+        observe<kFast>(P, e, detx, dety, euc, sp, gp, a.obs + ((size_t)n * A + ag) * RS_OBS_DIM, status);   // R:794
+    }
+    status |= g.status;
+    if (status) S.status[n] |= status;
+}
+
+}  // namespace rs

@@ -1,0 +1,158 @@
+// sm_100a kernels + C-ABI entry points for the RadSearch env step / reset (include/radsearch_b200.h).
+// Build: radiation_ppo_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "rs_env_impl.cuh"
+#include "rs_error.h"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+thread_local char g_err[256] = "";
+
+int fail(const char *msg) { return rs_set_error(msg); }
+
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock) step_kernel(rs::Params P, RsState S, rs::StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int4 *srects = reinterpret_cast<int4 *>(smem);                                  // [k_max][kBlock]
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);  // [4*k_max][kBlock]
+    const int n = blockIdx.x * kBlock + threadIdx.x;
+    if (n >= a.n_env) return;
+    rs::step_env<kFast>(P, S, a, n, rs::Col<int4>{srects + threadIdx.x, kBlock},
+                        rs::Col<double>{sdsrc + threadIdx.x, kBlock});
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
+                                                        const uint8_t *new_mask, int flags) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int4 *srects = reinterpret_cast<int4 *>(smem);
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
+    uint32_t *svis = reinterpret_cast<uint32_t *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    int n;
+    if (flags & RS_F_RESET_LIST) {
+        if (i >= *S.reset_count) return;
+        n = S.reset_list[i];
+    } else {
+        if (i >= a.n_env) return;
+        n = i;
+        if (mask && !mask[n]) return;
+    }
+    const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
+    rs::reset_env<kFast>(P, S, a, n, new_obs, rs::Col<int4>{srects + threadIdx.x, kBlock},
+                         rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<uint32_t>{svis + threadIdx.x, kBlock});
+}
+
+int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
+    if (!cfg || !st) return fail("cfg/state is NULL");
+    if (n_env <= 0) return fail("n_env must be positive");
+    if (cfg->n_agents < 1 || cfg->n_agents > RS_MAX_A) return fail("n_agents out of range [1, 8]");
+    if (cfg->k_max < 0 || cfg->k_max > RS_MAX_K) return fail("k_max out of range [0, 8]");
+    if (cfg->obstruction_count < -1 || cfg->obstruction_count > 7) return fail("obstruction_count out of range [-1, 7]");
+    if (cfg->obstruction_count > cfg->k_max || (cfg->obstruction_count == -1 && cfg->k_max < 5))
+        return fail("k_max smaller than the number of obstructions that can be drawn");
+    if (cfg->max_ep_len < 1 || cfg->max_ep_len > 32767) return fail("max_ep_len out of range [1, 32767]");
+    if (cfg->bbox[2] - cfg->obs_area[1] <= cfg->bbox[0] + cfg->obs_area[0]) return fail("empty search area");
+    if (!st->src || !st->rad || !st->meta || !st->det || !st->best || !st->aflags || !st->status)
+        return fail("RsState has NULL members");
+    if (cfg->k_max > 0 && (!st->rects || !st->dsrc || !st->vis)) return fail("RsState obstruction tables are NULL");
+    return 0;
+}
+
+size_t step_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(double)); }
+size_t reset_smem(const RsConfig *cfg) { return step_smem(cfg) + (size_t)cfg->k_max * kBlock * 4 * sizeof(uint32_t); }
+
+}  // namespace
+
+int rs_set_error(const char *msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg);
+    return -1;
+}
+
+extern "C" {
+
+int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, float *obs, float *reward,
+            float *team_reward, uint8_t *done, uint8_t *info, uint8_t *ended, float *final_obs, int32_t n_env,
+            uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms, int32_t n_uniforms,
+            int32_t flags, void *stream) {
+    if (int rc = check_cfg(cfg, st, n_env)) return rc;
+    if (!obs) return fail("obs is NULL");
+    if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
+    if ((flags & RS_F_AUTO_RESET) && (!st->reset_list || !st->reset_count)) return fail("auto-reset needs reset_list/reset_count");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (flags & RS_F_AUTO_RESET) {
+        cudaError_t e = cudaMemsetAsync(st->reset_count, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    rs::Params P = rs::make_params(*cfg);
+    rs::StepArgs a;
+    a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
+    a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
+    a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
+    const int grid = (n_env + kBlock - 1) / kBlock;
+    const size_t smem = step_smem(cfg);
+    const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    if (fast) step_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a);
+    else step_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a);
+    return (int)cudaGetLastError();
+}
+
+static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
+                        const uint8_t *new_mask, int flags, cudaStream_t s) {
+    rs::Params P = rs::make_params(*cfg);
+    const int grid = (a.n_env + kBlock - 1) / kBlock;
+    const size_t smem = reset_smem(cfg);
+    const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
+    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
+    return (int)cudaGetLastError();
+}
+
+int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, const uint8_t *new_obstacles_mask,
+             float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms,
+             int32_t n_uniforms, int32_t flags, void *stream) {
+    if (int rc = check_cfg(cfg, st, n_env)) return rc;
+    if (!obs) return fail("obs is NULL");
+    if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
+    if ((flags & RS_F_RESET_LIST) && (!st->reset_list || !st->reset_count)) return fail("list reset needs reset_list/reset_count");
+    rs::ResetArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
+    a.uniforms = uniforms; a.n_uniforms = n_uniforms;
+    return launch_reset(cfg, st, a, reset_mask, new_obstacles_mask, flags, static_cast<cudaStream_t>(stream));
+}
+
+int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src, const int32_t *det,
+                      const int32_t *intensity, const int32_t *bkg, const int32_t *rects, int32_t k_in,
+                      const int32_t *num_obs, float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed,
+                      uint64_t step_ctr, const double *uniforms, int32_t n_uniforms, void *stream) {
+    if (int rc = check_cfg(cfg, st, n_env)) return rc;
+    if (!obs || !src || !det || !intensity || !bkg || !num_obs) return fail("scenario arrays must not be NULL");
+    if (k_in < 0 || (k_in > 0 && !rects)) return fail("rects is NULL");
+    if (k_in > cfg->k_max) return fail("k_in exceeds k_max");
+    if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
+    rs::ResetArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
+    a.uniforms = uniforms; a.n_uniforms = n_uniforms;
+    a.in_src = src; a.in_det = det; a.in_intensity = intensity; a.in_bkg = bkg; a.in_rects = rects;
+    a.in_num_obs = num_obs; a.k_in = k_in;
+    return launch_reset(cfg, st, a, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+const char *rs_last_error(void) { return g_err; }
+int rs_version(void) { return RS_VERSION; }
+int rs_sizeof_config(void) { return (int)sizeof(RsConfig); }
+int rs_sizeof_state(void) { return (int)sizeof(RsState); }
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// TEST INFRASTRUCTURE ONLY -- lets g++ compile radiation_ppo_b200/csrc/rs_env_impl.cuh as host code so that the
+// kernel logic can be checked against the oracle in the (GPU-less) build container.  Never linked into the product.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+
+struct int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+using std::max;
+using std::min;
+
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }

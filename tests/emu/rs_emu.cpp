@@ -1,0 +1,72 @@
+// TEST INFRASTRUCTURE ONLY -- host build of the step / reset kernel bodies (one loop iteration per CUDA thread) with
+// the same C entry-point shapes as include/radsearch_b200.h, operating on host memory.  Used by
+// tests/test_kernel_logic_emu.py to compare the kernel logic with the oracle where no GPU exists.
+#define RS_HOST_EMU 1
+#include "../../radiation_ppo_b200/csrc/rs_env_impl.cuh"
+
+#include <vector>
+
+extern "C" {
+
+int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, float *obs, float *reward,
+             float *team_reward, uint8_t *done, uint8_t *info, uint8_t *ended, float *final_obs, int32_t n_env,
+             uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms, int32_t n_uniforms,
+             int32_t flags) {
+    rs::Params P = rs::make_params(*cfg);
+    rs::StepArgs a;
+    a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
+    a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
+    a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
+    if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
+    std::vector<int4> rects(RS_MAX_K);
+    std::vector<double> dsrc(4 * RS_MAX_K);
+    const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    for (int n = 0; n < n_env; n++) {
+        if (fast) rs::step_env<true>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1});
+        else rs::step_env<false>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1});
+    }
+    return 0;
+}
+
+static int run_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
+                     const uint8_t *new_mask, int flags) {
+    rs::Params P = rs::make_params(*cfg);
+    std::vector<int4> rects(RS_MAX_K);
+    std::vector<double> dsrc(4 * RS_MAX_K);
+    std::vector<uint32_t> vis(4 * RS_MAX_K);
+    const int count = (flags & RS_F_RESET_LIST) ? *st->reset_count : a.n_env;
+    const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
+    for (int i = 0; i < count; i++) {
+        int n = i;
+        if (flags & RS_F_RESET_LIST) n = st->reset_list[i];
+        else if (mask && !mask[n]) continue;
+        const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
+        if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
+        else rs::reset_env<false>(P, *st, a, n, new_obs, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
+    }
+    return 0;
+}
+
+int emu_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, const uint8_t *new_obstacles_mask,
+              float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms,
+              int32_t n_uniforms, int32_t flags) {
+    rs::ResetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
+    a.uniforms = uniforms; a.n_uniforms = n_uniforms;
+    return run_reset(cfg, st, a, reset_mask, new_obstacles_mask, flags);
+}
+
+int emu_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src, const int32_t *det,
+                       const int32_t *intensity, const int32_t *bkg, const int32_t *rects, int32_t k_in,
+                       const int32_t *num_obs, float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed,
+                       uint64_t step_ctr, const double *uniforms, int32_t n_uniforms) {
+    rs::ResetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
+    a.uniforms = uniforms; a.n_uniforms = n_uniforms;
+    a.in_src = src; a.in_det = det; a.in_intensity = intensity; a.in_bkg = bkg; a.in_rects = rects;
+    a.in_num_obs = num_obs; a.k_in = k_in;
+    return run_reset(cfg, st, a, nullptr, nullptr, 0);
+}
+}
