@@ -1,0 +1,304 @@
+"""bench.py -- RadSearch env-steps/s (5 obstructions) on N B200s of one node, plus GAE GB/s, roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs-per-gpu E]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one batched environment step of every env on every GPU: rs_step (all agents: move, collision, shortest
+path, LOS, expected counts, Philox+Poisson, 8 sensors, reward/terminal, caller rules) followed by rs_reset for the envs
+that finished (auto-reset).  Workload = BASELINE.json configs[4]: 131,072 envs per GPU, 5 obstructions, enforced
+boundaries, uniform random actions 0..7, episodes staggered so that ~1/120 of the envs reset at every step.
+Weak scaling: envs shard independently over ranks, no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RadSearch env-steps/sec (5 obstructions)"
+UNIT = "env-steps/s"
+K_OBS = 5
+BYTES_PER_ENV_STEP = 122 + 32 * K_OBS        # algorithmic bytes per env-step, single agent
+GAE_BYTES_PER_ELEM = 17                      # rew 4 + val 4 + path_end 1 + adv 4 + ret 4
+T_EPOCH = 480
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(n_envs: int, T: int, threads: int):
+    """The oracle's scalar per-env loop (reference semantics, OpenMP over envs) on the host cores."""
+    from oracle import c_oracle as co
+
+    ob = co.OracleBatch(n_envs, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=threads)
+    ob.reset(0)
+    t0 = time.perf_counter()
+    n, chk = ob.rollout(T, 1, epoch_end_last=False)
+    dt = time.perf_counter() - t0
+    return n / dt, dt, chk
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port of the reference's per-env loop) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+
+    cores = os.cpu_count() or 1
+    n = 4096
+    ob = co.OracleBatch(n, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=cores)
+    ob.reset(0)
+    ctr = 1
+    for _ in range(args.warmup):
+        ob.rollout(1, ctr, epoch_end_last=False); ctr += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ob.rollout(1, ctr, epoch_end_last=False); ctr += 1
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": "RadSearch env step, 5 obstructions, enforced boundaries, random actions, auto-reset; "
+                                   f"bounded sample of {n} envs per step (of 131072 per GPU)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} envs x {args.steps} steps, oracle/radsearch_oracle.c (scalar per-env loop, OpenMP)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=12)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--ring", type=int, default=4, help="env batches cycled so that each step's state comes from HBM")
+    ap.add_argument("--exact-poisson", action="store_true", help="fp64 numpy-exact PTRS acceptance instead of fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import radiation_ppo_b200 as rp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    N, K, W, R = args.envs_per_gpu, args.steps, max(args.warmup, 3), max(args.ring, 1)
+    fast = not args.exact_poisson
+
+    # ---- R independent env batches of N envs (global env ids: rank-major, then ring slot) --------------------------
+    envs = []
+    for r in range(R):
+        e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=dev,
+                         env_id_offset=(rank * R + r) * N, auto_reset=True, fast_poisson=fast)
+        # stagger the episodes: steady state of a training run (about 1/120 of the envs finish at every step)
+        g = torch.Generator(device=dev).manual_seed(1000 + rank * R + r)
+        e._meta.add_(torch.randint(0, 120, (N,), generator=g, device=dev, dtype=torch.int32) << 16)
+        envs.append(e)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    n_act = 16
+    actions = torch.randint(0, 8, (n_act, N, 1), generator=g, device=dev, dtype=torch.int32)   # resident in HBM
+    state_mb = R * N * (BYTES_PER_ENV_STEP + 160 + 80) / 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        return envs[i % R].step_batch(actions[i % n_act], epoch_end=False)
+
+    # ---- device-resident throughput: `value` -----------------------------------------------------------------------
+    for i in range(W):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        one_step(W + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = N * world * K / (total_ms / 1e3)
+
+    # ---- roofline pass: CUDA events around the step kernel alone (same stream), averaged over K launches ------------
+    import ctypes as C
+    from radiation_ppo_b200 import _lib as L
+
+    lib = L.load()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for i in range(K):
+        e = envs[i % R]
+        a = actions[i % n_act]
+        e._ctr += 1
+        kev[i][0].record()
+        L.check(lib.rs_step(C.byref(e._cfg), C.byref(e._st), C.c_void_p(a.data_ptr()), C.c_void_p(e.obs.data_ptr()),
+                            C.c_void_p(e.reward.data_ptr()), C.c_void_p(e.team_reward.data_ptr()),
+                            C.c_void_p(e.done_flags.data_ptr()), C.c_void_p(e.info_flags.data_ptr()),
+                            C.c_void_p(e.ended.data_ptr()), C.c_void_p(e.final_obs.data_ptr()), N, e.env_id_offset,
+                            e.seed, e._ctr, None, 0, L.F_AUTO_RESET | (L.F_FAST_POISSON if fast else 0), stream), "rs_step")
+        kev[i][1].record()
+        L.check(lib.rs_reset(C.byref(e._cfg), C.byref(e._st), None, None, C.c_void_p(e.obs.data_ptr()), N,
+                             e.env_id_offset, e.seed, e._ctr, None, 0,
+                             L.F_RESET_LIST | (L.F_FAST_POISSON if fast else 0), stream), "rs_reset")
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / K
+    peak, peak_src = measured_peak_gbs()
+    achieved = BYTES_PER_ENV_STEP * N / (k_ms / 1e3) / 1e9
+
+    # ---- GAE over the [T, N] rollout buffer ("GAE GB/s vs HBM peak") -------------------------------------------------
+    T = T_EPOCH
+    rew = -0.5 * torch.rand(T, N, generator=g, device=dev) * 1.5
+    val = torch.randn(T, N, generator=g, device=dev)
+    end = (torch.rand(T, N, generator=g, device=dev) < 1 / 100).to(torch.uint8)
+    end[T - 1] = 1
+    boot = torch.randn(T, N, generator=g, device=dev) * end
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    for _ in range(3):
+        rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=1)
+    torch.cuda.synchronize()
+    gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in gev:
+        a.record()
+        rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=1)
+        b.record()
+    torch.cuda.synchronize()
+    gae_ms = sorted(a.elapsed_time(b) for a, b in gev)[len(gev) // 2]
+    gae_gbs = GAE_BYTES_PER_ELEM * T * N / (gae_ms / 1e3) / 1e9
+    del rew, val, end, boot, adv, ret
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----------------
+    h_act = torch.randint(0, 8, (n_act, N, 1), dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((N, 1, 11), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((N, 1), dtype=torch.float32).pin_memory()
+    h_end = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((N, 1), dtype=torch.int32, device=dev)
+
+    def e2e_step(i):
+        d_act.copy_(h_act[i % n_act], non_blocking=True)
+        obs, rw, team, done, info, ended = envs[i % R].step_batch(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rw, non_blocking=True)
+        h_end.copy_(ended, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()       # the caller reads the results before choosing actions
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    Ke = min(K, 120)
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = N * world * Ke / float(e2e_s.item())
+    h2d, d2h = N * 4, N * (44 + 4 + 1)
+
+    status = int(sum(int((e.status & ~2).any()) for e in envs))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": f"RadSearch env step + auto-reset, {N} envs/GPU (BASELINE configs[4]), 5 obstructions, "
+                                   "enforced boundaries, 1 agent, uniform random actions, staggered 120-step episodes",
+                       "envs_per_gpu": N, "obstructions": K_OBS, "poisson": "fp32-acceptance PTRS" if fast else "numpy-exact PTRS",
+                       "l2": f"ring of {R} env batches ({state_mb:.0f} MB of state) cycled: every step reads its state from HBM",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_ms,
+                         "kernel_env_steps_per_s": N / (k_ms / 1e3)},
+            "gae": {"T": T, "N": N, "ms": gae_ms, "achieved": gae_gbs, "peak": peak, "unit": "GB/s", "frac": gae_gbs / peak,
+                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<16>"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "note": "pinned host actions -> device, step+reset, obs/reward/ended -> pinned host, sync per step"},
+            "gpu_launches": 2 * K, "clocks": clocks, "status_flags_raised": status,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            v1, dt1, _ = cpu_baseline(256, 60, cores)                 # calibrate
+            n_s = max(256, min(16384, int(256 * 12.0 / max(dt1, 1e-3)) // 256 * 256))
+            v, dt, _ = cpu_baseline(n_s, 60, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_s} envs x 60 steps in {dt:.1f}s, oracle/radsearch_oracle.c "
+                                              "(scalar per-env loop with per-step Dijkstra, OpenMP over envs)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

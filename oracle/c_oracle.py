@@ -201,10 +201,13 @@ class OracleBatch:
                              C.c_int32(self.threads))
         return self.outs
 
-    def rollout(self, T: int, step_ctr0: int = 0):
+    def rollout(self, T: int, step_ctr0: int = 0, epoch_end_last: bool = True):
+        """T steps of the per-env loop (random actions, timeout / done resets; new obstructions after the last step
+        when epoch_end_last)."""
         chk = C.c_double(0.0)
         n = lib().orc_rollout(C.byref(self.cfg), _p(self.envs), C.c_int32(self.n), C.c_int32(T), C.c_uint64(self.seed),
-                              C.c_uint32(self.env_id0), C.c_uint64(step_ctr0), C.c_int32(self.threads), C.byref(chk))
+                              C.c_uint32(self.env_id0), C.c_uint64(step_ctr0), C.c_int32(int(epoch_end_last)),
+                              C.c_int32(self.threads), C.byref(chk))
         return int(n), float(chk.value)
 
     def shortest_path(self, i: int, det) -> float:

@@ -722,7 +722,7 @@ void orc_reset_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const uint8_t 
 /* the per-env Python loop of train.py:321-549 / test_environment/ppo.py:495-573 without the policy: uniform random
  * actions 0..7 (Philox domain 3), timeout at max_ep_len, reset on done/timeout, new obstructions at the epoch end. */
 int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint64_t seed, uint32_t env_id0,
-                    uint64_t step_ctr0, int32_t threads, double *checksum) {
+                    uint64_t step_ctr0, int32_t epoch_end_last, int32_t threads, double *checksum) {
     set_threads(threads);
     int A = c->n_agents;
     double total = 0.0;
@@ -745,7 +745,7 @@ int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint
             acc += out.obs[0][0] + out.reward[0];
             int timeout = e->ep_len == c->max_ep_len;                      /* train.py:394-405 */
             int over = e->done || timeout;
-            int epoch_ended = t == T - 1;
+            int epoch_ended = epoch_end_last && t == T - 1;
             if (over || epoch_ended) orc_reset(c, e, epoch_ended, seed, env_id0 + (uint32_t)i, ctr, NULL, 0, &out);
         }
         total += acc;

@@ -111,7 +111,7 @@ void orc_reset_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const uint8_t 
                      OrcStepOut *outs, int32_t threads);
 /* rollout with the caller rules of train.py:394-405,446-548 (auto-reset, epoch end); returns env-steps done */
 int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint64_t seed, uint32_t env_id0,
-                    uint64_t step_ctr0, int32_t threads, double *checksum);
+                    uint64_t step_ctr0, int32_t epoch_end_last, int32_t threads, double *checksum);
 
 void orc_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
              int32_t T, int32_t N, double gamma, double lam, int32_t threads);

@@ -1,0 +1,15 @@
+"""radiation_ppo_b200 -- B200-native (sm_100a) RadSearch environment step + PPO rollout/GAE path.
+
+Drop-in for the per-env Python loop of bentotten/radiation_ppo: `RadSearch` keeps the gym reset/step/observation API of
+gym_rad_search.envs.RadSearch, `PPOBuffer` the interface of algos.multiagent.ppo.PPOBuffer; the work runs in hand-written
+CUDA kernels behind the C ABI declared in include/radsearch_b200.h.  There is no CPU fallback.
+"""
+from . import _lib
+from ._lib import RadSearchLibraryError
+from .envs.rad_search_env import RadSearch, StepResult
+from .ppo_buffer import (BatchedPPOBuffer, PPOBuffer, advantage_statistics, combined_shape, gae_advantages,
+                         normalize_advantages_)
+from .dist import shard_range
+
+__all__ = ["RadSearch", "StepResult", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
+           "normalize_advantages_", "combined_shape", "shard_range", "RadSearchLibraryError", "_lib"]

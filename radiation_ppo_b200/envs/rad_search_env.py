@@ -1,0 +1,435 @@
+"""Batched, GPU-resident RadSearch with the reference's gym API.
+
+Mirrors /root/reference/gym_rad_search/gym_rad_search/envs/rad_search_env.py::RadSearch (constructor kwargs R:320-390,
+`reset()` R:730-797, `step(action)` R:443-728, `refresh_environment` R:799-874, attributes read by
+algos/multiagent/main.py:538-567 and train.py:279-533).  With ``num_envs == 1`` the methods return the reference's
+4-tuples of dicts keyed by agent id; with ``num_envs > 1`` the same names hold CUDA tensors.  All work runs in the
+hand-written kernels behind include/radsearch_b200.h; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+A_SIZE = 9                      # R:66
+DETECTABLE_DIRECTIONS = 8       # R:67
+DET_STEP = 100.0                # R:68
+DET_STEP_FRAC = 71.0            # R:69
+DIST_TH = 110.0                 # R:70
+EPSILON = 0.0000001             # R:74
+
+
+class StepResult(NamedTuple):   # R:248-252
+    observation: Dict[int, Any]
+    reward: Dict[int, float]
+    terminal: Dict[int, bool]
+    info: Dict[int, Dict[Any, Any]]
+
+
+class Discrete:
+    """Minimal stand-in for gym.spaces.Discrete (R:355)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        self.shape = ()
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (R:364)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+class _AgentView:
+    """Read-only view of one agent of one environment (Agent dataclass fields R:255-300)."""
+
+    def __init__(self, env: "RadSearch", agent_id: int):
+        self._env, self.id = env, agent_id
+
+    @property
+    def det_coords(self) -> Tuple[float, float]:
+        d = self._env._det[self.id, 0].tolist()
+        return (float(d[0]), float(d[1]))
+
+    @property
+    def prev_det_dist(self) -> float:
+        return float(self._env._best[self.id, 0].item())
+
+    @property
+    def out_of_bounds_count(self) -> int:
+        return int(self._env._aflags[self.id, 0].item()) & 0xFFFFFF
+
+    @property
+    def obstacle_blocking(self) -> bool:
+        return bool((int(self._env._aflags[self.id, 0].item()) >> 24) & 1)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class RadSearch:
+    """RadSearch environment(s) on one GPU.
+
+    Reference kwargs (same names and meaning): ``bbox``, ``observation_area``, ``np_random``, ``obstruction_count``,
+    ``enforce_grid_boundaries``, ``number_agents``, ``save_gif`` (ignored), ``DEBUG`` (unsupported).
+    Additive kwargs: ``num_envs``, ``device``, ``seed`` (Philox key; drawn from ``np_random`` when omitted),
+    ``env_id_offset`` (global id of env 0: results do not depend on how envs are sharded over ranks),
+    ``steps_per_episode`` / ``auto_reset`` (the caller rules of train.py:394-405 applied on the device),
+    ``fast_poisson`` (fp32 acceptance test in the PTRS sampler), ``count_law`` (0 reference, 1 inverse square).
+    """
+
+    metadata = {"render.modes": ["human"], "video.frames_per_second": 5}
+    continuous = False
+
+    def __init__(
+        self,
+        bbox: Sequence[Sequence[float]] = ((0.0, 0.0), (2700.0, 0.0), (2700.0, 2700.0), (0.0, 2700.0)),
+        observation_area: Sequence[float] = (200.0, 500.0),
+        np_random: Optional[np.random.Generator] = None,
+        obstruction_count: int = 0,
+        enforce_grid_boundaries: bool = False,
+        save_gif: bool = False,
+        number_agents: int = 1,
+        DEBUG: bool = False,
+        *,
+        num_envs: int = 1,
+        device: Union[str, torch.device, None] = None,
+        seed: Optional[int] = None,
+        env_id_offset: int = 0,
+        steps_per_episode: int = 120,
+        auto_reset: bool = False,
+        fast_poisson: bool = False,
+        count_law: int = 0,
+        k_max: Optional[int] = None,
+    ) -> None:
+        if DEBUG:
+            raise NotImplementedError("the reference's DEBUG hard-codes (R:373-378, 782-784) are not reproduced")
+        if not torch.cuda.is_available():
+            raise L.RadSearchLibraryError("RadSearch needs a CUDA device: the B200 kernels have no CPU fallback")
+        self._lib = L.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise L.RadSearchLibraryError("RadSearch needs a CUDA device: the B200 kernels have no CPU fallback")
+        xs = [float(p[0]) for p in bbox]
+        ys = [float(p[1]) for p in bbox]
+        for v in (*xs, *ys, *observation_area):
+            if float(v) != int(v):
+                raise ValueError("bbox / observation_area must be integer-valued (SURVEY N1: lattice geometry)")
+        self.bbox = tuple((float(p[0]), float(p[1])) for p in bbox)
+        self.observation_area = (float(observation_area[0]), float(observation_area[1]))
+        self.np_random = np_random if np_random is not None else np.random.default_rng(0)
+        self.obstruction_count = int(obstruction_count)
+        self.enforce_grid_boundaries = bool(enforce_grid_boundaries)
+        self.save_gif = save_gif
+        self.number_agents = int(number_agents)
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self.fast_poisson = bool(fast_poisson)
+        self.env_id_offset = int(env_id_offset)
+        self.seed = int(seed) if seed is not None else int(self.np_random.integers(0, 2**63 - 1))
+
+        cfg = L.RsConfig()
+        cfg.bbox[0], cfg.bbox[1], cfg.bbox[2], cfg.bbox[3] = int(min(xs)), int(min(ys)), int(max(xs)), int(max(ys))
+        cfg.obs_area[0], cfg.obs_area[1] = int(observation_area[0]), int(observation_area[1])
+        cfg.enforce = int(self.enforce_grid_boundaries)
+        cfg.n_agents = self.number_agents
+        cfg.obstruction_count = self.obstruction_count
+        cfg.count_law = int(count_law)
+        cfg.max_ep_len = int(steps_per_episode)
+        if k_max is None:
+            k_max = 5 if self.obstruction_count == -1 else max(self.obstruction_count, 0)
+        cfg.k_max = int(k_max)
+        self._cfg = cfg
+
+        b0x, b0y, b1x, b1y = cfg.bbox[0], cfg.bbox[1], cfg.bbox[2], cfg.bbox[3]
+        lo, hi = cfg.obs_area[0], cfg.obs_area[1]
+        self.search_area = ((float(b0x + lo), float(b0y + lo)), (float(b1x - hi), float(b0y + lo)),
+                            (float(b1x - hi), float(b1y - hi)), (float(b0x + lo), float(b1y - hi)))   # R:393-420
+        self.max_dist = float(np.hypot(self.search_area[2][0] - self.search_area[1][0],
+                                       self.search_area[2][1] - self.search_area[1][1]))              # R:423-425
+        assert self.max_dist > 1000, "Maximum distance available is too small, unable to spawn source and detector 1000 cm apart"
+        self.scale = 1 / self.search_area[2][1]                                                        # R:435
+        self.scaled_grid_max = (1, 1)
+        self.step_size = DET_STEP
+        self.action_space = Discrete(A_SIZE)
+        self.number_actions = A_SIZE
+        self.detectable_directions = DETECTABLE_DIRECTIONS
+        self.observation_space = Box(0, np.inf, shape=(L.OBS_DIM,), dtype=np.float32)
+        self.background_radiation_bounds = (10, 51)
+        self.radiation_intensity_bounds = (1e6, 10e6)
+        self.coord_noise = False
+        self.epoch_end = True                                                                          # R:421
+        self.epoch_cnt = 0
+        self.iter_count = 0
+        self._ctr = 0                      # Philox step counter: one tick per kernel call that draws numbers
+
+        N, A, K = self.num_envs, self.number_agents, cfg.k_max
+        dev = self.device
+        z = lambda *s, dt=torch.int32: torch.zeros(*s, dtype=dt, device=dev)     # noqa: E731
+        self._src, self._rad = z(N, 2), z(N, 2)
+        self._rects = z(max(K, 1), N, 4)
+        self._meta = z(N)
+        self._det = z(A, N, 2)
+        self._best = z(A, N, dt=torch.float64)
+        self._aflags = z(A, N)
+        self._dsrc = z(max(4 * K, 1), N, dt=torch.float64)
+        self._vis = z(max(4 * K, 1), N)
+        self._status = z(N)
+        self._reset_list, self._reset_count = z(N), z(1)
+        self._st = L.RsState(*[t.data_ptr() for t in (
+            self._src, self._rad, self._rects, self._meta, self._det, self._best, self._aflags, self._dsrc, self._vis,
+            self._status, self._reset_list, self._reset_count)])
+        self.obs = z(N, A, L.OBS_DIM, dt=torch.float32)
+        self.final_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
+        self.reward = z(N, A, dt=torch.float32)
+        self.team_reward = z(N, dt=torch.float32)
+        self.done_flags = z(N, A, dt=torch.uint8)
+        self.info_flags = z(N, A, dt=torch.uint8)
+        self.ended = z(N, dt=torch.uint8)
+        self.agents = {i: _AgentView(self, i) for i in range(A)}
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # raw batched entry points (tensors in, tensors out; asynchronous on the current stream)
+    # ------------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _base_flags(self) -> int:
+        return L.F_FAST_POISSON if self.fast_poisson else 0
+
+    def reset_batch(self, mask: Optional[torch.Tensor] = None, new_obstacles: Union[bool, torch.Tensor] = False,
+                    uniforms: Optional[torch.Tensor] = None, from_list: bool = False) -> torch.Tensor:
+        """Reset the selected envs (all when ``mask`` is None); returns the observation tensor [N, A, 11]."""
+        flags = self._base_flags()
+        new_mask = None
+        if isinstance(new_obstacles, torch.Tensor):
+            new_mask = new_obstacles.to(device=self.device, dtype=torch.uint8).contiguous()
+        elif new_obstacles:
+            flags |= L.F_NEW_OBSTACLES
+        if from_list:
+            flags |= L.F_RESET_LIST
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        u = None if uniforms is None else uniforms.to(device=self.device, dtype=torch.float64).contiguous()
+        self._ctr += 1
+        with torch.cuda.device(self.device):
+            L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), _ptr(m), _ptr(new_mask), _ptr(self.obs),
+                                       self.num_envs, self.env_id_offset, self.seed, self._ctr, _ptr(u),
+                                       0 if u is None else u.shape[-1], flags, self._stream()), "rs_reset")
+        return self.obs
+
+    def step_batch(self, actions: Optional[torch.Tensor], epoch_end: bool = False,
+                   uniforms: Optional[torch.Tensor] = None, auto_reset: Optional[bool] = None):
+        """One step for every env.  actions: int32 CUDA tensor [N] or [N, A] (None = the reference's step(None) probe).
+        Returns (obs, reward, team_reward, done, info, ended); with auto-reset, envs that finished have already been
+        reset, `obs` holds their first observation and `final_obs` the last one of the finished episode."""
+        ar = self.auto_reset if auto_reset is None else auto_reset
+        flags = self._base_flags() | (L.F_AUTO_RESET if ar else 0) | (L.F_EPOCH_END if (ar and epoch_end) else 0)
+        a = None
+        if actions is not None:
+            a = actions.to(device=self.device, dtype=torch.int32).reshape(self.num_envs, self.number_agents).contiguous()
+        u = None if uniforms is None else uniforms.to(device=self.device, dtype=torch.float64).contiguous()
+        self._ctr += 1
+        with torch.cuda.device(self.device):
+            L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
+                                      _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
+                                      _ptr(self.ended), _ptr(self.final_obs) if ar else None, self.num_envs,
+                                      self.env_id_offset, self.seed, self._ctr, _ptr(u),
+                                      0 if u is None else u.shape[-1], flags, self._stream()), "rs_step")
+            if ar:
+                rflags = self._base_flags() | L.F_RESET_LIST | (L.F_NEW_OBSTACLES if epoch_end else 0)
+                L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(self.obs),
+                                           self.num_envs, self.env_id_offset, self.seed, self._ctr, None, 0, rflags,
+                                           self._stream()), "rs_reset")
+        return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+
+    def load_scenarios(self, src, det, intensity, bkg, rects=None, num_obs=None,
+                       uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Batched refresh_environment (R:799-874): inject scenarios instead of sampling them.  rects: [N, K, 4] as
+        x0,y0,x1,y1 (K <= k_max), num_obs: [N].  Returns the initial observations."""
+        dev = self.device
+        ti = lambda x, shape: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(   # noqa: E731
+            device=dev, dtype=torch.int32).reshape(shape).contiguous()
+        N = self.num_envs
+        s, d = ti(src, (N, 2)), ti(det, (N, 2))
+        it, bk = ti(intensity, (N,)), ti(bkg, (N,))
+        if rects is None or self._cfg.k_max == 0:
+            r, k_in = None, 0
+            no = torch.zeros(N, dtype=torch.int32, device=dev)
+        else:
+            r = torch.as_tensor(np.asarray(rects) if not isinstance(rects, torch.Tensor) else rects).to(
+                device=dev, dtype=torch.int32).contiguous()
+            k_in = int(r.shape[1])
+            no = ti(num_obs, (N,))
+        u = None if uniforms is None else uniforms.to(device=dev, dtype=torch.float64).contiguous()
+        self._ctr += 1
+        with torch.cuda.device(dev):
+            L.check(self._lib.rs_load_scenarios(C.byref(self._cfg), C.byref(self._st), _ptr(s), _ptr(d), _ptr(it),
+                                                _ptr(bk), _ptr(r), k_in, _ptr(no), _ptr(self.obs), N,
+                                                self.env_id_offset, self.seed, self._ctr, _ptr(u),
+                                                0 if u is None else u.shape[-1], self._stream()), "rs_load_scenarios")
+        self.epoch_end = False
+        return self.obs
+
+    # ------------------------------------------------------------------------------------------------------------
+    # state views
+    # ------------------------------------------------------------------------------------------------------------
+    @property
+    def status(self) -> torch.Tensor:
+        return self._status
+
+    @property
+    def num_obs(self):
+        v = self._meta & 0xFF
+        return int(v[0].item()) if self.num_envs == 1 else v
+
+    @property
+    def done(self):
+        v = ((self._meta >> 8) & 1).bool()
+        return bool(v[0].item()) if self.num_envs == 1 else v
+
+    @property
+    def steps_in_episode(self) -> torch.Tensor:
+        return self._meta >> 16
+
+    @property
+    def src_coords(self):
+        if self.num_envs == 1:
+            s = self._src[0].tolist()
+            return (float(s[0]), float(s[1]))
+        return self._src
+
+    @property
+    def intensity(self):
+        return int(self._rad[0, 0].item()) if self.num_envs == 1 else self._rad[:, 0]
+
+    @property
+    def bkg_intensity(self):
+        return int(self._rad[0, 1].item()) if self.num_envs == 1 else self._rad[:, 1]
+
+    @property
+    def det_coords(self) -> torch.Tensor:
+        """[A, N, 2] detector coordinates."""
+        return self._det
+
+    @property
+    def obs_coord(self):
+        """Obstruction vertex lists [(x,y),(x,y+h),(x+w,y+h),(x+w,y)] of env 0 (R:975-983); batched: rects [K,N,4]."""
+        if self.num_envs > 1:
+            return self._rects
+        out = []
+        r = self._rects[:, 0].tolist()
+        for k in range(self.num_obs):
+            x0, y0, x1, y1 = (float(v) for v in r[k])
+            out.append([(x0, y0), (x0, y1), (x1, y1), (x1, y0)])
+        return out
+
+    def get_agent_outOfBounds_count(self, id: int) -> int:      # R:1764
+        return self.agents[id].out_of_bounds_count
+
+    def ping(self):
+        return "PONG"
+
+    def render(self, *args, **kwargs):
+        """Rendering (R:1308-1762) is out of scope for the B200 path."""
+        return None
+
+    # ------------------------------------------------------------------------------------------------------------
+    # gym API
+    # ------------------------------------------------------------------------------------------------------------
+    def _pack(self):
+        A = self.number_agents
+        if self.num_envs > 1:
+            info = {
+                "out_of_bounds": (self.info_flags & L.I_OOB) != 0,
+                "out_of_bounds_count": (self._aflags & 0xFFFFFF).transpose(0, 1),
+                "blocked": (self.info_flags & L.I_BLOCKED) != 0,
+                "collision": (self.info_flags & L.I_COLLISION) != 0,
+                "scale": self.scale,
+                "ended": self.ended,
+                "final_observation": self.final_obs,
+            }
+            return (self.obs, {"team_reward": self.team_reward, "individual_reward": self.reward},
+                    self.done_flags != 0, info)
+        obs = self.obs[0].double().cpu().numpy()
+        rew = self.reward[0].double().cpu().numpy()
+        team = float(self.team_reward[0].item())
+        done = self.done_flags[0].cpu().numpy()
+        inf = self.info_flags[0].cpu().numpy()
+        oobc = (self._aflags[:, 0] & 0xFFFFFF).cpu().numpy()
+        r2 = lambda v: round(float(v), 2)                                   # noqa: E731  rewards are 2-decimal values
+        return (
+            {i: obs[i].copy() for i in range(A)},
+            {"team_reward": r2(team), "individual_reward": {i: r2(rew[i]) for i in range(A)}},
+            {i: bool(done[i]) for i in range(A)},
+            {i: {"out_of_bounds": bool(inf[i] & L.I_OOB), "out_of_bounds_count": int(oobc[i]),
+                 "blocked": bool(inf[i] & L.I_BLOCKED), "scale": self.scale} for i in range(A)},
+        )
+
+    def reset(self):
+        """R:730-797.  New obstructions are drawn only when ``epoch_end`` was set (train.py:484)."""
+        new_obs = bool(self.epoch_end)
+        self.reset_batch(mask=None, new_obstacles=new_obs)
+        if new_obs:
+            self.epoch_cnt += 1
+            self.epoch_end = False
+        self.iter_count = 0
+        self.done_flags.zero_()
+        self.info_flags.zero_()
+        self.reward.zero_()
+        self.team_reward.zero_()
+        out = self._pack()
+        if self.num_envs == 1:
+            # the probe step of R:794 reports round(-0.5 * sp / max_dist, 2) with sp = prev_det_dist (R:551-567)
+            ind = {i: round(-0.5 * self.agents[i].prev_det_dist / self.max_dist, 2) for i in range(self.number_agents)}
+            team = None
+            for r in ind.values():                                       # R:661-665
+                if not team:
+                    team = r
+                elif team < r:
+                    team = r
+            out = (out[0], {"team_reward": team, "individual_reward": ind}, out[2], out[3])
+        return out
+
+    def step(self, action=None):
+        """R:443-728.  ``action``: int (applied to every agent; -1 = idle), dict {agent_id: action}, None (probe), or for
+        ``num_envs > 1`` an integer tensor [N] / [N, A]."""
+        A = self.number_agents
+        if action is None:
+            acts = None
+        elif isinstance(action, torch.Tensor):
+            acts = action
+        elif isinstance(action, dict):
+            if sorted(action.keys()) != list(range(A)):
+                raise ValueError("the batched kernels need an action for every agent (reference dict keyed 0..A-1)")
+            for a in action.values():
+                assert int(a) in range(A_SIZE)
+            acts = torch.tensor([[int(action[i]) for i in range(A)]] * self.num_envs, dtype=torch.int32)
+        elif isinstance(action, (int, np.integer)):
+            a = 8 if int(action) == -1 else int(action)                   # R:620-623
+            assert a in range(A_SIZE)
+            acts = torch.full((self.num_envs, A), a, dtype=torch.int32)
+        else:
+            raise ValueError("Incompatible Action type")
+        self.step_batch(acts)
+        if acts is not None:
+            self.iter_count += 1
+        return self._pack()
+
+    def refresh_environment(self, env_dict: Dict, id: int, num_obs: int = 0):
+        """R:799-874: load scenario ``env_<id>`` of a saved test-environment dict into every env of this instance."""
+        from ..scenario_io import scenario_arrays
+
+        arr = scenario_arrays(env_dict, [id] * self.num_envs, k_max=self._cfg.k_max, with_obstacles=num_obs > 0)
+        self.load_scenarios(**arr)
+        self.iter_count = 1
+        self.done_flags.zero_()
+        obs = self._pack()[0]
+        return obs

@@ -1,0 +1,246 @@
+"""GPU parity tests (pytest -m gpu): the CUDA env step / reset path, called through the product API and the C ABI,
+against the oracle (oracle/radsearch_oracle.c) and the golden vectors recorded from the unmodified reference.
+
+Bars (BASELINE.json north_star): bit-exact detector positions, collision / LOS / blocked / out-of-bounds flags,
+termination, reset indices, Poisson counts (injected uniforms AND the shared Philox stream), rewards, best distances;
+sensor values within 1e-5 relative in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+import radiation_ppo_b200 as rp  # noqa: E402
+from radiation_ppo_b200 import _lib as L  # noqa: E402
+
+
+def make_pair(n, A=1, oc=5, enforce=True, seed=11, env_id0=3, max_ep_len=120, **kw):
+    env = rp.RadSearch(obstruction_count=oc, enforce_grid_boundaries=enforce, number_agents=A, num_envs=n, seed=seed,
+                       env_id_offset=env_id0, steps_per_episode=max_ep_len, **kw)
+    ob = co.OracleBatch(n, co.default_config(n_agents=A, obstruction_count=oc, enforce=int(enforce),
+                                             max_ep_len=max_ep_len), seed=seed, env_id0=env_id0)
+    ob.reset(env._ctr)          # the constructor reset used counter env._ctr
+    return env, ob
+
+
+@pytest.mark.parametrize("n,A,oc,enforce,T,idle", [(1024, 1, 5, True, 130, 0.0), (1024, 1, -1, False, 100, 0.0),
+                                                   (512, 4, 5, True, 90, 0.15), (256, 1, 0, True, 40, 0.0),
+                                                   (300, 2, 7, True, 70, 0.1), (37, 1, 3, False, 50, 0.0)])
+def test_rollout_matches_oracle(n, A, oc, enforce, T, idle):
+    env, ob = make_pair(n, A, oc, enforce, seed=100 + n)
+    v = pu.GpuView(env)
+    pu.compare_state(v, ob, A)
+    pu.compare_obs(v.obs, ob.outs["obs"][:, :A])
+    rng = np.random.default_rng(n)
+    seen = dict(los=0, sens=0, done=0)
+    for t in range(T):
+        acts = rng.integers(0, 8, size=(n, A))
+        acts[rng.random((n, A)) < idle] = 8
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+        ob.step(acts, env._ctr)
+        v = pu.GpuView(env)
+        pu.compare_state(v, ob, A)
+        o, e = ob.outs, ob.envs
+        pu.compare_obs(v.obs, o["obs"][:, :A])
+        np.testing.assert_array_equal(v.reward, o["reward"][:, :A].astype(np.float32))
+        np.testing.assert_array_equal(v.done, o["done"][:, :A])
+        np.testing.assert_array_equal(v.team_reward, o["team_reward"].astype(np.float32))
+        info_ref = e["oob"][:, :A] | (e["blocked"][:, :A] * 2) | (e["collision"][:, :A] * 4) | (e["los_blocked"][:, :A] * 8)
+        np.testing.assert_array_equal(v.info & 15, info_ref)
+        seen["los"] += int(((v.info & 8) != 0).sum()); seen["sens"] += int((v.obs[:, :, 3:] > 0).sum()); seen["done"] += int(v.done.sum())
+        mask = (e["done"] == 1) | (e["ep_len"] == 120) | ((t + 1) % 45 == 0)
+        if mask.any():
+            newm = np.full(n, (t + 1) % 45 == 0)
+            env.reset_batch(mask=torch.as_tensor(mask), new_obstacles=torch.as_tensor(newm))
+            ob.reset(env._ctr, mask=mask, new_obstacles=newm)
+            v = pu.GpuView(env)
+            pu.compare_state(v, ob, A)
+            pu.compare_obs(v.obs, ob.outs["obs"][:, :A], sel=np.where(mask)[0])
+    assert seen["sens"] > 0 and (oc == 0 or seen["los"] > 0)
+
+
+def test_auto_reset_follows_caller_rules():
+    """train.py:394-405, 446-548 applied on the device: timeout, terminal, epoch end, reset indices, final obs."""
+    n, A, T, ML = 2048, 1, 130, 40
+    env, ob = make_pair(n, A, 5, True, seed=5, max_ep_len=ML, auto_reset=True)
+    rng = np.random.default_rng(0)
+    n_resets = 0
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 8, size=(n, A))
+        epoch_end = t % 60 == 0
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device), epoch_end=epoch_end)
+        ob.step(acts, env._ctr)
+        e = ob.envs
+        terminal, timeout = e["done"] == 1, e["ep_len"] == ML
+        want = terminal * 1 | timeout * 2 | ((terminal | timeout | epoch_end) * 4)
+        mask = (want & 4) != 0
+        final = ob.outs["obs"][:, :A].copy()
+        rew = ob.outs["reward"][:, :A].astype(np.float32).copy()
+        if mask.any():
+            ob.reset(env._ctr, mask=mask, new_obstacles=np.full(n, epoch_end))
+        v = pu.GpuView(env)
+        np.testing.assert_array_equal(v.ended, want)
+        np.testing.assert_array_equal(v.reward, rew)
+        pu.compare_obs(v.final_obs, final, sel=np.where(mask)[0])
+        pu.compare_state(v, ob, A)
+        np.testing.assert_array_equal(v.ep_len, e["ep_len"])
+        # observation handed to the policy next: first obs of the new episode where reset, else the step's obs
+        nxt = np.where(mask[:, None, None], ob.outs["obs"][:, :A], final)
+        pu.compare_obs(v.obs, nxt)
+        n_resets += int(mask.sum())
+    assert n_resets > n
+
+
+@pytest.mark.parametrize("name", list(pu.STEP_FILES))
+def test_reference_records_replayed_on_gpu(name):
+    """Every recorded call of the unmodified reference, replayed from its pre-state with its own uniforms injected."""
+    g = pu.load_golden(name)
+    kw = pu.STEP_FILES[name]
+    A, n = kw["n_agents"], len(g["is_reset"])
+    env = rp.RadSearch(obstruction_count=kw["obstruction_count"], enforce_grid_boundaries=bool(kw["enforce"]),
+                       number_agents=A, num_envs=n, seed=1, k_max=7)
+    dev = env.device
+    u = torch.as_tensor(g["out_uniforms"], device=dev)
+    env.load_scenarios(g["pre_src"], g["pre_det"][:, 0], g["pre_intensity"], g["pre_bkg"], g["pre_rects"][:, :7],
+                       g["pre_num_obs"], uniforms=u)
+    is_reset = g["is_reset"].astype(bool)
+    v = pu.GpuView(env)
+    r = np.where(is_reset)[0]
+    if len(r):
+        pu.compare_obs(v.obs, g["out_obs"], sel=r)
+        np.testing.assert_array_equal(v.best[:, r].T, g["pre_best"][r])
+    env._det.copy_(torch.as_tensor(g["pre_det"].transpose(1, 0, 2).copy(), device=dev))
+    env._best.copy_(torch.as_tensor(g["pre_best"].T.copy(), device=dev))
+    env._aflags.copy_(torch.as_tensor((g["pre_oob_count"] | (g["pre_blocked"] << 24)).T.copy(), device=dev))
+    env._meta.copy_(torch.as_tensor(g["pre_num_obs"] | (g["pre_done"] << 8), device=dev))
+    acts = np.where(is_reset[:, None], 8, g["out_actions"])
+    env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=dev), uniforms=u)
+    v = pu.GpuView(env)
+    s = np.where(~is_reset)[0]
+    pu.compare_obs(v.obs, g["out_obs"], sel=s)
+    np.testing.assert_array_equal(v.reward[s], g["out_reward"][s].astype(np.float32))
+    np.testing.assert_array_equal(v.done[s], g["out_done"][s])
+    np.testing.assert_array_equal(v.team_reward[s], g["out_team_reward"][s].astype(np.float32))
+    np.testing.assert_array_equal(v.det[:, s].transpose(1, 0, 2), g["out_det"][s])
+    np.testing.assert_array_equal(v.best[:, s].T, g["out_best"][s])
+    np.testing.assert_array_equal((v.aflags[:, s] & 0xFFFFFF).T, g["out_oob_count"][s])
+    np.testing.assert_array_equal(((v.aflags[:, s] >> 24) & 1).T, g["out_blocked"][s])
+    np.testing.assert_array_equal(((v.info[s] & 8) != 0).astype(int), g["out_los"][s])
+    np.testing.assert_array_equal(((v.info[s] & 1) != 0).astype(int), g["out_oob"][s])
+    assert not (v.status[s] & ~np.uint32(L.ST_LAMBDA_INF)).any()
+
+
+def test_saved_evaluation_scenarios_against_oracle():
+    """The reference's test_env_dict_obs*_v4 scenarios (inputs) through rs_load_scenarios + 30 steps vs the oracle."""
+    sc = pu.load_golden("scenarios_v4")
+    for k in (0, 1, 3, 5, 7):
+        arr = {key: sc[f"obs{k}_{key}"] for key in ("src", "det", "intensity", "bkg", "rects", "num_obs")}
+        n = len(arr["src"])
+        env = rp.RadSearch(obstruction_count=k, enforce_grid_boundaries=True, num_envs=n, seed=77, k_max=7)
+        env.load_scenarios(**arr)
+        ob = co.OracleBatch(n, co.default_config(obstruction_count=k, enforce=1), seed=77)
+        ob.load_scenarios(arr["src"], arr["det"], arr["intensity"], arr["bkg"], arr["rects"], arr["num_obs"])
+        ob.step(None, env._ctr)
+        ob.envs["iter_count"] = 0
+        ob.envs["ep_len"] = 0
+        # the probe draws from Philox domain 2 on the GPU (reset) and domain 0 in the oracle's step(None): compare
+        # everything but the count here, the counts in the steps below
+        v = pu.GpuView(env)
+        np.testing.assert_array_equal(v.best[0], ob.envs["best"][:, 0])
+        np.testing.assert_allclose(v.obs[:, 0, 1:], ob.outs["obs"][:, 0, 1:].astype(np.float32), rtol=1e-5)
+        rng = np.random.default_rng(k)
+        for t in range(30):
+            acts = rng.integers(0, 8, size=(n, 1))
+            env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+            ob.step(acts, env._ctr)
+            v = pu.GpuView(env)
+            pu.compare_state(v, ob, 1)
+            pu.compare_obs(v.obs, ob.outs["obs"][:, :1])
+
+
+def test_poisson_philox_distribution_ks_against_numpy():
+    """Counts drawn from the Philox stream (exact and fp32-acceptance samplers) vs numpy.random.Generator.poisson."""
+    from scipy import stats
+
+    sc = pu.load_golden("scenarios_v4")
+    arr = {key: sc[f"obs0_{key}"][:1].repeat(40000, axis=0) for key in ("src", "det", "intensity", "bkg")}
+    for lam_case in range(3):
+        a = {k: v.copy() for k, v in arr.items()}
+        if lam_case == 1:
+            a["intensity"][:] = 1000000; a["bkg"][:] = 10
+            a["det"][:] = a["src"] + np.array([1400, 1400])        # far: lambda ~ 515
+        if lam_case == 2:
+            a["det"][:] = a["src"] + np.array([110, 0]); a["intensity"][:] = 9999999   # lambda ~ 9.1e4
+        d = (a["det"][0] - a["src"][0]).astype(float)
+        lam = a["intensity"][0] / np.hypot(*d) + a["bkg"][0]
+        ref = np.random.default_rng(0).poisson(lam, 200000)
+        for fast in (False, True):
+            env = rp.RadSearch(obstruction_count=0, enforce_grid_boundaries=True, num_envs=40000, seed=9 + lam_case,
+                               fast_poisson=fast)
+            env.load_scenarios(**a)
+            counts = []
+            for _ in range(3):
+                env.step_batch(None)
+                counts.append(env.obs[:, 0, 0].cpu().numpy())
+            c = np.concatenate(counts)
+            p = stats.ks_2samp(c, ref).pvalue
+            assert p > 1e-3, (lam, fast, p)
+            assert abs(c.mean() - lam) < 5 * np.sqrt(lam / len(c)), (lam, fast, c.mean())
+            assert abs(c.var() / lam - 1) < 0.03, (lam, fast, c.var())
+
+
+def test_single_env_gym_api_matches_reference_shapes():
+    env = rp.RadSearch(obstruction_count=3, enforce_grid_boundaries=True, np_random=np.random.default_rng(2))
+    obs, rew, done, info = env.reset()
+    assert set(obs) == {0} and obs[0].shape == (11,) and obs[0].dtype == np.float64
+    assert set(rew) == {"team_reward", "individual_reward"} and done == {0: False}
+    assert set(info[0]) == {"out_of_bounds", "out_of_bounds_count", "blocked", "scale"}
+    assert env.observation_space.shape[0] == 11 and env.detectable_directions == 8 and env.number_actions == 9
+    assert env.search_area[2] == (2200.0, 2200.0) and env.max_dist == 2000.0 and env.scale == 1 / 2200.0
+    x, y = env.agents[0].det_coords
+    assert obs[0][1] == np.float32(x / 2200.0) and len(env.obs_coord) == 3
+    obs2, rew2, done2, info2 = env.step({0: 4})
+    x2, y2 = env.agents[0].det_coords
+    assert (x2, y2) in ((x + 100, y), (x, y))
+    assert rew2["individual_reward"][0] == round(rew2["individual_reward"][0], 2)
+    o3 = env.step(-1)            # idle (R:620-623)
+    assert env.agents[0].det_coords == (x2, y2) and env.iter_count == 2
+    env.epoch_end = True
+    env.reset()
+    assert env.epoch_cnt == 2 and env.iter_count == 0
+    with pytest.raises(ValueError):
+        env.step("left")
+
+
+def test_full_size_properties_65536_envs():
+    """BASELINE config sizes: invariants that hold for every env (no oracle at this size)."""
+    n = 65536
+    env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, num_envs=n, seed=3, auto_reset=True)
+    g = torch.Generator(device=env.device).manual_seed(0)
+    prev_best = env._best.clone()
+    tot_reset = 0
+    for t in range(1, 241):
+        acts = torch.randint(0, 8, (n, 1), generator=g, device=env.device, dtype=torch.int32)
+        obs, rew, team, done, info, ended = env.step_batch(acts, epoch_end=(t % 120 == 0))
+        rs = (ended & 4) != 0
+        # detector stays inside the arena, never strictly inside an obstruction; best is a running minimum
+        det = env._det[0]
+        assert bool(((det >= 0) & (det < 2700)).all())
+        r = env._rects
+        inside = ((r[:, :, 0] < det[None, :, 0]) & (det[None, :, 0] < r[:, :, 2]) & (r[:, :, 1] < det[None, :, 1]) &
+                  (det[None, :, 1] < r[:, :, 3]))
+        assert not bool(inside.any())
+        keep = ~rs
+        assert bool((env._best[0][keep] <= prev_best[0][keep]).all())
+        prev_best = env._best.clone()
+        # rewards are two-decimal values; +0.1 exactly when done or improved; done => reset scheduled
+        assert bool(((rew * 100).round() / 100 == rew).all())
+        assert bool((rs | ~(done[:, 0] != 0)).all())
+        assert bool((obs[:, :, 3:] >= 0).all()) and bool((obs[:, :, 3:] <= 1).all()) and bool((obs[:, :, 0] >= 0).all())
+        tot_reset += int(rs.sum())
+    assert int((env.status & ~2).any()) == 0
+    assert tot_reset >= 2 * n
+    assert int(env.steps_in_episode.max()) <= 120

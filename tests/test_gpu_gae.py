@@ -1,0 +1,202 @@
+"""GPU parity tests (pytest -m gpu) of the GAE / returns / advantage-normalisation kernels and the PPOBuffer mirror."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+import radiation_ppo_b200 as rp  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def run_gae(rew, val, end, boot, variant, stats=False):
+    d = dev()
+    s = torch.zeros(2, dtype=torch.float64, device=d) if stats else None
+    adv, ret = rp.gae_advantages(torch.as_tensor(rew, device=d), torch.as_tensor(val, device=d),
+                                 torch.as_tensor(end, device=d), torch.as_tensor(boot, device=d), stats=s, variant=variant)
+    return adv.cpu().numpy(), ret.cpu().numpy(), (None if s is None else s.cpu().numpy())
+
+
+@pytest.mark.parametrize("T,N", [(480, 1024), (96, 24), (480, 4099), (7, 3), (1, 1), (33, 9)])
+def test_gae_thread_per_column_is_bit_exact(T, N):
+    rew, val, end, boot = pu.synthetic_rollout(T, N, seed=T + N, max_ep=min(120, T))
+    a0, r0 = co.gae(rew, val, end, boot)
+    a1, r1, st = run_gae(rew, val, end, boot, variant=1, stats=True)
+    np.testing.assert_array_equal(a1, a0)
+    np.testing.assert_array_equal(r1, r0)
+    np.testing.assert_allclose(st, [a0.astype(np.float64).sum(), (a0.astype(np.float64) ** 2).sum()], rtol=1e-12)
+
+
+@pytest.mark.parametrize("T,N", [(480, 1024), (96, 24), (480, 1021), (7, 3), (1, 1), (33, 9), (1000, 64)])
+def test_gae_warp_scan_within_tolerance(T, N):
+    """fp32 outputs within 1e-5 relative of the reference recurrence (the scan re-associates the fp64 sums)."""
+    rew, val, end, boot = pu.synthetic_rollout(T, N, seed=T * 3 + N, max_ep=min(120, T))
+    a0, r0 = co.gae(rew, val, end, boot)
+    a1, r1, st = run_gae(rew, val, end, boot, variant=2, stats=True)
+    np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r1, r0, rtol=1e-5, atol=1e-6)
+    assert (a1 != a0).mean() < 0.01          # in practice the fp32 roundings coincide almost everywhere
+    np.testing.assert_allclose(st[0], a0.astype(np.float64).sum(), rtol=1e-6, atol=1e-4)
+
+
+def test_gae_golden_reference_ppobuffer():
+    g = pu.load_golden("ref_gae")
+    for variant in (1, 2):
+        a, r, _ = run_gae(g["rew"], g["val"], g["end"], g["boot"], variant)
+        if variant == 1:
+            np.testing.assert_array_equal(a, g["adv"])
+            np.testing.assert_array_equal(r, g["ret"])
+        else:
+            np.testing.assert_allclose(a, g["adv"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(r, g["ret"], rtol=1e-5, atol=1e-6)
+
+
+def test_gae_full_size_properties():
+    """Config 3 size (T=480, N=65536): linearity in the rewards and agreement of both variants; oracle on a slice."""
+    T, N = 480, 65536
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(1)
+    rew = -0.5 * torch.rand(T, N, generator=g, device=d) * 1.5
+    val = torch.randn(T, N, generator=g, device=d)
+    end = (torch.rand(T, N, generator=g, device=d) < 1 / 90).to(torch.uint8)
+    end[T - 1] = 1
+    boot = torch.randn(T, N, generator=g, device=d) * end
+    a1, r1 = rp.gae_advantages(rew, val, end, boot, variant=1)
+    a2, r2 = rp.gae_advantages(rew, val, end, boot, variant=2)
+    assert torch.allclose(a1, a2, rtol=1e-5, atol=1e-6) and torch.allclose(r1, r2, rtol=1e-5, atol=1e-6)
+    # linearity: GAE(2*rew, 2*val, 2*boot) == 2*GAE(rew, val, boot) exactly (powers of two)
+    a3, r3 = rp.gae_advantages(2 * rew, 2 * val, end, 2 * boot, variant=1)
+    assert torch.equal(a3, 2 * a1) and torch.equal(r3, 2 * r1)
+    sl = slice(1000, 1064)
+    a0, r0 = co.gae(rew[:, sl].cpu().numpy(), val[:, sl].cpu().numpy(), end[:, sl].cpu().numpy(), boot[:, sl].cpu().numpy())
+    np.testing.assert_array_equal(a1[:, sl].cpu().numpy(), a0)
+    np.testing.assert_array_equal(r1[:, sl].cpu().numpy(), r0)
+
+
+def test_advantage_normalisation_matches_reference_statistics():
+    d = dev()
+    x = torch.randn(480 * 1024 + 3, device=d) * 3 + 0.7
+    mean, std = rp.advantage_statistics(x)
+    xs = x.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(mean.item(), xs.mean(), rtol=1e-12)
+    np.testing.assert_allclose(std.item(), xs.std(), rtol=1e-12)
+    y = x.clone()
+    rp.normalize_advantages_(y, mean.float().double(), std.float().double())
+    want = (x.cpu().numpy() - np.float32(xs.mean())) / np.float32(xs.std())        # float32 math as in P:446
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=2e-7, atol=1e-7)
+
+
+# ---- the reference's own PPOBuffer unit tests (unit_tests/test_PPO.py), restated against the mirror -----------------
+def manual_gae(gamma, lamb, rewards, values, last_val):          # unit_tests/test_PPO.py:156-191 (Helpers)
+    n = len(rewards)
+    adv = np.zeros(n + 1)
+    last_adv, last_value = 0, last_val
+    for t in reversed(range(n)):
+        delta = rewards[t] + gamma * last_value - values[t]
+        last_adv = delta + gamma * lamb * last_adv
+        adv[t] = last_adv
+        last_value = values[t]
+    return adv[:-1]
+
+
+def manual_rtg(rews, gamma):                                      # unit_tests/test_PPO.py:193-209
+    out, acc = [], 0
+    for r in reversed(rews):
+        acc = r + acc * gamma
+        out.insert(0, acc)
+    return out
+
+
+def test_ppobuffer_init_quick_reset_store():                      # unit_tests/test_PPO.py:300-453
+    buf = rp.PPOBuffer(observation_dimension=11, max_size=2, max_episode_length=2, number_agents=2)
+    buf.ptr = 1; buf.path_start_idx = 1; buf.episode_lengths_buffer.append(1)
+    buf.quick_reset()
+    assert buf.ptr == 0 and buf.path_start_idx == 0 and len(buf.episode_lengths_buffer) == 0
+    obs = np.array([41.0, 0.42181818, 0.92181818, 0, 0, 0, 0, 0, 0, 0, 0], dtype=np.float32)
+    src = np.array([788.0, 306.0])
+    for i in range(2):
+        buf.store(obs=obs, act=1, rew=-0.46, val=-0.26629042625427246, logp=-1.777620792388916, src=src,
+                  full_observation={0: obs, 1: obs}, heatmap_stacks=None, terminal=False)
+        assert buf.obs_buf.shape == (2, 11) and np.array_equal(buf.obs_buf[i].cpu().numpy(), obs)
+        assert buf.act_buf.shape == (2,) and buf.act_buf[i].item() == 1
+        assert buf.rew_buf[i].item() == pytest.approx(-0.46) and buf.val_buf[i].item() == pytest.approx(-0.26629042625427246)
+        assert buf.source_tar.shape == (2, 2) and np.array_equal(buf.source_tar[i].cpu().numpy(), src)
+        assert buf.logp_buf[i].item() == pytest.approx(-1.777620792388916) and buf.ptr == i + 1
+    with pytest.raises(AssertionError):
+        buf.store(obs=obs, act=1, rew=0, val=0, logp=0, src=src)
+    buf.store_episode_length(7)
+    assert buf.episode_lengths_buffer == [7]
+
+
+def test_ppobuffer_gae_hardcoded_and_with_storage():              # unit_tests/test_PPO.py:462-571
+    rewards = np.array([-0.46, -0.48, -0.46, -0.45, -0.45, -0.47, -0.48, -0.48, -0.48, -0.49])
+    values = np.array([-0.26629043, -0.26634163, -0.26718464, -0.26631153, -0.26637784, -0.26601458, -0.26657045,
+                       -0.2666973, -0.26680088, -0.26717135])
+    last_val = -0.26717135
+    buf = rp.PPOBuffer(observation_dimension=11, max_size=10, max_episode_length=2, number_agents=2)
+    buf.rew_buf = rewards          # the reference test assigns numpy arrays straight into the fields
+    buf.val_buf = values
+    buf.ptr = 10
+    buf.GAE_advantage_and_rewardsToGO(last_state_value=last_val)
+    for want, got in zip(manual_rtg(np.append(rewards, last_val).tolist(), 0.99)[:-1], buf.ret_buf.tolist()):
+        assert want == pytest.approx(got)
+    for want, got in zip(manual_gae(0.99, 0.90, rewards, values, last_val), buf.adv_buf.tolist()):
+        assert want == pytest.approx(got)
+    assert buf.path_start_idx == 10
+    buf = rp.PPOBuffer(observation_dimension=11, max_size=10, max_episode_length=2, number_agents=2)
+    for i in range(3):
+        buf.store(obs=np.zeros(11, np.float32), act=0, rew=rewards[i], val=values[i], logp=0, src=np.zeros((1, 2), np.float32))
+    buf.GAE_advantage_and_rewardsToGO(last_state_value=values[2])
+    for want, got in zip(manual_gae(0.99, 0.90, rewards[:3], values[:3], values[2]), buf.adv_buf.tolist()):
+        assert want == pytest.approx(got)
+    for want, got in zip(manual_rtg(np.append(rewards[:3], values[2]).tolist(), 0.99)[:-1], buf.ret_buf.tolist()):
+        assert want == pytest.approx(got)
+
+
+def test_ppobuffer_get_matches_reference_semantics():             # P:425-502, unit_tests/test_PPO.py:573-660
+    rng = np.random.default_rng(0)
+    T = 12
+    buf = rp.PPOBuffer(observation_dimension=11, max_size=T, max_episode_length=5, number_agents=1)
+    obs = rng.normal(size=(T, 11)).astype(np.float32)
+    rew, val = rng.normal(size=T).astype(np.float32), rng.normal(size=T).astype(np.float32)
+    for t in range(T):
+        buf.store(obs=obs[t], act=t % 8, rew=rew[t], val=val[t], logp=-1.5, src=np.array([788.0, 306.0]))
+        if t in (4, 9):
+            buf.GAE_advantage_and_rewardsToGO(0.0)
+            buf.store_episode_length(5)
+    buf.GAE_advantage_and_rewardsToGO(float(val[-1]))
+    adv_before = buf.adv_buf.cpu().numpy().copy()
+    data = buf.get()
+    assert buf.ptr == 0 and buf.path_start_idx == 0 and len(buf.episode_lengths_buffer) == 0
+    assert set(data) == {"obs", "act", "ret", "adv", "logp", "loc_pred", "ep_len", "ep_form"}
+    np.testing.assert_array_equal(data["obs"].cpu().numpy(), obs)
+    np.testing.assert_array_equal(data["act"].cpu().numpy(), np.arange(T) % 8)
+    want = (adv_before - np.float32(adv_before.astype(np.float64).mean())) / np.float32(adv_before.astype(np.float64).std())
+    np.testing.assert_allclose(data["adv"].cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    assert data["ep_len"].item() == 10 and len(data["ep_form"]) == 3
+    assert [e[0].shape for e in data["ep_form"]] == [(5, 17), (5, 17), (2, 17)]
+
+
+def test_batched_buffer_end_to_end_against_oracle():
+    T, N = 64, 256
+    rew, val, end, boot = pu.synthetic_rollout(T, N, seed=9, max_ep=30)
+    d = dev()
+    buf = rp.BatchedPPOBuffer(11, T, N)
+    for t in range(T):
+        buf.store_batch(torch.zeros(N, 11, device=d), torch.zeros(N, device=d), torch.as_tensor(rew[t], device=d),
+                        torch.as_tensor(val[t], device=d), torch.zeros(N, device=d),
+                        end=torch.as_tensor(end[t], device=d), boot=torch.as_tensor(boot[t], device=d))
+    buf.finish_paths(variant=1)
+    a0, r0 = co.gae(rew, val, end, boot)
+    np.testing.assert_array_equal(buf.adv_buf.cpu().numpy(), a0)
+    np.testing.assert_array_equal(buf.ret_buf.cpu().numpy(), r0)
+    data = buf.get()
+    m, s = a0.astype(np.float64).mean(), a0.astype(np.float64).std()
+    np.testing.assert_allclose(data["adv"].cpu().numpy().reshape(T, N), (a0 - np.float32(m)) / np.float32(s), rtol=1e-6, atol=1e-6)
+    assert data["obs"].shape == (T * N, 11) and buf.ptr == 0

@@ -1,0 +1,126 @@
+"""CPU tests of the KERNEL SOURCE: radiation_ppo_b200/csrc/rs_env_impl.cuh compiled as host C++ (tests/emu) and compared
+with the oracle and with the golden vectors of the reference.  This is a debugging aid for the GPU-less build container;
+the real parity tests are the `-m gpu` ones that call the CUDA library through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from radiation_ppo_b200 import _lib as L
+from tests import parity_util as pu
+from tests.emu.harness import EmuEnv, make_config
+
+
+compare_state, compare_obs = pu.compare_state, pu.compare_obs
+
+
+@pytest.mark.parametrize("n,A,oc,enforce,T,idle", [(192, 1, 5, True, 130, 0.0), (128, 1, -1, False, 90, 0.0),
+                                                   (96, 3, 4, True, 80, 0.2), (64, 1, 0, True, 40, 0.0),
+                                                   (48, 2, 7, True, 60, 0.1)])
+def test_emulated_kernels_match_oracle_rollout(n, A, oc, enforce, T, idle):
+    seed = 1000 + n
+    cfg = make_config(n_agents=A, obstruction_count=oc, enforce=enforce)
+    ob = co.OracleBatch(n, co.default_config(n_agents=A, obstruction_count=oc, enforce=int(enforce)), seed=seed, env_id0=7)
+    em = EmuEnv(n, cfg, seed=seed, env_id0=7)
+    em.reset(0, flags=L.F_NEW_OBSTACLES)
+    ob.reset(0)
+    compare_state(em, ob, A)
+    compare_obs(em.obs, ob.outs["obs"][:, :A])
+    rng = np.random.default_rng(seed)
+    seen = dict(los=0, sens=0, done=0, blocked=0)
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 8, size=(n, A))
+        acts[rng.random((n, A)) < idle] = 8
+        em.step(acts, t)
+        ob.step(acts, t)
+        compare_state(em, ob, A)
+        o, e = ob.outs, ob.envs
+        compare_obs(em.obs, o["obs"][:, :A])
+        np.testing.assert_array_equal(em.reward, o["reward"][:, :A].astype(np.float32))
+        np.testing.assert_array_equal(em.done, o["done"][:, :A])
+        np.testing.assert_array_equal(em.team_reward, o["team_reward"].astype(np.float32))
+        info_ref = e["oob"][:, :A] | (e["blocked"][:, :A] * 2) | (e["collision"][:, :A] * 4) | (e["los_blocked"][:, :A] * 8)
+        np.testing.assert_array_equal(em.info & 15, info_ref)
+        seen["los"] += int((em.info & 8).astype(bool).sum()); seen["sens"] += int((em.obs[:, :, 3:] > 0).sum())
+        seen["done"] += int(em.done.sum()); seen["blocked"] += int((em.info & 2).astype(bool).sum())
+        mask = (e["done"] == 1) | (e["ep_len"] == 120) | (t % 45 == 0)
+        if mask.any():
+            newm = np.full(n, t % 45 == 0)
+            em.reset(t, mask=mask, new_mask=newm)
+            ob.reset(t, mask=mask, new_obstacles=newm)
+            compare_state(em, ob, A)
+            compare_obs(em.obs, ob.outs["obs"][:, :A], sel=np.where(mask)[0])
+    assert seen["sens"] > 0 and (oc == 0 or seen["los"] > 0)
+
+
+def test_emulated_auto_reset_matches_caller_rules():
+    n, A, T = 160, 1, 150
+    cfg = make_config(n_agents=A, obstruction_count=5, enforce=True, max_ep_len=40)
+    ocfg = co.default_config(n_agents=A, obstruction_count=5, enforce=1, max_ep_len=40)
+    ob = co.OracleBatch(n, ocfg, seed=5)
+    em = EmuEnv(n, cfg, seed=5)
+    em.reset(0, flags=L.F_NEW_OBSTACLES)
+    ob.reset(0)
+    rng = np.random.default_rng(0)
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 8, size=(n, A))
+        epoch_end = t % 60 == 0
+        em.step(acts, t, flags=L.F_AUTO_RESET | (L.F_EPOCH_END if epoch_end else 0))
+        ob.step(acts, t)
+        e = ob.envs
+        terminal, timeout = e["done"] == 1, e["ep_len"] == 40
+        want = terminal * 1 | timeout * 2 | ((terminal | timeout | epoch_end) * 4)
+        np.testing.assert_array_equal(em.ended, want)
+        mask = (want & 4) != 0
+        final = ob.outs["obs"][:, :A].copy()
+        assert em.reset_count[0] == mask.sum()
+        assert sorted(em.reset_list[: mask.sum()]) == list(np.where(mask)[0])
+        compare_obs(em.final_obs, final, sel=np.where(mask)[0])
+        em.reset(t, flags=L.F_RESET_LIST | (L.F_NEW_OBSTACLES if epoch_end else 0))
+        if mask.any():
+            ob.reset(t, mask=mask, new_obstacles=np.full(n, epoch_end))
+        compare_state(em, ob, A)
+        np.testing.assert_array_equal(em.ep_len, e["ep_len"])
+
+
+def _load_records_into_emu(g, kw):
+    n, A = len(g["is_reset"]), kw["n_agents"]
+    oc = kw["obstruction_count"]
+    cfg = make_config(n_agents=A, obstruction_count=oc, enforce=bool(kw["enforce"]), k_max=7)
+    em = EmuEnv(n, cfg)
+    em.load_scenarios(g["pre_src"], g["pre_det"][:, 0], g["pre_intensity"], g["pre_bkg"], g["pre_rects"][:, :7],
+                      g["pre_num_obs"], uniforms=g["out_uniforms"])
+    return em
+
+
+@pytest.mark.parametrize("name", list(pu.STEP_FILES))
+def test_emulated_kernels_reproduce_reference_records(name):
+    """Every recorded reference call, replayed from its recorded pre-state with the recorded uniforms."""
+    g = pu.load_golden(name)
+    kw = pu.STEP_FILES[name]
+    A = kw["n_agents"]
+    em = _load_records_into_emu(g, kw)
+    is_reset = g["is_reset"].astype(bool)
+    # reset records: load_scenarios already took the step(None) probe with the recorded uniforms
+    r = np.where(is_reset)[0]
+    if len(r):
+        compare_obs(em.obs, g["out_obs"], sel=r)
+        np.testing.assert_array_equal(em.best[:, r].T, g["pre_best"][r])
+    # step records: restore the remaining pre-state (agents may stand at different places) and step
+    for a in range(A):
+        em.det[a] = g["pre_det"][:, a]
+        em.best[a] = g["pre_best"][:, a]
+        em.aflags[a] = g["pre_oob_count"][:, a] | (g["pre_blocked"][:, a] << 24)
+    em.meta[:] = g["pre_num_obs"] | (g["pre_done"] << 8)
+    em.step(np.where(is_reset[:, None], 8, g["out_actions"]), 1, uniforms=g["out_uniforms"])
+    s = np.where(~is_reset)[0]
+    compare_obs(em.obs, g["out_obs"], sel=s)
+    np.testing.assert_array_equal(em.reward[s], g["out_reward"][s].astype(np.float32))
+    np.testing.assert_array_equal(em.done[s], g["out_done"][s])
+    np.testing.assert_array_equal(em.team_reward[s], g["out_team_reward"][s].astype(np.float32))
+    np.testing.assert_array_equal(em.det[:, s].transpose(1, 0, 2), g["out_det"][s])
+    np.testing.assert_array_equal(em.best[:, s].T, g["out_best"][s])
+    np.testing.assert_array_equal((em.aflags[:, s] & 0xFFFFFF).T, g["out_oob_count"][s])
+    np.testing.assert_array_equal(((em.aflags[:, s] >> 24) & 1).T, g["out_blocked"][s])
+    np.testing.assert_array_equal(((em.info[s] & 8) != 0).astype(int), g["out_los"][s])
+    np.testing.assert_array_equal(((em.info[s] & 1) != 0).astype(int), g["out_oob"][s])
+    assert not (em.status[s] & ~np.uint32(L.ST_LAMBDA_INF)).any()

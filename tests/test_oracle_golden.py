@@ -1,0 +1,130 @@
+"""CPU tests: the oracle (oracle/radsearch_oracle.c) against the golden vectors recorded from the unmodified reference
+(tools/make_golden.py), numpy's own poisson, Python's round, the Philox known-answer vectors and scipy's lfilter."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from tests import parity_util as pu
+
+
+@pytest.mark.parametrize("name", list(pu.STEP_FILES))
+def test_oracle_reproduces_reference_records(name):
+    g = pu.load_golden(name)
+    kw = pu.STEP_FILES[name]
+    envs, outs = pu.step_records_with_oracle(g, kw)
+    assert not envs["status"].any()
+    pu.assert_matches_golden(g, envs, outs, kw["n_agents"], obs_exact=True, label=name)
+    np.testing.assert_array_equal(envs["sp"][:, : kw["n_agents"]], g["out_sp"])
+    np.testing.assert_array_equal(envs["los_blocked"][:, : kw["n_agents"]], g["out_los"])
+    np.testing.assert_array_equal(outs["lam"][:, : kw["n_agents"]], g["out_lam"])
+
+
+def test_reset_records_shortest_path_matches_reference():
+    # prev_det_dist recorded after reference resets == oracle shortest path from the same scenario
+    for name, kw in pu.STEP_FILES.items():
+        g = pu.load_golden(name)
+        ob = pu.oracle_load_records(g, kw)
+        idx = np.where(g["is_reset"])[0]
+        for i in idx[:40]:
+            assert ob.shortest_path(i, g["pre_det"][i, 0]) == g["pre_best"][i, 0]
+
+
+def test_action_lut_matches_get_step():
+    lut = pu.load_golden("action_lut")["step"]
+    want = [(-100, 0), (-71, 71), (0, 100), (71, 71), (100, 0), (71, -71), (0, -100), (-71, -71), (0, 0)]
+    np.testing.assert_array_equal(lut, np.array(want, np.float64))
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert co.philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert co.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert co.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_poisson_identical_to_numpy_under_injected_uniforms():
+    rng = np.random.default_rng(123)
+    lams = np.concatenate([np.random.default_rng(1).uniform(10, 100000, 20000),
+                           np.random.default_rng(2).uniform(0.01, 10, 4000),
+                           np.random.default_rng(3).uniform(10, 60, 16000), [0.0, 10.0, 9.999999]])
+    for lam in lams:
+        st = copy.deepcopy(rng.bit_generator.state)
+        k = rng.poisson(lam)
+        probe = np.random.Generator(np.random.PCG64())
+        probe.bit_generator.state = st
+        k2, status = co.poisson_injected(float(lam), probe.random(64))
+        assert (k2, status) == (k, 0), lam
+
+
+def test_round2_is_python_round():
+    rng = np.random.default_rng(0)
+    xs = list(rng.uniform(-2, 0.2, 20000)) + [-0.5 * s / 2000.0 for s in range(0, 6000)] + [
+        i / 1000.0 for i in range(-300, 100)] + [0.125, -0.125, 0.375, 0.1, 2.675, -0.285, 1e-17]
+    for x in xs:
+        assert co.round2(float(x)) == round(float(x), 2), x
+
+
+def test_gae_golden_reference_ppobuffer():
+    g = pu.load_golden("ref_gae")
+    adv, ret = co.gae(g["rew"], g["val"], g["end"], g["boot"])
+    np.testing.assert_array_equal(adv, g["adv"])
+    np.testing.assert_array_equal(ret, g["ret"])
+    # the float32-ndarray bootstrap variant (RADA2C_core.py:549) agrees to the stated tolerance
+    np.testing.assert_allclose(adv, g["adv32"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(ret, g["ret32"], rtol=1e-5, atol=2e-6)
+    # known-answer vectors of unit_tests/test_PPO.py:259-286, 462-497
+    T = 10
+    rew = g["kat_rewards"].astype(np.float32).reshape(T, 1)
+    val = g["kat_values"].astype(np.float32).reshape(T, 1)
+    end = np.zeros((T, 1), np.uint8)
+    boot = np.zeros((T, 1), np.float32)
+    boot[-1] = g["kat_last_val"]
+    a, r = co.gae(rew, val, end, boot)
+    np.testing.assert_allclose(a[:, 0], g["kat_adv"], rtol=1e-5)
+    np.testing.assert_allclose(r[:, 0], g["kat_ret"], rtol=1e-5)
+
+
+def test_gae_matches_scipy_lfilter_restatement():
+    rew, val, end, boot = pu.synthetic_rollout(200, 37, seed=5, max_ep=50)
+    a0, r0 = pu.gae_numpy_reference(rew, val, end, boot)
+    a1, r1 = co.gae(rew, val, end, boot)
+    np.testing.assert_array_equal(a1, a0)
+    np.testing.assert_array_equal(r1, r0)
+
+
+def test_oracle_reset_distribution_matches_reference():
+    """Philox-driven reset sampler vs 1500 resets of the reference (PCG64): same marginals (two-sample KS / chi2)."""
+    from scipy import stats
+
+    g = pu.load_golden("ref_reset_stats")
+    rows = g["rows"]
+    cfg = co.default_config(obstruction_count=-1, enforce=1)
+    ob = co.OracleBatch(6000, cfg, seed=4242)
+    ob.reset(0)
+    e = ob.envs
+    assert not e["status"].any()
+    mine = dict(num_obs=e["num_obs"], src_x=e["src"][:, 0], src_y=e["src"][:, 1], det_x=e["det"][:, 0, 0],
+                det_y=e["det"][:, 0, 1], intensity=e["intensity"], bkg=e["bkg"], sp=e["best"][:, 0],
+                los_blocked=e["los_blocked"][:, 0])
+    cols = list(g["cols"])
+    for name in ("src_x", "src_y", "det_x", "det_y", "intensity", "bkg", "sp"):
+        p = stats.ks_2samp(rows[:, cols.index(name)], mine[name]).pvalue
+        assert p > 1e-3, (name, p)
+    # num_obs is re-drawn only every third reference reset; compare the histogram loosely
+    ref_hist = np.bincount(rows[:, 0].astype(int), minlength=6)[1:] / len(rows)
+    my_hist = np.bincount(mine["num_obs"], minlength=6)[1:] / ob.n
+    assert np.abs(ref_hist - my_hist).max() < 0.06
+    assert abs(rows[:, cols.index("los_blocked")].mean() - mine["los_blocked"].mean()) < 0.05
+    # structural invariants of a valid scenario
+    for i in range(0, ob.n, 7):
+        k = e["num_obs"][i]
+        r = e["rect"][i, :k]
+        for a in range(k):
+            assert 200 <= r[a, 0] < 1980 and 200 <= r[a, 2] - r[a, 0] < 500 and 200 <= r[a, 3] - r[a, 1] < 500
+            for b in range(a + 1, k):
+                assert r[a, 2] < r[b, 0] or r[b, 2] < r[a, 0] or r[a, 3] < r[b, 1] or r[b, 3] < r[a, 1]
+        d = e["det"][i, 0].astype(np.int64) - e["src"][i].astype(np.int64)
+        assert d @ d >= 1000000

@@ -175,6 +175,7 @@ def record_probes(seed, n_scenarios, probes_per_scenario, obstruction_count=5, e
         env.epoch_end = True
         env.reset()
         for _ in range(probes_per_scenario):
+            env.iter_count = int(prng.integers(0, 2))
             same = prng.random() < 0.3
             base = None
             for i in range(A):
@@ -184,9 +185,15 @@ def record_probes(seed, n_scenarios, probes_per_scenario, obstruction_count=5, e
                         break
                     base = None
                 base = p
-                env.agents[i].det_coords = (float(p[0]), float(p[1]))
-                env.agents[i].detector = vis.Point(float(p[0]), float(p[1]))
-            env.iter_count = int(prng.integers(0, 2))
+                ag = env.agents[i]
+                ag.det_coords = (float(p[0]), float(p[1]))
+                ag.detector = vis.Point(float(p[0]), float(p[1]))
+                # keep the agent self-consistent, as refresh_environment does (R:864-868): sp/euc belong to the new
+                # position; the running minimum may be anything at or around it
+                ag.sp_dist = env.world.shortest_path(env.source, ag.detector, env.vis_graph, m.EPSILON).length()
+                ag.euc_dist = m.dist_p(ag.det_coords, env.src_coords)
+                # (at iter_count == 0 the reference takes sp from prev_det_dist, R:551-553: they must agree there)
+                ag.prev_det_dist = ag.sp_dist + (float(prng.choice([0.0, 0.0, -37.5, 60.25])) if env.iter_count else 0.0)
             env.done = False
             acts = [int(prng.integers(0, 9)) for _ in range(A)]
             pre = _pre_full(env)
