@@ -237,7 +237,8 @@ def test_full_size_properties_65536_envs():
         assert bool((env._best[0][keep] <= prev_best[0][keep]).all())
         prev_best = env._best.clone()
         # rewards are two-decimal values; +0.1 exactly when done or improved; done => reset scheduled
-        assert bool(((rew * 100).round() / 100 == rew).all())
+        r64 = rew.double()
+        assert bool((((r64 * 100).round() / 100).float() == rew).all())
         assert bool((rs | ~(done[:, 0] != 0)).all())
         assert bool((obs[:, :, 3:] >= 0).all()) and bool((obs[:, :, 3:] <= 1).all()) and bool((obs[:, :, 0] >= 0).all())
         tot_reset += int(rs.sum())
