@@ -54,6 +54,7 @@ __device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx
 
 __device__ __forceinline__ double dist_int(int dx, int dy) { return sqrt((double)(dx * dx + dy * dy)); }
 
+// Straightforward form (used by the reset path): direct segment if visible, else min over corners.
 __device__ __forceinline__ double shortest_path(const EnvView &e, int px, int py) {
     if (visible(e, px, py, e.sx, e.sy)) return dist_int(px - e.sx, py - e.sy);
     double best = __longlong_as_double(0x7ff0000000000000LL);
@@ -69,15 +70,91 @@ __device__ __forceinline__ double shortest_path(const EnvView &e, int px, int py
     return best;
 }
 
-// is_intersect R:1133-1146, including the leftover `not isclose(sqrt(euc_dist), sp_dist, abs_tol=0.1)` clause
-__device__ __forceinline__ bool los_blocked(const EnvView &e, int px, int py, double euc, double sp) {
+// One pass over the rectangles for the segment detector -> source: `direct` = mutually visible (shortest path is the
+// segment), `blocked` = boundary_distance < 0.001 for some rectangle (R:1139-1141, without the isclose clause).
+__device__ __forceinline__ void source_segment(const EnvView &e, int px, int py, bool &direct, bool &blocked) {
+    const int dx = e.sx - px, dy = e.sy - py;
+    const int l2 = dx * dx + dy * dy;
+    const int xlo = min(px, e.sx) - 1, xhi = max(px, e.sx) + 1, ylo = min(py, e.sy) - 1, yhi = max(py, e.sy) + 1;
+    bool vis_ok = true, blk = false;
+    for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        const int h = seg_rect(px, py, e.sx, e.sy, r);
+        vis_ok = vis_ok && !(h & 1);
+        bool b = (h & 2) && !(in_rect_open(px, py, r) && in_rect_open(e.sx, e.sy, r));
+        // near-corner clause: only for |pq| > 1000 and a rectangle whose box comes within 1 of the segment's box
+        if (!b && l2 > 1000000 && r.x <= xhi && xlo <= r.z && r.y <= yhi && ylo <= r.w) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int wx = corner_x(r, i) - px, wy = corner_y(r, i) - py;
+                const int t = wx * dx + wy * dy;
+                int cr = wx * dy - wy * dx;
+                cr = cr < 0 ? -cr : cr;
+                b = b || (t >= 0 && t <= l2 && cr <= 3 && cr * cr * 1000000 < l2);
+            }
+        }
+        blk = blk || b;
+    }
+    direct = vis_ok;
+    blocked = blk;
+}
+
+// Hot-path form: the same minimum, found with few visibility tests.  `hint` is the corner that was optimal at the
+// previous step (any value is allowed: it only seeds the upper bound).  Every corner gets a float LOWER bound of its
+// candidate length (round-down conversions), kept in the thread's smem column; corners are then tested in order of
+// increasing bound, each lane walking its own list while the warp stays converged, until no bound is below the best
+// exact candidate.  Exactly the value of shortest_path().
+__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<float> lb, int px, int py, int &hint) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const int nc = 4 * e.num_obs;
+    double best = inf;
+    int besti = -1;
+    if (hint < nc) {
+        const int4 r = e.rects[hint >> 2];
+        const int cx = corner_x(r, hint & 3), cy = corner_y(r, hint & 3);
+        const double ds = e.dsrc[hint];
+        if (ds < inf && visible(e, px, py, cx, cy)) { best = ds + dist_int(px - cx, py - cy); besti = hint; }
+    }
+    for (int c = 0; c < nc; c++) {
+        const int4 r = e.rects[c >> 2];
+        const int ddx = px - corner_x(r, c & 3), ddy = py - corner_y(r, c & 3);
+        lb[c] = __fadd_rd(__double2float_rd(e.dsrc[c]), __fsqrt_rd(__int2float_rd(ddx * ddx + ddy * ddy)));
+    }
+    uint32_t tested = besti >= 0 ? (1u << besti) : 0u;
+    for (int it = 0; it < nc; it++) {
+        int c = -1;
+        float m = __int_as_float(0x7f800000);
+        for (int j = 0; j < nc; j++) {
+            const float v = lb[j];
+            if (!((tested >> j) & 1u) && v < m) { m = v; c = j; }
+        }
+        if (c < 0 || !((double)m < best)) break;
+        tested |= 1u << c;
+        const int4 r = e.rects[c >> 2];
+        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+        const double cand = e.dsrc[c] + dist_int(px - cx, py - cy);
+        if (cand < best && visible(e, px, py, cx, cy)) { best = cand; besti = c; }
+    }
+    if (besti >= 0) hint = besti;
+    return best;
+}
+
+// the leftover `not isclose(sqrt(euc_dist), sp_dist, abs_tol=0.1)` clause of is_intersect (R:1141-1143): it can only
+// hold for euc_dist <= 2 because sp_dist >= euc_dist
+__device__ __forceinline__ bool isclose_quirk(double euc, double sp) {
+    if (euc > 2.0 && sp >= euc) return false;
     const double a = sqrt(euc), b = sp;
     const double diff = fabs(a - b), big = fmax(fabs(a), fabs(b));
     const double tol = fmax(1e-09 * big, 0.1);
-    if (a == b || (isfinite(a) && isfinite(b) && diff <= tol)) return false;
-    bool hit = false;
-    for (int k = 0; k < e.num_obs; k++) hit = hit || los_blocked_rect(px, py, e.sx, e.sy, e.rects[k]);
-    return hit;
+    return a == b || (isfinite(a) && isfinite(b) && diff <= tol);
+}
+
+// is_intersect R:1133-1146
+__device__ __forceinline__ bool los_blocked(const EnvView &e, int px, int py, double euc, double sp) {
+    if (isclose_quirk(euc, sp)) return false;
+    bool direct, blocked;
+    source_segment(e, px, py, direct, blocked);
+    return blocked;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -147,19 +224,21 @@ __device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int p
         if (r.x - 100 <= px && px <= r.z + 100 && r.y - 100 <= py && py <= r.w + 100) cand |= 1 << k;
     }
     if (cand) {
-        int hits_best = -1, best_k = 0;
-        int hits[RS_MAX_K];
+        unsigned long long hits = 0ull;              // 8 bits per rectangle (obs_idx_ls R:1190)
+        // per-direction running state across this lane's candidate rectangles (index order, R:1186-1217)
+        int inter_d[8], dmin_d[8];
 #pragma unroll
-        for (int k = 0; k < RS_MAX_K; k++) hits[k] = 0;
+        for (int d = 0; d < 8; d++) { inter_d[d] = 0; dmin_d[d] = -1; }
+        int todo = cand;
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int4 r = e.rects[k];
+            int hk = 0;
 #pragma unroll
-        for (int d = 0; d < 8; d++) {
-            const int sx = step_dx(d), sy = step_dy(d);
-            int inter = 0;
-            int dmin = -1;
-#pragma unroll
-            for (int k = 0; k < RS_MAX_K; k++) {
-                if (!((cand >> k) & 1)) continue;
-                const int4 r = e.rects[k];
+            for (int d = 0; d < 8; d++) {
+                const int sx = step_dx(d), sy = step_dy(d);
+                int inter = inter_d[d], dmin = dmin_d[d];
                 // edge order R:1000-1006: (p0,p1) left, (p0,p3) bottom, (p2,p1) top, (p2,p3) right
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
@@ -179,26 +258,29 @@ __device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int p
                     if (inter < 2 && hit) {
                         dmin = (dmin < 0 || d2 < dmin) ? d2 : dmin;
                         inter++;
-                        hits[k]++;
+                        hk++;
                     }
                 }
+                inter_d[d] = inter; dmin_d[d] = dmin;
             }
-            best_d2[d] = dmin;
+            hits |= (unsigned long long)hk << (8 * k);
         }
+#pragma unroll
+        for (int d = 0; d < 8; d++) best_d2[d] = dmin_d[d];
         int ones = 0;
 #pragma unroll
         for (int d = 0; d < 8; d++) ones += (best_d2[d] == 0);
         if (ones > 3) {
             // max(zip(obs_idx_ls, self.poly)) R:1222-1226: most hits, ties -> lexicographically largest vertex list
-#pragma unroll
-            for (int k = 0; k < RS_MAX_K; k++) {
-                if (k >= e.num_obs) continue;
-                bool take = hits[k] > hits_best;
-                if (!take && hits[k] == hits_best) {
+            int hits_best = -1, best_k = 0;
+            for (int k = 0; k < e.num_obs; k++) {
+                const int hk = (int)((hits >> (8 * k)) & 0xffull);
+                bool take = hk > hits_best;
+                if (!take && hk == hits_best) {
                     const int4 a = e.rects[k], b = e.rects[best_k];
                     take = (a.x != b.x) ? (a.x > b.x) : ((a.y != b.y) ? (a.y > b.y) : ((a.w != b.w) ? (a.w > b.w) : (a.z > b.z)));
                 }
-                if (take) { hits_best = hits[k]; best_k = k; }
+                if (take) { hits_best = hk; best_k = k; }
             }
             correct_coords(px, py, e.rects[best_k], out, status);
 #pragma unroll
@@ -228,11 +310,10 @@ __device__ __forceinline__ bool in_obstruction(const EnvView &e, int px, int py)
     return blocked;
 }
 
-// measurement + sensors + observation row for one agent at (px,py).  R:495-502, 570-593
+// measurement + sensors + observation row for one agent at (px,py).  R:498-502, 570-593
 template <bool kFast>
-__device__ __forceinline__ bool observe(const Params &P, const EnvView &e, int px, int py, double euc, double sp,
+__device__ __forceinline__ void observe(const Params &P, const EnvView &e, int px, int py, double euc, bool blocked_los,
                                         Rng &g, float *obs_row, uint32_t &status) {
-    const bool blocked_los = los_blocked(e, px, py, euc, sp);
     double lam;
     if (blocked_los) lam = (double)e.bkg;
     else {
@@ -253,7 +334,6 @@ __device__ __forceinline__ bool observe(const Params &P, const EnvView &e, int p
     obs_row[2] = (float)((double)py * P.inv_scale);
 #pragma unroll
     for (int d = 0; d < 8; d++) obs_row[3 + d] = s[d];
-    return blocked_los;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -270,9 +350,11 @@ struct StepArgs {
     int n_uniforms, flags;
 };
 
+// obs_rows: where this env's A x 11 observation rows go (the CTA's shared-memory tile; the kernel stores the tile to
+// a.obs with coalesced vector stores afterwards).  Returns true when the env was scheduled for reset.
 template <bool kFast>
-__device__ __forceinline__ void step_env(const Params &P, const RsState &S, const StepArgs &a, int n, Col<int4> rects,
-                                         Col<double> dsrc) {
+__device__ __forceinline__ bool step_env(const Params &P, const RsState &S, const StepArgs &a, int n, Col<int4> rects,
+                                         Col<double> dsrc, Col<float> lb, float *obs_rows) {
     const int N = a.n_env, A = P.n_agents;
     const int meta = S.meta[n];
     EnvView e;
@@ -325,13 +407,18 @@ __device__ __forceinline__ void step_env(const Params &P, const RsState &S, cons
         if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
         // the reference keeps stale sp/euc when the detector did not move; recomputing them at the unchanged position
         // gives the same numbers (R:528-567)
-        const double sp = shortest_path(e, det.x, det.y);
         const double euc = dist_int(det.x - e.sx, det.y - e.sy);
+        bool direct, blocked_raw;
+        source_segment(e, det.x, det.y, direct, blocked_raw);
+        int hint = (af >> 25) & 31;
+        const double sp = direct ? euc : shortest_path_pruned(e, lb, det.x, det.y, hint);
+        af = (af & ~(31 << 25)) | (hint << 25);
+        const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);   // is_intersect R:1133-1146
+        if (blocked_los) info |= RS_I_LOS_BLOCKED;
         Rng g;
         if (a.uniforms) g.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
         else g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 0, (uint32_t)ag, a.step_ctr);
-        float *row = a.obs + ((size_t)n * A + ag) * RS_OBS_DIM;
-        if (observe<kFast>(P, e, det.x, det.y, euc, sp, g, row, status)) info |= RS_I_LOS_BLOCKED;
+        observe<kFast>(P, e, det.x, det.y, euc, blocked_los, g, obs_rows + ag * RS_OBS_DIM, status);
         double reward;
         if (moved) {                                                    // R:507-522
             info |= RS_I_MOVED;
@@ -356,26 +443,32 @@ __device__ __forceinline__ void step_env(const Params &P, const RsState &S, cons
     if (a.team_reward) a.team_reward[n] = (float)max_reward;
     int ended = done ? RS_E_TERMINAL : 0;
     if (have_act) ep_len += 1;
+    bool scheduled = false;
     if (a.flags & RS_F_AUTO_RESET) {                                    // T:394-405, 446-548
         const bool timeout = ep_len == P.max_ep_len;
         if (timeout) ended |= RS_E_TIMEOUT;
         if (done || timeout || (a.flags & RS_F_EPOCH_END)) {
             ended |= RS_E_RESET;
+            scheduled = true;
             const int slot = atomicAdd(S.reset_count, 1);
             S.reset_list[slot] = n;
             if (a.final_obs) {
-                for (int i = 0; i < A * RS_OBS_DIM; i++)
-                    a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = a.obs[(size_t)n * A * RS_OBS_DIM + i];
+                for (int i = 0; i < A * RS_OBS_DIM; i++) a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = obs_rows[i];
             }
         }
     }
     if (a.ended) a.ended[n] = (uint8_t)ended;
     S.meta[n] = e.num_obs | (done << 8) | (ep_len << 16);
     if (status) S.status[n] |= status;
+    return scheduled;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// reset R:730-797: scenario sampling (Philox domain 1), per-episode tables, initial observation (step(None) probe)
+// reset R:730-797: scenario sampling (Philox domain 1), per-episode tables, initial observation (step(None) probe).
+// Cooperative form: `nl` lanes (a warp on the GPU, 1 in the host emulation) share one environment.  The sequential
+// rejection sampling runs redundantly on every lane (same Philox stream, no divergence); the per-corner work
+// (visibility rows, source visibility, Dijkstra relaxations, table stores) is strided over the lanes through the
+// warp's shared-memory scratch, separated by __syncwarp().
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rand_point(const Params &P, Rng &g, int &x, int &y) {     // R:1026-1036
     const uint32_t span = (uint32_t)(P.sx1 - P.sx0);
@@ -408,6 +501,12 @@ __device__ __forceinline__ int create_obstructions(const Params &P, Rng &g, Col<
     }
     status |= RS_ST_REJECT_CAP;
     return num_obs;
+}
+
+__device__ __forceinline__ bool los_blocked_any(const EnvView &e, int px, int py, int qx, int qy) {
+    bool hit = false;
+    for (int k = 0; k < e.num_obs; k++) hit = hit || los_blocked_rect(px, py, qx, qy, e.rects[k]);
+    return hit;
 }
 
 __device__ __forceinline__ void sample_source_loc_pos(const Params &P, Rng &g, const EnvView &e, int &sx, int &sy,
@@ -447,58 +546,6 @@ __device__ __forceinline__ void sample_source_loc_pos(const Params &P, Rng &g, c
     sx = srcx; sy = srcy; dx_ = detx; dy_ = dety;
 }
 
-// corner-to-corner visibility masks (depends on the obstructions only)
-__device__ __forceinline__ void build_visibility(const EnvView &e, Col<uint32_t> vis) {
-    const int nc = 4 * e.num_obs;
-    for (int c = 0; c < nc; c++) vis[c] = 0u;
-    for (int c = 0; c < nc; c++) {
-        const int4 rc = e.rects[c >> 2];
-        const int cx = corner_x(rc, c & 3), cy = corner_y(rc, c & 3);
-        uint32_t m = vis[c];
-        for (int c2 = c + 1; c2 < nc; c2++) {
-            const int4 r2 = e.rects[c2 >> 2];
-            if (visible(e, cx, cy, corner_x(r2, c2 & 3), corner_y(r2, c2 & 3))) {
-                m |= 1u << c2;
-                vis[c2] = vis[c2] | (1u << c);
-            }
-        }
-        vis[c] = m;
-    }
-}
-
-// dsrc[c] = shortest path length source -> corner c: Dijkstra on the corner visibility graph, sums accumulated from
-// the source outwards (the order Polyline::length() adds them)
-__device__ __forceinline__ void build_dsrc(const EnvView &e, Col<uint32_t> vis) {
-    const int nc = 4 * e.num_obs;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    for (int c = 0; c < nc; c++) {
-        const int4 r = e.rects[c >> 2];
-        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
-        e.dsrc[c] = visible(e, e.sx, e.sy, cx, cy) ? dist_int(cx - e.sx, cy - e.sy) : inf;
-    }
-    uint32_t fin = 0;
-    for (int it = 0; it < nc; it++) {
-        int u = -1;
-        double du = inf;
-        for (int c = 0; c < nc; c++) {
-            const double d = e.dsrc[c];
-            if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
-        }
-        if (u < 0) break;
-        fin |= 1u << u;
-        const int4 ru = e.rects[u >> 2];
-        const int ux = corner_x(ru, u & 3), uy = corner_y(ru, u & 3);
-        uint32_t m = vis[u] & ~fin;
-        while (m) {
-            const int w = __ffs(m) - 1;
-            m &= m - 1;
-            const int4 rw = e.rects[w >> 2];
-            const double nd = du + dist_int(ux - corner_x(rw, w & 3), uy - corner_y(rw, w & 3));
-            if (nd < e.dsrc[w]) e.dsrc[w] = nd;
-        }
-    }
-}
-
 struct ResetArgs {
     float *obs;
     int n_env;
@@ -511,34 +558,57 @@ struct ResetArgs {
     int k_in;
 };
 
+#ifdef RS_HOST_EMU
+#define RS_SYNCWARP()
+#else
+#define RS_SYNCWARP() __syncwarp()
+#endif
+
 template <bool kFast>
 __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, const ResetArgs &a, int n,
-                                          bool new_obstacles, Col<int4> rects, Col<double> dsrc, Col<uint32_t> vis) {
+                                          bool new_obstacles, int lane, int nl, int4 *w_rects, double *w_dsrc,
+                                          uint32_t *w_vis) {
     const int N = a.n_env, A = P.n_agents;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
     uint32_t status = 0;
     EnvView e;
-    e.rects = rects; e.dsrc = dsrc;
+    e.rects = Col<int4>{w_rects, 1};
+    e.dsrc = Col<double>{w_dsrc, 1};
     Rng g;
     g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, a.step_ctr);
     const bool inject = a.in_src != nullptr;
-    int detx, dety;
+    RS_SYNCWARP();                                                      // scratch is reused between environments
     if (inject) {                                                       // refresh_environment R:799-874
         e.num_obs = min(a.in_num_obs[n], P.k_max);
-        for (int k = 0; k < e.num_obs; k++)
-            rects[k] = reinterpret_cast<const int4 *>(a.in_rects)[(size_t)n * a.k_in + k];
+        for (int k = lane; k < e.num_obs; k += nl)
+            w_rects[k] = reinterpret_cast<const int4 *>(a.in_rects)[(size_t)n * a.k_in + k];
         new_obstacles = true;
     } else if (new_obstacles) {
-        e.num_obs = create_obstructions(P, g, rects, status);           // R:744-762
+        e.num_obs = create_obstructions(P, g, e.rects, status);         // R:744-762 (every lane writes the same values)
     } else {
         e.num_obs = S.meta[n] & 0xff;
-        for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-        for (int c = 0; c < 4 * e.num_obs; c++) vis[c] = S.vis[(size_t)c * N + n];
+        for (int k = lane; k < e.num_obs; k += nl) w_rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+        for (int c = lane; c < 4 * e.num_obs; c += nl) w_vis[c] = S.vis[(size_t)c * N + n];
     }
+    RS_SYNCWARP();
+    const int nc = 4 * e.num_obs;
     if (new_obstacles) {
-        build_visibility(e, vis);
-        for (int k = 0; k < e.num_obs; k++) reinterpret_cast<int4 *>(S.rects)[(size_t)k * N + n] = rects[k];
-        for (int c = 0; c < 4 * e.num_obs; c++) S.vis[(size_t)c * N + n] = vis[c];
+        // corner-to-corner visibility rows (depend on the obstructions only): lane c owns row c
+        for (int c = lane; c < nc; c += nl) {
+            const int4 rc = w_rects[c >> 2];
+            const int cx = corner_x(rc, c & 3), cy = corner_y(rc, c & 3);
+            uint32_t m = 0u;
+            for (int c2 = 0; c2 < nc; c2++) {
+                if (c2 == c) continue;
+                const int4 r2 = w_rects[c2 >> 2];
+                if (visible(e, cx, cy, corner_x(r2, c2 & 3), corner_y(r2, c2 & 3))) m |= 1u << c2;
+            }
+            w_vis[c] = m;
+            S.vis[(size_t)c * N + n] = m;
+        }
+        for (int k = lane; k < e.num_obs; k += nl) reinterpret_cast<int4 *>(S.rects)[(size_t)k * N + n] = w_rects[k];
     }
+    int detx, dety;
     if (inject) {
         e.sx = a.in_src[2 * n]; e.sy = a.in_src[2 * n + 1];
         detx = a.in_det[2 * n]; dety = a.in_det[2 * n + 1];
@@ -548,25 +618,64 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         e.intensity = 1000000 + (int)g.below(9000000u);                  // R:778
         e.bkg = 10 + (int)g.below(41u);                                  // R:779
     }
-    build_dsrc(e, vis);
-    for (int c = 0; c < 4 * e.num_obs; c++) S.dsrc[(size_t)c * N + n] = dsrc[c];
-    reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
-    reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
-    S.meta[n] = e.num_obs;                                               // done = 0, ep_len = 0   R:739-740
+    // dsrc[c] = shortest path length source -> corner c: Dijkstra on the corner visibility graph, sums accumulated
+    // from the source outwards (the order Polyline::length() adds them)
+    for (int c = lane; c < nc; c += nl) {
+        const int4 r = w_rects[c >> 2];
+        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+        w_dsrc[c] = visible(e, e.sx, e.sy, cx, cy) ? dist_int(cx - e.sx, cy - e.sy) : inf;
+    }
+    RS_SYNCWARP();
+    uint32_t fin = 0;
+    for (int it = 0; it < nc; it++) {
+        int u = -1;
+        double du = inf;
+        for (int c = 0; c < nc; c++) {                                   // every lane scans: uniform result
+            const double d = w_dsrc[c];
+            if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
+        }
+        if (u < 0) break;
+        fin |= 1u << u;
+        const int4 ru = w_rects[u >> 2];
+        const int ux = corner_x(ru, u & 3), uy = corner_y(ru, u & 3);
+        const uint32_t m = w_vis[u] & ~fin;
+        RS_SYNCWARP();
+        for (int w = lane; w < nc; w += nl) {
+            if (!((m >> w) & 1u)) continue;
+            const int4 rw = w_rects[w >> 2];
+            const double nd = du + dist_int(ux - corner_x(rw, w & 3), uy - corner_y(rw, w & 3));
+            if (nd < w_dsrc[w]) w_dsrc[w] = nd;
+        }
+        RS_SYNCWARP();
+    }
+    for (int c = lane; c < nc; c += nl) S.dsrc[(size_t)c * N + n] = w_dsrc[c];
     const double sp = shortest_path(e, detx, dety);                      // prev_det_dist R:771-776
     const double euc = dist_int(detx - e.sx, dety - e.sy);
+    bool direct, blocked_raw;
+    source_segment(e, detx, dety, direct, blocked_raw);
+    const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);
+    if (lane == 0) {
+        reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
+        reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
+        S.meta[n] = e.num_obs;                                           // done = 0, ep_len = 0   R:739-740
+    }
     for (int ag = 0; ag < A; ag++) {
         const size_t ia = (size_t)ag * N + n;
-        reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
-        S.best[ia] = sp;
-        S.aflags[ia] = 0;                                                // Agent.reset R:289-300
         Rng gp;
         if (a.uniforms) gp.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
         else gp.init_philox(a.seed, a.env_id0 + (uint32_t)n, 2, (uint32_t)ag, a.step_ctr);
-        observe<kFast>(P, e, detx, dety, euc, sp, gp, a.obs + ((size_t)n * A + ag) * RS_OBS_DIM, status);   // R:794
+        float row[RS_OBS_DIM];
+        observe<kFast>(P, e, detx, dety, euc, blocked_los, gp, row, status);   // R:794
+        if (lane == 0) {
+            reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
+            S.best[ia] = sp;
+            S.aflags[ia] = 0;                                            // Agent.reset R:289-300
+#pragma unroll
+            for (int i = 0; i < RS_OBS_DIM; i++) a.obs[((size_t)n * A + ag) * RS_OBS_DIM + i] = row[i];
+        }
     }
     status |= g.status;
-    if (status) S.status[n] |= status;
+    if (status && lane == 0) S.status[n] |= status;
 }
 
 }  // namespace rs

@@ -16,37 +16,54 @@ thread_local char g_err[256] = "";
 
 int fail(const char *msg) { return rs_set_error(msg); }
 
+// smem per CTA: rects [K][128] int4 | dsrc [4K][128] f64 | lb [4K][128] f32 | obs tile [128][A*11] f32
 template <bool kFast>
 __global__ void __launch_bounds__(kBlock) step_kernel(rs::Params P, RsState S, rs::StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int4 *srects = reinterpret_cast<int4 *>(smem);                                  // [k_max][kBlock]
-    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);  // [4*k_max][kBlock]
-    const int n = blockIdx.x * kBlock + threadIdx.x;
-    if (n >= a.n_env) return;
-    rs::step_env<kFast>(P, S, a, n, rs::Col<int4>{srects + threadIdx.x, kBlock},
-                        rs::Col<double>{sdsrc + threadIdx.x, kBlock});
+    int4 *srects = reinterpret_cast<int4 *>(smem);
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
+    float *slb = reinterpret_cast<float *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    float *sobs = slb + (size_t)4 * P.k_max * kBlock;
+    const int row = P.n_agents * RS_OBS_DIM;
+    const int n0 = blockIdx.x * kBlock;
+    const int n = n0 + threadIdx.x;
+    if (n < a.n_env)
+        rs::step_env<kFast>(P, S, a, n, rs::Col<int4>{srects + threadIdx.x, kBlock},
+                            rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<float>{slb + threadIdx.x, kBlock},
+                            sobs + threadIdx.x * row);
+    __syncthreads();
+    // the CTA's observation rows are contiguous in a.obs: coalesced 16-byte stores
+    const int cnt = min(kBlock, a.n_env - n0) * row;
+    float *dst = a.obs + (size_t)n0 * row;                 // n0 * row * 4 bytes is a multiple of 16
+    const int n4 = cnt >> 2;
+    for (int i = threadIdx.x; i < n4; i += kBlock)
+        reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(sobs)[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kBlock) dst[i] = sobs[i];
 }
+
+// One warp per environment to reset, persistent grid: warps stride over the work list (or over all envs with a mask).
+constexpr int kResetWarps = kBlock / 32;
 
 template <bool kFast>
 __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
                                                         const uint8_t *new_mask, int flags) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int4 *srects = reinterpret_cast<int4 *>(smem);
-    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
-    uint32_t *svis = reinterpret_cast<uint32_t *>(sdsrc + (size_t)4 * P.k_max * kBlock);
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    int n;
-    if (flags & RS_F_RESET_LIST) {
-        if (i >= *S.reset_count) return;
-        n = S.reset_list[i];
-    } else {
-        if (i >= a.n_env) return;
-        n = i;
-        if (mask && !mask[n]) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp scratch: rects [K] int4 | dsrc [4K] f64 | vis [4K] u32
+    const size_t per_warp = (size_t)P.k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
+    unsigned char *base = smem + per_warp * w;
+    int4 *w_rects = reinterpret_cast<int4 *>(base);
+    double *w_dsrc = reinterpret_cast<double *>(w_rects + P.k_max);
+    uint32_t *w_vis = reinterpret_cast<uint32_t *>(w_dsrc + 4 * P.k_max);
+    const int total = (flags & RS_F_RESET_LIST) ? *S.reset_count : a.n_env;
+    const int stride = gridDim.x * kResetWarps;
+    for (int i = blockIdx.x * kResetWarps + w; i < total; i += stride) {
+        int n = i;
+        if (flags & RS_F_RESET_LIST) n = S.reset_list[i];
+        else if (mask && !mask[n]) continue;
+        const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
+        rs::reset_env<kFast>(P, S, a, n, new_obs, lane, 32, w_rects, w_dsrc, w_vis);
     }
-    const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
-    rs::reset_env<kFast>(P, S, a, n, new_obs, rs::Col<int4>{srects + threadIdx.x, kBlock},
-                         rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<uint32_t>{svis + threadIdx.x, kBlock});
 }
 
 int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
@@ -65,8 +82,14 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
     return 0;
 }
 
-size_t step_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(double)); }
-size_t reset_smem(const RsConfig *cfg) { return step_smem(cfg) + (size_t)cfg->k_max * kBlock * 4 * sizeof(uint32_t); }
+size_t step_smem(const RsConfig *cfg) {
+    return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(float)) +
+           (size_t)kBlock * cfg->n_agents * RS_OBS_DIM * sizeof(float);
+}
+size_t reset_smem(const RsConfig *cfg) {
+    return (size_t)kResetWarps * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
+}
+constexpr int kResetGrid = 148 * 8;      // persistent: 8 CTAs of 4 warps per SM
 
 }  // namespace
 
@@ -98,6 +121,10 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     const int grid = (n_env + kBlock - 1) / kBlock;
     const size_t smem = step_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (fast) step_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a);
     else step_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a);
     return (int)cudaGetLastError();
@@ -106,13 +133,10 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
                         const uint8_t *new_mask, int flags, cudaStream_t s) {
     rs::Params P = rs::make_params(*cfg);
-    const int grid = (a.n_env + kBlock - 1) / kBlock;
+    const int need = (a.n_env + kResetWarps - 1) / kResetWarps;
+    const int grid = need < kResetGrid ? need : kResetGrid;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
     if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
     else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
     return (int)cudaGetLastError();

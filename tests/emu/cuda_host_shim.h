@@ -29,3 +29,9 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+// round-down conversions used for the shortest-path lower bounds
+static inline float __double2float_rd(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
+static inline float __int2float_rd(int x) { float f = (float)x; if ((double)f > (double)x) f = nextafterf(f, -INFINITY); return f; }
+static inline float __fsqrt_rd(float v) { float f = sqrtf(v); if ((double)f * (double)f > (double)v) f = nextafterf(f, -INFINITY); return f; }
+static inline float __fadd_rd(float a, float b) { return __double2float_rd((double)a + (double)b); }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

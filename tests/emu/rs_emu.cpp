@@ -20,10 +20,13 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
     std::vector<int4> rects(RS_MAX_K);
     std::vector<double> dsrc(4 * RS_MAX_K);
+    std::vector<float> lb(4 * RS_MAX_K);
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    const int row = cfg->n_agents * RS_OBS_DIM;
     for (int n = 0; n < n_env; n++) {
-        if (fast) rs::step_env<true>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1});
-        else rs::step_env<false>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1});
+        float *rows = obs + (size_t)n * row;      // the CUDA kernel stages these rows in shared memory first
+        if (fast) rs::step_env<true>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1}, rows);
+        else rs::step_env<false>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1}, rows);
     }
     return 0;
 }
@@ -41,8 +44,9 @@ static int run_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs
         if (flags & RS_F_RESET_LIST) n = st->reset_list[i];
         else if (mask && !mask[n]) continue;
         const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
-        if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
-        else rs::reset_env<false>(P, *st, a, n, new_obs, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
+        // one "lane" plays the whole warp: the lane-strided loops degenerate to plain loops
+        if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, 0, 1, rects.data(), dsrc.data(), vis.data());
+        else rs::reset_env<false>(P, *st, a, n, new_obs, 0, 1, rects.data(), dsrc.data(), vis.data());
     }
     return 0;
 }
