@@ -108,6 +108,11 @@ int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src
                       const int32_t *num_obs, float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed,
                       uint64_t step_ctr, const double *uniforms, int32_t n_uniforms, void *stream);
 
+/* Shortest-path length source -> pts[n] (int32 [N][2], device) for every env, by the step kernel's pruned search
+ * (R:491-493 semantics); out: double [N].  variant 0 = the step kernel's pruned search, 1 = plain min over all corners. */
+int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,
+                           int32_t variant, void *stream);
+
 /* GAE-lambda advantages and rewards-to-go over a [T][N] rollout.  path_end[t][n] != 0 where the caller finished a
  * trajectory after step t; boot[t][n] = bootstrap value passed there (read only where path_end or t == T-1).
  * stats (nullable): double[2] device accumulators += {sum(adv), sum(adv^2)} (zero them first).

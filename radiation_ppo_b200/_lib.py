@@ -15,7 +15,7 @@ E_TERMINAL, E_TIMEOUT, E_RESET = 1, 2, 4
 ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, ST_COORD_RANGE = 1, 2, 4, 8, 16, 32
 
 EXPORTS = [
-    "rs_step", "rs_reset", "rs_load_scenarios", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
+    "rs_step", "rs_reset", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
     "rs_version", "rs_sizeof_config", "rs_sizeof_state",
 ]
 
@@ -59,6 +59,9 @@ def declare(lib, prefix="rs_"):
     f = getattr(lib, prefix + "load_scenarios")
     f.restype = i32
     f.argtypes = [cfgp, stp, vp, vp, vp, vp, vp, i32, vp, vp, i32, u32, u64, u64, vp, i32] + tail
+    f = getattr(lib, prefix + "query_shortest_path")
+    f.restype = i32
+    f.argtypes = [cfgp, stp, vp, vp, i32, i32] + tail
     if prefix == "rs_":
         lib.rs_gae.restype = i32
         lib.rs_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f64, f64, vp, i32, vp]

@@ -47,8 +47,20 @@ struct EnvView {
 // shortest path source -> p around the rectangles (R:491-493) from the per-episode table dsrc[corner]
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx, int qy) {
+    // the open segment can only meet an open rectangle whose box overlaps the segment's box; each lane walks its own
+    // (short) list of such rectangles so that the warp stays converged
+    const int xlo = min(px, qx), xhi = max(px, qx), ylo = min(py, qy), yhi = max(py, qy);
+    uint32_t m = 0u;
+    for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        if (r.x < xhi && xlo < r.z && r.y < yhi && ylo < r.w) m |= 1u << k;
+    }
     bool hit = false;
-    for (int k = 0; k < e.num_obs; k++) hit = hit || (seg_rect(px, py, qx, qy, e.rects[k]) & 1);
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        hit = hit || (seg_rect(px, py, qx, qy, e.rects[k]) & 1);
+    }
     return !hit;
 }
 
@@ -77,13 +89,20 @@ __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py,
     const int l2 = dx * dx + dy * dy;
     const int xlo = min(px, e.sx) - 1, xhi = max(px, e.sx) + 1, ylo = min(py, e.sy) - 1, yhi = max(py, e.sy) + 1;
     bool vis_ok = true, blk = false;
+    uint32_t m = 0u;
     for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        if (r.x <= xhi && xlo <= r.z && r.y <= yhi && ylo <= r.w) m |= 1u << k;
+    }
+    while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
         const int4 r = e.rects[k];
         const int h = seg_rect(px, py, e.sx, e.sy, r);
         vis_ok = vis_ok && !(h & 1);
         bool b = (h & 2) && !(in_rect_open(px, py, r) && in_rect_open(e.sx, e.sy, r));
-        // near-corner clause: only for |pq| > 1000 and a rectangle whose box comes within 1 of the segment's box
-        if (!b && l2 > 1000000 && r.x <= xhi && xlo <= r.z && r.y <= yhi && ylo <= r.w) {
+        // near-corner clause: only for |pq| > 1000
+        if (!b && l2 > 1000000) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int wx = corner_x(r, i) - px, wy = corner_y(r, i) - py;
@@ -115,15 +134,26 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<flo
         const double ds = e.dsrc[hint];
         if (ds < inf && visible(e, px, py, cx, cy)) { best = ds + dist_int(px - cx, py - cy); besti = hint; }
     }
+    // Only a corner at which the path can bend tautly around its rectangle can be the first vertex of a shortest
+    // path: seen from p, both edges of the rectangle at that corner lie on one (closed) side of the line p -> corner.
+    // For an axis-aligned rectangle that is u.x*u.y <= 0 at p0/p2 and >= 0 at p1/p3 (u = corner - p).  A bend at any
+    // other visible corner can be cut short by >= 1e-8 (lattice geometry), far above the fp64 rounding of the sums,
+    // so dropping those corners cannot change the minimum.
+    const float pos_inf = __int_as_float(0x7f800000);
     for (int c = 0; c < nc; c++) {
         const int4 r = e.rects[c >> 2];
-        const int ddx = px - corner_x(r, c & 3), ddy = py - corner_y(r, c & 3);
-        lb[c] = __fadd_rd(__double2float_rd(e.dsrc[c]), __fsqrt_rd(__int2float_rd(ddx * ddx + ddy * ddy)));
+        const int ux = corner_x(r, c & 3) - px, uy = corner_y(r, c & 3) - py;
+        const int pr = ux * uy;
+        const bool tangent = (c & 1) ? (pr >= 0) : (pr <= 0);
+        // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
+        const float f2 = __int2float_rd(ux * ux + uy * uy);
+        const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
+        lb[c] = tangent ? __fadd_rd(__double2float_rd(e.dsrc[c]), sq) : pos_inf;
     }
     uint32_t tested = besti >= 0 ? (1u << besti) : 0u;
     for (int it = 0; it < nc; it++) {
         int c = -1;
-        float m = __int_as_float(0x7f800000);
+        float m = pos_inf;
         for (int j = 0; j < nc; j++) {
             const float v = lb[j];
             if (!((tested >> j) & 1u) && v < m) { m = v; c = j; }
@@ -465,7 +495,8 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
 
 // ---------------------------------------------------------------------------------------------------------------
 // reset R:730-797: scenario sampling (Philox domain 1), per-episode tables, initial observation (step(None) probe).
-// Cooperative form: `nl` lanes (a warp on the GPU, 1 in the host emulation) share one environment.  The sequential
+// Cooperative form: `nl` lanes (32, 8 or 1 on the GPU depending on how many envs reset; 1 in the host emulation)
+// share one environment; sync_mask names them.  The sequential
 // rejection sampling runs redundantly on every lane (same Philox stream, no divergence); the per-corner work
 // (visibility rows, source visibility, Dijkstra relaxations, table stores) is strided over the lanes through the
 // warp's shared-memory scratch, separated by __syncwarp().
@@ -558,26 +589,43 @@ struct ResetArgs {
     int k_in;
 };
 
+// shortest path source -> (px,py) of env n, for rs_query_shortest_path
+__device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int px, int py, int variant, Col<int4> rects,
+                                           Col<double> dsrc, Col<float> lb) {
+    EnvView e;
+    e.rects = rects; e.dsrc = dsrc;
+    e.num_obs = S.meta[n] & 0xff;
+    const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
+    e.sx = src.x; e.sy = src.y; e.intensity = 0; e.bkg = 0;
+    for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = S.dsrc[(size_t)c * N + n];
+    if (variant == 1) return shortest_path(e, px, py);
+    bool direct, blocked;
+    source_segment(e, px, py, direct, blocked);
+    int hint = 31;
+    return direct ? dist_int(px - e.sx, py - e.sy) : shortest_path_pruned(e, lb, px, py, hint);
+}
+
 #ifdef RS_HOST_EMU
-#define RS_SYNCWARP()
+#define RS_SYNCWARP(m)
 #else
-#define RS_SYNCWARP() __syncwarp()
+#define RS_SYNCWARP(m) __syncwarp(m)
 #endif
 
 template <bool kFast>
 __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, const ResetArgs &a, int n,
-                                          bool new_obstacles, int lane, int nl, int4 *w_rects, double *w_dsrc,
-                                          uint32_t *w_vis) {
+                                          bool new_obstacles, int lane, int nl, uint32_t sync_mask,
+                                          Col<int4> w_rects, Col<double> w_dsrc, Col<uint32_t> w_vis) {
     const int N = a.n_env, A = P.n_agents;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     uint32_t status = 0;
     EnvView e;
-    e.rects = Col<int4>{w_rects, 1};
-    e.dsrc = Col<double>{w_dsrc, 1};
+    e.rects = w_rects;
+    e.dsrc = w_dsrc;
     Rng g;
     g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, a.step_ctr);
     const bool inject = a.in_src != nullptr;
-    RS_SYNCWARP();                                                      // scratch is reused between environments
+    RS_SYNCWARP(sync_mask);                                                      // scratch is reused between environments
     if (inject) {                                                       // refresh_environment R:799-874
         e.num_obs = min(a.in_num_obs[n], P.k_max);
         for (int k = lane; k < e.num_obs; k += nl)
@@ -590,7 +638,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         for (int k = lane; k < e.num_obs; k += nl) w_rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
         for (int c = lane; c < 4 * e.num_obs; c += nl) w_vis[c] = S.vis[(size_t)c * N + n];
     }
-    RS_SYNCWARP();
+    RS_SYNCWARP(sync_mask);
     const int nc = 4 * e.num_obs;
     if (new_obstacles) {
         // corner-to-corner visibility rows (depend on the obstructions only): lane c owns row c
@@ -625,7 +673,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         w_dsrc[c] = visible(e, e.sx, e.sy, cx, cy) ? dist_int(cx - e.sx, cy - e.sy) : inf;
     }
-    RS_SYNCWARP();
+    RS_SYNCWARP(sync_mask);
     uint32_t fin = 0;
     for (int it = 0; it < nc; it++) {
         int u = -1;
@@ -639,14 +687,14 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const int4 ru = w_rects[u >> 2];
         const int ux = corner_x(ru, u & 3), uy = corner_y(ru, u & 3);
         const uint32_t m = w_vis[u] & ~fin;
-        RS_SYNCWARP();
+        RS_SYNCWARP(sync_mask);
         for (int w = lane; w < nc; w += nl) {
             if (!((m >> w) & 1u)) continue;
             const int4 rw = w_rects[w >> 2];
             const double nd = du + dist_int(ux - corner_x(rw, w & 3), uy - corner_y(rw, w & 3));
             if (nd < w_dsrc[w]) w_dsrc[w] = nd;
         }
-        RS_SYNCWARP();
+        RS_SYNCWARP(sync_mask);
     }
     for (int c = lane; c < nc; c += nl) S.dsrc[(size_t)c * N + n] = w_dsrc[c];
     const double sp = shortest_path(e, detx, dety);                      // prev_det_dist R:771-776

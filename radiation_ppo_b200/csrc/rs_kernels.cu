@@ -18,7 +18,7 @@ int fail(const char *msg) { return rs_set_error(msg); }
 
 // smem per CTA: rects [K][128] int4 | dsrc [4K][128] f64 | lb [4K][128] f32 | obs tile [128][A*11] f32
 template <bool kFast>
-__global__ void __launch_bounds__(kBlock) step_kernel(rs::Params P, RsState S, rs::StepArgs a) {
+__global__ void __launch_bounds__(kBlock, 4) step_kernel(rs::Params P, RsState S, rs::StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *srects = reinterpret_cast<int4 *>(smem);
     double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
@@ -41,28 +41,42 @@ __global__ void __launch_bounds__(kBlock) step_kernel(rs::Params P, RsState S, r
     for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kBlock) dst[i] = sobs[i];
 }
 
-// One warp per environment to reset, persistent grid: warps stride over the work list (or over all envs with a mask).
-constexpr int kResetWarps = kBlock / 32;
+__global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState S, const int32_t *pts, double *out,
+                                                           int n_env, int variant) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int4 *srects = reinterpret_cast<int4 *>(smem);
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
+    float *slb = reinterpret_cast<float *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    const int n = blockIdx.x * kBlock + threadIdx.x;
+    if (n >= n_env) return;
+    out[n] = rs::query_sp(S, n, n_env, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock},
+                          rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<float>{slb + threadIdx.x, kBlock});
+}
 
+// Reset: a persistent grid whose threads team up in groups of `nl` lanes per environment.  Few envs to reset (the
+// steady state: ~N/120 per step) -> a whole warp per env for low latency; a bulk reset (epoch end, synchronised
+// timeouts) -> one thread per env, which wastes no lanes on the sequential rejection sampling.
 template <bool kFast>
 __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
                                                         const uint8_t *new_mask, int flags) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp scratch: rects [K] int4 | dsrc [4K] f64 | vis [4K] u32
-    const size_t per_warp = (size_t)P.k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
-    unsigned char *base = smem + per_warp * w;
-    int4 *w_rects = reinterpret_cast<int4 *>(base);
-    double *w_dsrc = reinterpret_cast<double *>(w_rects + P.k_max);
-    uint32_t *w_vis = reinterpret_cast<uint32_t *>(w_dsrc + 4 * P.k_max);
     const int total = (flags & RS_F_RESET_LIST) ? *S.reset_count : a.n_env;
-    const int stride = gridDim.x * kResetWarps;
-    for (int i = blockIdx.x * kResetWarps + w; i < total; i += stride) {
+    const int nl = total > 32768 ? 1 : (total > 4096 ? 8 : 32);
+    const int G = kBlock / nl;                          // groups (environments in flight) per CTA
+    const int g = threadIdx.x / nl, lane = threadIdx.x % nl;
+    const uint32_t sync_mask = nl == 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) & ~(nl - 1)));
+    // scratch columns, element i of group g at [i * G + g]: rects [K] int4 | dsrc [4K] f64 | vis [4K] u32
+    int4 *srects = reinterpret_cast<int4 *>(smem);
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
+    uint32_t *svis = reinterpret_cast<uint32_t *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    const int stride = gridDim.x * G;
+    for (int i = blockIdx.x * G + g; i < total; i += stride) {
         int n = i;
         if (flags & RS_F_RESET_LIST) n = S.reset_list[i];
         else if (mask && !mask[n]) continue;
         const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
-        rs::reset_env<kFast>(P, S, a, n, new_obs, lane, 32, w_rects, w_dsrc, w_vis);
+        rs::reset_env<kFast>(P, S, a, n, new_obs, lane, nl, sync_mask, rs::Col<int4>{srects + g, G},
+                             rs::Col<double>{sdsrc + g, G}, rs::Col<uint32_t>{svis + g, G});
     }
 }
 
@@ -87,7 +101,7 @@ size_t step_smem(const RsConfig *cfg) {
            (size_t)kBlock * cfg->n_agents * RS_OBS_DIM * sizeof(float);
 }
 size_t reset_smem(const RsConfig *cfg) {
-    return (size_t)kResetWarps * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
+    return (size_t)kBlock * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
 }
 constexpr int kResetGrid = 148 * 8;      // persistent: 8 CTAs of 4 warps per SM
 
@@ -133,10 +147,14 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
                         const uint8_t *new_mask, int flags, cudaStream_t s) {
     rs::Params P = rs::make_params(*cfg);
-    const int need = (a.n_env + kResetWarps - 1) / kResetWarps;
+    const int need = (a.n_env + 3) / 4;                 // one warp per env is the widest teaming
     const int grid = need < kResetGrid ? need : kResetGrid;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
     else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
     return (int)cudaGetLastError();
@@ -172,6 +190,16 @@ int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src
     a.in_src = src; a.in_det = det; a.in_intensity = intensity; a.in_bkg = bkg; a.in_rects = rects;
     a.in_num_obs = num_obs; a.k_in = k_in;
     return launch_reset(cfg, st, a, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,
+                           int32_t variant, void *stream) {
+    if (int rc = check_cfg(cfg, st, n_env)) return rc;
+    if (!pts || !out) return fail("pts/out is NULL");
+    rs::Params P = rs::make_params(*cfg);
+    const int grid = (n_env + kBlock - 1) / kBlock;
+    sp_query_kernel<<<grid, kBlock, step_smem(cfg), static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
+    return (int)cudaGetLastError();
 }
 
 const char *rs_last_error(void) { return g_err; }

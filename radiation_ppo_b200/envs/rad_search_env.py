@@ -278,6 +278,16 @@ class RadSearch:
         self.epoch_end = False
         return self.obs
 
+    def shortest_path_to(self, points: torch.Tensor, variant: int = 0) -> torch.Tensor:
+        """Shortest-path length from each env's source to points[n] (int tensor [N, 2]) around its obstructions
+        (world.shortest_path(...).length(), R:491-493) -> float64 tensor [N]."""
+        pts = points.to(device=self.device, dtype=torch.int32).reshape(self.num_envs, 2).contiguous()
+        out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.rs_query_shortest_path(C.byref(self._cfg), C.byref(self._st), _ptr(pts), _ptr(out),
+                                                     self.num_envs, int(variant), self._stream()), "rs_query_shortest_path")
+        return out
+
     # ------------------------------------------------------------------------------------------------------------
     # state views
     # ------------------------------------------------------------------------------------------------------------

@@ -34,4 +34,5 @@ static inline float __double2float_rd(double x) { float f = (float)x; if ((doubl
 static inline float __int2float_rd(int x) { float f = (float)x; if ((double)f > (double)x) f = nextafterf(f, -INFINITY); return f; }
 static inline float __fsqrt_rd(float v) { float f = sqrtf(v); if ((double)f * (double)f > (double)v) f = nextafterf(f, -INFINITY); return f; }
 static inline float __fadd_rd(float a, float b) { return __double2float_rd((double)a + (double)b); }
+static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

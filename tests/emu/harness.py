@@ -110,6 +110,13 @@ class EmuEnv:
                                       self.env_id0, self.seed, step_ctr, _vp(u), 0 if u is None else u.shape[-1])
         assert rc == 0
 
+    def query_sp(self, pts, variant=0):
+        p = np.ascontiguousarray(pts, np.int32)
+        out = np.zeros(self.n, np.float64)
+        rc = emu().emu_query_shortest_path(C.byref(self.cfg), C.byref(self.st), _vp(p), _vp(out), self.n, variant)
+        assert rc == 0
+        return out
+
     # views in the oracle's terms
     @property
     def num_obs(self):

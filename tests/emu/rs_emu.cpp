@@ -31,6 +31,18 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     return 0;
 }
 
+int emu_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,
+                            int32_t variant) {
+    std::vector<int4> rects(RS_MAX_K);
+    std::vector<double> dsrc(4 * RS_MAX_K);
+    std::vector<float> lb(4 * RS_MAX_K);
+    (void)cfg;
+    for (int n = 0; n < n_env; n++)
+        out[n] = rs::query_sp(*st, n, n_env, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1},
+                              rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1});
+    return 0;
+}
+
 static int run_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
                      const uint8_t *new_mask, int flags) {
     rs::Params P = rs::make_params(*cfg);
@@ -45,8 +57,8 @@ static int run_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs
         else if (mask && !mask[n]) continue;
         const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
         // one "lane" plays the whole warp: the lane-strided loops degenerate to plain loops
-        if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, 0, 1, rects.data(), dsrc.data(), vis.data());
-        else rs::reset_env<false>(P, *st, a, n, new_obs, 0, 1, rects.data(), dsrc.data(), vis.data());
+        if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, 0, 1, 1u, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
+        else rs::reset_env<false>(P, *st, a, n, new_obs, 0, 1, 1u, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
     }
     return 0;
 }

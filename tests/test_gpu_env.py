@@ -245,3 +245,45 @@ def test_full_size_properties_65536_envs():
     assert int((env.status & ~2).any()) == 0
     assert tot_reset >= 2 * n
     assert int(env.steps_in_episode.max()) <= 120
+
+
+@pytest.mark.parametrize("n", [3000, 6000, 40000])
+def test_reset_teaming_modes_match_oracle(n):
+    """The reset kernel teams 32 / 8 / 1 lanes per env depending on how many envs reset: all three give the oracle's state."""
+    env, ob = make_pair(n, 1, -1, True, seed=n)
+    v = pu.GpuView(env)
+    pu.compare_state(v, ob, 1)
+    pu.compare_obs(v.obs, ob.outs["obs"][:, :1])
+    env.reset_batch(new_obstacles=False)
+    ob.reset(env._ctr, new_obstacles=np.zeros(n, np.uint8))
+    v = pu.GpuView(env)
+    pu.compare_state(v, ob, 1)
+    pu.compare_obs(v.obs, ob.outs["obs"][:, :1])
+    np.testing.assert_array_equal(v.best[0], ob.envs["best"][:, 0])
+
+
+@pytest.mark.parametrize("oc", [1, 5, 7, -1])
+def test_pruned_shortest_path_is_bit_identical_on_gpu(oc):
+    n = 4096
+    env, ob = make_pair(n, 1, oc, True, seed=900 + oc)
+    rng = np.random.default_rng(oc + 3)
+    rects = env._rects.cpu().numpy()
+    num_obs = (env._meta & 0xFF).cpu().numpy()
+    for rep in range(3):
+        pts = rng.integers(0, 2700, size=(n, 2))
+        for i in range(n):
+            k = num_obs[i]
+            if k and rng.random() < 0.6:
+                r = rects[rng.integers(0, k), i]
+                c = [(r[0], r[1]), (r[0], r[3]), (r[2], r[3]), (r[2], r[1])][rng.integers(0, 4)]
+                pts[i] = (c[0] + rng.integers(-120, 121) * (rng.random() < 0.7), c[1] + rng.integers(-120, 121) * (rng.random() < 0.7))
+            for kk in range(k):
+                r = rects[kk, i]
+                if r[0] < pts[i, 0] < r[2] and r[1] < pts[i, 1] < r[3]:
+                    pts[i, 0] = r[0]
+        pts = np.clip(pts, 0, 2699)
+        a = env.shortest_path_to(torch.as_tensor(pts), 0).cpu().numpy()
+        b = env.shortest_path_to(torch.as_tensor(pts), 1).cpu().numpy()
+        c = np.array([ob.shortest_path(i, pts[i]) for i in range(n)])
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)

@@ -124,3 +124,39 @@ def test_emulated_kernels_reproduce_reference_records(name):
     np.testing.assert_array_equal(((em.info[s] & 8) != 0).astype(int), g["out_los"][s])
     np.testing.assert_array_equal(((em.info[s] & 1) != 0).astype(int), g["out_oob"][s])
     assert not (em.status[s] & ~np.uint32(L.ST_LAMBDA_INF)).any()
+
+
+def _sp_probe_points(rng, em_rects, num_obs, n):
+    """Points spread over the arena plus points hugging obstruction edges / corners (never strictly inside one)."""
+    pts = rng.integers(0, 2700, size=(n, 2))
+    for i in range(n):
+        k = num_obs[i]
+        if k and rng.random() < 0.6:
+            r = em_rects[rng.integers(0, k), i]
+            c = [(r[0], r[1]), (r[0], r[3]), (r[2], r[3]), (r[2], r[1])][rng.integers(0, 4)]
+            pts[i] = (c[0] + rng.integers(-120, 121) * (rng.random() < 0.7), c[1] + rng.integers(-120, 121) * (rng.random() < 0.7))
+        for kk in range(k):
+            r = em_rects[kk, i]
+            if r[0] < pts[i, 0] < r[2] and r[1] < pts[i, 1] < r[3]:
+                pts[i, 0] = r[0]
+    return np.clip(pts, 0, 2699)
+
+
+@pytest.mark.parametrize("oc", [1, 3, 5, 7, -1])
+def test_pruned_shortest_path_is_bit_identical(oc):
+    """The step kernel's pruned search (tangent corners, float lower bounds, hint) == plain min over all corners ==
+    the oracle's per-call Dijkstra, to the last bit of the float64 sum."""
+    n = 1500
+    cfg = make_config(obstruction_count=oc, enforce=True)
+    em = EmuEnv(n, cfg, seed=321 + oc)
+    em.reset(0, flags=L.F_NEW_OBSTACLES)
+    ob = co.OracleBatch(n, co.default_config(obstruction_count=oc, enforce=1), seed=321 + oc)
+    ob.reset(0)
+    rng = np.random.default_rng(oc + 10)
+    for rep in range(4):
+        pts = _sp_probe_points(rng, em.rects, em.num_obs, n)
+        a = em.query_sp(pts, 0)
+        b = em.query_sp(pts, 1)
+        c = np.array([ob.shortest_path(i, pts[i]) for i in range(n)])
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
