@@ -282,7 +282,7 @@ def main():
                          "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_ms,
                          "kernel_env_steps_per_s": N / (k_ms / 1e3)},
             "gae": {"T": T, "N": N, "ms": gae_ms, "achieved": gae_gbs, "peak": peak, "unit": "GB/s", "frac": gae_gbs / peak,
-                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<16>"},
+                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "note": "pinned host actions -> device, step+reset, obs/reward/ended -> pinned host, sync per step"},
             "gpu_launches": 2 * K, "clocks": clocks, "status_flags_raised": status,

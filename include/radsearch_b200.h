@@ -116,7 +116,8 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
 /* GAE-lambda advantages and rewards-to-go over a [T][N] rollout.  path_end[t][n] != 0 where the caller finished a
  * trajectory after step t; boot[t][n] = bootstrap value passed there (read only where path_end or t == T-1).
  * stats (nullable): double[2] device accumulators += {sum(adv), sum(adv^2)} (zero them first).
- * variant: 0 auto, 1 thread-per-column, 2 warp-shuffle scan along T. */
+ * variant: 0 auto, 1 thread-per-column (bit-exact vs the reference recurrence), 2 warp-shuffle scan along T,
+ * 3/4 force the 8-deep / 16-deep thread-per-column instantiation (tuning). */
 int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
            int32_t T, int32_t N, double gamma, double lam, double *stats, int32_t variant, void *stream);
 

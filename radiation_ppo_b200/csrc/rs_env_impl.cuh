@@ -678,9 +678,23 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     for (int it = 0; it < nc; it++) {
         int u = -1;
         double du = inf;
-        for (int c = 0; c < nc; c++) {                                   // every lane scans: uniform result
-            const double d = w_dsrc[c];
-            if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
+#ifndef RS_HOST_EMU
+        if (nl == 32) {
+            // lane c holds corner c: butterfly min over (distance, index), lowest index on ties like the scan below
+            if (lane < nc && !((fin >> lane) & 1)) { du = w_dsrc[lane]; if (du < inf) u = lane; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, du, o);
+                const int ou = __shfl_xor_sync(0xffffffffu, u, o);
+                if (ou >= 0 && (u < 0 || od < du || (od == du && ou < u))) { du = od; u = ou; }
+            }
+        } else
+#endif
+        {
+            for (int c = 0; c < nc; c++) {                               // every lane scans: uniform result
+                const double d = w_dsrc[c];
+                if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
+            }
         }
         if (u < 0) break;
         fin |= 1u << u;
@@ -696,11 +710,23 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         }
         RS_SYNCWARP(sync_mask);
     }
-    for (int c = lane; c < nc; c += nl) S.dsrc[(size_t)c * N + n] = w_dsrc[c];
-    const double sp = shortest_path(e, detx, dety);                      // prev_det_dist R:771-776
     const double euc = dist_int(detx - e.sx, dety - e.sy);
     bool direct, blocked_raw;
     source_segment(e, detx, dety, direct, blocked_raw);
+    // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
+    for (int c = lane; c < nc; c += nl) {
+        const double ds = w_dsrc[c];
+        S.dsrc[(size_t)c * N + n] = ds;
+        const int4 r = w_rects[c >> 2];
+        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+        double cand = inf;
+        if (!direct && ds < inf && visible(e, detx, dety, cx, cy)) cand = ds + dist_int(detx - cx, dety - cy);
+        w_dsrc[c] = cand;
+    }
+    RS_SYNCWARP(sync_mask);
+    double sp = direct ? euc : inf;
+    if (!direct)
+        for (int c = 0; c < nc; c++) sp = fmin(sp, w_dsrc[c]);
     const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);
     if (lane == 0) {
         reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);

@@ -22,26 +22,33 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kColsBlock = 128;
 
-template <int U>
-__global__ void __launch_bounds__(kColsBlock) gae_cols_kernel(const float *__restrict__ rew, const float *__restrict__ val,
-                                                              const uint8_t *__restrict__ pe, const float *__restrict__ boot,
-                                                              float *__restrict__ adv, float *__restrict__ ret, int T, int N,
-                                                              double gamma, double gl, double *stats) {
+template <int U, int MINB>
+__global__ void __launch_bounds__(kColsBlock, MINB) gae_cols_kernel(const float *__restrict__ rew, const float *__restrict__ val,
+                                                                    const uint8_t *__restrict__ pe, const float *__restrict__ boot,
+                                                                    float *__restrict__ adv, float *__restrict__ ret, int T, int N,
+                                                                    double gamma, double gl, double *stats) {
     const int n = blockIdx.x * kColsBlock + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     if (n < N) {
         double nv = 0.0, na = 0.0, nr = 0.0;
+        float r[U], v[U], r2[U], v2[U];
+        uint8_t e[U], e2[U];
+        // software pipeline: the loads of chunk i+1 are issued before the dependent fp64 chain of chunk i runs
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = T - 1 - j;
+            if (t >= 0) {
+                const size_t i = (size_t)t * N + n;
+                r[j] = __ldcs(rew + i); v[j] = __ldcs(val + i); e[j] = __ldcs(pe + i);
+            }
+        }
         for (int t0 = T - 1; t0 >= 0; t0 -= U) {
-            float r[U], v[U];
-            uint8_t e[U];
 #pragma unroll
             for (int j = 0; j < U; j++) {
-                const int t = t0 - j;
+                const int t = t0 - U - j;
                 if (t >= 0) {
                     const size_t i = (size_t)t * N + n;
-                    r[j] = __ldcs(rew + i);
-                    v[j] = __ldcs(val + i);
-                    e[j] = __ldcs(pe + i);
+                    r2[j] = __ldcs(rew + i); v2[j] = __ldcs(val + i); e2[j] = __ldcs(pe + i);
                 }
             }
 #pragma unroll
@@ -65,6 +72,8 @@ __global__ void __launch_bounds__(kColsBlock) gae_cols_kernel(const float *__res
                     nv = vv; na = a; nr = g;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < U; j++) { r[j] = r2[j]; v[j] = v2[j]; e[j] = e2[j]; }
         }
     }
     if (stats) {
@@ -260,7 +269,14 @@ int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const fl
         gae_scan_kernel<<<grid, kScanBlock, scan_smem, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
     } else {
         const int grid = (N + kColsBlock - 1) / kColsBlock;
-        gae_cols_kernel<16><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        // 16 loads in flight per array when there are few columns; 8 (<= 72 registers, 7 CTAs per SM) when the columns
+        // would otherwise not all be resident in one wave (N = 131072: 886 threads per SM)
+        if (variant == 5)
+            gae_cols_kernel<4, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 3 || (variant != 4 && (long long)grid > 148LL * 4))
+            gae_cols_kernel<8, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else
+            gae_cols_kernel<16, 1><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
     }
     return (int)cudaGetLastError();
 }

@@ -198,7 +198,9 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
     if (!pts || !out) return fail("pts/out is NULL");
     rs::Params P = rs::make_params(*cfg);
     const int grid = (n_env + kBlock - 1) / kBlock;
-    sp_query_kernel<<<grid, kBlock, step_smem(cfg), static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
+    const size_t smem = step_smem(cfg);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(sp_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sp_query_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
     return (int)cudaGetLastError();
 }
 
