@@ -80,7 +80,7 @@ def cpu_baseline(n_envs: int, T: int, threads: int):
     from oracle import c_oracle as co
 
     ob = co.OracleBatch(n_envs, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=threads)
-    ob.reset(0)
+    ob.reset()
     t0 = time.perf_counter()
     n, chk = ob.rollout(T, 1, epoch_end_last=False)
     dt = time.perf_counter() - t0
@@ -97,7 +97,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n = 4096
     ob = co.OracleBatch(n, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=cores)
-    ob.reset(0)
+    ob.reset()
     ctr = 1
     for _ in range(args.warmup):
         ob.rollout(1, ctr, epoch_end_last=False); ctr += 1
@@ -127,6 +127,8 @@ def main():
     ap.add_argument("--ring", type=int, default=4, help="env batches cycled so that each step's state comes from HBM")
     ap.add_argument("--exact-poisson", action="store_true", help="fp64 numpy-exact PTRS acceptance instead of fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="synchronous reset kernel after every step")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -151,10 +153,12 @@ def main():
     envs = []
     for r in range(R):
         e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=dev,
-                         env_id_offset=(rank * R + r) * N, auto_reset=True, fast_poisson=fast)
+                         env_id_offset=(rank * R + r) * N, auto_reset=True, fast_poisson=fast,
+                         prefetch=not args.no_prefetch, use_cuda_graph=not (args.no_graph or args.no_prefetch))
         # stagger the episodes: steady state of a training run (about 1/120 of the envs finish at every step)
         g = torch.Generator(device=dev).manual_seed(1000 + rank * R + r)
         e._meta.add_(torch.randint(0, 120, (N,), generator=g, device=dev, dtype=torch.int32) << 16)
+        torch.cuda.synchronize()
         envs.append(e)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     n_act = 16
@@ -276,6 +280,9 @@ def main():
                                    "enforced boundaries, 1 agent, uniform random actions, staggered 120-step episodes",
                        "envs_per_gpu": N, "obstructions": K_OBS, "poisson": "fp32-acceptance PTRS" if fast else "numpy-exact PTRS",
                        "l2": f"ring of {R} env batches ({state_mb:.0f} MB of state) cycled: every step reads its state from HBM",
+                       "resets": ("next episodes prefetched by rs_prepare on a parallel graph branch / side stream"
+                                  if not args.no_prefetch else "synchronous rs_reset after every step"),
+                       "launch": "CUDA graph replay" if not (args.no_graph or args.no_prefetch) else "stream launches",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -285,7 +292,7 @@ def main():
                     "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "note": "pinned host actions -> device, step+reset, obs/reward/ended -> pinned host, sync per step"},
-            "gpu_launches": 2 * K, "clocks": clocks, "status_flags_raised": status,
+            "gpu_launches": (4 if not args.no_prefetch else 2) * K, "clocks": clocks, "status_flags_raised": status,
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

@@ -35,6 +35,11 @@ extern "C" {
 #define RS_F_RESET_LIST 4        /* rs_reset: reset the envs rs_step scheduled (RsState.reset_list / reset_count)  */
 #define RS_F_NEW_OBSTACLES 8     /* rs_reset: draw new obstructions for every env being reset (env.epoch_end)      */
 #define RS_F_FAST_POISSON 16     /* Philox path only: fp32 acceptance test in the PTRS sampler (KS-equivalent)     */
+#define RS_F_PREFETCH 32         /* rs_step: finished envs take their next episode from the prefetched scenario    */
+                                 /* (RsState.nx_*) when it is ready, else they go to the reset list as usual       */
+#define RS_F_REFILL_LIST 64      /* rs_prepare: prepare the envs of refill list `parity`; else all envs            */
+#define RS_F_DEVICE_CTR 128      /* read the step counter from RsState.ctr_dev (CUDA-graph replay); rs_bump_ctr     */
+#define RS_F_PARITY1 256         /* which of the two refill lists rs_step / rs_reset push to (rs_prepare drains)    */
 
 /* info[n][a] bits */
 #define RS_I_OOB 1               /* Agent.out_of_bounds     R:919, 931 */
@@ -82,6 +87,18 @@ typedef struct RsState {
     uint32_t *status;            /* [N]       RS_ST_* bits, sticky until cleared by the caller                   */
     int32_t *reset_list;         /* [N]       envs scheduled for reset by the last rs_step                       */
     int32_t *reset_count;        /* [1]                                                                          */
+    uint32_t *epi;               /* [N]       episode sequence number: keys the reset draws (seed, env id, episode)  */
+    /* prefetched next episode (optional, RS_F_PREFETCH; NULL otherwise) */
+    int32_t *nx_src;             /* [N][2]                                                                        */
+    int32_t *nx_det;             /* [N][2]    all agents start at the same point (R:771-773)                       */
+    int32_t *nx_rad;             /* [N][2]                                                                        */
+    double *nx_best;             /* [N]                                                                           */
+    double *nx_dsrc;             /* [4K][N]                                                                       */
+    float *nx_obs;               /* [N][A][11] first observation of the prefetched episode                        */
+    uint32_t *nx_seq;            /* [N]       episode number the prefetched scenario belongs to (0 = none)         */
+    int32_t *refill_list;        /* [2][N]    envs whose prefetched scenario was consumed (two lists, ping-pong)   */
+    int32_t *refill_count;       /* [2]                                                                           */
+    uint64_t *ctr_dev;           /* [1]       device-side step counter (RS_F_DEVICE_CTR)                           */
 } RsState;
 
 /* One environment step for n_env environments (all agents).  actions[N][A] in 0..8 (8 = idle), or NULL for the
@@ -100,6 +117,16 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, const uint8_t *new_obstacles_mask,
              float *obs, int32_t n_env, uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms,
              int32_t n_uniforms, int32_t flags, void *stream);
+
+/* Prefetch: compute the NEXT episode (number epi[n]+1) of the selected envs into RsState.nx_* without touching the
+ * running episode.  The scenario is a pure function of (seed, env id, episode number, obstructions), so an env that
+ * takes it from the prefetch buffer and one that is reset by rs_reset get identical state.  Intended to run on a side
+ * stream / parallel graph branch next to rs_step.  flags: RS_F_REFILL_LIST (+RS_F_PARITY1) or all envs. */
+int rs_prepare(const RsConfig *cfg, const RsState *st, int32_t n_env, uint32_t env_id0, uint64_t seed, int32_t flags,
+               void *stream);
+
+/* *RsState.ctr_dev += 1 (one thread): lets a captured CUDA graph of rs_step/rs_reset advance the Philox step counter. */
+int rs_bump_ctr(const RsState *st, void *stream);
 
 /* Scenario injection: src[N][2], det[N][2], intensity[N], bkg[N], rects[N][k_in][4] (x0,y0,x1,y1), num_obs[N] -- all
  * int32 device arrays.  Builds the per-episode tables and writes the initial observation (a step(None) probe). */

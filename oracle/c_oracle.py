@@ -34,6 +34,7 @@ ENV_DTYPE = np.dtype(
         ("iter_count", np.int32),
         ("ep_len", np.int32),
         ("status", np.uint32),
+        ("episode", np.uint32),
     ],
     align=True,
 )
@@ -181,13 +182,14 @@ class OracleBatch:
                                 i32(*det[i]), C.c_int32(int(intensity[i])), C.c_int32(int(bkg[i])),
                                 _p(rects[i]), C.c_int32(int(num_obs[i])))
 
-    def reset(self, step_ctr: int, mask=None, new_obstacles=None, uniforms=None):
+    def reset(self, mask=None, new_obstacles=None, uniforms=None):
+        """reset() for the selected envs; draws keyed by (seed, env id, episode number)."""
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         no = None if new_obstacles is None else np.ascontiguousarray(new_obstacles, dtype=np.uint8)
         u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
         n_inj = 0 if u is None else u.shape[-1]
         lib().orc_reset_batch(C.byref(self.cfg), _p(self.envs), C.c_int32(self.n), _p(m), _p(no), C.c_uint64(self.seed),
-                              C.c_uint32(self.env_id0), C.c_uint64(step_ctr), _p(u), C.c_int32(n_inj), _p(self.outs),
+                              C.c_uint32(self.env_id0), _p(u), C.c_int32(n_inj), _p(self.outs),
                               C.c_int32(self.threads))
         return self.outs
 

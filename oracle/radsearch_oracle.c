@@ -632,7 +632,8 @@ static void sample_source_loc_pos(const OrcConfig *c, OrcEnv *e, OrcRng *g, int3
 }
 
 static void finish_reset(const OrcConfig *c, OrcEnv *e, const int32_t det[2], uint64_t seed, uint32_t env_id,
-                         uint64_t step_ctr, const double *inj_u, int32_t n_inj, OrcStepOut *out) {
+                         const double *inj_u, int32_t n_inj, OrcStepOut *out) {
+    const uint64_t step_ctr = (uint64_t)e->episode;
     for (int ag = 0; ag < c->n_agents; ag++) {
         e->det[ag][0] = det[0]; e->det[ag][1] = det[1];
         e->oob[ag] = 0; e->oob_count[ag] = 0; e->blocked[ag] = 0; e->collision[ag] = 0;   /* Agent.reset R:289-300 */
@@ -649,22 +650,25 @@ static void finish_reset(const OrcConfig *c, OrcEnv *e, const int32_t det[2], ui
     e->iter_count = 0;                                                     /* R:796 */
 }
 
-void orc_reset(const OrcConfig *c, OrcEnv *e, int new_obstacles, uint64_t seed, uint32_t env_id, uint64_t step_ctr,
+void orc_reset(const OrcConfig *c, OrcEnv *e, int new_obstacles, uint64_t seed, uint32_t env_id,
                const double *inj_u, int32_t n_inj, OrcStepOut *out) {
     OrcRng g;
-    orc_rng_philox(&g, seed, env_id, 1, 0, step_ctr, &e->status);
+    e->episode += 1;
+    orc_rng_philox(&g, seed, env_id, 1, 0, (uint64_t)e->episode, &e->status);
     if (new_obstacles) create_obstructions(c, e, &g);                      /* R:744-762 */
     int32_t det[2];
     sample_source_loc_pos(c, e, &g, det);                                  /* R:764-769 */
     e->intensity = 1000000 + (int32_t)orc_rng_below(&g, 9000000);          /* R:778 integers(1e6, 10e6) */
     e->bkg = 10 + (int32_t)orc_rng_below(&g, 41);                          /* R:779 integers(10, 51)    */
-    finish_reset(c, e, det, seed, env_id, step_ctr, inj_u, n_inj, out);
+    finish_reset(c, e, det, seed, env_id, inj_u, n_inj, out);
 }
 
 /* refresh_environment R:799-874 (scenario injection); prev_det_dist is set after the probe step, as in R:864-868 */
 void orc_load_scenario(const OrcConfig *c, OrcEnv *e, const int32_t src[2], const int32_t det[2], int32_t intensity,
                        int32_t bkg, const int32_t *rects, int32_t num_obs) {
+    const uint32_t episode = e->episode;
     memset(e, 0, sizeof(*e));
+    e->episode = episode;
     e->num_obs = num_obs;
     for (int k = 0; k < num_obs; k++) memcpy(e->rect[k], rects + 4 * k, 4 * sizeof(int32_t));
     e->src[0] = src[0]; e->src[1] = src[1];
@@ -707,14 +711,14 @@ void orc_step_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const int32_t *
 }
 
 void orc_reset_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const uint8_t *mask, const uint8_t *new_obs_mask,
-                     uint64_t seed, uint32_t env_id0, uint64_t step_ctr, const double *inj_u, int32_t n_inj,
-                     OrcStepOut *outs, int32_t threads) {
+                     uint64_t seed, uint32_t env_id0, const double *inj_u, int32_t n_inj, OrcStepOut *outs,
+                     int32_t threads) {
     set_threads(threads);
     int A = c->n_agents;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int32_t i = 0; i < n; i++) {
         if (mask && !mask[i]) continue;
-        orc_reset(c, &envs[i], new_obs_mask ? new_obs_mask[i] : 1, seed, env_id0 + (uint32_t)i, step_ctr,
+        orc_reset(c, &envs[i], new_obs_mask ? new_obs_mask[i] : 1, seed, env_id0 + (uint32_t)i,
                   inj_u ? inj_u + (size_t)i * A * n_inj : NULL, n_inj, &outs[i]);
     }
 }
@@ -746,7 +750,7 @@ int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint
             int timeout = e->ep_len == c->max_ep_len;                      /* train.py:394-405 */
             int over = e->done || timeout;
             int epoch_ended = epoch_end_last && t == T - 1;
-            if (over || epoch_ended) orc_reset(c, e, epoch_ended, seed, env_id0 + (uint32_t)i, ctr, NULL, 0, &out);
+            if (over || epoch_ended) orc_reset(c, e, epoch_ended, seed, env_id0 + (uint32_t)i, NULL, 0, &out);
         }
         total += acc;
     }

@@ -54,6 +54,7 @@ typedef struct {
     int32_t iter_count;
     int32_t ep_len;               /* caller-side steps_in_episode            */
     uint32_t status;
+    uint32_t episode;             /* resets so far: keys the reset draws     */
 } OrcEnv;
 
 typedef struct {
@@ -97,7 +98,8 @@ void orc_sensors(const OrcConfig *c, OrcEnv *e, int agent, double out[8]);
 
 void orc_step(const OrcConfig *c, OrcEnv *e, const int32_t *actions /* NULL = step(None); per agent 0..8 */,
               OrcRng *rngs /* one per agent */, OrcStepOut *out);
-void orc_reset(const OrcConfig *c, OrcEnv *e, int new_obstacles, uint64_t seed, uint32_t env_id, uint64_t step_ctr,
+/* the draws of a reset are keyed by (seed, env_id, ++e->episode): a scenario does not depend on when it is computed */
+void orc_reset(const OrcConfig *c, OrcEnv *e, int new_obstacles, uint64_t seed, uint32_t env_id,
                const double *inj_u, int32_t n_inj, OrcStepOut *out);
 void orc_load_scenario(const OrcConfig *c, OrcEnv *e, const int32_t src[2], const int32_t det[2], int32_t intensity,
                        int32_t bkg, const int32_t *rects, int32_t num_obs);
@@ -107,8 +109,8 @@ void orc_step_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const int32_t *
                     uint32_t env_id0, uint64_t step_ctr, const double *inj_u, int32_t n_inj, OrcStepOut *outs,
                     int32_t threads);
 void orc_reset_batch(const OrcConfig *c, OrcEnv *envs, int32_t n, const uint8_t *mask, const uint8_t *new_obs_mask,
-                     uint64_t seed, uint32_t env_id0, uint64_t step_ctr, const double *inj_u, int32_t n_inj,
-                     OrcStepOut *outs, int32_t threads);
+                     uint64_t seed, uint32_t env_id0, const double *inj_u, int32_t n_inj, OrcStepOut *outs,
+                     int32_t threads);
 /* rollout with the caller rules of train.py:394-405,446-548 (auto-reset, epoch end); returns env-steps done */
 int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint64_t seed, uint32_t env_id0,
                     uint64_t step_ctr0, int32_t epoch_end_last, int32_t threads, double *checksum);

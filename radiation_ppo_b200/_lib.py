@@ -10,12 +10,13 @@ LIB_PATH = os.path.join(HERE, "_C", "libradsearch_b200.so")
 
 OBS_DIM, MAX_K, MAX_A = 11, 8, 8
 F_AUTO_RESET, F_EPOCH_END, F_RESET_LIST, F_NEW_OBSTACLES, F_FAST_POISSON = 1, 2, 4, 8, 16
+F_PREFETCH, F_REFILL_LIST, F_DEVICE_CTR, F_PARITY1 = 32, 64, 128, 256
 I_OOB, I_BLOCKED, I_COLLISION, I_LOS_BLOCKED, I_MOVED = 1, 2, 4, 8, 16
 E_TERMINAL, E_TIMEOUT, E_RESET = 1, 2, 4
 ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, ST_COORD_RANGE = 1, 2, 4, 8, 16, 32
 
 EXPORTS = [
-    "rs_step", "rs_reset", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
+    "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
     "rs_version", "rs_sizeof_config", "rs_sizeof_state",
 ]
 
@@ -35,7 +36,9 @@ class RsConfig(C.Structure):
 
 class RsState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count")]
+        "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count",
+        "epi", "nx_src", "nx_det", "nx_rad", "nx_best", "nx_dsrc", "nx_obs", "nx_seq", "refill_list", "refill_count",
+        "ctr_dev")]
 
 
 class RadSearchLibraryError(RuntimeError):
@@ -59,6 +62,9 @@ def declare(lib, prefix="rs_"):
     f = getattr(lib, prefix + "load_scenarios")
     f.restype = i32
     f.argtypes = [cfgp, stp, vp, vp, vp, vp, vp, i32, vp, vp, i32, u32, u64, u64, vp, i32] + tail
+    f = getattr(lib, prefix + "prepare")
+    f.restype = i32
+    f.argtypes = [cfgp, stp, i32, u32, u64, i32] + tail
     f = getattr(lib, prefix + "query_shortest_path")
     f.restype = i32
     f.argtypes = [cfgp, stp, vp, vp, i32, i32] + tail
@@ -69,6 +75,8 @@ def declare(lib, prefix="rs_"):
         lib.rs_adv_stats.argtypes = [vp, i64, vp, vp, vp]
         lib.rs_adv_normalize.restype = i32
         lib.rs_adv_normalize.argtypes = [vp, i64, vp, vp, vp]
+        lib.rs_bump_ctr.restype = i32
+        lib.rs_bump_ctr.argtypes = [stp, vp]
         lib.rs_last_error.restype = C.c_char_p
         lib.rs_version.restype = i32
         lib.rs_sizeof_config.restype = i32

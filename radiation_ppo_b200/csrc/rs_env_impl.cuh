@@ -378,6 +378,7 @@ struct StepArgs {
     uint64_t seed, step_ctr;
     const double *uniforms;
     int n_uniforms, flags;
+    int parity;         // refill list that consumed prefetch slots are pushed to
 };
 
 // obs_rows: where this env's A x 11 observation rows go (the CTA's shared-memory tile; the kernel stores the tile to
@@ -398,6 +399,7 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
     for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
     for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = S.dsrc[(size_t)c * N + n];
     uint32_t status = 0;
+    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
 
     int propx[RS_MAX_A], propy[RS_MAX_A];
     const bool have_act = a.actions != nullptr;
@@ -447,7 +449,7 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
         if (blocked_los) info |= RS_I_LOS_BLOCKED;
         Rng g;
         if (a.uniforms) g.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
-        else g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 0, (uint32_t)ag, a.step_ctr);
+        else g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 0, (uint32_t)ag, step_ctr);
         observe<kFast>(P, e, det.x, det.y, euc, blocked_los, g, obs_rows + ag * RS_OBS_DIM, status);
         double reward;
         if (moved) {                                                    // R:507-522
@@ -480,10 +482,38 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
         if (done || timeout || (a.flags & RS_F_EPOCH_END)) {
             ended |= RS_E_RESET;
             scheduled = true;
-            const int slot = atomicAdd(S.reset_count, 1);
-            S.reset_list[slot] = n;
             if (a.final_obs) {
                 for (int i = 0; i < A * RS_OBS_DIM; i++) a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = obs_rows[i];
+            }
+            bool swapped = false;
+            if ((a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
+                // the next episode was prepared ahead of time (rs_prepare): adopt it here, no reset kernel needed
+                const uint32_t want = S.epi[n] + 1u;
+                const uint32_t tag = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n);
+                if (tag == want) {
+                    __threadfence();
+                    reinterpret_cast<int2 *>(S.src)[n] = reinterpret_cast<const int2 *>(S.nx_src)[n];
+                    reinterpret_cast<int2 *>(S.rad)[n] = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+                    const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
+                    const double b0 = S.nx_best[n];
+                    for (int ag = 0; ag < A; ag++) {
+                        const size_t ia = (size_t)ag * N + n;
+                        reinterpret_cast<int2 *>(S.det)[ia] = d0;
+                        S.best[ia] = b0;
+                        S.aflags[ia] = 0;
+                    }
+                    for (int c = 0; c < 4 * e.num_obs; c++) S.dsrc[(size_t)c * N + n] = S.nx_dsrc[(size_t)c * N + n];
+                    for (int i = 0; i < A * RS_OBS_DIM; i++) obs_rows[i] = S.nx_obs[(size_t)n * A * RS_OBS_DIM + i];
+                    S.epi[n] = want;
+                    done = 0; ep_len = 0;
+                    swapped = true;
+                    const int slot = atomicAdd(S.refill_count + a.parity, 1);
+                    S.refill_list[(size_t)a.parity * N + slot] = n;
+                }
+            }
+            if (!swapped) {
+                const int slot = atomicAdd(S.reset_count, 1);
+                S.reset_list[slot] = n;
             }
         }
     }
@@ -587,6 +617,8 @@ struct ResetArgs {
     // scenario injection (all nullptr when sampling)
     const int32_t *in_src, *in_det, *in_intensity, *in_bkg, *in_rects, *in_num_obs;
     int k_in;
+    int prepare;        // 1: write the scenario of episode epi[n]+1 into the prefetch buffers (RsState.nx_*) only
+    int parity;         // which refill list a synchronous reset pushes the env to (-1: none)
 };
 
 // shortest path source -> (px,py) of env n, for rs_query_shortest_path
@@ -622,8 +654,12 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     EnvView e;
     e.rects = w_rects;
     e.dsrc = w_dsrc;
+    // the draws of a reset are keyed by the env's episode number, not by wall-clock step: the scenario of episode e
+    // is a pure function of (seed, env id, e, obstructions), whoever computes it and whenever
+    const uint32_t ep_seq = S.epi[n] + 1u;
+    const bool prepare = a.prepare != 0;
     Rng g;
-    g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, a.step_ctr);
+    g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, (uint64_t)ep_seq);
     const bool inject = a.in_src != nullptr;
     RS_SYNCWARP(sync_mask);                                                      // scratch is reused between environments
     if (inject) {                                                       // refresh_environment R:799-874
@@ -714,9 +750,10 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     bool direct, blocked_raw;
     source_segment(e, detx, dety, direct, blocked_raw);
     // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
+    double *dsrc_out = prepare ? S.nx_dsrc : S.dsrc;
     for (int c = lane; c < nc; c += nl) {
         const double ds = w_dsrc[c];
-        S.dsrc[(size_t)c * N + n] = ds;
+        dsrc_out[(size_t)c * N + n] = ds;
         const int4 r = w_rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         double cand = inf;
@@ -729,24 +766,50 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         for (int c = 0; c < nc; c++) sp = fmin(sp, w_dsrc[c]);
     const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);
     if (lane == 0) {
-        reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
-        reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
-        S.meta[n] = e.num_obs;                                           // done = 0, ep_len = 0   R:739-740
+        if (prepare) {
+            reinterpret_cast<int2 *>(S.nx_src)[n] = make_int2(e.sx, e.sy);
+            reinterpret_cast<int2 *>(S.nx_rad)[n] = make_int2(e.intensity, e.bkg);
+            reinterpret_cast<int2 *>(S.nx_det)[n] = make_int2(detx, dety);
+            S.nx_best[n] = sp;
+        } else {
+            reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
+            reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
+            S.meta[n] = e.num_obs;                                       // done = 0, ep_len = 0   R:739-740
+            S.epi[n] = ep_seq;
+        }
     }
+    float *obs_out = prepare ? S.nx_obs : a.obs;
     for (int ag = 0; ag < A; ag++) {
         const size_t ia = (size_t)ag * N + n;
         Rng gp;
         if (a.uniforms) gp.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
-        else gp.init_philox(a.seed, a.env_id0 + (uint32_t)n, 2, (uint32_t)ag, a.step_ctr);
+        else gp.init_philox(a.seed, a.env_id0 + (uint32_t)n, 2, (uint32_t)ag, (uint64_t)ep_seq);
         float row[RS_OBS_DIM];
         observe<kFast>(P, e, detx, dety, euc, blocked_los, gp, row, status);   // R:794
         if (lane == 0) {
-            reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
-            S.best[ia] = sp;
-            S.aflags[ia] = 0;                                            // Agent.reset R:289-300
+            if (!prepare) {
+                reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
+                S.best[ia] = sp;
+                S.aflags[ia] = 0;                                        // Agent.reset R:289-300
+            }
 #pragma unroll
-            for (int i = 0; i < RS_OBS_DIM; i++) a.obs[((size_t)n * A + ag) * RS_OBS_DIM + i] = row[i];
+            for (int i = 0; i < RS_OBS_DIM; i++) obs_out[((size_t)n * A + ag) * RS_OBS_DIM + i] = row[i];
         }
+    }
+    if (prepare) {
+        // publish: the tag is written last, after the data (lanes' table stores included)
+        __threadfence();
+        RS_SYNCWARP(sync_mask);
+        if (lane == 0) {
+#ifdef RS_HOST_EMU
+            S.nx_seq[n] = ep_seq;
+#else
+            atomicExch(S.nx_seq + n, ep_seq);
+#endif
+        }
+    } else if (lane == 0 && a.parity >= 0 && S.refill_list) {
+        const int slot = atomicAdd(S.refill_count + a.parity, 1);
+        S.refill_list[(size_t)a.parity * N + slot] = n;
     }
     status |= g.status;
     if (status && lane == 0) S.status[n] |= status;

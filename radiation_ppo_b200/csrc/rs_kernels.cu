@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kBlock, 4) step_kernel(rs::Params P, RsState S
     for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kBlock) dst[i] = sobs[i];
 }
 
+__global__ void bump_ctr_kernel(unsigned long long *ctr) { *ctr += 1ull; }
+
 __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState S, const int32_t *pts, double *out,
                                                            int n_env, int variant) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -58,9 +60,10 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
 // timeouts) -> one thread per env, which wastes no lanes on the sequential rejection sampling.
 template <bool kFast>
 __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
-                                                        const uint8_t *new_mask, int flags) {
+                                                        const uint8_t *new_mask, int flags, const int32_t *list,
+                                                        const int32_t *count) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int total = (flags & RS_F_RESET_LIST) ? *S.reset_count : a.n_env;
+    const int total = list ? *count : a.n_env;
     const int nl = total > 32768 ? 1 : (total > 4096 ? 8 : 32);
     const int G = kBlock / nl;                          // groups (environments in flight) per CTA
     const int g = threadIdx.x / nl, lane = threadIdx.x % nl;
@@ -72,12 +75,19 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
     const int stride = gridDim.x * G;
     for (int i = blockIdx.x * G + g; i < total; i += stride) {
         int n = i;
-        if (flags & RS_F_RESET_LIST) n = S.reset_list[i];
+        if (list) n = list[i];
         else if (mask && !mask[n]) continue;
-        const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
+        const bool new_obs = !a.prepare && ((flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]));
         rs::reset_env<kFast>(P, S, a, n, new_obs, lane, nl, sync_mask, rs::Col<int4>{srects + g, G},
                              rs::Col<double>{sdsrc + g, G}, rs::Col<uint32_t>{svis + g, G});
     }
+}
+
+int check_prefetch(const RsConfig *cfg, const RsState *st) {
+    if (!st->nx_src || !st->nx_det || !st->nx_rad || !st->nx_best || !st->nx_obs || !st->nx_seq || !st->refill_list ||
+        !st->refill_count || (cfg->k_max > 0 && !st->nx_dsrc))
+        return fail("prefetch needs the RsState.nx_* / refill_* buffers");
+    return 0;
 }
 
 int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
@@ -90,7 +100,7 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
         return fail("k_max smaller than the number of obstructions that can be drawn");
     if (cfg->max_ep_len < 1 || cfg->max_ep_len > 32767) return fail("max_ep_len out of range [1, 32767]");
     if (cfg->bbox[2] - cfg->obs_area[1] <= cfg->bbox[0] + cfg->obs_area[0]) return fail("empty search area");
-    if (!st->src || !st->rad || !st->meta || !st->det || !st->best || !st->aflags || !st->status)
+    if (!st->src || !st->rad || !st->meta || !st->det || !st->best || !st->aflags || !st->status || !st->epi)
         return fail("RsState has NULL members");
     if (cfg->k_max > 0 && (!st->rects || !st->dsrc || !st->vis)) return fail("RsState obstruction tables are NULL");
     return 0;
@@ -122,16 +132,24 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     if (!obs) return fail("obs is NULL");
     if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
     if ((flags & RS_F_AUTO_RESET) && (!st->reset_list || !st->reset_count)) return fail("auto-reset needs reset_list/reset_count");
+    if ((flags & RS_F_PREFETCH) && !(flags & RS_F_AUTO_RESET)) return fail("RS_F_PREFETCH needs RS_F_AUTO_RESET");
+    if (flags & RS_F_PREFETCH) if (int rc = check_prefetch(cfg, st)) return rc;
+    if ((flags & RS_F_DEVICE_CTR) && !st->ctr_dev) return fail("RS_F_DEVICE_CTR needs RsState.ctr_dev");
+    const int parity = (flags & RS_F_PARITY1) ? 1 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (flags & RS_F_AUTO_RESET) {
         cudaError_t e = cudaMemsetAsync(st->reset_count, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return (int)e;
+        if (flags & RS_F_PREFETCH) {
+            e = cudaMemsetAsync(st->refill_count + parity, 0, sizeof(int32_t), s);
+            if (e != cudaSuccess) return (int)e;
+        }
     }
     rs::Params P = rs::make_params(*cfg);
     rs::StepArgs a;
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
-    a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
+    a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags; a.parity = parity;
     const int grid = (n_env + kBlock - 1) / kBlock;
     const size_t smem = step_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
@@ -145,7 +163,7 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 }
 
 static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
-                        const uint8_t *new_mask, int flags, cudaStream_t s) {
+                        const uint8_t *new_mask, int flags, const int32_t *list, const int32_t *count, cudaStream_t s) {
     rs::Params P = rs::make_params(*cfg);
     const int need = (a.n_env + 3) / 4;                 // one warp per env is the widest teaming
     const int grid = need < kResetGrid ? need : kResetGrid;
@@ -155,8 +173,8 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
         cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
-    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags);
+    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count);
+    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count);
     return (int)cudaGetLastError();
 }
 
@@ -171,7 +189,37 @@ int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, 
     std::memset(&a, 0, sizeof(a));
     a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
     a.uniforms = uniforms; a.n_uniforms = n_uniforms;
-    return launch_reset(cfg, st, a, reset_mask, new_obstacles_mask, flags, static_cast<cudaStream_t>(stream));
+    a.prepare = 0;
+    a.parity = -1;
+    if (flags & RS_F_PREFETCH) {
+        if (int rc = check_prefetch(cfg, st)) return rc;
+        a.parity = (flags & RS_F_PARITY1) ? 1 : 0;
+    }
+    const bool use_list = flags & RS_F_RESET_LIST;
+    return launch_reset(cfg, st, a, reset_mask, new_obstacles_mask, flags, use_list ? st->reset_list : nullptr,
+                        use_list ? st->reset_count : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int rs_prepare(const RsConfig *cfg, const RsState *st, int32_t n_env, uint32_t env_id0, uint64_t seed, int32_t flags,
+               void *stream) {
+    if (int rc = check_cfg(cfg, st, n_env)) return rc;
+    if (int rc = check_prefetch(cfg, st)) return rc;
+    rs::ResetArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.obs = nullptr; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
+    a.prepare = 1;
+    a.parity = -1;
+    const int parity = (flags & RS_F_PARITY1) ? 1 : 0;
+    const bool use_list = flags & RS_F_REFILL_LIST;
+    return launch_reset(cfg, st, a, nullptr, nullptr, flags & RS_F_FAST_POISSON,
+                        use_list ? st->refill_list + (size_t)parity * n_env : nullptr,
+                        use_list ? st->refill_count + parity : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int rs_bump_ctr(const RsState *st, void *stream) {
+    if (!st || !st->ctr_dev) return fail("RsState.ctr_dev is NULL");
+    bump_ctr_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(st->ctr_dev));
+    return (int)cudaGetLastError();
 }
 
 int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src, const int32_t *det,
@@ -189,7 +237,9 @@ int rs_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src
     a.uniforms = uniforms; a.n_uniforms = n_uniforms;
     a.in_src = src; a.in_det = det; a.in_intensity = intensity; a.in_bkg = bkg; a.in_rects = rects;
     a.in_num_obs = num_obs; a.k_in = k_in;
-    return launch_reset(cfg, st, a, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream));
+    a.prepare = 0;
+    a.parity = -1;
+    return launch_reset(cfg, st, a, nullptr, nullptr, 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,

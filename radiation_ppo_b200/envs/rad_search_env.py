@@ -82,7 +82,11 @@ class RadSearch:
     Additive kwargs: ``num_envs``, ``device``, ``seed`` (Philox key; drawn from ``np_random`` when omitted),
     ``env_id_offset`` (global id of env 0: results do not depend on how envs are sharded over ranks),
     ``steps_per_episode`` / ``auto_reset`` (the caller rules of train.py:394-405 applied on the device),
-    ``fast_poisson`` (fp32 acceptance test in the PTRS sampler), ``count_law`` (0 reference, 1 inverse square).
+    ``fast_poisson`` (fp32 acceptance test in the PTRS sampler), ``count_law`` (0 reference, 1 inverse square),
+    ``prefetch`` (with auto_reset: the next episode of every env is prepared ahead of time by ``rs_prepare`` on a side
+    stream, so a finished env adopts it inside the step kernel instead of waiting for a reset kernel; results are
+    identical either way), ``use_cuda_graph`` (with prefetch: the step / reset / prepare launches are captured once
+    and replayed; the Philox step counter then lives on the device).
     """
 
     metadata = {"render.modes": ["human"], "video.frames_per_second": 5}
@@ -108,6 +112,8 @@ class RadSearch:
         fast_poisson: bool = False,
         count_law: int = 0,
         k_max: Optional[int] = None,
+        prefetch: bool = False,
+        use_cuda_graph: bool = False,
     ) -> None:
         if DEBUG:
             raise NotImplementedError("the reference's DEBUG hard-codes (R:373-378, 782-784) are not reproduced")
@@ -133,6 +139,8 @@ class RadSearch:
         self.auto_reset = bool(auto_reset)
         self.fast_poisson = bool(fast_poisson)
         self.env_id_offset = int(env_id_offset)
+        self.prefetch = bool(prefetch) and self.auto_reset
+        self.use_cuda_graph = bool(use_cuda_graph) and self.prefetch
         self.seed = int(seed) if seed is not None else int(self.np_random.integers(0, 2**63 - 1))
 
         cfg = L.RsConfig()
@@ -183,9 +191,32 @@ class RadSearch:
         self._vis = z(max(4 * K, 1), N)
         self._status = z(N)
         self._reset_list, self._reset_count = z(N), z(1)
-        self._st = L.RsState(*[t.data_ptr() for t in (
-            self._src, self._rad, self._rects, self._meta, self._det, self._best, self._aflags, self._dsrc, self._vis,
-            self._status, self._reset_list, self._reset_count)])
+        self._epi = z(N)
+        ptrs = [self._src, self._rad, self._rects, self._meta, self._det, self._best, self._aflags, self._dsrc, self._vis,
+                self._status, self._reset_list, self._reset_count, self._epi]
+        if self.prefetch:
+            self._nx_src, self._nx_det, self._nx_rad = z(N, 2), z(N, 2), z(N, 2)
+            self._nx_best = z(N, dt=torch.float64)
+            self._nx_dsrc = z(max(4 * K, 1), N, dt=torch.float64)
+            self._nx_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
+            self._nx_seq = z(N)
+            self._refill_list, self._refill_count = z(2, N), z(2)
+            ptrs += [self._nx_src, self._nx_det, self._nx_rad, self._nx_best, self._nx_dsrc, self._nx_obs, self._nx_seq,
+                     self._refill_list, self._refill_count]
+        else:
+            ptrs += [None] * 9
+        self._ctr_dev = z(1, dt=torch.int64)
+        ptrs.append(self._ctr_dev)
+        self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
+        self._par = 0                       # refill-list parity of the next step
+        self._side = torch.cuda.Stream(device=dev) if self.prefetch else None
+        self._ev_main = torch.cuda.Event()
+        self._ev_side = [torch.cuda.Event(), torch.cuda.Event()]
+        self._side_pending = False          # a prepare launch is in flight on the side stream
+        self._refill_pending = False        # the list of parity self._par ^ 1 holds envs waiting for rs_prepare
+        self._graphs = {}
+        self._act_buf = z(N, A)
+        self._ctr_dev_val = 0               # host mirror of *ctr_dev (graph replays advance both)
         self.obs = z(N, A, L.OBS_DIM, dt=torch.float32)
         self.final_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
         self.reward = z(N, A, dt=torch.float32)
@@ -219,10 +250,13 @@ class RadSearch:
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
         u = None if uniforms is None else uniforms.to(device=self.device, dtype=torch.float64).contiguous()
         self._ctr += 1
+        self._quiesce_prefetch()
         with torch.cuda.device(self.device):
             L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), _ptr(m), _ptr(new_mask), _ptr(self.obs),
                                        self.num_envs, self.env_id_offset, self.seed, self._ctr, _ptr(u),
                                        0 if u is None else u.shape[-1], flags, self._stream()), "rs_reset")
+            if self.prefetch:
+                self._launch_prepare(0, use_list=False)      # next episodes of everybody, against the current obstructions
         return self.obs
 
     def step_batch(self, actions: Optional[torch.Tensor], epoch_end: bool = False,
@@ -231,12 +265,16 @@ class RadSearch:
         Returns (obs, reward, team_reward, done, info, ended); with auto-reset, envs that finished have already been
         reset, `obs` holds their first observation and `final_obs` the last one of the finished episode."""
         ar = self.auto_reset if auto_reset is None else auto_reset
-        flags = self._base_flags() | (L.F_AUTO_RESET if ar else 0) | (L.F_EPOCH_END if (ar and epoch_end) else 0)
         a = None
         if actions is not None:
             a = actions.to(device=self.device, dtype=torch.int32).reshape(self.num_envs, self.number_agents).contiguous()
         u = None if uniforms is None else uniforms.to(device=self.device, dtype=torch.float64).contiguous()
         self._ctr += 1
+        if ar and self.prefetch and a is not None and u is None:
+            self._step_prefetch(a, epoch_end)
+            return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+        self._quiesce_prefetch()
+        flags = self._base_flags() | (L.F_AUTO_RESET if ar else 0) | (L.F_EPOCH_END if (ar and epoch_end) else 0)
         with torch.cuda.device(self.device):
             L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
                                       _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
@@ -249,6 +287,95 @@ class RadSearch:
                                            self.num_envs, self.env_id_offset, self.seed, self._ctr, None, 0, rflags,
                                            self._stream()), "rs_reset")
         return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+
+    # ---- prefetch machinery -------------------------------------------------------------------------------------
+    def _quiesce_prefetch(self) -> None:
+        """Make the main stream wait for any rs_prepare in flight and forget pending refill lists (the envs in them
+        simply take the synchronous reset path next time): called before anything that rewrites env state wholesale."""
+        if not self.prefetch:
+            return
+        if self._side_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_pending = False
+        self._refill_pending = False
+
+    def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool) -> None:
+        """rs_step + rs_reset(list) on the current stream for refill parity p."""
+        pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0) | (L.F_DEVICE_CTR if device_ctr else 0)
+        flags = self._base_flags() | L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0)
+        L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
+                                  _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
+                                  _ptr(self.ended), _ptr(self.final_obs), self.num_envs, self.env_id_offset, self.seed,
+                                  self._ctr, None, 0, flags, self._stream()), "rs_step")
+        rflags = self._base_flags() | L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0)
+        L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(self.obs), self.num_envs,
+                                   self.env_id_offset, self.seed, self._ctr, None, 0, rflags, self._stream()), "rs_reset")
+
+    def _launch_prepare(self, p: int, use_list: bool = True) -> None:
+        flags = self._base_flags() | (L.F_REFILL_LIST if use_list else 0) | (L.F_PARITY1 if p else 0)
+        L.check(self._lib.rs_prepare(C.byref(self._cfg), C.byref(self._st), self.num_envs, self.env_id_offset, self.seed,
+                                     flags, self._stream()), "rs_prepare")
+
+    def _step_prefetch(self, a: torch.Tensor, epoch_end: bool) -> None:
+        """One auto-reset step with the next episodes prepared off the critical path.
+
+        Step t pushes the envs that consumed their prefetched scenario to refill list p = t & 1; rs_prepare for that
+        list runs on the side stream (or a parallel graph branch) next to step t+1, which uses list p ^ 1."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        p = self._par
+        with torch.cuda.device(dev):
+            if epoch_end:
+                # new obstructions for everybody: nothing may be preparing scenarios against the old ones
+                self._quiesce_prefetch()
+                self._launch_step_sequence(a, p, True, False)
+                self._refill_pending = True             # every env was pushed to list p by the reset
+                self._par = p ^ 1
+                return
+            if self.use_cuda_graph:
+                self._act_buf.copy_(a)
+                key = (p, self._refill_pending)
+                g = self._graphs.get(key)
+                if g is None:
+                    g = self._capture(p, self._refill_pending)
+                    self._graphs[key] = g
+                if self._ctr_dev_val != self._ctr:
+                    self._ctr_dev.fill_(self._ctr)
+                g.replay()
+                self._ctr_dev_val = self._ctr + 1
+            else:
+                if self._refill_pending:
+                    self._ev_main.record(main)
+                    self._side.wait_event(self._ev_main)            # list p^1 is complete
+                    with torch.cuda.stream(self._side):
+                        self._launch_prepare(p ^ 1)
+                        self._ev_side[p].record(self._side)
+                if self._side_pending:
+                    main.wait_event(self._ev_side[p ^ 1])           # the prepare that drained list p has finished
+                self._side_pending = self._refill_pending
+                self._launch_step_sequence(a, p, False, False)
+            self._refill_pending = True
+            self._par = p ^ 1
+
+    def _capture(self, p: int, with_prepare: bool):
+        """Capture {rs_step -> rs_reset(list) -> bump counter} with rs_prepare(previous list) as a parallel branch."""
+        dev = self.device
+        L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")   # load the kernel before capture
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(g, stream=cap):
+                if with_prepare:
+                    self._side.wait_stream(cap)
+                    with torch.cuda.stream(self._side):
+                        self._launch_prepare(p ^ 1)
+                self._launch_step_sequence(self._act_buf, p, False, True)
+                L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")
+                if with_prepare:
+                    cap.wait_stream(self._side)
+        self._ctr_dev_val = -1                           # capture does not execute; force a refresh before the replay
+        return g
 
     def load_scenarios(self, src, det, intensity, bkg, rects=None, num_obs=None,
                        uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -270,11 +397,14 @@ class RadSearch:
             no = ti(num_obs, (N,))
         u = None if uniforms is None else uniforms.to(device=dev, dtype=torch.float64).contiguous()
         self._ctr += 1
+        self._quiesce_prefetch()
         with torch.cuda.device(dev):
             L.check(self._lib.rs_load_scenarios(C.byref(self._cfg), C.byref(self._st), _ptr(s), _ptr(d), _ptr(it),
                                                 _ptr(bk), _ptr(r), k_in, _ptr(no), _ptr(self.obs), N,
                                                 self.env_id_offset, self.seed, self._ctr, _ptr(u),
                                                 0 if u is None else u.shape[-1], self._stream()), "rs_load_scenarios")
+            if self.prefetch:
+                self._launch_prepare(0, use_list=False)
         self.epoch_end = False
         return self.obs
 

@@ -28,6 +28,7 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
+static inline void __threadfence() {}
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 // round-down conversions used for the shortest-path lower bounds
 static inline float __double2float_rd(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }

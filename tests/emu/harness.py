@@ -75,6 +75,17 @@ class EmuEnv:
         self.status = np.zeros(n, np.uint32)
         self.reset_list = np.zeros(n, np.int32)
         self.reset_count = np.zeros(1, np.int32)
+        self.epi = np.zeros(n, np.uint32)
+        self.nx_src = np.zeros((n, 2), np.int32)
+        self.nx_det = np.zeros((n, 2), np.int32)
+        self.nx_rad = np.zeros((n, 2), np.int32)
+        self.nx_best = np.zeros(n, np.float64)
+        self.nx_dsrc = np.zeros((max(4 * K, 1), n), np.float64)
+        self.nx_obs = np.zeros((n, A, 11), np.float32)
+        self.nx_seq = np.zeros(n, np.uint32)
+        self.refill_list = np.zeros((2, n), np.int32)
+        self.refill_count = np.zeros(2, np.int32)
+        self.ctr_dev = np.zeros(1, np.uint64)
         self.st = L.RsState(*[_vp(getattr(self, f)) for f, _ in L.RsState._fields_])
         self.obs = np.zeros((n, A, 11), np.float32)
         self.final_obs = np.zeros((n, A, 11), np.float32)
@@ -108,6 +119,10 @@ class EmuEnv:
         rc = emu().emu_load_scenarios(C.byref(self.cfg), C.byref(self.st), _vp(arrs[0]), _vp(arrs[1]), _vp(arrs[2]),
                                       _vp(arrs[3]), _vp(arrs[4]), k_in, _vp(arrs[5]), _vp(self.obs), self.n,
                                       self.env_id0, self.seed, step_ctr, _vp(u), 0 if u is None else u.shape[-1])
+        assert rc == 0
+
+    def prepare(self, flags=0):
+        rc = emu().emu_prepare(C.byref(self.cfg), C.byref(self.st), self.n, self.env_id0, self.seed, flags)
         assert rc == 0
 
     def query_sp(self, pts, variant=0):

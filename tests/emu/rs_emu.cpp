@@ -17,7 +17,9 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
+    a.parity = (flags & RS_F_PARITY1) ? 1 : 0;
     if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
+    if ((flags & RS_F_AUTO_RESET) && (flags & RS_F_PREFETCH)) st->refill_count[a.parity] = 0;
     std::vector<int4> rects(RS_MAX_K);
     std::vector<double> dsrc(4 * RS_MAX_K);
     std::vector<float> lb(4 * RS_MAX_K);
@@ -44,18 +46,19 @@ int emu_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_
 }
 
 static int run_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
-                     const uint8_t *new_mask, int flags) {
+                     const uint8_t *new_mask, int flags, const int32_t *list = nullptr, const int32_t *cnt = nullptr) {
     rs::Params P = rs::make_params(*cfg);
     std::vector<int4> rects(RS_MAX_K);
     std::vector<double> dsrc(4 * RS_MAX_K);
     std::vector<uint32_t> vis(4 * RS_MAX_K);
-    const int count = (flags & RS_F_RESET_LIST) ? *st->reset_count : a.n_env;
+    if ((flags & RS_F_RESET_LIST) && !list) { list = st->reset_list; cnt = st->reset_count; }
+    const int count = list ? *cnt : a.n_env;
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
     for (int i = 0; i < count; i++) {
         int n = i;
-        if (flags & RS_F_RESET_LIST) n = st->reset_list[i];
+        if (list) n = list[i];
         else if (mask && !mask[n]) continue;
-        const bool new_obs = (flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]);
+        const bool new_obs = !a.prepare && ((flags & RS_F_NEW_OBSTACLES) || (new_mask && new_mask[n]));
         // one "lane" plays the whole warp: the lane-strided loops degenerate to plain loops
         if (fast) rs::reset_env<true>(P, *st, a, n, new_obs, 0, 1, 1u, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
         else rs::reset_env<false>(P, *st, a, n, new_obs, 0, 1, 1u, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<uint32_t>{vis.data(), 1});
@@ -70,7 +73,19 @@ int emu_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask,
     memset(&a, 0, sizeof(a));
     a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;
     a.uniforms = uniforms; a.n_uniforms = n_uniforms;
+    a.parity = (flags & RS_F_PREFETCH) ? ((flags & RS_F_PARITY1) ? 1 : 0) : -1;
     return run_reset(cfg, st, a, reset_mask, new_obstacles_mask, flags);
+}
+
+int emu_prepare(const RsConfig *cfg, const RsState *st, int32_t n_env, uint32_t env_id0, uint64_t seed, int32_t flags) {
+    rs::ResetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.prepare = 1; a.parity = -1;
+    const int parity = (flags & RS_F_PARITY1) ? 1 : 0;
+    const bool use_list = flags & RS_F_REFILL_LIST;
+    return run_reset(cfg, st, a, nullptr, nullptr, flags & RS_F_FAST_POISSON,
+                     use_list ? st->refill_list + (size_t)parity * n_env : nullptr,
+                     use_list ? st->refill_count + parity : nullptr);
 }
 
 int emu_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *src, const int32_t *det,
@@ -83,6 +98,7 @@ int emu_load_scenarios(const RsConfig *cfg, const RsState *st, const int32_t *sr
     a.uniforms = uniforms; a.n_uniforms = n_uniforms;
     a.in_src = src; a.in_det = det; a.in_intensity = intensity; a.in_bkg = bkg; a.in_rects = rects;
     a.in_num_obs = num_obs; a.k_in = k_in;
+    a.parity = -1;
     return run_reset(cfg, st, a, nullptr, nullptr, 0);
 }
 }

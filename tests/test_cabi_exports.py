@@ -26,7 +26,7 @@ def declared_functions():
 def test_every_declared_symbol_is_exported(lib):
     names = declared_functions()
     assert {"rs_step", "rs_reset", "rs_load_scenarios", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
-            "rs_version"} <= set(names)
+            "rs_version", "rs_prepare", "rs_bump_ctr", "rs_query_shortest_path"} <= set(names)
     for n in names:
         assert hasattr(lib, n), n
 
@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layout_and_version(lib):
     assert lib.rs_version() == 1
     assert lib.rs_sizeof_config() == C.sizeof(L.RsConfig) == 48
-    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 96
+    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 184
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):

@@ -77,12 +77,12 @@ def test_results_do_not_depend_on_sharding():
 
     n = 64
     full = co.OracleBatch(n, co.default_config(obstruction_count=3), seed=5, env_id0=0)
-    full.reset(0)
+    full.reset()
     parts = []
     for r in range(2):
         lo, hi = rdist.shard_range(n, r, 2)
         p = co.OracleBatch(hi - lo, co.default_config(obstruction_count=3), seed=5, env_id0=lo)
-        p.reset(0)
+        p.reset()
         parts.append(p)
     acts = np.random.default_rng(1).integers(0, 8, (n, 1))
     full.step(acts, 1)

@@ -22,7 +22,7 @@ def test_emulated_kernels_match_oracle_rollout(n, A, oc, enforce, T, idle):
     ob = co.OracleBatch(n, co.default_config(n_agents=A, obstruction_count=oc, enforce=int(enforce)), seed=seed, env_id0=7)
     em = EmuEnv(n, cfg, seed=seed, env_id0=7)
     em.reset(0, flags=L.F_NEW_OBSTACLES)
-    ob.reset(0)
+    ob.reset()
     compare_state(em, ob, A)
     compare_obs(em.obs, ob.outs["obs"][:, :A])
     rng = np.random.default_rng(seed)
@@ -46,7 +46,7 @@ def test_emulated_kernels_match_oracle_rollout(n, A, oc, enforce, T, idle):
         if mask.any():
             newm = np.full(n, t % 45 == 0)
             em.reset(t, mask=mask, new_mask=newm)
-            ob.reset(t, mask=mask, new_obstacles=newm)
+            ob.reset(mask=mask, new_obstacles=newm)
             compare_state(em, ob, A)
             compare_obs(em.obs, ob.outs["obs"][:, :A], sel=np.where(mask)[0])
     assert seen["sens"] > 0 and (oc == 0 or seen["los"] > 0)
@@ -59,7 +59,7 @@ def test_emulated_auto_reset_matches_caller_rules():
     ob = co.OracleBatch(n, ocfg, seed=5)
     em = EmuEnv(n, cfg, seed=5)
     em.reset(0, flags=L.F_NEW_OBSTACLES)
-    ob.reset(0)
+    ob.reset()
     rng = np.random.default_rng(0)
     for t in range(1, T + 1):
         acts = rng.integers(0, 8, size=(n, A))
@@ -77,7 +77,7 @@ def test_emulated_auto_reset_matches_caller_rules():
         compare_obs(em.final_obs, final, sel=np.where(mask)[0])
         em.reset(t, flags=L.F_RESET_LIST | (L.F_NEW_OBSTACLES if epoch_end else 0))
         if mask.any():
-            ob.reset(t, mask=mask, new_obstacles=np.full(n, epoch_end))
+            ob.reset(mask=mask, new_obstacles=np.full(n, epoch_end))
         compare_state(em, ob, A)
         np.testing.assert_array_equal(em.ep_len, e["ep_len"])
 
@@ -151,7 +151,7 @@ def test_pruned_shortest_path_is_bit_identical(oc):
     em = EmuEnv(n, cfg, seed=321 + oc)
     em.reset(0, flags=L.F_NEW_OBSTACLES)
     ob = co.OracleBatch(n, co.default_config(obstruction_count=oc, enforce=1), seed=321 + oc)
-    ob.reset(0)
+    ob.reset()
     rng = np.random.default_rng(oc + 10)
     for rep in range(4):
         pts = _sp_probe_points(rng, em.rects, em.num_obs, n)
@@ -160,3 +160,46 @@ def test_pruned_shortest_path_is_bit_identical(oc):
         c = np.array([ob.shortest_path(i, pts[i]) for i in range(n)])
         np.testing.assert_array_equal(a, b)
         np.testing.assert_array_equal(a, c)
+
+
+@pytest.mark.parametrize("skip_some_prepares", [False, True])
+def test_emulated_prefetch_gives_the_same_rollout(skip_some_prepares):
+    """RS_F_PREFETCH: finished envs adopt the scenario rs_prepare computed ahead of time.  Because a scenario is a pure
+    function of (seed, env id, episode number, obstructions) the rollout equals the oracle's synchronous resets,
+    whether a prefetched scenario was ready or not."""
+    n, A, T, ML = 200, 2, 170, 25
+    cfg = make_config(n_agents=A, obstruction_count=4, enforce=True, max_ep_len=ML)
+    ob = co.OracleBatch(n, co.default_config(n_agents=A, obstruction_count=4, enforce=1, max_ep_len=ML), seed=8)
+    em = EmuEnv(n, cfg, seed=8)
+    em.reset(0, flags=L.F_NEW_OBSTACLES)
+    ob.reset()
+    em.prepare()                                            # everybody's second episode
+    assert (em.nx_seq == em.epi + 1).all()
+    rng = np.random.default_rng(1)
+    used_prefetch = used_sync = 0
+    for t in range(1, T + 1):
+        p = t & 1
+        pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0)
+        acts = rng.integers(0, 8, size=(n, A))
+        epoch_end = t % 70 == 0
+        em.step(acts, t, flags=L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0))
+        ob.step(acts, t)
+        e = ob.envs
+        mask = (e["done"] == 1) | (e["ep_len"] == ML) | epoch_end
+        final = ob.outs["obs"][:, :A].copy()
+        used_prefetch += int(em.refill_count[p])
+        used_sync += int(em.reset_count[0])
+        assert em.refill_count[p] + em.reset_count[0] == mask.sum()
+        compare_obs(em.final_obs, final, sel=np.where(mask)[0])
+        em.reset(t, flags=L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0))
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.full(n, epoch_end))
+        compare_state(em, ob, A)
+        np.testing.assert_array_equal(em.ep_len, e["ep_len"])
+        np.testing.assert_array_equal(em.epi, e["episode"])
+        nxt = np.where(mask[:, None, None], ob.outs["obs"][:, :A], final)
+        compare_obs(em.obs, nxt)
+        if not (skip_some_prepares and t % 3 == 0):
+            em.prepare(flags=L.F_REFILL_LIST | (L.F_PARITY1 if p else 0))
+    assert used_prefetch >= 3 * n
+    assert (used_sync > n) if skip_some_prepares else True

@@ -103,7 +103,7 @@ def test_oracle_reset_distribution_matches_reference():
     rows = g["rows"]
     cfg = co.default_config(obstruction_count=-1, enforce=1)
     ob = co.OracleBatch(6000, cfg, seed=4242)
-    ob.reset(0)
+    ob.reset()
     e = ob.envs
     assert not e["status"].any()
     mine = dict(num_obs=e["num_obs"], src_x=e["src"][:, 0], src_y=e["src"][:, 1], det_x=e["det"][:, 0, 0],
