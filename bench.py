@@ -159,6 +159,7 @@ def main():
         g = torch.Generator(device=dev).manual_seed(1000 + rank * R + r)
         e._meta.add_(torch.randint(0, 120, (N,), generator=g, device=dev, dtype=torch.int32) << 16)
         torch.cuda.synchronize()
+        e.capture_graphs()
         envs.append(e)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     n_act = 16

@@ -36,7 +36,9 @@ extern "C" {
 #define RS_F_NEW_OBSTACLES 8     /* rs_reset: draw new obstructions for every env being reset (env.epoch_end)      */
 #define RS_F_FAST_POISSON 16     /* Philox path only: fp32 acceptance test in the PTRS sampler (KS-equivalent)     */
 #define RS_F_PREFETCH 32         /* rs_step: finished envs take their next episode from the prefetched scenario    */
-                                 /* (RsState.nx_*) when it is ready, else they go to the reset list as usual       */
+                                 /* (RsState.nx_*) when it is ready, else they go to the reset list as usual; envs  */
+                                 /* that took it are appended to refill list `parity` (the caller zeroes            */
+                                 /* refill_count[parity] when it starts a list and drains it with rs_prepare)       */
 #define RS_F_REFILL_LIST 64      /* rs_prepare: prepare the envs of refill list `parity`; else all envs            */
 #define RS_F_DEVICE_CTR 128      /* read the step counter from RsState.ctr_dev (CUDA-graph replay); rs_bump_ctr     */
 #define RS_F_PARITY1 256         /* which of the two refill lists rs_step / rs_reset push to (rs_prepare drains)    */
@@ -78,11 +80,12 @@ typedef struct RsState {
     int32_t *src;                /* [N][2]    source x,y                                                        */
     int32_t *rad;                /* [N][2]    intensity, background                                             */
     int32_t *rects;              /* [K][N][4] x0,y0,x1,y1 (16-byte rows; slot k of env n at (k*N+n)*4)          */
-    int32_t *meta;               /* [N]       num_obs | done<<8 | ep_len<<16                                    */
+    int32_t *meta;               /* [N]       num_obs | done<<8 | dsrc table<<9 | ep_len<<16                             */
     int32_t *det;                /* [A][N][2] detector x,y                                                      */
     double *best;                /* [A][N]    Agent.prev_det_dist (running minimum of the shortest-path length)  */
     int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24                       */
-    double *dsrc;                /* [4K][N]   shortest-path length source -> obstruction corner c (inf if none)  */
+    double *dsrc;                /* [2][4K][N] shortest-path length source -> obstruction corner c (inf if none);       */
+                                 /*           two tables: the running episode's (meta bit 9) and the prefetched one     */
     uint32_t *vis;               /* [4K][N]   corner-to-corner visibility bit masks                              */
     uint32_t *status;            /* [N]       RS_ST_* bits, sticky until cleared by the caller                   */
     int32_t *reset_list;         /* [N]       envs scheduled for reset by the last rs_step                       */
@@ -93,7 +96,7 @@ typedef struct RsState {
     int32_t *nx_det;             /* [N][2]    all agents start at the same point (R:771-773)                       */
     int32_t *nx_rad;             /* [N][2]                                                                        */
     double *nx_best;             /* [N]                                                                           */
-    double *nx_dsrc;             /* [4K][N]                                                                       */
+    double *nx_dsrc;             /* unused (the prefetched table is the idle half of dsrc)                           */
     float *nx_obs;               /* [N][A][11] first observation of the prefetched episode                        */
     uint32_t *nx_seq;            /* [N]       episode number the prefetched scenario belongs to (0 = none)         */
     int32_t *refill_list;        /* [2][N]    envs whose prefetched scenario was consumed (two lists, ping-pong)   */

@@ -392,12 +392,16 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
     e.rects = rects; e.dsrc = dsrc;
     e.num_obs = meta & 0xff;
     int done = (meta >> 8) & 1;
+    int sel = (meta >> 9) & 1;            // which of the two dsrc tables belongs to the running episode
     int ep_len = meta >> 16;
     const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
     const int2 rad = reinterpret_cast<const int2 *>(S.rad)[n];
     e.sx = src.x; e.sy = src.y; e.intensity = rad.x; e.bkg = rad.y;
     for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = S.dsrc[(size_t)c * N + n];
+    {
+        const double *tab = S.dsrc + (size_t)sel * 4 * P.k_max * N;
+        for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = tab[(size_t)c * N + n];
+    }
     uint32_t status = 0;
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
 
@@ -492,20 +496,30 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
                 const uint32_t tag = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n);
                 if (tag == want) {
                     __threadfence();
-                    reinterpret_cast<int2 *>(S.src)[n] = reinterpret_cast<const int2 *>(S.nx_src)[n];
-                    reinterpret_cast<int2 *>(S.rad)[n] = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+                    // independent loads first (one memory latency), then the stores; the source-distance table is not
+                    // copied: rs_prepare wrote the idle one of the two tables, flipping `sel` adopts it
+                    const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
+                    const int2 r0 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
                     const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
                     const double b0 = S.nx_best[n];
+                    const float *nxo = S.nx_obs + (size_t)n * A * RS_OBS_DIM;
+                    for (int ag = 0; ag < A; ag++) {
+                        float row[RS_OBS_DIM];
+#pragma unroll
+                        for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[ag * RS_OBS_DIM + i];
+#pragma unroll
+                        for (int i = 0; i < RS_OBS_DIM; i++) obs_rows[ag * RS_OBS_DIM + i] = row[i];
+                    }
+                    reinterpret_cast<int2 *>(S.src)[n] = s0;
+                    reinterpret_cast<int2 *>(S.rad)[n] = r0;
                     for (int ag = 0; ag < A; ag++) {
                         const size_t ia = (size_t)ag * N + n;
                         reinterpret_cast<int2 *>(S.det)[ia] = d0;
                         S.best[ia] = b0;
                         S.aflags[ia] = 0;
                     }
-                    for (int c = 0; c < 4 * e.num_obs; c++) S.dsrc[(size_t)c * N + n] = S.nx_dsrc[(size_t)c * N + n];
-                    for (int i = 0; i < A * RS_OBS_DIM; i++) obs_rows[i] = S.nx_obs[(size_t)n * A * RS_OBS_DIM + i];
                     S.epi[n] = want;
-                    done = 0; ep_len = 0;
+                    done = 0; ep_len = 0; sel ^= 1;
                     swapped = true;
                     const int slot = atomicAdd(S.refill_count + a.parity, 1);
                     S.refill_list[(size_t)a.parity * N + slot] = n;
@@ -518,7 +532,7 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
         }
     }
     if (a.ended) a.ended[n] = (uint8_t)ended;
-    S.meta[n] = e.num_obs | (done << 8) | (ep_len << 16);
+    S.meta[n] = e.num_obs | (done << 8) | (sel << 9) | (ep_len << 16);
     if (status) S.status[n] |= status;
     return scheduled;
 }
@@ -622,15 +636,17 @@ struct ResetArgs {
 };
 
 // shortest path source -> (px,py) of env n, for rs_query_shortest_path
-__device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int px, int py, int variant, Col<int4> rects,
-                                           Col<double> dsrc, Col<float> lb) {
+__device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int k_max, int px, int py, int variant,
+                                           Col<int4> rects, Col<double> dsrc, Col<float> lb) {
     EnvView e;
     e.rects = rects; e.dsrc = dsrc;
-    e.num_obs = S.meta[n] & 0xff;
+    const int meta = S.meta[n];
+    e.num_obs = meta & 0xff;
     const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
     e.sx = src.x; e.sy = src.y; e.intensity = 0; e.bkg = 0;
     for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = S.dsrc[(size_t)c * N + n];
+    const double *tab = S.dsrc + (size_t)((meta >> 9) & 1) * 4 * k_max * N;
+    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = tab[(size_t)c * N + n];
     if (variant == 1) return shortest_path(e, px, py);
     bool direct, blocked;
     source_segment(e, px, py, direct, blocked);
@@ -658,6 +674,8 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     // is a pure function of (seed, env id, e, obstructions), whoever computes it and whenever
     const uint32_t ep_seq = S.epi[n] + 1u;
     const bool prepare = a.prepare != 0;
+    // a synchronous reset keeps the env's current dsrc table; rs_prepare fills the idle one
+    const int sel = ((S.meta[n] >> 9) & 1) ^ (prepare ? 1 : 0);
     Rng g;
     g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, (uint64_t)ep_seq);
     const bool inject = a.in_src != nullptr;
@@ -750,7 +768,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     bool direct, blocked_raw;
     source_segment(e, detx, dety, direct, blocked_raw);
     // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
-    double *dsrc_out = prepare ? S.nx_dsrc : S.dsrc;
+    double *dsrc_out = S.dsrc + (size_t)sel * 4 * P.k_max * N;
     for (int c = lane; c < nc; c += nl) {
         const double ds = w_dsrc[c];
         dsrc_out[(size_t)c * N + n] = ds;
@@ -774,7 +792,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         } else {
             reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
             reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
-            S.meta[n] = e.num_obs;                                       // done = 0, ep_len = 0   R:739-740
+            S.meta[n] = e.num_obs | (sel << 9);                          // done = 0, ep_len = 0   R:739-740
             S.epi[n] = ep_seq;
         }
     }

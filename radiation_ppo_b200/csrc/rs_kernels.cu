@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rs_env_impl.cuh"
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
     float *slb = reinterpret_cast<float *>(sdsrc + (size_t)4 * P.k_max * kBlock);
     const int n = blockIdx.x * kBlock + threadIdx.x;
     if (n >= n_env) return;
-    out[n] = rs::query_sp(S, n, n_env, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock},
+    out[n] = rs::query_sp(S, n, n_env, P.k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock},
                           rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<float>{slb + threadIdx.x, kBlock});
 }
 
@@ -64,7 +65,9 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
                                                         const int32_t *count) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int total = list ? *count : a.n_env;
-    const int nl = total > 32768 ? 1 : (total > 4096 ? 8 : 32);
+    // rs_prepare runs off the critical path: one thread per env wastes no lanes; a reset the step is waiting for
+    // teams up lanes for latency
+    const int nl = a.prepare ? 1 : (total > 32768 ? 1 : (total > 4096 ? 8 : 32));
     const int G = kBlock / nl;                          // groups (environments in flight) per CTA
     const int g = threadIdx.x / nl, lane = threadIdx.x % nl;
     const uint32_t sync_mask = nl == 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) & ~(nl - 1)));
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
 
 int check_prefetch(const RsConfig *cfg, const RsState *st) {
     if (!st->nx_src || !st->nx_det || !st->nx_rad || !st->nx_best || !st->nx_obs || !st->nx_seq || !st->refill_list ||
-        !st->refill_count || (cfg->k_max > 0 && !st->nx_dsrc))
+        !st->refill_count)
         return fail("prefetch needs the RsState.nx_* / refill_* buffers");
     return 0;
 }
@@ -140,10 +143,6 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     if (flags & RS_F_AUTO_RESET) {
         cudaError_t e = cudaMemsetAsync(st->reset_count, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return (int)e;
-        if (flags & RS_F_PREFETCH) {
-            e = cudaMemsetAsync(st->refill_count + parity, 0, sizeof(int32_t), s);
-            if (e != cudaSuccess) return (int)e;
-        }
     }
     rs::Params P = rs::make_params(*cfg);
     rs::StepArgs a;
@@ -165,8 +164,14 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetArgs &a, const uint8_t *mask,
                         const uint8_t *new_mask, int flags, const int32_t *list, const int32_t *count, cudaStream_t s) {
     rs::Params P = rs::make_params(*cfg);
-    const int need = (a.n_env + 3) / 4;                 // one warp per env is the widest teaming
-    const int grid = need < kResetGrid ? need : kResetGrid;
+    int need = (a.n_env + 3) / 4;                       // one warp per env is the widest teaming
+    int cap = kResetGrid;
+    if (a.prepare) {                                    // one thread per env, kept small: it shares the GPU with rs_step
+        need = (a.n_env + kBlock - 1) / kBlock;
+        const char *g = getenv("RS_PREPARE_GRID");
+        cap = g ? atoi(g) : 148;
+    }
+    const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
     if (smem > 48 * 1024) {

@@ -187,7 +187,7 @@ class RadSearch:
         self._det = z(A, N, 2)
         self._best = z(A, N, dt=torch.float64)
         self._aflags = z(A, N)
-        self._dsrc = z(max(4 * K, 1), N, dt=torch.float64)
+        self._dsrc = z(2, max(4 * K, 1), N, dt=torch.float64)
         self._vis = z(max(4 * K, 1), N)
         self._status = z(N)
         self._reset_list, self._reset_count = z(N), z(1)
@@ -197,23 +197,23 @@ class RadSearch:
         if self.prefetch:
             self._nx_src, self._nx_det, self._nx_rad = z(N, 2), z(N, 2), z(N, 2)
             self._nx_best = z(N, dt=torch.float64)
-            self._nx_dsrc = z(max(4 * K, 1), N, dt=torch.float64)
+            self._nx_dsrc = None
             self._nx_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
             self._nx_seq = z(N)
             self._refill_list, self._refill_count = z(2, N), z(2)
-            ptrs += [self._nx_src, self._nx_det, self._nx_rad, self._nx_best, self._nx_dsrc, self._nx_obs, self._nx_seq,
+            ptrs += [self._nx_src, self._nx_det, self._nx_rad, self._nx_best, None, self._nx_obs, self._nx_seq,
                      self._refill_list, self._refill_count]
         else:
             ptrs += [None] * 9
         self._ctr_dev = z(1, dt=torch.int64)
         ptrs.append(self._ctr_dev)
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
-        self._par = 0                       # refill-list parity of the next step
-        self._side = torch.cuda.Stream(device=dev) if self.prefetch else None
+        self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
+        self._side = torch.cuda.Stream(device=dev, priority=int(__import__('os').environ.get('RS_SIDE_PRIO', '-1'))) if self.prefetch else None
         self._ev_main = torch.cuda.Event()
         self._ev_side = [torch.cuda.Event(), torch.cuda.Event()]
-        self._side_pending = False          # a prepare launch is in flight on the side stream
-        self._refill_pending = False        # the list of parity self._par ^ 1 holds envs waiting for rs_prepare
+        self._pending = [False, False]      # list holds envs waiting for rs_prepare
+        self._inflight = [False, False]     # an rs_prepare draining the list is running on the side stream
         self._graphs = {}
         self._act_buf = z(N, A)
         self._ctr_dev_val = 0               # host mirror of *ctr_dev (graph replays advance both)
@@ -289,18 +289,28 @@ class RadSearch:
         return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
 
     # ---- prefetch machinery -------------------------------------------------------------------------------------
+    # Steps are grouped in blocks of PREFETCH_PERIOD; the envs that adopt their prefetched episode during block b are
+    # appended to refill list b & 1, and one rs_prepare launch (one thread per env: throughput, not latency) drains that
+    # list on a high-priority side stream while block b+1 runs.  An episode lasts >= 9 steps (source and detector
+    # start >= 1000 apart, a step is <= 100.4, the goal radius is 110), so the next scenario is back in place in time;
+    # if it ever is not, the env simply takes the synchronous reset path -- the resulting state is the same.
+    PREFETCH_PERIOD = int(__import__('os').environ.get('RS_PERIOD', '3'))
+
     def _quiesce_prefetch(self) -> None:
         """Make the main stream wait for any rs_prepare in flight and forget pending refill lists (the envs in them
-        simply take the synchronous reset path next time): called before anything that rewrites env state wholesale."""
+        take the synchronous reset path next time): called before anything that rewrites env state wholesale."""
         if not self.prefetch:
             return
-        if self._side_pending:
+        if any(self._inflight):
             torch.cuda.current_stream(self.device).wait_stream(self._side)
-            self._side_pending = False
-        self._refill_pending = False
+        self._inflight = [False, False]
+        self._pending = [False, False]
+        self._blk_pos = 0
 
-    def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool) -> None:
-        """rs_step + rs_reset(list) on the current stream for refill parity p."""
+    def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool, first: bool) -> None:
+        """[zero refill list p] + rs_step + rs_reset(list) on the current stream."""
+        if first:
+            self._refill_count[p:p + 1].zero_()
         pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0) | (L.F_DEVICE_CTR if device_ctr else 0)
         flags = self._base_flags() | L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0)
         L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
@@ -317,48 +327,56 @@ class RadSearch:
                                      flags, self._stream()), "rs_prepare")
 
     def _step_prefetch(self, a: torch.Tensor, epoch_end: bool) -> None:
-        """One auto-reset step with the next episodes prepared off the critical path.
-
-        Step t pushes the envs that consumed their prefetched scenario to refill list p = t & 1; rs_prepare for that
-        list runs on the side stream (or a parallel graph branch) next to step t+1, which uses list p ^ 1."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
-        p = self._par
+        p, first = self._blk_par, self._blk_pos == 0
         with torch.cuda.device(dev):
             if epoch_end:
                 # new obstructions for everybody: nothing may be preparing scenarios against the old ones
                 self._quiesce_prefetch()
-                self._launch_step_sequence(a, p, True, False)
-                self._refill_pending = True             # every env was pushed to list p by the reset
-                self._par = p ^ 1
+                self._launch_step_sequence(a, p, True, False, True)
+                self._pending[p] = True                 # the reset pushed every env to list p
+                self._blk_par, self._blk_pos = p ^ 1, 0
                 return
+            if first:
+                if self._pending[p ^ 1]:                # the previous block's list -> rs_prepare on the side stream
+                    self._ev_main.record(main)
+                    self._side.wait_event(self._ev_main)
+                    with torch.cuda.stream(self._side):
+                        self._launch_prepare(p ^ 1)
+                        self._ev_side[p ^ 1].record(self._side)
+                    self._pending[p ^ 1], self._inflight[p ^ 1] = False, True
+                if self._inflight[p]:                   # list p is about to be reused: its rs_prepare must be done
+                    main.wait_event(self._ev_side[p])
+                    self._inflight[p] = False
             if self.use_cuda_graph:
                 self._act_buf.copy_(a)
-                key = (p, self._refill_pending)
+                key = (p, first)
                 g = self._graphs.get(key)
                 if g is None:
-                    g = self._capture(p, self._refill_pending)
-                    self._graphs[key] = g
+                    g = self._graphs[key] = self._capture(p, first)
                 if self._ctr_dev_val != self._ctr:
                     self._ctr_dev.fill_(self._ctr)
                 g.replay()
                 self._ctr_dev_val = self._ctr + 1
             else:
-                if self._refill_pending:
-                    self._ev_main.record(main)
-                    self._side.wait_event(self._ev_main)            # list p^1 is complete
-                    with torch.cuda.stream(self._side):
-                        self._launch_prepare(p ^ 1)
-                        self._ev_side[p].record(self._side)
-                if self._side_pending:
-                    main.wait_event(self._ev_side[p ^ 1])           # the prepare that drained list p has finished
-                self._side_pending = self._refill_pending
-                self._launch_step_sequence(a, p, False, False)
-            self._refill_pending = True
-            self._par = p ^ 1
+                self._launch_step_sequence(a, p, False, False, first)
+            self._pending[p] = True
+            self._blk_pos += 1
+            if self._blk_pos == self.PREFETCH_PERIOD:
+                self._blk_par, self._blk_pos = p ^ 1, 0
 
-    def _capture(self, p: int, with_prepare: bool):
-        """Capture {rs_step -> rs_reset(list) -> bump counter} with rs_prepare(previous list) as a parallel branch."""
+    def capture_graphs(self) -> None:
+        """Capture the four step-graph variants (refill list 0/1 x first-step-of-block) ahead of time."""
+        if not self.use_cuda_graph:
+            return
+        for p in (0, 1):
+            for first in (False, True):
+                if (p, first) not in self._graphs:
+                    self._graphs[(p, first)] = self._capture(p, first)
+
+    def _capture(self, p: int, first: bool):
+        """Capture {[zero list p] -> rs_step -> rs_reset(list) -> bump the device step counter} once; replayed per step."""
         dev = self.device
         L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")   # load the kernel before capture
         torch.cuda.synchronize(dev)
@@ -366,14 +384,8 @@ class RadSearch:
         cap = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(cap):
             with torch.cuda.graph(g, stream=cap):
-                if with_prepare:
-                    self._side.wait_stream(cap)
-                    with torch.cuda.stream(self._side):
-                        self._launch_prepare(p ^ 1)
-                self._launch_step_sequence(self._act_buf, p, False, True)
+                self._launch_step_sequence(self._act_buf, p, False, True, first)
                 L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")
-                if with_prepare:
-                    cap.wait_stream(self._side)
         self._ctr_dev_val = -1                           # capture does not execute; force a refresh before the replay
         return g
 

@@ -70,7 +70,7 @@ class EmuEnv:
         self.det = np.zeros((A, n, 2), np.int32)
         self.best = np.zeros((A, n), np.float64)
         self.aflags = np.zeros((A, n), np.int32)
-        self.dsrc = np.zeros((max(4 * K, 1), n), np.float64)
+        self.dsrc = np.zeros((2 * max(4 * K, 1), n), np.float64)
         self.vis = np.zeros((max(4 * K, 1), n), np.uint32)
         self.status = np.zeros(n, np.uint32)
         self.reset_list = np.zeros(n, np.int32)

@@ -19,7 +19,6 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
     a.parity = (flags & RS_F_PARITY1) ? 1 : 0;
     if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
-    if ((flags & RS_F_AUTO_RESET) && (flags & RS_F_PREFETCH)) st->refill_count[a.parity] = 0;
     std::vector<int4> rects(RS_MAX_K);
     std::vector<double> dsrc(4 * RS_MAX_K);
     std::vector<float> lb(4 * RS_MAX_K);
@@ -38,9 +37,8 @@ int emu_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_
     std::vector<int4> rects(RS_MAX_K);
     std::vector<double> dsrc(4 * RS_MAX_K);
     std::vector<float> lb(4 * RS_MAX_K);
-    (void)cfg;
     for (int n = 0; n < n_env; n++)
-        out[n] = rs::query_sp(*st, n, n_env, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1},
+        out[n] = rs::query_sp(*st, n, n_env, cfg->k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1},
                               rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1});
     return 0;
 }

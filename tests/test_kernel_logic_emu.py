@@ -182,6 +182,7 @@ def test_emulated_prefetch_gives_the_same_rollout(skip_some_prepares):
         pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0)
         acts = rng.integers(0, 8, size=(n, A))
         epoch_end = t % 70 == 0
+        em.refill_count[p] = 0                              # the caller starts list p
         em.step(acts, t, flags=L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0))
         ob.step(acts, t)
         e = ob.envs
