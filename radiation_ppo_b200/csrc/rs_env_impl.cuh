@@ -139,27 +139,34 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<flo
     // For an axis-aligned rectangle that is u.x*u.y <= 0 at p0/p2 and >= 0 at p1/p3 (u = corner - p).  A bend at any
     // other visible corner can be cut short by >= 1e-8 (lattice geometry), far above the fp64 rounding of the sums,
     // so dropping those corners cannot change the minimum.
-    const float pos_inf = __int_as_float(0x7f800000);
+    // The survivors go into a compact list in the thread's smem column as sortable keys: the float bound with the
+    // corner index in its 5 low mantissa bits (bound lowered by 32 ulp first, so it stays a lower bound).
+    int m_cnt = 0;
     for (int c = 0; c < nc; c++) {
         const int4 r = e.rects[c >> 2];
         const int ux = corner_x(r, c & 3) - px, uy = corner_y(r, c & 3) - py;
         const int pr = ux * uy;
         const bool tangent = (c & 1) ? (pr >= 0) : (pr <= 0);
-        // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
-        const float f2 = __int2float_rd(ux * ux + uy * uy);
-        const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
-        lb[c] = tangent ? __fadd_rd(__double2float_rd(e.dsrc[c]), sq) : pos_inf;
-    }
-    uint32_t tested = besti >= 0 ? (1u << besti) : 0u;
-    for (int it = 0; it < nc; it++) {
-        int c = -1;
-        float m = pos_inf;
-        for (int j = 0; j < nc; j++) {
-            const float v = lb[j];
-            if (!((tested >> j) & 1u) && v < m) { m = v; c = j; }
+        const double ds = e.dsrc[c];
+        if (tangent && ds < inf && c != besti) {
+            // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
+            const float f2 = __int2float_rd(ux * ux + uy * uy);
+            const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
+            const float bound = __fadd_rd(__double2float_rd(ds), sq);
+            lb[m_cnt++] = __int_as_float(((__float_as_int(bound) & ~31) - 32 + c) & 0x7fffffff);
         }
-        if (c < 0 || !((double)m < best)) break;
-        tested |= 1u << c;
+    }
+    const float pos_inf = __int_as_float(0x7f800000);
+    for (int it = 0; it < m_cnt; it++) {
+        int j = -1;
+        float m = pos_inf;
+        for (int i = 0; i < m_cnt; i++) {
+            const float v = lb[i];
+            if (v < m) { m = v; j = i; }
+        }
+        if (j < 0 || !((double)m < best)) break;
+        lb[j] = pos_inf;                                 // taken
+        const int c = __float_as_int(m) & 31;
         const int4 r = e.rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         const double cand = e.dsrc[c] + dist_int(px - cx, py - cy);
@@ -319,8 +326,10 @@ __device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int p
     }
 #pragma unroll
     for (int d = 0; d < 8; d++) {
-        if (best_d2[d] == -1) out[d] = 0.0f;
-        else if (best_d2[d] >= 0) out[d] = __fdiv_rn(110.0f - __fsqrt_rn((float)best_d2[d]), 110.0f);
+        // (110 - dist)/110; 0 = no hit, exactly 1 on the edge; straight-line code (MUFU.RSQ, ~3e-7 relative)
+        const float f2 = (float)max(best_d2[d], 1);
+        const float v = (110.0f - f2 * rsqrtf(f2)) * (1.0f / 110.0f);
+        if (best_d2[d] != -2) out[d] = best_d2[d] < 0 ? 0.0f : (best_d2[d] == 0 ? 1.0f : v);
     }
     if (P.enforce) {                                           // R:1232-1259
         if (px - 110 < P.bx0) { if (out[0] != 0.0f) status |= RS_ST_WALL_ASSERT; out[0] = __fdiv_rn(110.0f - fabsf((float)(px - P.bx0)), 110.0f); }
@@ -392,7 +401,7 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
     e.rects = rects; e.dsrc = dsrc;
     e.num_obs = meta & 0xff;
     int done = (meta >> 8) & 1;
-    int sel = (meta >> 9) & 1;            // which of the two dsrc tables belongs to the running episode
+    const int sel = (meta >> 9) & 1;      // which of the two dsrc tables belongs to the running episode
     int ep_len = meta >> 16;
     const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
     const int2 rad = reinterpret_cast<const int2 *>(S.rad)[n];
@@ -489,46 +498,8 @@ __device__ __forceinline__ bool step_env(const Params &P, const RsState &S, cons
             if (a.final_obs) {
                 for (int i = 0; i < A * RS_OBS_DIM; i++) a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = obs_rows[i];
             }
-            bool swapped = false;
-            if ((a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
-                // the next episode was prepared ahead of time (rs_prepare): adopt it here, no reset kernel needed
-                const uint32_t want = S.epi[n] + 1u;
-                const uint32_t tag = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n);
-                if (tag == want) {
-                    __threadfence();
-                    // independent loads first (one memory latency), then the stores; the source-distance table is not
-                    // copied: rs_prepare wrote the idle one of the two tables, flipping `sel` adopts it
-                    const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
-                    const int2 r0 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
-                    const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
-                    const double b0 = S.nx_best[n];
-                    const float *nxo = S.nx_obs + (size_t)n * A * RS_OBS_DIM;
-                    for (int ag = 0; ag < A; ag++) {
-                        float row[RS_OBS_DIM];
-#pragma unroll
-                        for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[ag * RS_OBS_DIM + i];
-#pragma unroll
-                        for (int i = 0; i < RS_OBS_DIM; i++) obs_rows[ag * RS_OBS_DIM + i] = row[i];
-                    }
-                    reinterpret_cast<int2 *>(S.src)[n] = s0;
-                    reinterpret_cast<int2 *>(S.rad)[n] = r0;
-                    for (int ag = 0; ag < A; ag++) {
-                        const size_t ia = (size_t)ag * N + n;
-                        reinterpret_cast<int2 *>(S.det)[ia] = d0;
-                        S.best[ia] = b0;
-                        S.aflags[ia] = 0;
-                    }
-                    S.epi[n] = want;
-                    done = 0; ep_len = 0; sel ^= 1;
-                    swapped = true;
-                    const int slot = atomicAdd(S.refill_count + a.parity, 1);
-                    S.refill_list[(size_t)a.parity * N + slot] = n;
-                }
-            }
-            if (!swapped) {
-                const int slot = atomicAdd(S.reset_count, 1);
-                S.reset_list[slot] = n;
-            }
+            const int slot = atomicAdd(S.reset_count, 1);
+            S.reset_list[slot] = n;
         }
     }
     if (a.ended) a.ended[n] = (uint8_t)ended;
@@ -676,9 +647,45 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     const bool prepare = a.prepare != 0;
     // a synchronous reset keeps the env's current dsrc table; rs_prepare fills the idle one
     const int sel = ((S.meta[n] >> 9) & 1) ^ (prepare ? 1 : 0);
+    const bool inject = a.in_src != nullptr;
+    if (!prepare && !inject && !new_obstacles && a.parity >= 0) {
+        // RS_F_PREFETCH: rs_prepare may already have computed this very episode (same seed, env, episode number,
+        // obstructions): adopt it -- a handful of copies by one lane -- instead of recomputing it
+        const uint32_t tag = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n);
+        if (tag == ep_seq) {
+            __threadfence();
+            if (lane == 0) {
+                const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
+                const int2 r0 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+                const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
+                const double b0 = S.nx_best[n];
+                const int meta = S.meta[n];
+                const float *nxo = S.nx_obs + (size_t)n * A * RS_OBS_DIM;
+                float *dst = a.obs + (size_t)n * A * RS_OBS_DIM;
+                for (int ag = 0; ag < A; ag++) {
+                    float row[RS_OBS_DIM];
+#pragma unroll
+                    for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[ag * RS_OBS_DIM + i];
+#pragma unroll
+                    for (int i = 0; i < RS_OBS_DIM; i++) dst[ag * RS_OBS_DIM + i] = row[i];
+                    const size_t ia = (size_t)ag * N + n;
+                    reinterpret_cast<int2 *>(S.det)[ia] = d0;
+                    S.best[ia] = b0;
+                    S.aflags[ia] = 0;
+                }
+                reinterpret_cast<int2 *>(S.src)[n] = s0;
+                reinterpret_cast<int2 *>(S.rad)[n] = r0;
+                // the source-distance table is not copied: rs_prepare wrote the idle one of the two, flip the selector
+                S.meta[n] = (meta & 0xff) | ((((meta >> 9) & 1) ^ 1) << 9);
+                S.epi[n] = ep_seq;
+                const int slot = atomicAdd(S.refill_count + a.parity, 1);
+                S.refill_list[(size_t)a.parity * N + slot] = n;
+            }
+            return;
+        }
+    }
     Rng g;
     g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 1, 0, (uint64_t)ep_seq);
-    const bool inject = a.in_src != nullptr;
     RS_SYNCWARP(sync_mask);                                                      // scratch is reused between environments
     if (inject) {                                                       // refresh_environment R:799-874
         e.num_obs = min(a.in_num_obs[n], P.k_max);

@@ -42,7 +42,11 @@ __global__ void __launch_bounds__(kBlock, 4) step_kernel(rs::Params P, RsState S
     for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kBlock) dst[i] = sobs[i];
 }
 
-__global__ void bump_ctr_kernel(unsigned long long *ctr) { *ctr += 1ull; }
+// end of a captured step: advance the device step counter and empty the reset list for the next replay
+__global__ void bump_ctr_kernel(unsigned long long *ctr, int *reset_count) {
+    *ctr += 1ull;
+    if (reset_count) *reset_count = 0;
+}
 
 __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState S, const int32_t *pts, double *out,
                                                            int n_env, int variant) {
@@ -135,12 +139,10 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     if (!obs) return fail("obs is NULL");
     if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
     if ((flags & RS_F_AUTO_RESET) && (!st->reset_list || !st->reset_count)) return fail("auto-reset needs reset_list/reset_count");
-    if ((flags & RS_F_PREFETCH) && !(flags & RS_F_AUTO_RESET)) return fail("RS_F_PREFETCH needs RS_F_AUTO_RESET");
-    if (flags & RS_F_PREFETCH) if (int rc = check_prefetch(cfg, st)) return rc;
     if ((flags & RS_F_DEVICE_CTR) && !st->ctr_dev) return fail("RS_F_DEVICE_CTR needs RsState.ctr_dev");
     const int parity = (flags & RS_F_PARITY1) ? 1 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (flags & RS_F_AUTO_RESET) {
+    if ((flags & RS_F_AUTO_RESET) && !(flags & RS_F_DEVICE_CTR)) {     // with RS_F_DEVICE_CTR rs_bump_ctr empties the list
         cudaError_t e = cudaMemsetAsync(st->reset_count, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return (int)e;
     }
@@ -223,7 +225,8 @@ int rs_prepare(const RsConfig *cfg, const RsState *st, int32_t n_env, uint32_t e
 
 int rs_bump_ctr(const RsState *st, void *stream) {
     if (!st || !st->ctr_dev) return fail("RsState.ctr_dev is NULL");
-    bump_ctr_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(st->ctr_dev));
+    bump_ctr_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(st->ctr_dev),
+                                                                   st->reset_count);
     return (int)cudaGetLastError();
 }
 

@@ -357,6 +357,7 @@ class RadSearch:
                     g = self._graphs[key] = self._capture(p, first)
                 if self._ctr_dev_val != self._ctr:
                     self._ctr_dev.fill_(self._ctr)
+                    self._reset_count.zero_()           # a stream-launched step may have left entries behind
                 g.replay()
                 self._ctr_dev_val = self._ctr + 1
             else:

@@ -36,4 +36,5 @@ static inline float __int2float_rd(int x) { float f = (float)x; if ((double)f > 
 static inline float __fsqrt_rd(float v) { float f = sqrtf(v); if ((double)f * (double)f > (double)v) f = nextafterf(f, -INFINITY); return f; }
 static inline float __fadd_rd(float a, float b) { return __double2float_rd((double)a + (double)b); }
 static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
+static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

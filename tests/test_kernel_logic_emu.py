@@ -188,11 +188,13 @@ def test_emulated_prefetch_gives_the_same_rollout(skip_some_prepares):
         e = ob.envs
         mask = (e["done"] == 1) | (e["ep_len"] == ML) | epoch_end
         final = ob.outs["obs"][:, :A].copy()
-        used_prefetch += int(em.refill_count[p])
-        used_sync += int(em.reset_count[0])
-        assert em.refill_count[p] + em.reset_count[0] == mask.sum()
+        assert em.reset_count[0] == mask.sum()
+        ready = (em.nx_seq == em.epi + 1) & mask & (not epoch_end)
+        used_prefetch += int(ready.sum())
+        used_sync += int(mask.sum() - ready.sum())
         compare_obs(em.final_obs, final, sel=np.where(mask)[0])
         em.reset(t, flags=L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0))
+        assert em.refill_count[p] == mask.sum()          # adopted or recomputed, every reset env awaits rs_prepare
         if mask.any():
             ob.reset(mask=mask, new_obstacles=np.full(n, epoch_end))
         compare_state(em, ob, A)
