@@ -80,12 +80,12 @@ typedef struct RsState {
     int32_t *src;                /* [N][2]    source x,y                                                        */
     int32_t *rad;                /* [N][2]    intensity, background                                             */
     int32_t *rects;              /* [K][N][4] x0,y0,x1,y1 (16-byte rows; slot k of env n at (k*N+n)*4)          */
-    int32_t *meta;               /* [N]       num_obs | done<<8 | dsrc table<<9 | ep_len<<16                             */
+    int32_t *meta;               /* [N]       num_obs | done<<8 | ep_len<<16                      */
     int32_t *det;                /* [A][N][2] detector x,y                                                      */
     double *best;                /* [A][N]    Agent.prev_det_dist (running minimum of the shortest-path length)  */
     int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24                       */
-    double *dsrc;                /* [2][4K][N] shortest-path length source -> obstruction corner c (inf if none);       */
-                                 /*           two tables: the running episode's (meta bit 9) and the prefetched one     */
+    double *dsrc;                /* [N][4K]   shortest-path length source -> obstruction corner c (inf if none), env-major */
+                                 /*           (a unit gathers its own row on demand)                                          */
     uint32_t *vis;               /* [4K][N]   corner-to-corner visibility bit masks                              */
     uint32_t *status;            /* [N]       RS_ST_* bits, sticky until cleared by the caller                   */
     int32_t *reset_list;         /* [N]       envs scheduled for reset by the last rs_step                       */
@@ -96,7 +96,7 @@ typedef struct RsState {
     int32_t *nx_det;             /* [N][2]    all agents start at the same point (R:771-773)                       */
     int32_t *nx_rad;             /* [N][2]                                                                        */
     double *nx_best;             /* [N]                                                                           */
-    double *nx_dsrc;             /* unused (the prefetched table is the idle half of dsrc)                           */
+    double *nx_dsrc;             /* [N][4K]   source-distance row of the prefetched episode                            */
     float *nx_obs;               /* [N][A][11] first observation of the prefetched episode                        */
     uint32_t *nx_seq;            /* [N]       episode number the prefetched scenario belongs to (0 = none)         */
     int32_t *refill_list;        /* [2][N]    envs whose prefetched scenario was consumed (two lists, ping-pong)   */

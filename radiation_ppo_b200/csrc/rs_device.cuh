@@ -197,6 +197,63 @@ __device__ __forceinline__ long long poisson(Rng &g, double lam) {
     }
 }
 
+// Single-precision PTRS for RS_F_FAST_POISSON (Philox stream only; KS-equivalent to numpy, not bit-identical): the same
+// transformed-rejection algorithm with the hat/squeeze constants, the proposal offset (2a/us + b) * U and the acceptance
+// test in fp32 (the offset is below ~1.3e3, so its rounding error is ~1e-4 of a count), 24-bit uniforms placed at cell
+// centres (never 0 or 1), and lambda added in fp64.  One Philox4x32 block feeds two proposals.
+struct PtrsF32 {
+    float b, a, vr;
+    double lam;
+    __device__ __forceinline__ void init(double lam_) {
+        lam = lam_;
+        const float slam = sqrtf((float)lam_);
+        b = 0.931f + 2.53f * slam;
+        a = -0.059f + 0.02483f * b;
+        vr = 0.9277f - 3.6224f / (b - 2.0f);
+    }
+    // 0 = rejected, 1 = accepted by the squeeze, 2 = accepted by the full test (only tried when `full`)
+    __device__ __forceinline__ int propose(uint32_t xu, uint32_t xv, bool full, long long &k_out) const {
+        const float U = ((float)(xu >> 8) + 0.5f) * 5.9604644775390625e-08f - 0.5f;
+        const float V = ((float)(xv >> 8) + 0.5f) * 5.9604644775390625e-08f;
+        const float us = 0.5f - fabsf(U);
+        const float off = (2.0f * a / us + b) * U;
+        const long long k = (long long)floor((double)off + lam + 0.43);
+        k_out = k;
+        if (us >= 0.07f && V <= vr) return 1;
+        if (!full || k < 0 || (us < 0.013f && V > us)) return 0;
+        const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
+        const float lhs = RS_FAST_LOGF(V) + RS_FAST_LOGF(invalpha) - RS_FAST_LOGF(a / (us * us) + b);
+        const float fk = (float)k;
+        // -lam + k*log(lam) - lgamma(k+1) evaluated around k ~ lam without cancellation (Stirling):
+        // k*log1p((lam-k)/k) - (lam-k) - 0.5*log(2*pi*k) - 1/(12k);  exact lgamma for small k
+        float rhs;
+        if (fk >= 8.0f) {
+            const float fd = (float)(lam - (double)k);
+            rhs = fk * log1pf(fd / fk) - fd - 0.5f * RS_FAST_LOGF(6.28318531f * fk) - 0.0833333333f / fk;
+        } else {
+            const float flam = (float)lam;
+            rhs = -flam + fk * RS_FAST_LOGF(flam) - lgamma1p_fast(fk);
+        }
+        return lhs <= rhs ? 2 : 0;
+    }
+};
+
+// lam >= 10.  Counter block j of the stream (seed; env_id, domain|agent|j, step_ctr) serves proposals 2j and 2j+1.
+__device__ __forceinline__ long long poisson_f32(uint64_t seed, uint32_t env_id, uint32_t domain, uint32_t agent,
+                                                 uint64_t ctr, double lam) {
+    PtrsF32 s;
+    s.init(lam);
+    const uint32_t c1 = (domain << 24) | (agent << 16);
+    for (uint32_t j = 0; j < 500u; j++) {
+        uint32_t x[4];
+        philox4x32_10(env_id, c1 + j, (uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), x);
+        long long k;
+        if (s.propose(x[0], x[1], true, k)) return k;
+        if (s.propose(x[2], x[3], true, k)) return k;
+    }
+    return (long long)floor(lam);
+}
+
 // Python round(x, 2) R:613: decimal rounding of the exact binary value, ties to even.
 __device__ __forceinline__ double round2(double x) {
     const double p = __dmul_rn(x, 100.0);
@@ -220,56 +277,55 @@ __device__ __forceinline__ bool in_rect_open(int px, int py, int4 r) {
     return r.x < px && px < r.z && r.y < py && py < r.w;
 }
 
-// Liang-Barsky with rational parameters.  bit0: the open segment meets the OPEN rectangle (blocks visibility for the
-// shortest path); bit1: the closed segment meets the CLOSED rectangle.
-__device__ __forceinline__ int seg_rect(int px, int py, int qx, int qy, int4 r) {
+// Segment pq against the axis-aligned rectangle r by separating axes.  The four corner cross products
+//   cr[i] = (corner_i - p) x (q - p),  corners in the order p0 (x0,y0), p1 (x0,y1), p2 (x1,y1), p3 (x1,y0)
+// share four multiplications.  The open segment meets the OPEN rectangle (bit0: blocks visibility for the shortest
+// path) iff the open coordinate intervals overlap on both axes and the line strictly separates two corners: on the line
+// the x-slab, the y-slab and the segment are three open parameter intervals, pairwise intersecting by those three tests,
+// hence with a common point (Helly in one dimension).  The closed forms of the same tests give bit1: the closed
+// segment meets the CLOSED rectangle.  (p == q: bit0 is 0; never asked for a point strictly inside an obstruction.)
+// |coordinates| <= 16383 keeps every product below 2^30 and every difference inside int32.
+__device__ __forceinline__ int seg_rect(int px, int py, int qx, int qy, int4 r, int cr[4]) {
     const int dx = qx - px, dy = qy - py;
-    int ln = 0, ld = 1, hn = 1, hd = 1;
-    bool open_ok = true, closed_ok = true;
-    if (dx == 0) {
-        open_ok = (r.x < px) && (px < r.z);
-        closed_ok = (r.x <= px) && (px <= r.z);
-    } else {
-        const int en = dx > 0 ? r.x - px : px - r.z;
-        const int ex = dx > 0 ? r.z - px : px - r.x;
-        const int den = dx > 0 ? dx : -dx;
-        if (en > 0) { ln = en; ld = den; }
-        if (ex < den) { hn = ex; hd = den; }
+    const int a = (r.x - px) * dy, b = (r.z - px) * dy, c = (r.y - py) * dx, d = (r.w - py) * dx;
+    cr[0] = a - c; cr[1] = a - d; cr[2] = b - d; cr[3] = b - c;
+    const int mn = min(min(cr[0], cr[1]), min(cr[2], cr[3])), mx = max(max(cr[0], cr[1]), max(cr[2], cr[3]));
+    const int xlo = min(px, qx), xhi = max(px, qx), ylo = min(py, qy), yhi = max(py, qy);
+    const bool open_box = r.x < xhi && xlo < r.z && r.y < yhi && ylo < r.w;
+    const bool closed_box = r.x <= xhi && xlo <= r.z && r.y <= yhi && ylo <= r.w;
+    return (int)(open_box && mn < 0 && mx > 0) | ((int)(closed_box && mn <= 0 && mx >= 0) << 1);
+}
+__device__ __forceinline__ int seg_rect(int px, int py, int qx, int qy, int4 r) {
+    int cr[4];
+    return seg_rect(px, py, qx, qy, r, cr);
+}
+
+// a rectangle corner whose projection lies inside pq within 0.001 of it: cross^2 * 1e6 < |pq|^2 (so |cross| <= 3 on
+// this lattice, and |pq| > 1000); cr[] from seg_rect
+__device__ __forceinline__ bool corner_grazes(int px, int py, int dx, int dy, int l2, int4 r, const int cr[4]) {
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ac = cr[i] < 0 ? -cr[i] : cr[i];
+        if (ac <= 3 && ac * ac * 1000000 < l2) {
+            const int wx = ((i < 2) ? r.x : r.z) - px, wy = ((i == 0 || i == 3) ? r.y : r.w) - py;
+            const int t = wx * dx + wy * dy;
+            hit = hit || (t >= 0 && t <= l2);
+        }
     }
-    if (dy == 0) {
-        open_ok = open_ok && (r.y < py) && (py < r.w);
-        closed_ok = closed_ok && (r.y <= py) && (py <= r.w);
-    } else {
-        const int en = dy > 0 ? r.y - py : py - r.w;
-        const int ex = dy > 0 ? r.w - py : py - r.y;
-        const int den = dy > 0 ? dy : -dy;
-        if (en * ld > ln * den) { ln = en; ld = den; }
-        if (ex * hd < hn * den) { hn = ex; hd = den; }
-    }
-    const int lhs = ln * hd, rhs = hn * ld;
-    return (int)(open_ok && lhs < rhs) | ((int)(closed_ok && lhs <= rhs) << 1);
+    return hit;
 }
 
 // vis.boundary_distance(Line_Segment(p,q), rect) < 0.001  (R:1110, 1141): touches/crosses the boundary, or a corner
 // whose projection lies inside the segment is within 0.001 of it (cross^2 * 1e6 < |pq|^2, |cross| <= 3).
 __device__ __forceinline__ bool los_blocked_rect(int px, int py, int qx, int qy, int4 r) {
-    const int h = seg_rect(px, py, qx, qy, r);
+    int cr[4];
+    const int h = seg_rect(px, py, qx, qy, r, cr);
     if ((h & 2) && !(in_rect_open(px, py, r) && in_rect_open(qx, qy, r))) return true;
     const int dx = qx - px, dy = qy - py;
     const int l2 = dx * dx + dy * dy;
     if (l2 <= 1000000) return false;          // a corner with cross != 0 needs |pq| > 1000
-    bool hit = false;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int cx = (i < 2) ? r.x : r.z;
-        const int cy = (i == 0 || i == 3) ? r.y : r.w;
-        const int wx = cx - px, wy = cy - py;
-        const int t = wx * dx + wy * dy;
-        int cr = wx * dy - wy * dx;
-        cr = cr < 0 ? -cr : cr;
-        hit = hit || (t >= 0 && t <= l2 && cr <= 3 && cr * cr * 1000000 < l2);
-    }
-    return hit;
+    return corner_grazes(px, py, dx, dy, l2, r, cr);
 }
 
 __device__ __forceinline__ bool rects_touch(int4 a, int4 b) {

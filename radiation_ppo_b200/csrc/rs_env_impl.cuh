@@ -98,32 +98,32 @@ __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py,
         const int k = __ffs(m) - 1;
         m &= m - 1;
         const int4 r = e.rects[k];
-        const int h = seg_rect(px, py, e.sx, e.sy, r);
+        int cr[4];
+        const int h = seg_rect(px, py, e.sx, e.sy, r, cr);
         vis_ok = vis_ok && !(h & 1);
         bool b = (h & 2) && !(in_rect_open(px, py, r) && in_rect_open(e.sx, e.sy, r));
         // near-corner clause: only for |pq| > 1000
-        if (!b && l2 > 1000000) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int wx = corner_x(r, i) - px, wy = corner_y(r, i) - py;
-                const int t = wx * dx + wy * dy;
-                int cr = wx * dy - wy * dx;
-                cr = cr < 0 ? -cr : cr;
-                b = b || (t >= 0 && t <= l2 && cr <= 3 && cr * cr * 1000000 < l2);
-            }
-        }
+        if (!b && l2 > 1000000) b = corner_grazes(px, py, dx, dy, l2, r, cr);
         blk = blk || b;
     }
     direct = vis_ok;
     blocked = blk;
 }
 
-// Hot-path form: the same minimum, found with few visibility tests.  `hint` is the corner that was optimal at the
-// previous step (any value is allowed: it only seeds the upper bound).  Every corner gets a float LOWER bound of its
-// candidate length (round-down conversions), kept in the thread's smem column; corners are then tested in order of
-// increasing bound, each lane walking its own list while the warp stays converged, until no bound is below the best
-// exact candidate.  Exactly the value of shortest_path().
-__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<float> lb, int px, int py, int &hint) {
+// Hot-path form: the same minimum, found with few visibility tests.  drow = the env's source-distance row (4 doubles
+// per rectangle, 16-byte aligned).  `hint` is the corner that was optimal at the previous step (any value is allowed:
+// it only seeds the upper bound).  A corner can improve on the current best only if
+//   (1) the path can bend tautly around its rectangle there: seen from p, both edges of the rectangle at that corner lie
+//       on one (closed) side of the line p -> corner, i.e. u.x*u.y <= 0 at p0/p2 and >= 0 at p1/p3 (u = corner - p).
+//       A bend at any other visible corner can be cut short by >= 1e-8 (lattice geometry), far above the fp64 rounding
+//       of the sums, so dropping those corners cannot change the minimum;
+//   (2) dsrc[c] < best (its candidate is dsrc[c] + |u|);
+//   (3) a float LOWER bound of its candidate (round-down conversions) is below best.
+// The few survivors go into the thread's shared-memory column as sortable keys (bound with the corner index in its 5
+// low mantissa bits, lowered by 32 ulp first so that it stays a lower bound) and are tested in order of increasing
+// bound until no bound is below the best exact candidate.  Exactly the value of shortest_path().
+__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, Col<float> lb, int px,
+                                                       int py, int &hint) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int nc = 4 * e.num_obs;
     double best = inf;
@@ -131,29 +131,30 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<flo
     if (hint < nc) {
         const int4 r = e.rects[hint >> 2];
         const int cx = corner_x(r, hint & 3), cy = corner_y(r, hint & 3);
-        const double ds = e.dsrc[hint];
+        const double ds = drow[hint];
         if (ds < inf && visible(e, px, py, cx, cy)) { best = ds + dist_int(px - cx, py - cy); besti = hint; }
     }
-    // Only a corner at which the path can bend tautly around its rectangle can be the first vertex of a shortest
-    // path: seen from p, both edges of the rectangle at that corner lie on one (closed) side of the line p -> corner.
-    // For an axis-aligned rectangle that is u.x*u.y <= 0 at p0/p2 and >= 0 at p1/p3 (u = corner - p).  A bend at any
-    // other visible corner can be cut short by >= 1e-8 (lattice geometry), far above the fp64 rounding of the sums,
-    // so dropping those corners cannot change the minimum.
-    // The survivors go into a compact list in the thread's smem column as sortable keys: the float bound with the
-    // corner index in its 5 low mantissa bits (bound lowered by 32 ulp first, so it stays a lower bound).
     int m_cnt = 0;
-    for (int c = 0; c < nc; c++) {
-        const int4 r = e.rects[c >> 2];
-        const int ux = corner_x(r, c & 3) - px, uy = corner_y(r, c & 3) - py;
-        const int pr = ux * uy;
-        const bool tangent = (c & 1) ? (pr >= 0) : (pr <= 0);
-        const double ds = e.dsrc[c];
-        if (tangent && ds < inf && c != besti) {
-            // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
-            const float f2 = __int2float_rd(ux * ux + uy * uy);
-            const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
-            const float bound = __fadd_rd(__double2float_rd(ds), sq);
-            lb[m_cnt++] = __int_as_float(((__float_as_int(bound) & ~31) - 32 + c) & 0x7fffffff);
+    for (int k = 0; k < e.num_obs; k++) {
+        const int4 r = e.rects[k];
+        const double2 d01 = reinterpret_cast<const double2 *>(drow)[2 * k];
+        const double2 d23 = reinterpret_cast<const double2 *>(drow)[2 * k + 1];
+        const int ux0 = r.x - px, ux1 = r.z - px, uy0 = r.y - py, uy1 = r.w - py;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int ux = (i < 2) ? ux0 : ux1, uy = (i == 0 || i == 3) ? uy0 : uy1;
+            const double ds = i == 0 ? d01.x : (i == 1 ? d01.y : (i == 2 ? d23.x : d23.y));
+            const int pr = ux * uy;
+            const bool tangent = (i & 1) ? (pr >= 0) : (pr <= 0);
+            const int c = 4 * k + i;
+            if (tangent && ds < best && c != besti) {
+                // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
+                const float f2 = __int2float_rd(ux * ux + uy * uy);
+                const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
+                const float bound = __fadd_rd(__double2float_rd(ds), sq);
+                const float key = __int_as_float(((__float_as_int(bound) & ~31) - 32 + c) & 0x7fffffff);
+                if ((double)key < best) lb[m_cnt++] = key;
+            }
         }
     }
     const float pos_inf = __int_as_float(0x7f800000);
@@ -169,7 +170,7 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, Col<flo
         const int c = __float_as_int(m) & 31;
         const int4 r = e.rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
-        const double cand = e.dsrc[c] + dist_int(px - cx, py - cy);
+        const double cand = drow[c] + dist_int(px - cx, py - cy);
         if (cand < best && visible(e, px, py, cx, cy)) { best = cand; besti = c; }
     }
     if (besti >= 0) hint = besti;
@@ -248,18 +249,23 @@ __device__ __forceinline__ void correct_coords(int px, int py, int4 r, float out
     }
 }
 
-__device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int px, int py, float out[8],
-                                        uint32_t &status) {
-    // squared distance of the best scored edge per direction; -1 = no hit
-    int best_d2[8];
-#pragma unroll
-    for (int d = 0; d < 8; d++) best_d2[d] = -1;
-    // candidate rectangles: a ray is at most 100 (71 per axis) long
+// candidate rectangles of the sensors: a ray is at most 100 (71 per axis) long
+__device__ __forceinline__ int sensor_candidates(const EnvView &e, int px, int py) {
     int cand = 0;
     for (int k = 0; k < e.num_obs; k++) {
         const int4 r = e.rects[k];
         if (r.x - 100 <= px && px <= r.z + 100 && r.y - 100 <= py && py <= r.w + 100) cand |= 1 << k;
     }
+    return cand;
+}
+
+// the obstruction part of obstruction_sensors (R:1186-1226) over the candidate rectangles `cand`
+__device__ __forceinline__ void sensors_rects(const EnvView &e, int px, int py, int cand, float out[8],
+                                              uint32_t &status) {
+    // squared distance of the best scored edge per direction; -1 = no hit
+    int best_d2[8];
+#pragma unroll
+    for (int d = 0; d < 8; d++) best_d2[d] = -1;
     if (cand) {
         unsigned long long hits = 0ull;              // 8 bits per rectangle (obs_idx_ls R:1190)
         // per-direction running state across this lane's candidate rectangles (index order, R:1186-1217)
@@ -331,12 +337,22 @@ __device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int p
         const float v = (110.0f - f2 * rsqrtf(f2)) * (1.0f / 110.0f);
         if (best_d2[d] != -2) out[d] = best_d2[d] < 0 ? 0.0f : (best_d2[d] == 0 ? 1.0f : v);
     }
-    if (P.enforce) {                                           // R:1232-1259
+}
+
+// the wall part of obstruction_sensors (enforce_grid_boundaries, R:1232-1259); out = the 8 sensor values
+__device__ __forceinline__ void sensors_walls(const Params &P, int px, int py, float *out, uint32_t &status) {
+    {
         if (px - 110 < P.bx0) { if (out[0] != 0.0f) status |= RS_ST_WALL_ASSERT; out[0] = __fdiv_rn(110.0f - fabsf((float)(px - P.bx0)), 110.0f); }
         if (py - 110 < P.by0) { if (out[6] != 0.0f) status |= RS_ST_WALL_ASSERT; out[6] = __fdiv_rn(110.0f - fabsf((float)(py - P.by0)), 110.0f); }
         if (P.bx1 <= px + 110) { if (out[4] != 0.0f) status |= RS_ST_WALL_ASSERT; out[4] = __fdiv_rn(110.0f - fabsf((float)(P.bx1 - px)), 110.0f); }
         if (P.by1 <= py + 110) { if (out[2] != 0.0f) status |= RS_ST_WALL_ASSERT; out[2] = __fdiv_rn(110.0f - fabsf((float)(P.by1 - py)), 110.0f); }
     }
+}
+
+__device__ __forceinline__ void sensors(const Params &P, const EnvView &e, int px, int py, float out[8],
+                                        uint32_t &status) {
+    sensors_rects(e, px, py, sensor_candidates(e, px, py), out, status);
+    if (P.enforce) sensors_walls(P, px, py, out, status);
 }
 
 // in_obstruction R:1148-1170
@@ -389,124 +405,6 @@ struct StepArgs {
     int n_uniforms, flags;
     int parity;         // refill list that consumed prefetch slots are pushed to
 };
-
-// obs_rows: where this env's A x 11 observation rows go (the CTA's shared-memory tile; the kernel stores the tile to
-// a.obs with coalesced vector stores afterwards).  Returns true when the env was scheduled for reset.
-template <bool kFast>
-__device__ __forceinline__ bool step_env(const Params &P, const RsState &S, const StepArgs &a, int n, Col<int4> rects,
-                                         Col<double> dsrc, Col<float> lb, float *obs_rows) {
-    const int N = a.n_env, A = P.n_agents;
-    const int meta = S.meta[n];
-    EnvView e;
-    e.rects = rects; e.dsrc = dsrc;
-    e.num_obs = meta & 0xff;
-    int done = (meta >> 8) & 1;
-    const int sel = (meta >> 9) & 1;      // which of the two dsrc tables belongs to the running episode
-    int ep_len = meta >> 16;
-    const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
-    const int2 rad = reinterpret_cast<const int2 *>(S.rad)[n];
-    e.sx = src.x; e.sy = src.y; e.intensity = rad.x; e.bkg = rad.y;
-    for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-    {
-        const double *tab = S.dsrc + (size_t)sel * 4 * P.k_max * N;
-        for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = tab[(size_t)c * N + n];
-    }
-    uint32_t status = 0;
-    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
-
-    int propx[RS_MAX_A], propy[RS_MAX_A];
-    const bool have_act = a.actions != nullptr;
-    if (have_act && A > 1) {
-        for (int i = 0; i < A; i++) {
-            const int2 d = reinterpret_cast<const int2 *>(S.det)[(size_t)i * N + n];
-            const int act = a.actions[(size_t)n * A + i];
-            propx[i] = d.x + step_dx(act); propy[i] = d.y + step_dy(act);
-        }
-    }
-    bool have_max = false;
-    double max_reward = 0.0;
-    for (int ag = 0; ag < A; ag++) {
-        const size_t ia = (size_t)ag * N + n;
-        int2 det = reinterpret_cast<const int2 *>(S.det)[ia];
-        double best = S.best[ia];
-        int af = S.aflags[ia];
-        const int action = have_act ? a.actions[(size_t)n * A + ag] : -1;
-        int info = 0;
-        bool moved = false;
-        if (action >= 0) {                                              // take_action R:876-946
-            const int tx = det.x + step_dx(action), ty = det.y + step_dy(action);
-            int cnt = 0;
-            if (A > 1) for (int i = 0; i < A; i++) cnt += (propx[i] == tx && propy[i] == ty);
-            if (cnt > 1) info |= RS_I_COLLISION;
-            else {
-                bool roll = false;
-                if (P.enforce) {
-                    if (tx < P.bx0 || ty < P.by0 || P.bx1 <= tx || P.by1 <= ty) { info |= RS_I_OOB; af += 1; roll = true; }
-                } else {
-                    if (det.x < P.sx0 || det.y < P.sy0 || P.sx1 < det.x || P.sy1 < det.y) { info |= RS_I_OOB; af += 1; }
-                }
-                if (in_obstruction(e, tx, ty)) { roll = true; af |= 1 << 24; }
-                if (!roll) { det.x = tx; det.y = ty; moved = true; }
-            }
-        }
-        if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
-        // the reference keeps stale sp/euc when the detector did not move; recomputing them at the unchanged position
-        // gives the same numbers (R:528-567)
-        const double euc = dist_int(det.x - e.sx, det.y - e.sy);
-        bool direct, blocked_raw;
-        source_segment(e, det.x, det.y, direct, blocked_raw);
-        int hint = (af >> 25) & 31;
-        const double sp = direct ? euc : shortest_path_pruned(e, lb, det.x, det.y, hint);
-        af = (af & ~(31 << 25)) | (hint << 25);
-        const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);   // is_intersect R:1133-1146
-        if (blocked_los) info |= RS_I_LOS_BLOCKED;
-        Rng g;
-        if (a.uniforms) g.init_inject(a.uniforms + ((size_t)n * A + ag) * a.n_uniforms, a.n_uniforms);
-        else g.init_philox(a.seed, a.env_id0 + (uint32_t)n, 0, (uint32_t)ag, step_ctr);
-        observe<kFast>(P, e, det.x, det.y, euc, blocked_los, g, obs_rows + ag * RS_OBS_DIM, status);
-        double reward;
-        if (moved) {                                                    // R:507-522
-            info |= RS_I_MOVED;
-            if (sp < 110) { reward = 0.1; done = 1; }
-            else if (sp < best) { reward = 0.1; best = sp; }
-            else if (action == 8) reward = -1.0 * sp / P.max_dist;
-            else reward = -0.5 * sp / P.max_dist;
-        } else {
-            reward = -0.5 * sp / P.max_dist;                            // R:549, 567
-        }
-        reward = round2(reward);                                        // R:613
-        if (!have_max || max_reward == 0.0) { max_reward = reward; have_max = true; }   // R:661-665
-        else if (max_reward < reward) max_reward = reward;
-        if (af & (1 << 24)) info |= RS_I_BLOCKED;
-        reinterpret_cast<int2 *>(S.det)[ia] = det;
-        S.best[ia] = best;
-        S.aflags[ia] = af;
-        if (a.reward) a.reward[(size_t)n * A + ag] = (float)reward;
-        if (a.done) a.done[(size_t)n * A + ag] = (uint8_t)done;
-        if (a.info) a.info[(size_t)n * A + ag] = (uint8_t)info;
-    }
-    if (a.team_reward) a.team_reward[n] = (float)max_reward;
-    int ended = done ? RS_E_TERMINAL : 0;
-    if (have_act) ep_len += 1;
-    bool scheduled = false;
-    if (a.flags & RS_F_AUTO_RESET) {                                    // T:394-405, 446-548
-        const bool timeout = ep_len == P.max_ep_len;
-        if (timeout) ended |= RS_E_TIMEOUT;
-        if (done || timeout || (a.flags & RS_F_EPOCH_END)) {
-            ended |= RS_E_RESET;
-            scheduled = true;
-            if (a.final_obs) {
-                for (int i = 0; i < A * RS_OBS_DIM; i++) a.final_obs[(size_t)n * A * RS_OBS_DIM + i] = obs_rows[i];
-            }
-            const int slot = atomicAdd(S.reset_count, 1);
-            S.reset_list[slot] = n;
-        }
-    }
-    if (a.ended) a.ended[n] = (uint8_t)ended;
-    S.meta[n] = e.num_obs | (done << 8) | (sel << 9) | (ep_len << 16);
-    if (status) S.status[n] |= status;
-    return scheduled;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // reset R:730-797: scenario sampling (Philox domain 1), per-episode tables, initial observation (step(None) probe).
@@ -608,21 +506,20 @@ struct ResetArgs {
 
 // shortest path source -> (px,py) of env n, for rs_query_shortest_path
 __device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int k_max, int px, int py, int variant,
-                                           Col<int4> rects, Col<double> dsrc, Col<float> lb) {
+                                           Col<int4> rects, Col<float> lb) {
     EnvView e;
-    e.rects = rects; e.dsrc = dsrc;
+    e.rects = rects;
+    e.dsrc = Col<double>{S.dsrc + (size_t)n * 4 * k_max, 1};          // env-major table row
     const int meta = S.meta[n];
     e.num_obs = meta & 0xff;
     const int2 src = reinterpret_cast<const int2 *>(S.src)[n];
     e.sx = src.x; e.sy = src.y; e.intensity = 0; e.bkg = 0;
     for (int k = 0; k < e.num_obs; k++) rects[k] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-    const double *tab = S.dsrc + (size_t)((meta >> 9) & 1) * 4 * k_max * N;
-    for (int c = 0; c < 4 * e.num_obs; c++) dsrc[c] = tab[(size_t)c * N + n];
     if (variant == 1) return shortest_path(e, px, py);
     bool direct, blocked;
     source_segment(e, px, py, direct, blocked);
     int hint = 31;
-    return direct ? dist_int(px - e.sx, py - e.sy) : shortest_path_pruned(e, lb, px, py, hint);
+    return direct ? dist_int(px - e.sx, py - e.sy) : shortest_path_pruned(e, e.dsrc.p, lb, px, py, hint);
 }
 
 #ifdef RS_HOST_EMU
@@ -645,8 +542,6 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     // is a pure function of (seed, env id, e, obstructions), whoever computes it and whenever
     const uint32_t ep_seq = S.epi[n] + 1u;
     const bool prepare = a.prepare != 0;
-    // a synchronous reset keeps the env's current dsrc table; rs_prepare fills the idle one
-    const int sel = ((S.meta[n] >> 9) & 1) ^ (prepare ? 1 : 0);
     const bool inject = a.in_src != nullptr;
     if (!prepare && !inject && !new_obstacles && a.parity >= 0) {
         // RS_F_PREFETCH: rs_prepare may already have computed this very episode (same seed, env, episode number,
@@ -654,6 +549,11 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const uint32_t tag = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n);
         if (tag == ep_seq) {
             __threadfence();
+            {                                           // the prefetched source-distance row (env-major, 4K doubles)
+                const int nc0 = 4 * (S.meta[n] & 0xff);
+                const size_t row = (size_t)n * 4 * P.k_max;
+                for (int c = lane; c < nc0; c += nl) S.dsrc[row + c] = S.nx_dsrc[row + c];
+            }
             if (lane == 0) {
                 const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
                 const int2 r0 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
@@ -675,8 +575,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
                 }
                 reinterpret_cast<int2 *>(S.src)[n] = s0;
                 reinterpret_cast<int2 *>(S.rad)[n] = r0;
-                // the source-distance table is not copied: rs_prepare wrote the idle one of the two, flip the selector
-                S.meta[n] = (meta & 0xff) | ((((meta >> 9) & 1) ^ 1) << 9);
+                S.meta[n] = meta & 0xff;                                  // done = 0, ep_len = 0
                 S.epi[n] = ep_seq;
                 const int slot = atomicAdd(S.refill_count + a.parity, 1);
                 S.refill_list[(size_t)a.parity * N + slot] = n;
@@ -775,10 +674,10 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     bool direct, blocked_raw;
     source_segment(e, detx, dety, direct, blocked_raw);
     // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
-    double *dsrc_out = S.dsrc + (size_t)sel * 4 * P.k_max * N;
+    double *dsrc_out = (prepare ? S.nx_dsrc : S.dsrc) + (size_t)n * 4 * P.k_max;
     for (int c = lane; c < nc; c += nl) {
         const double ds = w_dsrc[c];
-        dsrc_out[(size_t)c * N + n] = ds;
+        dsrc_out[c] = ds;
         const int4 r = w_rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         double cand = inf;
@@ -799,7 +698,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         } else {
             reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
             reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
-            S.meta[n] = e.num_obs | (sel << 9);                          // done = 0, ep_len = 0   R:739-740
+            S.meta[n] = e.num_obs;                                       // done = 0, ep_len = 0   R:739-740
             S.epi[n] = ep_seq;
         }
     }

@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "rs_env_impl.cuh"
+#include "rs_step_tiled.cuh"
 #include "rs_error.h"
 
 namespace {
@@ -17,29 +17,241 @@ thread_local char g_err[256] = "";
 
 int fail(const char *msg) { return rs_set_error(msg); }
 
-// smem per CTA: rects [K][128] int4 | dsrc [4K][128] f64 | lb [4K][128] f32 | obs tile [128][A*11] f32
-template <bool kFast>
-__global__ void __launch_bounds__(kBlock, 4) step_kernel(rs::Params P, RsState S, rs::StepArgs a) {
+// ---------------------------------------------------------------------------------------------------------------
+// step kernel: tile program (rs_step_tiled.cuh).  A CTA of 128 threads owns E consecutive environments (128 / 64 / 32
+// for 1 / 2 / >2 agents).  Warp 0 issues one bulk-async copy (cp.async.bulk, the TMA engine's 1-D form) per state row --
+// each row of the structure-of-arrays state is one contiguous run of E elements in HBM -- completing on an mbarrier;
+// the phases then run on the shared-memory image, and the modified state rows and all outputs leave as bulk-async
+// stores.  A partial last tile (or a caller whose pointers are not 16-byte aligned) takes plain cooperative copies.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(mbar)),
+        "r"(parity)
+        : "memory");
+}
+
+struct RowDesc {
+    void *s;            // shared-memory row
+    void *g;            // the same row in HBM
+    uint32_t full;      // bytes of a full tile row
+    uint32_t valid;     // bytes of this tile's row (partial last tile)
+};
+
+// state rows read by the step: 0 src, 1 rad, 2 meta, 3 actions, 4.. rects[k], then det / best / aflags per agent
+__device__ __forceinline__ int n_rows_in(const rs::Tile &T) { return 4 + T.K + 3 * T.A; }
+__device__ __forceinline__ RowDesc row_in(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
+                                          int valid) {
+    const int E = T.E, A = T.A, K = T.K;
+    const size_t N = (size_t)a.n_env;
+    RowDesc r{nullptr, nullptr, 0u, 0u};
+    if (i == 0) r = RowDesc{T.src, S.src + 2 * (size_t)n0, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+    else if (i == 1) r = RowDesc{T.rad, S.rad + 2 * (size_t)n0, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+    else if (i == 2) r = RowDesc{T.meta, S.meta + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+    else if (i == 3) {
+        if (a.actions)
+            r = RowDesc{const_cast<int *>(T.act), const_cast<int32_t *>(a.actions) + (size_t)n0 * A, (uint32_t)(E * A) * 4u,
+                        (uint32_t)(valid * A) * 4u};
+    } else if (i < 4 + K) {
+        const int k = i - 4;
+        r = RowDesc{T.rects + k * E, S.rects + ((size_t)k * N + n0) * 4, (uint32_t)E * 16u, (uint32_t)valid * 16u};
+    } else {
+        const int j = i - 4 - K, ag = j / 3, w = j - 3 * ag;
+        const size_t off = (size_t)ag * N + n0;
+        if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+        else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+        else r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+    }
+    return r;
+}
+
+// rows written by the step: 0 meta, 1 obs, 2 reward, 3 team_reward, 4 done, 5 info, 6 ended, then det / best / aflags
+__device__ __forceinline__ int n_rows_out(const rs::Tile &T) { return 7 + 3 * T.A; }
+__device__ __forceinline__ RowDesc row_out(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
+                                           int valid) {
+    const int E = T.E, A = T.A;
+    const size_t N = (size_t)a.n_env;
+    const uint32_t uE = (uint32_t)(E * A), uV = (uint32_t)(valid * A);
+    RowDesc r{nullptr, nullptr, 0u, 0u};
+    switch (i) {
+        case 0: r = RowDesc{T.meta, S.meta + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u}; break;
+        case 1: r = RowDesc{T.obs, a.obs + (size_t)n0 * A * RS_OBS_DIM, uE * RS_OBS_DIM * 4u, uV * RS_OBS_DIM * 4u}; break;
+        case 2: if (a.reward) r = RowDesc{T.reward, a.reward + (size_t)n0 * A, uE * 4u, uV * 4u}; break;
+        case 3: if (a.team_reward) r = RowDesc{T.team, a.team_reward + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u}; break;
+        case 4: if (a.done) r = RowDesc{T.done, a.done + (size_t)n0 * A, uE, uV}; break;
+        case 5: if (a.info) r = RowDesc{T.info, a.info + (size_t)n0 * A, uE, uV}; break;
+        case 6: if (a.ended) r = RowDesc{T.ended, a.ended + n0, (uint32_t)E, (uint32_t)valid}; break;
+        default: {
+            const int j = i - 7, ag = j / 3, w = j - 3 * ag;
+            const size_t off = (size_t)ag * N + n0;
+            if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+            else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+            else r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+        }
+    }
+    return r;
+}
+
+// warp-aggregated append of unit u to a shared-memory work list (whole warps call this)
+__device__ __forceinline__ void list_push(bool flag, int u, uint16_t *list, int *count) {
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)u;
+}
+
+template <bool kFast, int E>
+__global__ void __launch_bounds__(kBlock, 5) step_kernel(const __grid_constant__ rs::Params P,
+                                                         const __grid_constant__ RsState S,
+                                                         const __grid_constant__ rs::StepArgs a,
+                                                         const __grid_constant__ rs::TileLayout L, int bulk_ok,
+                                                         uint32_t tx_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
-    int4 *srects = reinterpret_cast<int4 *>(smem);
-    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
-    float *slb = reinterpret_cast<float *>(sdsrc + (size_t)4 * P.k_max * kBlock);
-    float *sobs = slb + (size_t)4 * P.k_max * kBlock;
-    const int row = P.n_agents * RS_OBS_DIM;
-    const int n0 = blockIdx.x * kBlock;
-    const int n = n0 + threadIdx.x;
-    if (n < a.n_env)
-        rs::step_env<kFast>(P, S, a, n, rs::Col<int4>{srects + threadIdx.x, kBlock},
-                            rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<float>{slb + threadIdx.x, kBlock},
-                            sobs + threadIdx.x * row);
+    const int A = P.n_agents, K = P.k_max, U = E * A;
+    const rs::Tile T = rs::carve_tile(smem, L, E, A, K, a.actions != nullptr);
+    float *keys = reinterpret_cast<float *>(smem + L.keys);
+    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + L.lists);     // [3][U]: B, D, P
+    int *counters = reinterpret_cast<int *>(smem + L.counters);         // B, D, P, scheduled
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.mbar);
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * E;
+    const int valid = min(E, a.n_env - n0);
+    const bool bulk = bulk_ok && valid == E;
+
+    // ---- stage the tile ------------------------------------------------------------------------------------------
+    if (tid < 4) counters[tid] = 0;
+    const int nin = n_rows_in(T);
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, tx_bytes);
+        }
+        if (tid < 32) {
+            __syncwarp();
+            for (int i = tid; i < nin; i += 32) {
+                const RowDesc r = row_in(T, S, a, i, n0, valid);
+                if (r.full) bulk_g2s(r.s, r.g, r.full, mbar);
+            }
+        }
+        __syncthreads();                                    // the barrier object is initialised for everybody
+        mbar_wait(mbar, 0);
+    } else {
+        for (int i = 0; i < nin; i++) {
+            const RowDesc r = row_in(T, S, a, i, n0, valid);
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(r.g);
+            uint32_t *s = reinterpret_cast<uint32_t *>(r.s);
+            for (uint32_t w = tid; w < r.valid / 4u; w += kBlock) s[w] = g[w];
+        }
+        __syncthreads();
+    }
+    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
+
+    // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
+    for (int u0 = 0; u0 < U; u0 += kBlock) {
+        const int u = u0 + tid;
+        int uf = 0;
+        if (u < U && (u % E) < valid) uf = rs::phase_move<kFast>(P, S, a, T, n0, u, step_ctr);
+        list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
+        list_push(uf & rs::UF_NEED_D, u, lists + U, counters + 1);
+        list_push(uf & rs::UF_NEED_P, u, lists + 2 * U, counters + 2);
+    }
     __syncthreads();
-    // the CTA's observation rows are contiguous in a.obs: coalesced 16-byte stores
-    const int cnt = min(kBlock, a.n_env - n0) * row;
-    float *dst = a.obs + (size_t)n0 * row;                 // n0 * row * 4 bytes is a multiple of 16
-    const int n4 = cnt >> 2;
-    for (int i = threadIdx.x; i < n4; i += kBlock)
-        reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(sobs)[i];
-    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kBlock) dst[i] = sobs[i];
+
+    // ---- compacted phases: list j starts at the first warp the previous lists left idle -----------------------------------
+    {
+        const int cb = counters[0], cd = counters[1], cp = counters[2];
+        int off = 0;
+        for (int base = 0; base < cb; base += kBlock) {
+            const int j = base + ((tid - off) & (kBlock - 1));
+            if (j < cb) rs::phase_path(S, T, n0, lists[j], rs::Col<float>{keys + tid, kBlock});
+        }
+        off = (off + ((cb + 31) & ~31)) & (kBlock - 1);
+        for (int base = 0; base < cd; base += kBlock) {
+            const int j = base + ((tid - off) & (kBlock - 1));
+            if (j < cd) rs::phase_sense(S, T, n0, lists[U + j]);
+        }
+        off = (off + ((cd + 31) & ~31)) & (kBlock - 1);
+        for (int base = 0; base < cp; base += kBlock) {
+            const int j = base + ((tid - off) & (kBlock - 1));
+            if (j < cp) rs::phase_count<kFast>(P, S, a, T, n0, lists[2 * U + j], step_ctr);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase_commit: every environment; CTA-aggregated append to the reset work list ---------------------------------
+    for (int t0 = 0; t0 < E; t0 += kBlock) {
+        const int t = t0 + tid;
+        bool sched = false;
+        if (t < valid) sched = rs::phase_commit<kFast>(P, S, a, T, n0, t, step_ctr);
+        // reuse list B's storage for the scheduled env slots
+        list_push(sched, t, lists, counters + 3);
+    }
+    __syncthreads();
+    {
+        const int cs = counters[3];
+        if (cs > 0) {
+            __shared__ int s_base;
+            if (tid == 0) s_base = atomicAdd(S.reset_count, cs);
+            __syncthreads();
+            for (int j = tid; j < cs; j += kBlock) S.reset_list[s_base + j] = n0 + lists[j];
+        }
+    }
+
+    // ---- write the tile back ----------------------------------------------------------------------------------------
+    const int nout = n_rows_out(T);
+    if (bulk) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (tid < 32) {
+            for (int i = tid; i < nout; i += 32) {
+                const RowDesc r = row_out(T, S, a, i, n0, valid);
+                if (r.full) bulk_s2g(r.g, r.s, r.full);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released once it has been read
+        }
+    } else {
+        for (int i = 0; i < nout; i++) {
+            const RowDesc r = row_out(T, S, a, i, n0, valid);
+            const uint8_t *s = reinterpret_cast<const uint8_t *>(r.s);
+            uint8_t *g = reinterpret_cast<uint8_t *>(r.g);
+            if ((r.valid & 3u) == 0 && (reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
+                for (uint32_t w = tid; w < r.valid / 4u; w += kBlock)
+                    reinterpret_cast<uint32_t *>(g)[w] = reinterpret_cast<const uint32_t *>(s)[w];
+            } else {
+                for (uint32_t w = tid; w < r.valid; w += kBlock) g[w] = s[w];
+            }
+        }
+    }
 }
 
 // end of a captured step: advance the device step counter and empty the reset list for the next replay
@@ -52,12 +264,11 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
                                                            int n_env, int variant) {
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *srects = reinterpret_cast<int4 *>(smem);
-    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
-    float *slb = reinterpret_cast<float *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    float *slb = reinterpret_cast<float *>(srects + (size_t)P.k_max * kBlock);
     const int n = blockIdx.x * kBlock + threadIdx.x;
     if (n >= n_env) return;
     out[n] = rs::query_sp(S, n, n_env, P.k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock},
-                          rs::Col<double>{sdsrc + threadIdx.x, kBlock}, rs::Col<float>{slb + threadIdx.x, kBlock});
+                          rs::Col<float>{slb + threadIdx.x, kBlock});
 }
 
 // Reset: a persistent grid whose threads team up in groups of `nl` lanes per environment.  Few envs to reset (the
@@ -92,7 +303,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
 
 int check_prefetch(const RsConfig *cfg, const RsState *st) {
     if (!st->nx_src || !st->nx_det || !st->nx_rad || !st->nx_best || !st->nx_obs || !st->nx_seq || !st->refill_list ||
-        !st->refill_count)
+        !st->refill_count || (cfg->k_max > 0 && !st->nx_dsrc))
         return fail("prefetch needs the RsState.nx_* / refill_* buffers");
     return 0;
 }
@@ -113,10 +324,10 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
     return 0;
 }
 
-size_t step_smem(const RsConfig *cfg) {
-    return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(float)) +
-           (size_t)kBlock * cfg->n_agents * RS_OBS_DIM * sizeof(float);
-}
+// envs per CTA of the step kernel: 128 threads cover 128 / 128 / 128 / 256 (env, agent) units
+int step_tile_envs(int n_agents) { return n_agents == 1 ? 128 : (n_agents == 2 ? 64 : 32); }
+size_t query_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(float)); }
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 size_t reset_smem(const RsConfig *cfg) {
     return (size_t)kBlock * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
 }
@@ -151,15 +362,29 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags; a.parity = parity;
-    const int grid = (n_env + kBlock - 1) / kBlock;
-    const size_t smem = step_smem(cfg);
+    const int E = step_tile_envs(cfg->n_agents), A = cfg->n_agents, K = cfg->k_max;
+    const int grid = (n_env + E - 1) / E;
+    const rs::TileLayout L = rs::make_layout(E, A, K, kBlock);
+    const size_t smem = (size_t)L.total;
+    // bytes of one full tile's state rows (what the bulk copies of a CTA deliver to its mbarrier)
+    const uint32_t tx_bytes = (uint32_t)(E * (8 + 8 + 4) + (actions ? E * A * 4 : 0) + K * E * 16 + A * E * (8 + 8 + 4));
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    if (fast) step_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a);
-    else step_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a);
+    // bulk-async tile copies need 16-byte aligned rows: every array base (the tile offsets are multiples of 32 elements)
+    const int bulk_ok = aligned16(st->src) && aligned16(st->rad) && aligned16(st->rects) && aligned16(st->meta) &&
+                        aligned16(st->det) && aligned16(st->best) && aligned16(st->aflags) && aligned16(actions) &&
+                        aligned16(obs) && aligned16(reward) && aligned16(team_reward) && aligned16(done) &&
+                        aligned16(info) && aligned16(ended) &&
+                        (cfg->n_agents == 1 || n_env % 4 == 0);        // per-agent rows start at multiples of N elements
+#define RS_LAUNCH_STEP(FAST, TE)                                                                                    \
+    do {                                                                                                            \
+        if (smem > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(step_kernel<FAST, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        step_kernel<FAST, TE><<<grid, kBlock, smem, s>>>(P, *st, a, L, bulk_ok, tx_bytes);                          \
+    } while (0)
+    if (E == 128) { if (fast) RS_LAUNCH_STEP(true, 128); else RS_LAUNCH_STEP(false, 128); }
+    else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64); else RS_LAUNCH_STEP(false, 64); }
+    else { if (fast) RS_LAUNCH_STEP(true, 32); else RS_LAUNCH_STEP(false, 32); }
+#undef RS_LAUNCH_STEP
     return (int)cudaGetLastError();
 }
 
@@ -256,7 +481,7 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
     if (!pts || !out) return fail("pts/out is NULL");
     rs::Params P = rs::make_params(*cfg);
     const int grid = (n_env + kBlock - 1) / kBlock;
-    const size_t smem = step_smem(cfg);
+    const size_t smem = query_smem(cfg);
     if (smem > 48 * 1024) cudaFuncSetAttribute(sp_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sp_query_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
     return (int)cudaGetLastError();

@@ -187,7 +187,7 @@ class RadSearch:
         self._det = z(A, N, 2)
         self._best = z(A, N, dt=torch.float64)
         self._aflags = z(A, N)
-        self._dsrc = z(2, max(4 * K, 1), N, dt=torch.float64)
+        self._dsrc = z(N, max(4 * K, 1), dt=torch.float64)        # env-major: a unit gathers its own row
         self._vis = z(max(4 * K, 1), N)
         self._status = z(N)
         self._reset_list, self._reset_count = z(N), z(1)
@@ -197,11 +197,11 @@ class RadSearch:
         if self.prefetch:
             self._nx_src, self._nx_det, self._nx_rad = z(N, 2), z(N, 2), z(N, 2)
             self._nx_best = z(N, dt=torch.float64)
-            self._nx_dsrc = None
+            self._nx_dsrc = z(N, max(4 * K, 1), dt=torch.float64)
             self._nx_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
             self._nx_seq = z(N)
             self._refill_list, self._refill_count = z(2, N), z(2)
-            ptrs += [self._nx_src, self._nx_det, self._nx_rad, self._nx_best, None, self._nx_obs, self._nx_seq,
+            ptrs += [self._nx_src, self._nx_det, self._nx_rad, self._nx_best, self._nx_dsrc, self._nx_obs, self._nx_seq,
                      self._refill_list, self._refill_count]
         else:
             ptrs += [None] * 9

@@ -16,6 +16,7 @@
 
 struct int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 using std::max;

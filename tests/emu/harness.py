@@ -21,6 +21,7 @@ EMU_LIB = os.path.join(HERE, "librs_emu.so")
 def build_emu(force=False):
     srcs = [os.path.join(HERE, "rs_emu.cpp"), os.path.join(HERE, "cuda_host_shim.h"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_env_impl.cuh"),
+            os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_step_tiled.cuh"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_device.cuh"),
             os.path.join(ROOT, "include", "radsearch_b200.h")]
     if force or not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(s) for s in srcs):
@@ -70,7 +71,7 @@ class EmuEnv:
         self.det = np.zeros((A, n, 2), np.int32)
         self.best = np.zeros((A, n), np.float64)
         self.aflags = np.zeros((A, n), np.int32)
-        self.dsrc = np.zeros((2 * max(4 * K, 1), n), np.float64)
+        self.dsrc = np.zeros((n, max(4 * K, 1)), np.float64)
         self.vis = np.zeros((max(4 * K, 1), n), np.uint32)
         self.status = np.zeros(n, np.uint32)
         self.reset_list = np.zeros(n, np.int32)
@@ -80,7 +81,7 @@ class EmuEnv:
         self.nx_det = np.zeros((n, 2), np.int32)
         self.nx_rad = np.zeros((n, 2), np.int32)
         self.nx_best = np.zeros(n, np.float64)
-        self.nx_dsrc = np.zeros((max(4 * K, 1), n), np.float64)
+        self.nx_dsrc = np.zeros((n, max(4 * K, 1)), np.float64)
         self.nx_obs = np.zeros((n, A, 11), np.float32)
         self.nx_seq = np.zeros(n, np.uint32)
         self.refill_list = np.zeros((2, n), np.int32)

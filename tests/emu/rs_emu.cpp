@@ -2,7 +2,7 @@
 // the same C entry-point shapes as include/radsearch_b200.h, operating on host memory.  Used by
 // tests/test_kernel_logic_emu.py to compare the kernel logic with the oracle where no GPU exists.
 #define RS_HOST_EMU 1
-#include "../../radiation_ppo_b200/csrc/rs_env_impl.cuh"
+#include "../../radiation_ppo_b200/csrc/rs_step_tiled.cuh"
 
 #include <vector>
 
@@ -19,27 +19,72 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
     a.parity = (flags & RS_F_PARITY1) ? 1 : 0;
     if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
-    std::vector<int4> rects(RS_MAX_K);
-    std::vector<double> dsrc(4 * RS_MAX_K);
-    std::vector<float> lb(4 * RS_MAX_K);
+    // one-environment tiles (E = 1): copy the state rows in, run the phases in the kernel's order, copy the rows out
+    const int A = cfg->n_agents, K = cfg->k_max, N = n_env;
+    const rs::TileLayout L = rs::make_layout(1, A, K, 1);
+    std::vector<unsigned char> buf(L.total + 16);
+    unsigned char *base = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
+    rs::Tile T = rs::carve_tile(base, L, 1, A, K, actions != nullptr);
+    float *keys = reinterpret_cast<float *>(base + L.keys);
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
-    const int row = cfg->n_agents * RS_OBS_DIM;
     for (int n = 0; n < n_env; n++) {
-        float *rows = obs + (size_t)n * row;      // the CUDA kernel stages these rows in shared memory first
-        if (fast) rs::step_env<true>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1}, rows);
-        else rs::step_env<false>(P, *st, a, n, rs::Col<int4>{rects.data(), 1}, rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1}, rows);
+        T.src[0] = reinterpret_cast<const int2 *>(st->src)[n];
+        T.rad[0] = reinterpret_cast<const int2 *>(st->rad)[n];
+        T.meta[0] = st->meta[n];
+        for (int k = 0; k < K; k++) T.rects[k] = reinterpret_cast<const int4 *>(st->rects)[(size_t)k * N + n];
+        for (int ag = 0; ag < A; ag++) {
+            T.det[ag] = reinterpret_cast<const int2 *>(st->det)[(size_t)ag * N + n];
+            T.best[ag] = st->best[(size_t)ag * N + n];
+            T.af[ag] = st->aflags[(size_t)ag * N + n];
+            if (actions) const_cast<int *>(T.act)[ag] = actions[(size_t)n * A + ag];
+        }
+        for (int u = 0; u < A; u++) {
+            if (fast) rs::phase_move<true>(P, *st, a, T, n, u, step_ctr);
+            else rs::phase_move<false>(P, *st, a, T, n, u, step_ctr);
+        }
+        for (int u = 0; u < A; u++) {
+            const int uf = T.uflag[u];
+            if (uf & rs::UF_NEED_B) rs::phase_path(*st, T, n, u, rs::Col<float>{keys, 1});
+            if (uf & rs::UF_NEED_D) rs::phase_sense(*st, T, n, u);
+            if (uf & rs::UF_NEED_P) {
+                if (fast) rs::phase_count<true>(P, *st, a, T, n, u, step_ctr);
+                else rs::phase_count<false>(P, *st, a, T, n, u, step_ctr);
+            }
+        }
+        const bool sched = fast ? rs::phase_commit<true>(P, *st, a, T, n, 0, step_ctr)
+                                : rs::phase_commit<false>(P, *st, a, T, n, 0, step_ctr);
+        if (sched) st->reset_list[(*st->reset_count)++] = n;
+        st->meta[n] = T.meta[0];
+        for (int ag = 0; ag < A; ag++) {
+            reinterpret_cast<int2 *>(st->det)[(size_t)ag * N + n] = T.det[ag];
+            st->best[(size_t)ag * N + n] = T.best[ag];
+            st->aflags[(size_t)ag * N + n] = T.af[ag];
+            for (int i = 0; i < RS_OBS_DIM; i++) obs[((size_t)n * A + ag) * RS_OBS_DIM + i] = T.obs[ag * RS_OBS_DIM + i];
+            if (reward) reward[(size_t)n * A + ag] = T.reward[ag];
+            if (done) done[(size_t)n * A + ag] = T.done[ag];
+            if (info) info[(size_t)n * A + ag] = T.info[ag];
+        }
+        if (team_reward) team_reward[n] = T.team[0];
+        if (ended) ended[n] = T.ended[0];
     }
     return 0;
+}
+
+// bit0: open segment meets the open rectangle, bit1: closed segment meets the closed rectangle (rs_device.cuh::seg_rect)
+int emu_seg_rect(int px, int py, int qx, int qy, int x0, int y0, int x1, int y1) {
+    return rs::seg_rect(px, py, qx, qy, make_int4(x0, y0, x1, y1));
+}
+int emu_los_blocked_rect(int px, int py, int qx, int qy, int x0, int y0, int x1, int y1) {
+    return rs::los_blocked_rect(px, py, qx, qy, make_int4(x0, y0, x1, y1)) ? 1 : 0;
 }
 
 int emu_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,
                             int32_t variant) {
     std::vector<int4> rects(RS_MAX_K);
-    std::vector<double> dsrc(4 * RS_MAX_K);
     std::vector<float> lb(4 * RS_MAX_K);
     for (int n = 0; n < n_env; n++)
         out[n] = rs::query_sp(*st, n, n_env, cfg->k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1},
-                              rs::Col<double>{dsrc.data(), 1}, rs::Col<float>{lb.data(), 1});
+                              rs::Col<float>{lb.data(), 1});
     return 0;
 }
 

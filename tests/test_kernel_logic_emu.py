@@ -206,3 +206,85 @@ def test_emulated_prefetch_gives_the_same_rollout(skip_some_prepares):
             em.prepare(flags=L.F_REFILL_LIST | (L.F_PARITY1 if p else 0))
     assert used_prefetch >= 3 * n
     assert (used_sync > n) if skip_some_prepares else True
+
+
+def _clip_exact(px, py, qx, qy, x0, y0, x1, y1, closed):
+    """Liang-Barsky in exact rationals: does the (open|closed) segment meet the (open|closed) rectangle?"""
+    from fractions import Fraction as F
+    lo, hi = F(0), F(1)
+    for p0, d, a, b in ((px, qx - px, x0, x1), (py, qy - py, y0, y1)):
+        if d == 0:
+            if not ((a <= p0 <= b) if closed else (a < p0 < b)):
+                return False
+        else:
+            t0, t1 = F(a - p0, d), F(b - p0, d)
+            if t0 > t1:
+                t0, t1 = t1, t0
+            lo, hi = max(lo, t0), min(hi, t1)
+    return lo <= hi if closed else lo < hi
+
+
+def test_segment_rectangle_predicate_is_exact():
+    """rs_device.cuh::seg_rect (separating axes on shared cross products) against exact rational clipping, on random
+    and adversarial lattice inputs: corners, edges, axis-parallel and diagonal grazing segments."""
+    from tests.emu.harness import emu
+    lib = emu()
+    rng = np.random.default_rng(11)
+    n_checked = 0
+    for it in range(6000):
+        x0, y0 = (int(v) for v in rng.integers(-40, 40, 2))
+        x1, y1 = x0 + int(rng.integers(1, 30)), y0 + int(rng.integers(1, 30))
+        pool_x = [x0, x1, x0 - 1, x1 + 1, x0 + 1, x1 - 1, int(rng.integers(-60, 60)), int(rng.integers(-60, 60))]
+        pool_y = [y0, y1, y0 - 1, y1 + 1, y0 + 1, y1 - 1, int(rng.integers(-60, 60)), int(rng.integers(-60, 60))]
+        px, qx = (int(v) for v in rng.choice(pool_x, 2))
+        py, qy = (int(v) for v in rng.choice(pool_y, 2))
+        if (px, py) == (qx, qy):
+            continue
+        got = lib.emu_seg_rect(px, py, qx, qy, x0, y0, x1, y1)
+        want = int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, False)) | (int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, True)) << 1)
+        assert got == want, (px, py, qx, qy, x0, y0, x1, y1, got, want)
+        n_checked += 1
+    # arena-scale coordinates (products close to 2^30)
+    for it in range(3000):
+        x0, y0 = (int(v) for v in rng.integers(0, 2200, 2))
+        x1, y1 = x0 + int(rng.integers(200, 500)), y0 + int(rng.integers(200, 500))
+        px, py, qx, qy = (int(v) for v in rng.integers(-300, 3000, 4))
+        if it % 3 == 0:
+            px, py = x0, int(rng.integers(y0, y1 + 1))          # start on the left edge
+        got = lib.emu_seg_rect(px, py, qx, qy, x0, y0, x1, y1)
+        want = int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, False)) | (int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, True)) << 1)
+        assert got == want, (px, py, qx, qy, x0, y0, x1, y1, got, want)
+        n_checked += 1
+    assert n_checked > 8000
+
+
+@pytest.mark.parametrize("lam_case", [0, 1, 2, 3])
+def test_emulated_fast_poisson_is_ks_equivalent_to_numpy(lam_case):
+    """RS_F_FAST_POISSON (single-precision PTRS on the Philox stream, split into first proposal + full sampler by the
+    step phases) against numpy.random.Generator.poisson: KS test, mean and variance."""
+    from scipy import stats
+
+    n = 30000
+    src = np.tile(np.array([[400, 400]], np.int32), (n, 1))
+    det, inten, bkg = src + np.array([1400, 1400], np.int32), np.full(n, 1000000, np.int32), np.full(n, 10, np.int32)
+    if lam_case == 1:
+        det, inten = src + np.array([110, 0], np.int32), np.full(n, 9999999, np.int32)       # lambda ~ 9.1e4
+    if lam_case == 2:
+        det, inten, bkg = src + np.array([900, 300], np.int32), np.full(n, 3000000, np.int32), np.full(n, 25, np.int32)
+    if lam_case == 3:
+        det, inten, bkg = src + np.array([1500, 1500], np.int32), np.full(n, 1000000, np.int32), np.full(n, 10, np.int32)
+        inten[:] = 1000          # lambda ~ 10.5: just above the PTRS threshold
+    d = (det[0] - src[0]).astype(float)
+    lam = inten[0] / np.hypot(*d) + bkg[0]
+    ref = np.random.default_rng(0).poisson(lam, 200000)
+    cfg = make_config(n_agents=1, obstruction_count=0, enforce=True)
+    em = EmuEnv(n, cfg, seed=21 + lam_case)
+    em.load_scenarios(src, det, inten, bkg, np.zeros((n, 0, 4), np.int32), np.zeros(n, np.int32))
+    counts = []
+    for t in range(1, 4):
+        em.step(None, t, flags=L.F_FAST_POISSON)
+        counts.append(em.obs[:, 0, 0].copy())
+    c = np.concatenate(counts)
+    assert stats.ks_2samp(c, ref).pvalue > 1e-3, lam
+    assert abs(c.mean() - lam) < 5 * np.sqrt(lam / len(c)), (lam, c.mean())
+    assert abs(c.var() / lam - 1) < 0.03, (lam, c.var())
