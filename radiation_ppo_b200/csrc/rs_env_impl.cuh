@@ -112,18 +112,17 @@ __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py,
 
 // Hot-path form: the same minimum, found with few visibility tests.  drow = the env's source-distance row (4 doubles
 // per rectangle, 16-byte aligned).  `hint` is the corner that was optimal at the previous step (any value is allowed:
-// it only seeds the upper bound).  A corner can improve on the current best only if
+// it only seeds the upper bound `best`).  A corner c can improve on `best` only if
 //   (1) the path can bend tautly around its rectangle there: seen from p, both edges of the rectangle at that corner lie
 //       on one (closed) side of the line p -> corner, i.e. u.x*u.y <= 0 at p0/p2 and >= 0 at p1/p3 (u = corner - p).
 //       A bend at any other visible corner can be cut short by >= 1e-8 (lattice geometry), far above the fp64 rounding
 //       of the sums, so dropping those corners cannot change the minimum;
-//   (2) dsrc[c] < best (its candidate is dsrc[c] + |u|);
-//   (3) a float LOWER bound of its candidate (round-down conversions) is below best.
-// The few survivors go into the thread's shared-memory column as sortable keys (bound with the corner index in its 5
-// low mantissa bits, lowered by 32 ulp first so that it stays a lower bound) and are tested in order of increasing
-// bound until no bound is below the best exact candidate.  Exactly the value of shortest_path().
-__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, Col<float> lb, int px,
-                                                       int py, int &hint) {
+//   (2) dsrc[c] + max(|u.x|, |u.y|) < best: an exact (integer -> double) lower bound of its candidate dsrc[c] + |u|.
+// Pass A marks such corners in a per-thread bit mask with converged, branch-free code; pass B walks the thread's own
+// few marked corners (exact candidate, then the visibility test only if it would improve).  Exactly the value of
+// shortest_path().
+__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, int px, int py,
+                                                       int &hint) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int nc = 4 * e.num_obs;
     double best = inf;
@@ -134,40 +133,29 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const d
         const double ds = drow[hint];
         if (ds < inf && visible(e, px, py, cx, cy)) { best = ds + dist_int(px - cx, py - cy); besti = hint; }
     }
-    int m_cnt = 0;
+    uint32_t mask = 0u;
     for (int k = 0; k < e.num_obs; k++) {
         const int4 r = e.rects[k];
         const double2 d01 = reinterpret_cast<const double2 *>(drow)[2 * k];
         const double2 d23 = reinterpret_cast<const double2 *>(drow)[2 * k + 1];
         const int ux0 = r.x - px, ux1 = r.z - px, uy0 = r.y - py, uy1 = r.w - py;
+        const int ax0 = abs(ux0), ax1 = abs(ux1), ay0 = abs(uy0), ay1 = abs(uy1);
+        uint32_t m4 = 0u;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int ux = (i < 2) ? ux0 : ux1, uy = (i == 0 || i == 3) ? uy0 : uy1;
+            const int linf = max((i < 2) ? ax0 : ax1, (i == 0 || i == 3) ? ay0 : ay1);
             const double ds = i == 0 ? d01.x : (i == 1 ? d01.y : (i == 2 ? d23.x : d23.y));
             const int pr = ux * uy;
             const bool tangent = (i & 1) ? (pr >= 0) : (pr <= 0);
-            const int c = 4 * k + i;
-            if (tangent && ds < best && c != besti) {
-                // float lower bound of dsrc[c] + |u|: conversions round down, the approximate sqrt is shrunk by 2^-20
-                const float f2 = __int2float_rd(ux * ux + uy * uy);
-                const float sq = f2 * rsqrtf(fmaxf(f2, 1.0f)) * 0.99999905f;
-                const float bound = __fadd_rd(__double2float_rd(ds), sq);
-                const float key = __int_as_float(((__float_as_int(bound) & ~31) - 32 + c) & 0x7fffffff);
-                if ((double)key < best) lb[m_cnt++] = key;
-            }
+            if (tangent && ds + (double)linf < best) m4 |= 1u << i;
         }
+        mask |= m4 << (4 * k);
     }
-    const float pos_inf = __int_as_float(0x7f800000);
-    for (int it = 0; it < m_cnt; it++) {
-        int j = -1;
-        float m = pos_inf;
-        for (int i = 0; i < m_cnt; i++) {
-            const float v = lb[i];
-            if (v < m) { m = v; j = i; }
-        }
-        if (j < 0 || !((double)m < best)) break;
-        lb[j] = pos_inf;                                 // taken
-        const int c = __float_as_int(m) & 31;
+    if (besti >= 0) mask &= ~(1u << besti);
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
         const int4 r = e.rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         const double cand = drow[c] + dist_int(px - cx, py - cy);
@@ -506,7 +494,7 @@ struct ResetArgs {
 
 // shortest path source -> (px,py) of env n, for rs_query_shortest_path
 __device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int k_max, int px, int py, int variant,
-                                           Col<int4> rects, Col<float> lb) {
+                                           Col<int4> rects) {
     EnvView e;
     e.rects = rects;
     e.dsrc = Col<double>{S.dsrc + (size_t)n * 4 * k_max, 1};          // env-major table row
@@ -519,7 +507,7 @@ __device__ __forceinline__ double query_sp(const RsState &S, int n, int N, int k
     bool direct, blocked;
     source_segment(e, px, py, direct, blocked);
     int hint = 31;
-    return direct ? dist_int(px - e.sx, py - e.sy) : shortest_path_pruned(e, e.dsrc.p, lb, px, py, hint);
+    return direct ? dist_int(px - e.sx, py - e.sy) : shortest_path_pruned(e, e.dsrc.p, px, py, hint);
 }
 
 #ifdef RS_HOST_EMU

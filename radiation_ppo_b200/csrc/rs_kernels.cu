@@ -129,8 +129,8 @@ __device__ __forceinline__ void list_push(bool flag, int u, uint16_t *list, int 
     if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)u;
 }
 
-template <bool kFast, int E>
-__global__ void __launch_bounds__(kBlock, 5) step_kernel(const __grid_constant__ rs::Params P,
+template <bool kFast, int E, int kOcc>
+__global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
                                                          const __grid_constant__ rs::StepArgs a,
                                                          const __grid_constant__ rs::TileLayout L, int bulk_ok,
@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(kBlock, 5) step_kernel(const __grid_constant__
     extern __shared__ __align__(16) unsigned char smem[];
     const int A = P.n_agents, K = P.k_max, U = E * A;
     const rs::Tile T = rs::carve_tile(smem, L, E, A, K, a.actions != nullptr);
-    float *keys = reinterpret_cast<float *>(smem + L.keys);
     uint16_t *lists = reinterpret_cast<uint16_t *>(smem + L.lists);     // [3][U]: B, D, P
     int *counters = reinterpret_cast<int *>(smem + L.counters);         // B, D, P, scheduled
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.mbar);
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(kBlock, 5) step_kernel(const __grid_constant__
         int off = 0;
         for (int base = 0; base < cb; base += kBlock) {
             const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cb) rs::phase_path(S, T, n0, lists[j], rs::Col<float>{keys + tid, kBlock});
+            if (j < cb) rs::phase_path(S, T, n0, lists[j]);
         }
         off = (off + ((cb + 31) & ~31)) & (kBlock - 1);
         for (int base = 0; base < cd; base += kBlock) {
@@ -264,11 +263,9 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
                                                            int n_env, int variant) {
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *srects = reinterpret_cast<int4 *>(smem);
-    float *slb = reinterpret_cast<float *>(srects + (size_t)P.k_max * kBlock);
     const int n = blockIdx.x * kBlock + threadIdx.x;
     if (n >= n_env) return;
-    out[n] = rs::query_sp(S, n, n_env, P.k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock},
-                          rs::Col<float>{slb + threadIdx.x, kBlock});
+    out[n] = rs::query_sp(S, n, n_env, P.k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{srects + threadIdx.x, kBlock});
 }
 
 // Reset: a persistent grid whose threads team up in groups of `nl` lanes per environment.  Few envs to reset (the
@@ -326,7 +323,7 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
 
 // envs per CTA of the step kernel: 128 threads cover 128 / 128 / 128 / 256 (env, agent) units
 int step_tile_envs(int n_agents) { return n_agents == 1 ? 128 : (n_agents == 2 ? 64 : 32); }
-size_t query_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * (sizeof(int4) + 4 * sizeof(float)); }
+size_t query_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * sizeof(int4); }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 size_t reset_smem(const RsConfig *cfg) {
     return (size_t)kBlock * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
@@ -375,15 +372,18 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
                         aligned16(obs) && aligned16(reward) && aligned16(team_reward) && aligned16(done) &&
                         aligned16(info) && aligned16(ended) &&
                         (cfg->n_agents == 1 || n_env % 4 == 0);        // per-agent rows start at multiples of N elements
-#define RS_LAUNCH_STEP(FAST, TE)                                                                                    \
+    static const int occ_env = getenv("RS_STEP_OCC") ? atoi(getenv("RS_STEP_OCC")) : 0;      // tuning switch
+#define RS_LAUNCH_STEP(FAST, TE, OCC)                                                                               \
     do {                                                                                                            \
         if (smem > 48 * 1024)                                                                                       \
-            cudaFuncSetAttribute(step_kernel<FAST, TE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        step_kernel<FAST, TE><<<grid, kBlock, smem, s>>>(P, *st, a, L, bulk_ok, tx_bytes);                          \
+            cudaFuncSetAttribute(step_kernel<FAST, TE, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        step_kernel<FAST, TE, OCC><<<grid, kBlock, smem, s>>>(P, *st, a, L, bulk_ok, tx_bytes);                     \
     } while (0)
-    if (E == 128) { if (fast) RS_LAUNCH_STEP(true, 128); else RS_LAUNCH_STEP(false, 128); }
-    else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64); else RS_LAUNCH_STEP(false, 64); }
-    else { if (fast) RS_LAUNCH_STEP(true, 32); else RS_LAUNCH_STEP(false, 32); }
+    if (E == 128) {
+        if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6); else RS_LAUNCH_STEP(true, 128, 8); }
+        else RS_LAUNCH_STEP(false, 128, 6);
+    } else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64, 6); else RS_LAUNCH_STEP(false, 64, 6); }
+    else { if (fast) RS_LAUNCH_STEP(true, 32, 6); else RS_LAUNCH_STEP(false, 32, 6); }
 #undef RS_LAUNCH_STEP
     return (int)cudaGetLastError();
 }

@@ -49,7 +49,7 @@ struct Tile {
 };
 
 struct TileLayout {       // byte offsets of the arrays above inside the CTA's dynamic shared memory (all 16-aligned)
-    int rects, src, rad, meta, det, best, af, act, obs, reward, team, done, info, ended, ndet, sp, uflag, keys, lists,
+    int rects, src, rad, meta, det, best, af, act, obs, reward, team, done, info, ended, ndet, sp, uflag, lists,
         counters, mbar, total;
 };
 
@@ -76,7 +76,6 @@ __host__ __device__ inline TileLayout make_layout(int E, int A, int K, int threa
     L.ndet = o;    o += align16(U * 8);
     L.sp = o;      o += align16(U * 8);
     L.uflag = o;   o += align16(U * 4);
-    L.keys = o;    o += align16(4 * K * threads * 4);     // shortest-path candidate keys: one column per thread
     L.lists = o;   o += align16(3 * U * 2);
     L.counters = o; o += 16;
     L.mbar = o;    o += 16;
@@ -253,14 +252,14 @@ __device__ __forceinline__ int phase_move(const Params &P, const RsState &S, con
 }
 
 // ---- phase_path: units whose source segment is obstructed (list B) ----------------------------------------------------
-__device__ __forceinline__ void phase_path(const RsState &S, const Tile &T, int n0, int u, Col<float> keys) {
+__device__ __forceinline__ void phase_path(const RsState &S, const Tile &T, int n0, int u) {
     const int E = T.E;
     const int ag = u / E, t = u - ag * E;
     const EnvView e = tile_env(T, S, t, n0 + t);
     const int2 det = T.ndet[u];
     int af = T.af[u];
     int hint = (af >> 25) & 31;
-    T.sp[u] = shortest_path_pruned(e, e.dsrc.p, keys, det.x, det.y, hint);
+    T.sp[u] = shortest_path_pruned(e, e.dsrc.p, det.x, det.y, hint);
     T.af[u] = (af & ~(31 << 25)) | (hint << 25);
 }
 

@@ -25,7 +25,6 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     std::vector<unsigned char> buf(L.total + 16);
     unsigned char *base = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
     rs::Tile T = rs::carve_tile(base, L, 1, A, K, actions != nullptr);
-    float *keys = reinterpret_cast<float *>(base + L.keys);
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
     for (int n = 0; n < n_env; n++) {
         T.src[0] = reinterpret_cast<const int2 *>(st->src)[n];
@@ -44,7 +43,7 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
         }
         for (int u = 0; u < A; u++) {
             const int uf = T.uflag[u];
-            if (uf & rs::UF_NEED_B) rs::phase_path(*st, T, n, u, rs::Col<float>{keys, 1});
+            if (uf & rs::UF_NEED_B) rs::phase_path(*st, T, n, u);
             if (uf & rs::UF_NEED_D) rs::phase_sense(*st, T, n, u);
             if (uf & rs::UF_NEED_P) {
                 if (fast) rs::phase_count<true>(P, *st, a, T, n, u, step_ctr);
@@ -81,10 +80,8 @@ int emu_los_blocked_rect(int px, int py, int qx, int qy, int x0, int y0, int x1,
 int emu_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t *pts, double *out, int32_t n_env,
                             int32_t variant) {
     std::vector<int4> rects(RS_MAX_K);
-    std::vector<float> lb(4 * RS_MAX_K);
     for (int n = 0; n < n_env; n++)
-        out[n] = rs::query_sp(*st, n, n_env, cfg->k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1},
-                              rs::Col<float>{lb.data(), 1});
+        out[n] = rs::query_sp(*st, n, n_env, cfg->k_max, pts[2 * n], pts[2 * n + 1], variant, rs::Col<int4>{rects.data(), 1});
     return 0;
 }
 
