@@ -6,10 +6,10 @@ CUDA kernels behind the C ABI declared in include/radsearch_b200.h.  There is no
 """
 from . import _lib
 from ._lib import RadSearchLibraryError
-from .envs.rad_search_env import RadSearch, StepResult
+from .envs.rad_search_env import HostStepBuffers, RadSearch, StepResult
 from .ppo_buffer import (BatchedPPOBuffer, PPOBuffer, advantage_statistics, combined_shape, gae_advantages,
                          normalize_advantages_)
 from .dist import shard_range
 
-__all__ = ["RadSearch", "StepResult", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
+__all__ = ["RadSearch", "StepResult", "HostStepBuffers", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
            "normalize_advantages_", "combined_shape", "shard_range", "RadSearchLibraryError", "_lib"]

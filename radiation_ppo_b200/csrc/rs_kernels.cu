@@ -274,12 +274,12 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
 template <bool kFast>
 __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
                                                         const uint8_t *new_mask, int flags, const int32_t *list,
-                                                        const int32_t *count) {
+                                                        const int32_t *count, int prepare_nl) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int total = list ? *count : a.n_env;
     // rs_prepare runs off the critical path: one thread per env wastes no lanes; a reset the step is waiting for
     // teams up lanes for latency
-    const int nl = a.prepare ? 1 : (total > 32768 ? 1 : (total > 4096 ? 8 : 32));
+    const int nl = a.prepare ? prepare_nl : (total > 32768 ? 1 : (total > 4096 ? 8 : 32));
     const int G = kBlock / nl;                          // groups (environments in flight) per CTA
     const int g = threadIdx.x / nl, lane = threadIdx.x % nl;
     const uint32_t sync_mask = nl == 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) & ~(nl - 1)));
@@ -393,10 +393,12 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
     rs::Params P = rs::make_params(*cfg);
     int need = (a.n_env + 3) / 4;                       // one warp per env is the widest teaming
     int cap = kResetGrid;
-    if (a.prepare) {                                    // one thread per env, kept small: it shares the GPU with rs_step
-        need = (a.n_env + kBlock - 1) / kBlock;
-        const char *g = getenv("RS_PREPARE_GRID");
-        cap = g ? atoi(g) : 148;
+    static const int prep_nl_env = getenv("RS_PREPARE_NL") ? atoi(getenv("RS_PREPARE_NL")) : 1;      // tuning switches
+    static const int prep_grid_env = getenv("RS_PREPARE_GRID") ? atoi(getenv("RS_PREPARE_GRID")) : 148;
+    const int prepare_nl = (prep_nl_env == 8 || prep_nl_env == 32) ? prep_nl_env : 1;
+    if (a.prepare) {                                    // kept small: it shares the GPU with rs_step
+        need = (a.n_env + kBlock / prepare_nl - 1) / (kBlock / prepare_nl);
+        cap = prep_grid_env;
     }
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
@@ -405,8 +407,8 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
         cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count);
-    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count);
+    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);
+    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);
     return (int)cudaGetLastError();
 }
 

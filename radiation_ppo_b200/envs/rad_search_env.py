@@ -70,6 +70,23 @@ class _AgentView:
         return bool((int(self._env._aflags[self.id, 0].item()) >> 24) & 1)
 
 
+class HostStepBuffers:
+    """Pinned host memory for RadSearch.step_host (one block for all outputs, plus the action array)."""
+
+    def __init__(self, env: "RadSearch"):
+        self.actions = torch.zeros((env.num_envs, env.number_agents), dtype=torch.int32).pin_memory()
+        self.flat = torch.zeros(env._out_flat.numel(), dtype=torch.uint8).pin_memory()
+        for name, shape, dt, o, nbytes in env._out_layout:
+            setattr(self, name, self.flat[o:o + nbytes].view(dt).view(*shape))
+        self.event = torch.cuda.Event()
+        self.h2d_bytes = self.actions.numel() * 4
+        self.d2h_bytes = self.flat.numel()
+
+    def wait(self) -> "HostStepBuffers":
+        self.event.synchronize()
+        return self
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -217,13 +234,21 @@ class RadSearch:
         self._graphs = {}
         self._act_buf = z(N, A)
         self._ctr_dev_val = 0               # host mirror of *ctr_dev (graph replays advance both)
-        self.obs = z(N, A, L.OBS_DIM, dt=torch.float32)
+        # step outputs: views into ONE flat allocation (256-byte aligned segments) so that a host consumer gets them with
+        # a single device->host copy (step_host)
+        segs = [("obs", (N, A, L.OBS_DIM), torch.float32), ("reward", (N, A), torch.float32),
+                ("team_reward", (N,), torch.float32), ("done_flags", (N, A), torch.uint8),
+                ("info_flags", (N, A), torch.uint8), ("ended", (N,), torch.uint8)]
+        self._out_layout, off = [], 0
+        for name, shape, dt in segs:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._out_layout.append((name, shape, dt, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._out_flat = torch.zeros(off, dtype=torch.uint8, device=dev)
+        for name, shape, dt, o, nbytes in self._out_layout:
+            setattr(self, name, self._out_flat[o:o + nbytes].view(dt).view(*shape))
         self.final_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
-        self.reward = z(N, A, dt=torch.float32)
-        self.team_reward = z(N, dt=torch.float32)
-        self.done_flags = z(N, A, dt=torch.uint8)
-        self.info_flags = z(N, A, dt=torch.uint8)
-        self.ended = z(N, dt=torch.uint8)
+        self._host_stream = None
         self.agents = {i: _AgentView(self, i) for i in range(A)}
         self.reset()
 
@@ -289,12 +314,12 @@ class RadSearch:
         return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
 
     # ---- prefetch machinery -------------------------------------------------------------------------------------
-    # Steps are grouped in blocks of PREFETCH_PERIOD; the envs that adopt their prefetched episode during block b are
+    # Steps are grouped in blocks of PREFETCH_PERIOD (4: one rs_prepare launch must finish within a block); the envs that adopt their prefetched episode during block b are
     # appended to refill list b & 1, and one rs_prepare launch (one thread per env: throughput, not latency) drains that
     # list on a high-priority side stream while block b+1 runs.  An episode lasts >= 9 steps (source and detector
     # start >= 1000 apart, a step is <= 100.4, the goal radius is 110), so the next scenario is back in place in time;
     # if it ever is not, the env simply takes the synchronous reset path -- the resulting state is the same.
-    PREFETCH_PERIOD = int(__import__('os').environ.get('RS_PERIOD', '3'))
+    PREFETCH_PERIOD = int(__import__('os').environ.get('RS_PERIOD', '4'))
 
     def _quiesce_prefetch(self) -> None:
         """Make the main stream wait for any rs_prepare in flight and forget pending refill lists (the envs in them
@@ -350,7 +375,8 @@ class RadSearch:
                     main.wait_event(self._ev_side[p])
                     self._inflight[p] = False
             if self.use_cuda_graph:
-                self._act_buf.copy_(a)
+                if a.data_ptr() != self._act_buf.data_ptr():             # the caller may fill action_buffer in place
+                    self._act_buf.copy_(a)
                 key = (p, first)
                 g = self._graphs.get(key)
                 if g is None:
@@ -389,6 +415,34 @@ class RadSearch:
                 L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")
         self._ctr_dev_val = -1                           # capture does not execute; force a refresh before the replay
         return g
+
+    # ---- host-facing step: pinned host buffers in and out, asynchronous ------------------------------------------------
+    def host_buffers(self) -> "HostStepBuffers":
+        """Pinned host buffers for step_host: `.actions` int32 [N, A] to fill, and the step outputs as views of one
+        pinned block (`.obs`, `.reward`, `.team_reward`, `.done_flags`, `.info_flags`, `.ended`)."""
+        return HostStepBuffers(self)
+
+    def step_host(self, hb: "HostStepBuffers", epoch_end: bool = False,
+                  actions: Optional[torch.Tensor] = None) -> "HostStepBuffers":
+        """One step driven from the host: copies hb.actions host->device, runs the step (+ auto-reset), copies all step
+        outputs device->host in ONE transfer into hb, all asynchronously on this env's own stream; `hb.wait()` blocks
+        until the results are in host memory (`actions`: another pinned int32 [N, A] tensor to send instead of
+        hb.actions).  Independent env batches stepped this way overlap their copies with each
+        other's kernels (the copy engines and the SMs work concurrently)."""
+        if self._host_stream is None:
+            self._host_stream = torch.cuda.Stream(device=self.device)
+            self._host_stream.wait_stream(torch.cuda.current_stream(self.device))
+        h_act = hb.actions if actions is None else actions.reshape(self.num_envs, self.number_agents)
+        with torch.cuda.stream(self._host_stream):
+            if self.use_cuda_graph and self.auto_reset and not epoch_end:
+                self._act_buf.copy_(h_act, non_blocking=True)            # straight into the captured graph's action buffer
+                acts = self._act_buf
+            else:
+                acts = h_act.to(self.device, non_blocking=True)
+            self.step_batch(acts, epoch_end=epoch_end)
+            hb.flat.copy_(self._out_flat, non_blocking=True)
+            hb.event.record(self._host_stream)
+        return hb
 
     def load_scenarios(self, src, det, intensity, bkg, rects=None, num_obs=None,
                        uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -434,6 +488,12 @@ class RadSearch:
     # ------------------------------------------------------------------------------------------------------------
     # state views
     # ------------------------------------------------------------------------------------------------------------
+    @property
+    def action_buffer(self) -> torch.Tensor:
+        """int32 [N, A] device buffer the captured step graph reads its actions from: a policy that writes its sampled
+        actions here and passes this tensor to step_batch saves the device-to-device copy."""
+        return self._act_buf
+
     @property
     def status(self) -> torch.Tensor:
         return self._status

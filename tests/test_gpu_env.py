@@ -326,3 +326,28 @@ def test_prefetched_resets_match_oracle(graph):
     env.reset()
     ob.reset()
     pu.compare_state(pu.GpuView(env), ob, A)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_step_host_matches_step_batch(graph):
+    """RadSearch.step_host (pinned host actions in, one packed device->host copy out, the env's own stream) gives the
+    results of step_batch, also with several env batches in flight."""
+    n, T = 640, 40
+    kw = dict(obstruction_count=5, enforce_grid_boundaries=True, num_envs=n, seed=5, auto_reset=True,
+              steps_per_episode=25, prefetch=graph, use_cuda_graph=graph)
+    ref = [rp.RadSearch(env_id_offset=r * n, **kw) for r in range(2)]
+    hst = [rp.RadSearch(env_id_offset=r * n, **kw) for r in range(2)]
+    hbs = [e.host_buffers() for e in hst]
+    rng = np.random.default_rng(3)
+    acts = rng.integers(0, 8, size=(T, 2, n, 1)).astype(np.int32)
+    for t in range(T):
+        for r in range(2):
+            hbs[r].wait()
+            hbs[r].actions.copy_(torch.as_tensor(acts[t, r]))
+            hst[r].step_host(hbs[r])
+        for r in range(2):
+            ref[r].step_batch(torch.as_tensor(acts[t, r], device=ref[r].device))
+            hb = hbs[r].wait()
+            for name in ("obs", "reward", "team_reward", "done_flags", "info_flags", "ended"):
+                np.testing.assert_array_equal(getattr(hb, name).numpy(), getattr(ref[r], name).cpu().numpy(), err_msg=name)
+    assert hbs[0].d2h_bytes >= n * (44 + 4 + 4 + 3) and hbs[0].h2d_bytes == n * 4
