@@ -31,6 +31,17 @@ GAE_BYTES_PER_ELEM = 17                      # rew 4 + val 4 + p
 T_EPOCH = 480
 
 
+def measured_traffic(kernel: str, n_env: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        if t.get("n_env", t.get("N")) == n_env:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,11 +314,13 @@ def main():
                        "launch": "CUDA graph replay" if not (args.no_graph or args.no_prefetch) else "stream launches",
                        "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic("step_kernel", N), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * N,
                          "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_ms,
                          "kernel_env_steps_per_s": N / (k_ms / 1e3)},
             "gae": {"T": T, "N": N, "ms": gae_ms, "achieved": gae_gbs, "peak": peak, "unit": "GB/s", "frac": gae_gbs / peak,
-                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>"},
+                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>",
+                    "traffic": measured_traffic("gae_cols_kernel", N) if T == 480 else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "sync_value": e2e_vals["sync"],
                     "note": f"RadSearch.step_host: pinned host actions -> device, step+reset, all outputs (obs, rewards, "
