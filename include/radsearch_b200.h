@@ -15,6 +15,11 @@
  *   rs_load_scenarios  R:799-874   RadSearch.refresh_environment
  *   rs_gae             P:391-423   PPOBuffer.GAE_advantage_and_rewardsToGO (discount_cumsum P:62-85)
  *   rs_adv_normalize   P:445-446   advantage normalisation in PPOBuffer.get (statistics: mpi_tools.py:71-95)
+ *   RsConfig.standardize           per-episode running z-score of the count channel, fused into rs_step / rs_reset:
+ *                                  StatisticStandardization.update/standardize (algos/multiagent/NeuralNetworkCores/
+ *                                  RADTEAM_core.py:188-277) in the call order of train.py:305-311, 333-341, 436, 469, 509, 548;
+ *                                  mode 2 = StatBuff (algos/test_environment/core.py:55-79) + clip to [-8, 8]
+ *                                  (algos/test_environment/ppo.py:502, 518)
  */
 #ifndef RADSEARCH_B200_H
 #define RADSEARCH_B200_H
@@ -24,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RS_VERSION 1
+#define RS_VERSION 2
 #define RS_OBS_DIM 11            /* [count, x/2200, y/2200, 8 proximity sensors]            R:591-593 */
 #define RS_MAX_K 8               /* obstruction slots (env allows 0..7)                     R:317     */
 #define RS_MAX_A 8               /* agents per environment                                            */
@@ -73,6 +78,10 @@ typedef struct RsConfig {
     int32_t count_law;           /* 0 = reference (intensity/distance + bkg, R:498-502), 1 = inverse square     */
     int32_t max_ep_len;          /* steps_per_episode                           default 120           T:394     */
     int32_t k_max;               /* obstruction slots allocated in RsState (>= max num_obs)                     */
+    int32_t standardize;         /* 0 off; 1: obs[..][0] = (count - mean) / max(std, 1) with the per-episode running   */
+                                 /* (Welford) sample statistics that include this reading (RADTEAM_core.py:215-265);   */
+                                 /* 2: StatBuff rule (std == 0 -> 1) and the value clipped to [-8, 8].  Needs          */
+                                 /* RsState.st_mean / st_m2; the raw count goes to RsState.raw_count when not NULL.     */
 } RsConfig;
 
 /* Structure-of-arrays environment state in HBM; N = envs on this rank, A = n_agents, K = k_max.  All device pointers. */
@@ -102,6 +111,11 @@ typedef struct RsState {
     int32_t *refill_list;        /* [2][N]    envs whose prefetched scenario was consumed (two lists, ping-pong)   */
     int32_t *refill_count;       /* [2]                                                                           */
     uint64_t *ctr_dev;           /* [1]       device-side step counter (RS_F_DEVICE_CTR)                           */
+    /* per-episode running statistics of the count channel (optional, RsConfig.standardize != 0; NULL otherwise).      */
+    /* The number of readings seen is meta.ep_len + 1 (the reset observation, then one per step).                       */
+    double *st_mean;             /* [A][N]    running mean                                RADTEAM_core.py:198         */
+    double *st_m2;               /* [A][N]    aggregated squared distance from the mean   RADTEAM_core.py:200         */
+    float *raw_count;            /* [N][A]    the unstandardised count of the last observation (output, nullable)     */
 } RsState;
 
 /* One environment step for n_env environments (all agents).  actions[N][A] in 0..8 (8 = idle), or NULL for the

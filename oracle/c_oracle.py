@@ -221,6 +221,47 @@ class OracleBatch:
         return out
 
 
+class Stat(C.Structure):
+    _fields_ = [("mean", C.c_double), ("m2", C.c_double), ("std", C.c_double), ("count", C.c_int32)]
+
+
+class Standardizer:
+    """[n] independent running standardisers (RADTEAM_core.py:188-277 mode 1, test_environment StatBuff + clip mode 2)
+    driven the way train.py drives them: update(x) then standardize(x); reset(mask) at episode ends."""
+
+    def __init__(self, n: int, mode: int = 1):
+        self.n, self.mode = int(n), int(mode)
+        self.s = (Stat * self.n)()
+        self.reset()
+
+    def reset(self, mask=None):
+        for i in range(self.n):
+            if mask is None or mask[i]:
+                lib().orc_stat_reset(C.byref(self.s[i]))
+
+    def update_standardize(self, x, mask=None) -> np.ndarray:
+        f = lib().orc_stat_update_standardize
+        f.restype = C.c_double
+        x = np.asarray(x, np.float64).reshape(self.n)
+        z = np.zeros(self.n)
+        for i in range(self.n):
+            if mask is None or mask[i]:
+                z[i] = f(C.byref(self.s[i]), C.c_double(float(x[i])), C.c_int32(self.mode))
+        return z
+
+    @property
+    def mean(self):
+        return np.array([s.mean for s in self.s])
+
+    @property
+    def m2(self):
+        return np.array([s.m2 for s in self.s])
+
+    @property
+    def std(self):
+        return np.array([s.std for s in self.s])
+
+
 def gae(rew, val, path_end, boot, gamma=0.99, lam=0.90, threads=0):
     """Batched P:391-423 over [T, N] float32 arrays -> (adv, ret) float32."""
     rew = np.ascontiguousarray(rew, dtype=np.float32)

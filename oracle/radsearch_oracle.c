@@ -783,5 +783,32 @@ void orc_gae(const float *rew, const float *val, const uint8_t *path_end, const 
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Per-episode running standardisation of the count channel.                                                       */
+/* mode 1: StatisticStandardization.update then .standardize (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py   */
+/*         :215-265): Welford mean / M2, sample variance M2/(count-1), std = max(sqrt(var), 1).                      */
+/* mode 2: StatBuff.update (algos/test_environment/core.py:62-73): same recurrence, sig_obs = sqrt(var) with 0 -> 1, */
+/*         and the caller's np.clip((o - mu)/sig_obs, -8, 8) (algos/test_environment/ppo.py:502).                    */
+/* s = {mean, M2, std, count}; returns the z-score of x after the update.                                            */
+/* ------------------------------------------------------------------------------------------------------------ */
+double orc_stat_update_standardize(OrcStat *s, double x, int32_t mode) {
+    s->count += 1;
+    if (s->count == 1) {
+        s->mean = x;                                                       /* :236-238 (M2, std keep their defaults) */
+    } else {
+        double mean_new = s->mean + (x - s->mean) / (double)s->count;      /* :240 */
+        double m2_new = s->m2 + (x - s->mean) * (x - mean_new);            /* :241-243 */
+        s->mean = mean_new;
+        s->m2 = m2_new;
+        double sd = sqrt(m2_new / (double)(s->count - 1));                 /* :246-247 */
+        if (mode == 2) s->std = (sd == 0.0) ? 1.0 : sd;                    /* core.py:70-72 */
+        else s->std = sd > 1.0 ? sd : 1.0;                                 /* :247 max(sqrt(var), 1) */
+    }
+    double z = (x - s->mean) / s->std;                                     /* :265 */
+    if (mode == 2) z = z < -8.0 ? -8.0 : (z > 8.0 ? 8.0 : z);
+    return z;
+}
+void orc_stat_reset(OrcStat *s) { s->mean = 0.0; s->m2 = 0.0; s->std = 1.0; s->count = 0; }   /* :274-276 */
+
 int32_t orc_sizeof_env(void) { return (int32_t)sizeof(OrcEnv); }
 int32_t orc_sizeof_out(void) { return (int32_t)sizeof(OrcStepOut); }

@@ -117,6 +117,14 @@ int64_t orc_rollout(const OrcConfig *c, OrcEnv *envs, int32_t n, int32_t T, uint
 
 void orc_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
              int32_t T, int32_t N, double gamma, double lam, int32_t threads);
+/* per-episode running standardiser of the count channel (RADTEAM_core.py:188-277 / test_environment/core.py:55-79) */
+typedef struct {
+    double mean, m2, std;
+    int32_t count;
+} OrcStat;
+double orc_stat_update_standardize(OrcStat *s, double x, int32_t mode /* 1 RAD-TEAM rule, 2 StatBuff + clip 8 */);
+void orc_stat_reset(OrcStat *s);
+
 int32_t orc_sizeof_env(void);
 int32_t orc_sizeof_out(void);
 

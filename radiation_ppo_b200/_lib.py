@@ -31,6 +31,7 @@ class RsConfig(C.Structure):
         ("count_law", C.c_int32),
         ("max_ep_len", C.c_int32),
         ("k_max", C.c_int32),
+        ("standardize", C.c_int32),
     ]
 
 
@@ -38,7 +39,7 @@ class RsState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count",
         "epi", "nx_src", "nx_det", "nx_rad", "nx_best", "nx_dsrc", "nx_obs", "nx_seq", "refill_list", "refill_count",
-        "ctr_dev")]
+        "ctr_dev", "st_mean", "st_m2", "raw_count")]
 
 
 class RadSearchLibraryError(RuntimeError):

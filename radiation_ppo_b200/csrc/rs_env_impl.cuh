@@ -17,7 +17,7 @@ struct Params {
     int bx0, by0, bx1, by1;       // bbox
     int sx0, sy0, sx1, sy1;       // search area R:393-420
     int lo, hi;                   // observation_area
-    int enforce, n_agents, obstruction_count, count_law, max_ep_len, k_max;
+    int enforce, n_agents, obstruction_count, count_law, max_ep_len, k_max, standardize;
     double max_dist;              // R:423-425
     double inv_scale;             // 1 / search_area[2][1]  R:435
 };
@@ -29,6 +29,7 @@ __host__ __device__ inline Params make_params(const RsConfig &c) {
     p.sx0 = p.bx0 + p.lo; p.sy0 = p.by0 + p.lo; p.sx1 = p.bx1 - p.hi; p.sy1 = p.by1 - p.hi;
     p.enforce = c.enforce; p.n_agents = c.n_agents; p.obstruction_count = c.obstruction_count;
     p.count_law = c.count_law; p.max_ep_len = c.max_ep_len; p.k_max = c.k_max;
+    p.standardize = c.standardize;
     const double dy = (double)(p.sy1 - p.sy0);
     p.max_dist = sqrt(dy * dy);
     p.inv_scale = 1.0 / (double)p.sy1;
@@ -380,6 +381,32 @@ __device__ __forceinline__ void observe(const Params &P, const EnvView &e, int p
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Per-episode running standardisation of the count channel (RsConfig.standardize):
+// StatisticStandardization.update + standardize (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py:215-265) in the
+// caller's order (train.py:311, 339, 436, 469, 548: update with a reading, then standardize that same reading);
+// mode 2 = StatBuff.update (algos/test_environment/core.py:62-73) and np.clip(z, -8, 8) (test_environment/ppo.py:502).
+// n = number of readings of the episode including x; update == false only standardizes (step(None) probe).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double stat_std(int mode, int n, double m2) {
+    if (n <= 1) return 1.0;                                              // defaults after reset(): std = 1
+    const double sd = sqrt(m2 / (double)(n - 1));                        // sample variance
+    return mode == 2 ? (sd == 0.0 ? 1.0 : sd) : fmax(sd, 1.0);
+}
+__device__ __forceinline__ double stat_standardize(int mode, int n, double x, double &mean, double &m2, bool update) {
+    if (update) {
+        if (n <= 1) { mean = x; m2 = 0.0; }
+        else {
+            const double mean_new = mean + (x - mean) / (double)n;
+            m2 = m2 + (x - mean) * (x - mean_new);
+            mean = mean_new;
+        }
+    }
+    double z = (x - mean) / stat_std(mode, n, m2);
+    if (mode == 2) z = fmin(fmax(z, -8.0), 8.0);
+    return z;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // RadSearch.step R:443-728 for one environment (all agents), plus the caller rules T:394-405 when auto-reset is on
 // ---------------------------------------------------------------------------------------------------------------
 struct StepArgs {
@@ -554,9 +581,15 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
                     float row[RS_OBS_DIM];
 #pragma unroll
                     for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[ag * RS_OBS_DIM + i];
+                    const size_t ia = (size_t)ag * N + n;
+                    if (P.standardize) {                                   // first reading of the episode: z = 0
+                        S.st_mean[ia] = (double)row[0];
+                        S.st_m2[ia] = 0.0;
+                        if (S.raw_count) S.raw_count[(size_t)n * A + ag] = row[0];
+                        row[0] = 0.0f;
+                    }
 #pragma unroll
                     for (int i = 0; i < RS_OBS_DIM; i++) dst[ag * RS_OBS_DIM + i] = row[i];
-                    const size_t ia = (size_t)ag * N + n;
                     reinterpret_cast<int2 *>(S.det)[ia] = d0;
                     S.best[ia] = b0;
                     S.aflags[ia] = 0;
@@ -703,6 +736,12 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
                 reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
                 S.best[ia] = sp;
                 S.aflags[ia] = 0;                                        // Agent.reset R:289-300
+                if (P.standardize) {                                     // stat_buffers[id].reset(); .update(obs[0])
+                    S.st_mean[ia] = (double)row[0];                      // T:509, 548: first reading, z = 0
+                    S.st_m2[ia] = 0.0;
+                    if (S.raw_count) S.raw_count[(size_t)n * A + ag] = row[0];
+                    row[0] = 0.0f;
+                }
             }
 #pragma unroll
             for (int i = 0; i < RS_OBS_DIM; i++) obs_out[((size_t)n * A + ag) * RS_OBS_DIM + i] = row[i];

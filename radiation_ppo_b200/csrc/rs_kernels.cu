@@ -64,8 +64,10 @@ struct RowDesc {
     uint32_t valid;     // bytes of this tile's row (partial last tile)
 };
 
-// state rows read by the step: 0 src, 1 rad, 2 meta, 3 actions, 4.. rects[k], then det / best / aflags per agent
-__device__ __forceinline__ int n_rows_in(const rs::Tile &T) { return 4 + T.K + 3 * T.A; }
+// state rows read by the step: 0 src, 1 rad, 2 meta, 3 actions, 4.. rects[k], then det / best / aflags (/ running
+// count statistics when RsConfig.standardize) per agent
+__device__ __forceinline__ int rows_per_agent(const rs::Tile &T) { return T.stm ? 5 : 3; }
+__device__ __forceinline__ int n_rows_in(const rs::Tile &T) { return 4 + T.K + rows_per_agent(T) * T.A; }
 __device__ __forceinline__ RowDesc row_in(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
                                           int valid) {
     const int E = T.E, A = T.A, K = T.K;
@@ -82,17 +84,20 @@ __device__ __forceinline__ RowDesc row_in(const rs::Tile &T, const RsState &S, c
         const int k = i - 4;
         r = RowDesc{T.rects + k * E, S.rects + ((size_t)k * N + n0) * 4, (uint32_t)E * 16u, (uint32_t)valid * 16u};
     } else {
-        const int j = i - 4 - K, ag = j / 3, w = j - 3 * ag;
+        const int rpa = rows_per_agent(T), j = i - 4 - K, ag = j / rpa, w = j - rpa * ag;
         const size_t off = (size_t)ag * N + n0;
         if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
         else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-        else r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+        else if (w == 2) r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+        else if (w == 3) r = RowDesc{T.stm + ag * E, S.st_mean + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+        else r = RowDesc{T.stq + ag * E, S.st_m2 + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
     }
     return r;
 }
 
-// rows written by the step: 0 meta, 1 obs, 2 reward, 3 team_reward, 4 done, 5 info, 6 ended, then det / best / aflags
-__device__ __forceinline__ int n_rows_out(const rs::Tile &T) { return 7 + 3 * T.A; }
+// rows written by the step: 0 meta, 1 obs, 2 reward, 3 team_reward, 4 done, 5 info, 6 ended, 7 raw counts, then
+// det / best / aflags (/ running count statistics) per agent
+__device__ __forceinline__ int n_rows_out(const rs::Tile &T) { return 8 + rows_per_agent(T) * T.A; }
 __device__ __forceinline__ RowDesc row_out(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
                                            int valid) {
     const int E = T.E, A = T.A;
@@ -107,12 +112,15 @@ __device__ __forceinline__ RowDesc row_out(const rs::Tile &T, const RsState &S, 
         case 4: if (a.done) r = RowDesc{T.done, a.done + (size_t)n0 * A, uE, uV}; break;
         case 5: if (a.info) r = RowDesc{T.info, a.info + (size_t)n0 * A, uE, uV}; break;
         case 6: if (a.ended) r = RowDesc{T.ended, a.ended + n0, (uint32_t)E, (uint32_t)valid}; break;
+        case 7: if (T.raw && S.raw_count) r = RowDesc{T.raw, S.raw_count + (size_t)n0 * A, uE * 4u, uV * 4u}; break;
         default: {
-            const int j = i - 7, ag = j / 3, w = j - 3 * ag;
+            const int rpa = rows_per_agent(T), j = i - 8, ag = j / rpa, w = j - rpa * ag;
             const size_t off = (size_t)ag * N + n0;
             if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
             else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-            else r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+            else if (w == 2) r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
+            else if (w == 3) r = RowDesc{T.stm + ag * E, S.st_mean + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
+            else r = RowDesc{T.stq + ag * E, S.st_m2 + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
         }
     }
     return r;
@@ -318,6 +326,8 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
     if (!st->src || !st->rad || !st->meta || !st->det || !st->best || !st->aflags || !st->status || !st->epi)
         return fail("RsState has NULL members");
     if (cfg->k_max > 0 && (!st->rects || !st->dsrc || !st->vis)) return fail("RsState obstruction tables are NULL");
+    if (cfg->standardize < 0 || cfg->standardize > 2) return fail("standardize must be 0, 1 or 2");
+    if (cfg->standardize && (!st->st_mean || !st->st_m2)) return fail("standardize needs RsState.st_mean / st_m2");
     return 0;
 }
 
@@ -361,16 +371,18 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags; a.parity = parity;
     const int E = step_tile_envs(cfg->n_agents), A = cfg->n_agents, K = cfg->k_max;
     const int grid = (n_env + E - 1) / E;
-    const rs::TileLayout L = rs::make_layout(E, A, K, kBlock);
+    const rs::TileLayout L = rs::make_layout(E, A, K, kBlock, cfg->standardize);
     const size_t smem = (size_t)L.total;
     // bytes of one full tile's state rows (what the bulk copies of a CTA deliver to its mbarrier)
-    const uint32_t tx_bytes = (uint32_t)(E * (8 + 8 + 4) + (actions ? E * A * 4 : 0) + K * E * 16 + A * E * (8 + 8 + 4));
+    const uint32_t tx_bytes = (uint32_t)(E * (8 + 8 + 4) + (actions ? E * A * 4 : 0) + K * E * 16 + A * E * (8 + 8 + 4) +
+                                         (cfg->standardize ? A * E * 16 : 0));
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
     // bulk-async tile copies need 16-byte aligned rows: every array base (the tile offsets are multiples of 32 elements)
     const int bulk_ok = aligned16(st->src) && aligned16(st->rad) && aligned16(st->rects) && aligned16(st->meta) &&
                         aligned16(st->det) && aligned16(st->best) && aligned16(st->aflags) && aligned16(actions) &&
                         aligned16(obs) && aligned16(reward) && aligned16(team_reward) && aligned16(done) &&
-                        aligned16(info) && aligned16(ended) &&
+                        aligned16(info) && aligned16(ended) && aligned16(st->st_mean) && aligned16(st->st_m2) &&
+                        aligned16(st->raw_count) &&
                         (cfg->n_agents == 1 || n_env % 4 == 0);        // per-agent rows start at multiples of N elements
     static const int occ_env = getenv("RS_STEP_OCC") ? atoi(getenv("RS_STEP_OCC")) : 0;      // tuning switch
 #define RS_LAUNCH_STEP(FAST, TE, OCC)                                                                               \

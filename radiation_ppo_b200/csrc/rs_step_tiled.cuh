@@ -34,6 +34,7 @@ struct Tile {
     int2 *det;            // [A][E]
     double *best;         // [A][E]
     int *af;              // [A][E]
+    double *stm, *stq;    // [A][E]   running mean / squared distance of the count channel (nullptr: standardize off)
     const int *act;       // [E][A]   (nullptr: step(None) probe)
     // output rows (global layout of the tile)
     float *obs;           // [E][A][11]
@@ -41,6 +42,7 @@ struct Tile {
     float *team;          // [E]
     uint8_t *done, *info; // [E][A]
     uint8_t *ended;       // [E]
+    float *raw;           // [E][A]   unstandardised counts (standardize on)
     // per-unit scratch
     int2 *ndet;           // [U] position after take_action (committed by phase_commit: other agents' proposals are
                           //     computed from the old positions, R:645-648)
@@ -50,12 +52,12 @@ struct Tile {
 
 struct TileLayout {       // byte offsets of the arrays above inside the CTA's dynamic shared memory (all 16-aligned)
     int rects, src, rad, meta, det, best, af, act, obs, reward, team, done, info, ended, ndet, sp, uflag, lists,
-        counters, mbar, total;
+        counters, mbar, stm, stq, raw, total;
 };
 
 __host__ __device__ inline int align16(int v) { return (v + 15) & ~15; }
 
-__host__ __device__ inline TileLayout make_layout(int E, int A, int K, int threads) {
+__host__ __device__ inline TileLayout make_layout(int E, int A, int K, int threads, int standardize = 0) {
     TileLayout L;
     const int U = E * A;
     int o = 0;
@@ -79,6 +81,12 @@ __host__ __device__ inline TileLayout make_layout(int E, int A, int K, int threa
     L.lists = o;   o += align16(3 * U * 2);
     L.counters = o; o += 16;
     L.mbar = o;    o += 16;
+    L.stm = L.stq = L.raw = -1;                   // the default configuration keeps its footprint (8 CTAs per SM)
+    if (standardize) {
+        L.stm = o; o += align16(U * 8);
+        L.stq = o; o += align16(U * 8);
+        L.raw = o; o += align16(U * 4);
+    }
     L.total = o;
     return L;
 }
@@ -103,6 +111,9 @@ __host__ __device__ inline Tile carve_tile(unsigned char *base, const TileLayout
     T.ndet = reinterpret_cast<int2 *>(base + L.ndet);
     T.sp = reinterpret_cast<double *>(base + L.sp);
     T.uflag = reinterpret_cast<int *>(base + L.uflag);
+    T.stm = L.stm >= 0 ? reinterpret_cast<double *>(base + L.stm) : nullptr;
+    T.stq = L.stq >= 0 ? reinterpret_cast<double *>(base + L.stq) : nullptr;
+    T.raw = L.raw >= 0 ? reinterpret_cast<float *>(base + L.raw) : nullptr;
     return T;
 }
 
@@ -321,6 +332,13 @@ __device__ __forceinline__ bool phase_commit(const Params &P, const RsState &S, 
             blocked_los = blocked_los && !isclose_quirk(euc, sp);
             const double lam = unit_lambda(P, e, euc, blocked_los, status);
             row[0] = (float)unit_count<kFast>(a, n, A, ag, step_ctr, lam, status);
+        }
+        if (T.stm) {                                                    // T:436 update(next_obs[0]), T:339/469 standardize
+            const float x = row[0];
+            T.raw[t * A + ag] = x;
+            // readings of the episode so far: the reset observation + one per step (this one included)
+            row[0] = (float)stat_standardize(P.standardize, ep_len + (T.act ? 2 : 1), (double)x, T.stm[u], T.stq[u],
+                                             T.act != nullptr);
         }
         if (P.enforce) sensors_walls(P, det.x, det.y, row + 3, status);  // R:1232-1259
         int info = (uf & UF_COLLISION ? RS_I_COLLISION : 0) | (uf & UF_OOB ? RS_I_OOB : 0) |

@@ -103,7 +103,11 @@ class RadSearch:
     ``prefetch`` (with auto_reset: the next episode of every env is prepared ahead of time by ``rs_prepare`` on a side
     stream, so a finished env adopts it inside the step kernel instead of waiting for a reset kernel; results are
     identical either way), ``use_cuda_graph`` (with prefetch: the step / reset / prepare launches are captured once
-    and replayed; the Philox step counter then lives on the device).
+    and replayed; the Philox step counter then lives on the device), ``standardize`` (0 off; 1 / "radteam": the count
+    channel obs[..., 0] is replaced by its per-episode running z-score, StatisticStandardization of
+    RADTEAM_core.py:188-277 applied in train.py's order -- update(reading) then standardize(reading), reset with the
+    episode; 2 / "statbuff": the older StatBuff rule of algos/test_environment/core.py:55-79 with the clip to [-8, 8];
+    the unstandardised counts stay available as ``raw_count``).
     """
 
     metadata = {"render.modes": ["human"], "video.frames_per_second": 5}
@@ -131,6 +135,7 @@ class RadSearch:
         k_max: Optional[int] = None,
         prefetch: bool = False,
         use_cuda_graph: bool = False,
+        standardize: Union[int, str] = 0,
     ) -> None:
         if DEBUG:
             raise NotImplementedError("the reference's DEBUG hard-codes (R:373-378, 782-784) are not reproduced")
@@ -171,6 +176,11 @@ class RadSearch:
         if k_max is None:
             k_max = 5 if self.obstruction_count == -1 else max(self.obstruction_count, 0)
         cfg.k_max = int(k_max)
+        self.standardize = {"radteam": 1, "statbuff": 2}.get(standardize, standardize) if isinstance(standardize, str) \
+            else int(standardize)
+        if self.standardize not in (0, 1, 2):
+            raise ValueError("standardize must be 0, 1 ('radteam') or 2 ('statbuff')")
+        cfg.standardize = self.standardize
         self._cfg = cfg
 
         b0x, b0y, b1x, b1y = cfg.bbox[0], cfg.bbox[1], cfg.bbox[2], cfg.bbox[3]
@@ -224,6 +234,13 @@ class RadSearch:
             ptrs += [None] * 9
         self._ctr_dev = z(1, dt=torch.int64)
         ptrs.append(self._ctr_dev)
+        if self.standardize:
+            self._st_mean, self._st_m2 = z(A, N, dt=torch.float64), z(A, N, dt=torch.float64)
+            self.raw_count = z(N, A, dt=torch.float32)
+            ptrs += [self._st_mean, self._st_m2, self.raw_count]
+        else:
+            self._st_mean = self._st_m2 = self.raw_count = None
+            ptrs += [None] * 3
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
         self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
         self._side = torch.cuda.Stream(device=dev, priority=int(__import__('os').environ.get('RS_SIDE_PRIO', '-1'))) if self.prefetch else None

@@ -41,7 +41,7 @@ def emu():
 
 
 def make_config(n_agents=1, obstruction_count=5, enforce=True, k_max=None, max_ep_len=120, count_law=0,
-                bbox=(0, 0, 2700, 2700), obs_area=(200, 500)):
+                bbox=(0, 0, 2700, 2700), obs_area=(200, 500), standardize=0):
     c = L.RsConfig()
     for i, v in enumerate(bbox):
         c.bbox[i] = v
@@ -52,6 +52,7 @@ def make_config(n_agents=1, obstruction_count=5, enforce=True, k_max=None, max_e
     c.count_law = count_law
     c.max_ep_len = max_ep_len
     c.k_max = k_max if k_max is not None else (5 if obstruction_count == -1 else max(obstruction_count, 0))
+    c.standardize = standardize
     return c
 
 
@@ -87,6 +88,9 @@ class EmuEnv:
         self.refill_list = np.zeros((2, n), np.int32)
         self.refill_count = np.zeros(2, np.int32)
         self.ctr_dev = np.zeros(1, np.uint64)
+        self.st_mean = np.zeros((A, n), np.float64)
+        self.st_m2 = np.zeros((A, n), np.float64)
+        self.raw_count = np.zeros((n, A), np.float32)
         self.st = L.RsState(*[_vp(getattr(self, f)) for f, _ in L.RsState._fields_])
         self.obs = np.zeros((n, A, 11), np.float32)
         self.final_obs = np.zeros((n, A, 11), np.float32)

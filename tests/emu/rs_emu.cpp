@@ -21,7 +21,7 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
     // one-environment tiles (E = 1): copy the state rows in, run the phases in the kernel's order, copy the rows out
     const int A = cfg->n_agents, K = cfg->k_max, N = n_env;
-    const rs::TileLayout L = rs::make_layout(1, A, K, 1);
+    const rs::TileLayout L = rs::make_layout(1, A, K, 1, cfg->standardize);
     std::vector<unsigned char> buf(L.total + 16);
     unsigned char *base = buf.data() + ((16 - (reinterpret_cast<uintptr_t>(buf.data()) & 15)) & 15);
     rs::Tile T = rs::carve_tile(base, L, 1, A, K, actions != nullptr);
@@ -35,6 +35,7 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
             T.det[ag] = reinterpret_cast<const int2 *>(st->det)[(size_t)ag * N + n];
             T.best[ag] = st->best[(size_t)ag * N + n];
             T.af[ag] = st->aflags[(size_t)ag * N + n];
+            if (T.stm) { T.stm[ag] = st->st_mean[(size_t)ag * N + n]; T.stq[ag] = st->st_m2[(size_t)ag * N + n]; }
             if (actions) const_cast<int *>(T.act)[ag] = actions[(size_t)n * A + ag];
         }
         for (int u = 0; u < A; u++) {
@@ -58,6 +59,11 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
             reinterpret_cast<int2 *>(st->det)[(size_t)ag * N + n] = T.det[ag];
             st->best[(size_t)ag * N + n] = T.best[ag];
             st->aflags[(size_t)ag * N + n] = T.af[ag];
+            if (T.stm) {
+                st->st_mean[(size_t)ag * N + n] = T.stm[ag];
+                st->st_m2[(size_t)ag * N + n] = T.stq[ag];
+                if (st->raw_count) st->raw_count[(size_t)n * A + ag] = T.raw[ag];
+            }
             for (int i = 0; i < RS_OBS_DIM; i++) obs[((size_t)n * A + ag) * RS_OBS_DIM + i] = T.obs[ag * RS_OBS_DIM + i];
             if (reward) reward[(size_t)n * A + ag] = T.reward[ag];
             if (done) done[(size_t)n * A + ag] = T.done[ag];

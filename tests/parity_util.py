@@ -177,3 +177,29 @@ class GpuView:
         self.num_obs = self.meta & 0xFF
         self.env_done = (self.meta >> 8) & 1
         self.ep_len = self.meta >> 16
+
+
+class StandardizedOracle:
+    """The caller-side standardisation of train.py (RAD-A2C branch) around an OracleBatch: one running standardiser per
+    (env, agent), `update(reading)` then `standardize(reading)` for the reset observation (T:311, 548) and for every
+    next observation (T:436, 339, 469), `reset()` with the episode (T:509).  z holds the standardised count channel
+    of the current observation, final_z the one of the last observation of an episode that just ended."""
+
+    def __init__(self, ob, mode):
+        self.ob, self.A, self.mode = ob, ob.A, mode
+        self.st = co.Standardizer(ob.n * ob.A, mode)
+        self.z = np.zeros((ob.n, ob.A))
+
+    def _mask(self, env_mask):
+        return None if env_mask is None else np.repeat(np.asarray(env_mask, bool), self.A)
+
+    def after_reset(self, env_mask=None):
+        m = self._mask(env_mask)
+        self.st.reset(m)
+        z = self.st.update_standardize(self.ob.outs["obs"][:, :self.A, 0].reshape(-1), m).reshape(self.ob.n, self.A)
+        self.z = z if env_mask is None else np.where(np.asarray(env_mask, bool)[:, None], z, self.z)
+        return self.z
+
+    def after_step(self):
+        self.z = self.st.update_standardize(self.ob.outs["obs"][:, :self.A, 0].reshape(-1)).reshape(self.ob.n, self.A)
+        return self.z

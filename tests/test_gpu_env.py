@@ -351,3 +351,41 @@ def test_step_host_matches_step_batch(graph):
             for name in ("obs", "reward", "team_reward", "done_flags", "info_flags", "ended"):
                 np.testing.assert_array_equal(getattr(hb, name).numpy(), getattr(ref[r], name).cpu().numpy(), err_msg=name)
     assert hbs[0].d2h_bytes >= n * (44 + 4 + 4 + 3) and hbs[0].h2d_bytes == n * 4
+
+
+@pytest.mark.parametrize("mode,A,fast_path", [(1, 1, False), (2, 1, False), (1, 4, False), (1, 1, True)])
+def test_fused_count_standardizer_matches_callers_order(mode, A, fast_path):
+    """RsConfig.standardize: the count channel leaves rs_step / rs_reset as the per-episode running
+    z-score the RAD-A2C caller computes with StatisticStandardization (RADTEAM_core.py:188-277; mode 2: StatBuff of
+    test_environment/core.py:55-79 + clip 8) in train.py's order; the oracle restatement is pinned on the reference
+    classes (tests/golden/ref_standardize.npz).  Bar: the float64 z-score rounded to fp32, bit for bit; running mean and
+    M2 bit for bit; raw counts unchanged.  fast_path = prefetch + CUDA-graph replay (adopted resets)."""
+    n, T, ML = 2048, 100, 30
+    kw = dict(prefetch=True, use_cuda_graph=True) if fast_path else {}
+    env, ob = make_pair(n, A, 4, True, seed=31, max_ep_len=ML, auto_reset=True, standardize=mode, **kw)
+    so = pu.StandardizedOracle(ob, mode)
+    so.after_reset()
+    np.testing.assert_array_equal(env.obs[:, :, 0].cpu().numpy(), 0.0)
+    np.testing.assert_array_equal(env.raw_count.cpu().numpy(), ob.outs["obs"][:, :A, 0].astype(np.float32))
+    rng = np.random.default_rng(1)
+    big = 0
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 9, size=(n, A))
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+        ob.step(acts, env._ctr)
+        z = so.after_step()
+        e = ob.envs
+        mask = (e["done"] == 1) | (e["ep_len"] == ML)
+        raw = ob.outs["obs"][:, :A, 0].copy()
+        big += int((np.abs(z) > 3).sum())
+        np.testing.assert_array_equal(env.final_obs[:, :, 0].cpu().numpy()[mask], z[mask].astype(np.float32))
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.zeros(n))
+            z = so.after_reset(mask)
+            raw = np.where(mask[:, None], ob.outs["obs"][:, :A, 0], raw)
+        np.testing.assert_array_equal(env.obs[:, :, 0].cpu().numpy(), z.astype(np.float32))
+        np.testing.assert_array_equal(env.raw_count.cpu().numpy(), raw.astype(np.float32))
+        np.testing.assert_array_equal(env._st_mean.cpu().numpy().T, so.st.mean.reshape(n, A))
+        np.testing.assert_array_equal(env._st_m2.cpu().numpy().T, so.st.m2.reshape(n, A))
+    pu.compare_state(pu.GpuView(env), ob, A)
+    assert big > 0

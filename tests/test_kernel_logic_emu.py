@@ -288,3 +288,48 @@ def test_emulated_fast_poisson_is_ks_equivalent_to_numpy(lam_case):
     assert stats.ks_2samp(c, ref).pvalue > 1e-3, lam
     assert abs(c.mean() - lam) < 5 * np.sqrt(lam / len(c)), (lam, c.mean())
     assert abs(c.var() / lam - 1) < 0.03, (lam, c.var())
+
+
+@pytest.mark.parametrize("mode,A", [(1, 1), (2, 1), (1, 3)])
+def test_emulated_standardizer_follows_the_callers_order(mode, A):
+    """RsConfig.standardize: obs[..., 0] is the per-episode running z-score the RAD-A2C caller computes (train.py:311,
+    339, 436, 469, 509, 548) and raw_count keeps the Poisson count; the statistics restart with every reset, adopted
+    (prefetch) or synchronous; final_obs carries the standardised last observation used for the bootstrap value."""
+    n, T, ML = 96, 90, 30
+    cfg = make_config(n_agents=A, obstruction_count=3, enforce=True, max_ep_len=ML, standardize=mode)
+    ob = co.OracleBatch(n, co.default_config(n_agents=A, obstruction_count=3, enforce=1, max_ep_len=ML), seed=77)
+    so = pu.StandardizedOracle(ob, mode)
+    em = EmuEnv(n, cfg, seed=77)
+    em.reset(0, flags=L.F_NEW_OBSTACLES)
+    ob.reset()
+    so.after_reset()
+    np.testing.assert_array_equal(em.obs[:, :, 0], 0.0)                    # a first reading standardises to 0
+    np.testing.assert_array_equal(em.raw_count, ob.outs["obs"][:, :A, 0].astype(np.float32))
+    em.prepare()
+    rng = np.random.default_rng(3)
+    big = 0
+    for t in range(1, T + 1):
+        p = t & 1
+        pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0)
+        acts = rng.integers(0, 9, size=(n, A))
+        em.refill_count[p] = 0
+        em.step(acts, t, flags=L.F_AUTO_RESET | pf)
+        ob.step(acts, t)
+        z = so.after_step()
+        e = ob.envs
+        mask = (e["done"] == 1) | (e["ep_len"] == ML)
+        np.testing.assert_array_equal(em.raw_count, ob.outs["obs"][:, :A, 0].astype(np.float32))
+        np.testing.assert_array_equal(em.final_obs[mask][:, :, 0], z[mask].astype(np.float32))
+        big += int((np.abs(z) > 3).sum())
+        em.reset(t, flags=L.F_RESET_LIST | pf)
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.zeros(n))
+            z = so.after_reset(mask)
+        np.testing.assert_array_equal(em.obs[:, :, 0], z.astype(np.float32))
+        raw = np.where(mask[:, None], ob.outs["obs"][:, :A, 0], em.raw_count)
+        np.testing.assert_array_equal(em.raw_count, raw.astype(np.float32))
+        np.testing.assert_array_equal(em.st_mean.T, so.st.mean.reshape(n, A))
+        np.testing.assert_array_equal(em.st_m2.T, so.st.m2.reshape(n, A))
+        if t % 2:
+            em.prepare(flags=L.F_REFILL_LIST | (L.F_PARITY1 if p else 0))
+    assert big > 0

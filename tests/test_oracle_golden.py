@@ -128,3 +128,21 @@ def test_oracle_reset_distribution_matches_reference():
                 assert r[a, 2] < r[b, 0] or r[b, 2] < r[a, 0] or r[a, 3] < r[b, 1] or r[b, 3] < r[a, 1]
         d = e["det"][i, 0].astype(np.int64) - e["src"][i].astype(np.int64)
         assert d @ d >= 1000000
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_oracle_standardizer_reproduces_reference_classes(mode):
+    """oracle/radsearch_oracle.c::orc_stat_update_standardize against StatisticStandardization (RADTEAM_core.py:188-277,
+    mode 1) and StatBuff + np.clip(.., -8, 8) (algos/test_environment/core.py:55-79, ppo.py:502, mode 2), recorded from
+    the reference classes by tools/make_golden.py: z-scores, running mean, M2 and std bit for bit in float64."""
+    g = pu.load_golden("ref_standardize")
+    S = len(g["length"])
+    st = co.Standardizer(S, mode)
+    sfx = "1" if mode == 1 else "2"
+    for t in range(int(g["length"].max())):
+        live = g["length"] > t
+        z = st.update_standardize(g["x"][:, t], mask=live)
+        np.testing.assert_array_equal(z[live], g["z" + sfx][live, t])
+        np.testing.assert_array_equal(st.mean[live], g["mean" + sfx][live, t])
+        np.testing.assert_array_equal(st.m2[live], g["m2_" + sfx][live, t])
+        np.testing.assert_array_equal(st.std[live], g["std" + sfx][live, t])

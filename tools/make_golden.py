@@ -10,6 +10,9 @@
   ref_reset_stats.npz marginals of 1500 reference resets (distributional parity of the Philox sampler).
   scenarios_v4.npz    the reference's saved evaluation scenarios (inputs only), first 250 of each obstruction count.
   action_lut.npz      get_step(a) for a in 0..8.
+  ref_standardize.npz StatisticStandardization (RADTEAM_core.py:188-277) and StatBuff (test_environment/core.py:55-79)
+                      run over count sequences in the caller's order update(x); standardize(x): z-scores and the
+                      running mean / M2 / std after every reading.
 """
 from __future__ import annotations
 
@@ -80,6 +83,8 @@ def main():
         make_reset_stats(m)
     if want("scenarios"):
         make_scenarios()
+    if want("standardize"):
+        make_standardize()
 
 
 def make_gae():
@@ -171,6 +176,49 @@ def make_scenarios():
             sc[f"obs{k}_{key}"] = v
     np.savez_compressed(os.path.join(OUT, "scenarios_v4.npz"), **sc)
     print("scenarios done")
+
+
+def make_standardize():
+    import importlib
+
+    from oracle.ref_env import _prepare_path
+
+    _prepare_path()
+    core = importlib.import_module("algos.multiagent.NeuralNetworkCores.RADTEAM_core")
+    old = importlib.import_module("algos.test_environment.core")
+    rng = np.random.default_rng(21)
+    S, Lmax = 96, 121
+    x = np.zeros((S, Lmax))
+    length = np.zeros(S, np.int32)
+    out = {k: np.zeros((S, Lmax)) for k in ("z1", "mean1", "m2_1", "std1", "z2", "mean2", "m2_2", "std2")}
+    for s in range(S):
+        n = int(rng.integers(1, Lmax + 1))
+        length[s] = n
+        kind = s % 6
+        if kind == 0:                       # far from the source: background only, small spread (std clamps to 1)
+            seq = rng.poisson(float(rng.integers(10, 51)), n)
+        elif kind == 1:                     # approaching the source: counts grow by orders of magnitude
+            seq = rng.poisson(np.linspace(30.0, float(rng.integers(2000, 90000)), n))
+        elif kind == 2:                     # constant readings: sample variance exactly 0 (the two std rules differ)
+            seq = np.full(n, int(rng.integers(10, 5000)))
+        elif kind == 3:                     # spikes: |z| beyond 8 (mode 2 clips)
+            seq = rng.poisson(20.0, n)
+            seq[rng.integers(0, n)] = 9_000_000
+        elif kind == 4:                     # tiny spread: 0 < std < 1
+            seq = 1000 + (rng.random(n) < 0.1).astype(np.int64)
+        else:
+            seq = rng.poisson(rng.uniform(10, 9e4, n))
+        a, b = core.StatisticStandardization(), old.StatBuff()
+        for t, v in enumerate(seq):
+            v = float(v)
+            x[s, t] = v
+            a.update(v)
+            out["z1"][s, t], out["mean1"][s, t], out["m2_1"][s, t], out["std1"][s, t] = a.standardize(v), a.mean, a.square_dist_mean, a.std
+            b.update(v)
+            out["z2"][s, t] = np.clip((v - b.mu) / b.sig_obs, -8, 8)        # test_environment/ppo.py:502
+            out["mean2"][s, t], out["m2_2"][s, t], out["std2"][s, t] = b.mu, b.sig_sto, b.sig_obs
+    np.savez_compressed(os.path.join(OUT, "ref_standardize.npz"), x=x, length=length, **out)
+    print("ref_standardize", S, "sequences", flush=True)
 
 
 if __name__ == "__main__":
