@@ -47,6 +47,8 @@ extern "C" {
 #define RS_F_REFILL_LIST 64      /* rs_prepare: prepare the envs of refill list `parity`; else all envs            */
 #define RS_F_DEVICE_CTR 128      /* read the step counter from RsState.ctr_dev (CUDA-graph replay); rs_bump_ctr     */
 #define RS_F_PARITY1 256         /* which of the two refill lists rs_step / rs_reset push to (rs_prepare drains)    */
+#define RS_F_BUMP_CTR 512        /* rs_reset: the last CTA to finish does what rs_bump_ctr does (needs RsState.ticket) */
+#define RS_F_ZERO_REFILL 1024    /* rs_step: start refill list `parity` (refill_count[parity] = 0) before the resets   */
 
 /* info[n][a] bits */
 #define RS_I_OOB 1               /* Agent.out_of_bounds     R:919, 931 */
@@ -116,6 +118,7 @@ typedef struct RsState {
     double *st_mean;             /* [A][N]    running mean                                RADTEAM_core.py:198         */
     double *st_m2;               /* [A][N]    aggregated squared distance from the mean   RADTEAM_core.py:200         */
     float *raw_count;            /* [N][A]    the unstandardised count of the last observation (output, nullable)     */
+    uint32_t *ticket;            /* [1]       CTA completion counter of rs_reset (RS_F_BUMP_CTR), zero between launches   */
 } RsState;
 
 /* One environment step for n_env environments (all agents).  actions[N][A] in 0..8 (8 = idle), or NULL for the

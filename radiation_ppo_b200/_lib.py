@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "_C", "libradsearch_b200.so")
 
 OBS_DIM, MAX_K, MAX_A = 11, 8, 8
 F_AUTO_RESET, F_EPOCH_END, F_RESET_LIST, F_NEW_OBSTACLES, F_FAST_POISSON = 1, 2, 4, 8, 16
-F_PREFETCH, F_REFILL_LIST, F_DEVICE_CTR, F_PARITY1 = 32, 64, 128, 256
+F_PREFETCH, F_REFILL_LIST, F_DEVICE_CTR, F_PARITY1, F_BUMP_CTR, F_ZERO_REFILL = 32, 64, 128, 256, 512, 1024
 I_OOB, I_BLOCKED, I_COLLISION, I_LOS_BLOCKED, I_MOVED = 1, 2, 4, 8, 16
 E_TERMINAL, E_TIMEOUT, E_RESET = 1, 2, 4
 ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, ST_COORD_RANGE = 1, 2, 4, 8, 16, 32
@@ -39,7 +39,7 @@ class RsState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count",
         "epi", "nx_src", "nx_det", "nx_rad", "nx_best", "nx_dsrc", "nx_obs", "nx_seq", "refill_list", "refill_count",
-        "ctr_dev", "st_mean", "st_m2", "raw_count")]
+        "ctr_dev", "st_mean", "st_m2", "raw_count", "ticket")]
 
 
 class RadSearchLibraryError(RuntimeError):

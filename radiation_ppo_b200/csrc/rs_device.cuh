@@ -239,8 +239,8 @@ struct PtrsF32 {
 };
 
 // lam >= 10.  Counter block j of the stream (seed; env_id, domain|agent|j, step_ctr) serves proposals 2j and 2j+1.
-__device__ __forceinline__ long long poisson_f32(uint64_t seed, uint32_t env_id, uint32_t domain, uint32_t agent,
-                                                 uint64_t ctr, double lam) {
+__device__ __noinline__ long long poisson_f32(uint64_t seed, uint32_t env_id, uint32_t domain, uint32_t agent,
+                                              uint64_t ctr, double lam) {
     PtrsF32 s;
     s.init(lam);
     const uint32_t c1 = (domain << 24) | (agent << 16);

@@ -18,6 +18,7 @@ struct Params {
     int sx0, sy0, sx1, sy1;       // search area R:393-420
     int lo, hi;                   // observation_area
     int enforce, n_agents, obstruction_count, count_law, max_ep_len, k_max, standardize;
+    int tune;                     // RS_TUNE experiment bits (rs_step reads the environment variable once); 0 = default
     double max_dist;              // R:423-425
     double inv_scale;             // 1 / search_area[2][1]  R:435
 };
@@ -30,6 +31,7 @@ __host__ __device__ inline Params make_params(const RsConfig &c) {
     p.enforce = c.enforce; p.n_agents = c.n_agents; p.obstruction_count = c.obstruction_count;
     p.count_law = c.count_law; p.max_ep_len = c.max_ep_len; p.k_max = c.k_max;
     p.standardize = c.standardize;
+    p.tune = 0;
     const double dy = (double)(p.sy1 - p.sy0);
     p.max_dist = sqrt(dy * dy);
     p.inv_scale = 1.0 / (double)p.sy1;
@@ -122,12 +124,14 @@ __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py,
 // Pass A marks such corners in a per-thread bit mask with converged, branch-free code; pass B walks the thread's own
 // few marked corners (exact candidate, then the visibility test only if it would improve).  Exactly the value of
 // shortest_path().
-__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, int px, int py,
-                                                       int &hint) {
+// Pass A (+ the hint): returns the bit mask of the corners that may still improve on `best`; best / besti = the value
+// through the hint corner (inf / -1 when the hint is unusable).
+__device__ __forceinline__ uint32_t sp_seed_and_mask(const EnvView &e, const double *drow, int px, int py, int hint,
+                                                     double &best, int &besti) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int nc = 4 * e.num_obs;
-    double best = inf;
-    int besti = -1;
+    best = inf;
+    besti = -1;
     if (hint < nc) {
         const int4 r = e.rects[hint >> 2];
         const int cx = corner_x(r, hint & 3), cy = corner_y(r, hint & 3);
@@ -154,13 +158,28 @@ __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const d
         mask |= m4 << (4 * k);
     }
     if (besti >= 0) mask &= ~(1u << besti);
+    return mask;
+}
+
+// Pass B for one marked corner: its exact candidate if it beats `best` and is visible from p, else inf.
+__device__ __forceinline__ double sp_corner_candidate(const EnvView &e, const double *drow, int px, int py, int c,
+                                                      double best) {
+    const int4 r = e.rects[c >> 2];
+    const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+    const double cand = drow[c] + dist_int(px - cx, py - cy);
+    return (cand < best && visible(e, px, py, cx, cy)) ? cand : __longlong_as_double(0x7ff0000000000000LL);
+}
+
+__device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, int px, int py,
+                                                       int &hint) {
+    double best;
+    int besti;
+    uint32_t mask = sp_seed_and_mask(e, drow, px, py, hint, best, besti);
     while (mask) {
         const int c = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int4 r = e.rects[c >> 2];
-        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
-        const double cand = drow[c] + dist_int(px - cx, py - cy);
-        if (cand < best && visible(e, px, py, cx, cy)) { best = cand; besti = c; }
+        const double cand = sp_corner_candidate(e, drow, px, py, c, best);
+        if (cand < best) { best = cand; besti = c; }
     }
     if (besti >= 0) hint = besti;
     return best;
@@ -203,7 +222,7 @@ __device__ __forceinline__ bool ray_hits_vedge(int px, int py, int sx, int sy, i
 }
 __device__ __forceinline__ int clampdist(int v, int a, int b) { return v < a ? a - v : (v > b ? v - b : 0); }
 
-__device__ __forceinline__ void correct_coords(int px, int py, int4 r, float out[8], uint32_t &status) {
+__device__ __noinline__ void correct_coords(int px, int py, int4 r, float out[8], uint32_t &status) {
     int lo_d[8];
     int nstar = 0x7fffffff;
 #pragma unroll

@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
         __syncthreads();
     }
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
+    // a new refill list starts with this step: only the reset kernel that follows appends to it
+    if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
 
     // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
     for (int u0 = 0; u0 < U; u0 += kBlock) {
@@ -197,9 +199,78 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     {
         const int cb = counters[0], cd = counters[1], cp = counters[2];
         int off = 0;
-        for (int base = 0; base < cb; base += kBlock) {
-            const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cb) rs::phase_path(S, T, n0, lists[j]);
+        if (P.tune & 2) {
+            for (int base = 0; base < cb; base += kBlock) {
+                const int j = base + ((tid - off) & (kBlock - 1));
+                if (j < cb) rs::phase_path(S, T, n0, lists[j]);
+            }
+        } else {
+            // shortest path, flattened: (1) seed + marking pass per unit, the marked corners appended as (unit, corner)
+            // pairs to a tile-wide list (warp-aggregated reservation; the reward / team rows serve as scratch until
+            // phase_commit writes them); (2) one pair per thread: candidate, visibility, 64-bit atomicMin on the unit's
+            // running minimum (positive doubles order like their bit patterns); (3) the winners record the hint.
+            uint16_t *pairs = reinterpret_cast<uint16_t *>(T.reward);
+            const int pair_cap = (L.done - L.reward) / 2;
+            int *pair_count = counters + 3;                               // idle until phase_commit
+            const int lane = tid & 31;
+            for (int base = 0; base < cb; base += kBlock) {
+                const int j = base + tid;
+                uint32_t mask = 0u;
+                int u = -1, besti = -1;
+                double best = 0.0;
+                if (j < cb) {
+                    u = lists[j];
+                    mask = rs::phase_path_seed(S, T, n0, u, best, besti);
+                }
+                const int n = __popc(mask);
+                int pre = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                    if (lane >= o) pre += v;
+                }
+                const int tot = __shfl_sync(0xffffffffu, pre, 31);
+                int wbase = 0;
+                if (lane == 31 && tot) wbase = atomicAdd(pair_count, tot);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                const bool fits = wbase + tot <= pair_cap;
+                if (!fits)                                                // reserved but unused slots inside the list
+                    for (int i = wbase + lane; i < min(pair_cap, wbase + tot); i += 32) pairs[i] = 0xffffu;
+                if (u >= 0) {
+                    if (fits) {
+                        rs::phase_path_finish(T, u, best, besti);
+                        int pos = wbase + pre - n;
+                        while (mask) {
+                            pairs[pos++] = (uint16_t)((u << 5) | (__ffs(mask) - 1));
+                            mask &= mask - 1;
+                        }
+                    } else {
+                        rs::phase_path_walk(S, T, n0, u, mask, best, besti);
+                    }
+                }
+            }
+            __syncthreads();
+            const int np = min(*pair_count, pair_cap);
+            unsigned long long *spbits = reinterpret_cast<unsigned long long *>(T.sp);
+            for (int j = tid; j < np; j += kBlock) {
+                const uint32_t pr = pairs[j];
+                if (pr == 0xffffu) continue;
+                const int u = (int)(pr >> 5), c = (int)(pr & 31u);
+                const double cur = *reinterpret_cast<volatile double *>(T.sp + u);
+                const double cand = rs::phase_path_pair(S, T, n0, u, c, cur);
+                if (cand < cur) {
+                    atomicMin(spbits + u, (unsigned long long)__double_as_longlong(cand));
+                    pairs[j] = (uint16_t)(pr | 0x8000u);                   // a visible improver: may be the new hint
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < np; j += kBlock) {
+                const uint32_t pr = pairs[j];
+                if (pr == 0xffffu || !(pr & 0x8000u)) continue;
+                const int u = (int)((pr & 0x7fffu) >> 5), c = (int)(pr & 31u);
+                if (rs::phase_path_pair_value(S, T, n0, u, c) == T.sp[u]) T.af[u] = (T.af[u] & ~(31 << 25)) | (c << 25);
+            }
+            if (tid == 0) *pair_count = 0;
         }
         off = (off + ((cb + 31) & ~31)) & (kBlock - 1);
         for (int base = 0; base < cd; base += kBlock) {
@@ -304,6 +375,19 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
         rs::reset_env<kFast>(P, S, a, n, new_obs, lane, nl, sync_mask, rs::Col<int4>{srects + g, G},
                              rs::Col<double>{sdsrc + g, G}, rs::Col<uint32_t>{svis + g, G});
     }
+    if (flags & RS_F_BUMP_CTR) {
+        // tail of a captured step: the last CTA to finish advances the device step counter and empties the reset list
+        // (every CTA has read *count by then) -- what rs_bump_ctr does, without its launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(S.ticket, 1u) == gridDim.x - 1) {
+                *S.ticket = 0u;
+                *reinterpret_cast<unsigned long long *>(S.ctr_dev) += 1ull;
+                if (S.reset_count) *S.reset_count = 0;
+            }
+        }
+    }
 }
 
 int check_prefetch(const RsConfig *cfg, const RsState *st) {
@@ -358,6 +442,7 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
     if ((flags & RS_F_AUTO_RESET) && (!st->reset_list || !st->reset_count)) return fail("auto-reset needs reset_list/reset_count");
     if ((flags & RS_F_DEVICE_CTR) && !st->ctr_dev) return fail("RS_F_DEVICE_CTR needs RsState.ctr_dev");
+    if ((flags & RS_F_ZERO_REFILL) && !st->refill_count) return fail("RS_F_ZERO_REFILL needs RsState.refill_count");
     const int parity = (flags & RS_F_PARITY1) ? 1 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if ((flags & RS_F_AUTO_RESET) && !(flags & RS_F_DEVICE_CTR)) {     // with RS_F_DEVICE_CTR rs_bump_ctr empties the list
@@ -365,6 +450,8 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
         if (e != cudaSuccess) return (int)e;
     }
     rs::Params P = rs::make_params(*cfg);
+    static const int tune_env = getenv("RS_TUNE") ? atoi(getenv("RS_TUNE")) : 0;                 // experiment switches
+    P.tune = tune_env;
     rs::StepArgs a;
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
@@ -431,6 +518,7 @@ int rs_reset(const RsConfig *cfg, const RsState *st, const uint8_t *reset_mask, 
     if (!obs) return fail("obs is NULL");
     if (uniforms && n_uniforms < 2) return fail("n_uniforms must be >= 2 when uniforms are injected");
     if ((flags & RS_F_RESET_LIST) && (!st->reset_list || !st->reset_count)) return fail("list reset needs reset_list/reset_count");
+    if ((flags & RS_F_BUMP_CTR) && (!st->ticket || !st->ctr_dev)) return fail("RS_F_BUMP_CTR needs RsState.ticket and ctr_dev");
     rs::ResetArgs a;
     std::memset(&a, 0, sizeof(a));
     a.obs = obs; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed; a.step_ctr = step_ctr;

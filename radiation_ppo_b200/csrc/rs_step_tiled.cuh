@@ -217,7 +217,17 @@ __device__ __forceinline__ int phase_move(const Params &P, const RsState &S, con
     const double euc = dist_int(det.x - e.sx, det.y - e.sy);
     bool direct, blocked_raw;
     source_segment(e, det.x, det.y, direct, blocked_raw);
-    if (direct) uf |= UF_DIRECT; else uf |= UF_NEED_B;
+    if (direct) uf |= UF_DIRECT;
+    else {
+        uf |= UF_NEED_B;
+#ifndef RS_HOST_EMU
+        if (!(P.tune & 1)) {    // the env-major source-distance row (4K doubles) is wanted by phase_path: start it now
+            const char *row = reinterpret_cast<const char *>(S.dsrc + (size_t)n * 4 * T.K);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            if (T.K > 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+        }
+#endif
+    }
     if (blocked_raw) uf |= UF_BLOCKED_RAW;
     // sensor candidates: a ray is at most 100 long (71 per axis)
     int cand = 0;
@@ -272,6 +282,53 @@ __device__ __forceinline__ void phase_path(const RsState &S, const Tile &T, int 
     int hint = (af >> 25) & 31;
     T.sp[u] = shortest_path_pruned(e, e.dsrc.p, det.x, det.y, hint);
     T.af[u] = (af & ~(31 << 25)) | (hint << 25);
+}
+
+// The same phase cut in two for the CUDA kernel (rs_kernels.cu): the seed + marking pass per unit, then the marked
+// (unit, corner) pairs of the whole tile as independent work items -- a unit has ~2 marked corners on average but a
+// warp's slowest lane ~9, so walking them per thread leaves 4 lanes in 5 idle.
+__device__ __forceinline__ uint32_t phase_path_seed(const RsState &S, const Tile &T, int n0, int u, double &best,
+                                                    int &besti) {
+    const int E = T.E;
+    const int ag = u / E, t = u - ag * E;
+    const EnvView e = tile_env(T, S, t, n0 + t);
+    const int2 det = T.ndet[u];
+    return sp_seed_and_mask(e, e.dsrc.p, det.x, det.y, (T.af[u] >> 25) & 31, best, besti);
+}
+__device__ __forceinline__ void phase_path_finish(const Tile &T, int u, double best, int besti) {
+    T.sp[u] = best;
+    if (besti >= 0) T.af[u] = (T.af[u] & ~(31 << 25)) | (besti << 25);
+}
+// the rest of the per-thread walk (units whose pairs did not fit into the tile's pair list)
+__device__ __forceinline__ void phase_path_walk(const RsState &S, const Tile &T, int n0, int u, uint32_t mask,
+                                                double best, int besti) {
+    const int E = T.E;
+    const int ag = u / E, t = u - ag * E;
+    const EnvView e = tile_env(T, S, t, n0 + t);
+    const int2 det = T.ndet[u];
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double cand = sp_corner_candidate(e, e.dsrc.p, det.x, det.y, c, best);
+        if (cand < best) { best = cand; besti = c; }
+    }
+    phase_path_finish(T, u, best, besti);
+}
+// one (unit, corner) pair against the unit's current minimum `cur`: the candidate, or inf
+__device__ __forceinline__ double phase_path_pair(const RsState &S, const Tile &T, int n0, int u, int c, double cur) {
+    const int E = T.E;
+    const int ag = u / E, t = u - ag * E;
+    const EnvView e = tile_env(T, S, t, n0 + t);
+    const int2 det = T.ndet[u];
+    return sp_corner_candidate(e, e.dsrc.p, det.x, det.y, c, cur);
+}
+// the exact candidate of a pair again (hint update of the winners)
+__device__ __forceinline__ double phase_path_pair_value(const RsState &S, const Tile &T, int n0, int u, int c) {
+    const int E = T.E;
+    const int ag = u / E, t = u - ag * E;
+    const int4 r = T.rects[(c >> 2) * E + t];
+    const int2 det = T.ndet[u];
+    return S.dsrc[(size_t)(n0 + t) * 4 * T.K + c] + dist_int(det.x - corner_x(r, c & 3), det.y - corner_y(r, c & 3));
 }
 
 // ---- phase_sense: units within reach of an obstruction (list D) -------------------------------------------------------

@@ -9,6 +9,8 @@ hand-written kernels behind include/radsearch_b200.h; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import gc
+import weakref
 from typing import Any, Dict, NamedTuple, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -50,7 +52,11 @@ class _AgentView:
     """Read-only view of one agent of one environment (Agent dataclass fields R:255-300)."""
 
     def __init__(self, env: "RadSearch", agent_id: int):
-        self._env, self.id = env, agent_id
+        self._envref, self.id = weakref.ref(env), agent_id      # no reference cycle: an env is freed when dropped
+
+    @property
+    def _env(self) -> "RadSearch":
+        return self._envref()
 
     @property
     def det_coords(self) -> Tuple[float, float]:
@@ -241,6 +247,8 @@ class RadSearch:
         else:
             self._st_mean = self._st_m2 = self.raw_count = None
             ptrs += [None] * 3
+        self._ticket = z(1)
+        ptrs.append(self._ticket)
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
         self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
         self._side = torch.cuda.Stream(device=dev, priority=int(__import__('os').environ.get('RS_SIDE_PRIO', '-1'))) if self.prefetch else None
@@ -350,16 +358,17 @@ class RadSearch:
         self._blk_pos = 0
 
     def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool, first: bool) -> None:
-        """[zero refill list p] + rs_step + rs_reset(list) on the current stream."""
-        if first:
-            self._refill_count[p:p + 1].zero_()
+        """rs_step (which starts refill list p when `first`) + rs_reset(list) on the current stream; with the device
+        step counter the reset kernel's last CTA advances it (RS_F_BUMP_CTR): two launches per step."""
         pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0) | (L.F_DEVICE_CTR if device_ctr else 0)
-        flags = self._base_flags() | L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0)
+        flags = self._base_flags() | L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0) | \
+            (L.F_ZERO_REFILL if first else 0)
         L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
                                   _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
                                   _ptr(self.ended), _ptr(self.final_obs), self.num_envs, self.env_id_offset, self.seed,
                                   self._ctr, None, 0, flags, self._stream()), "rs_step")
-        rflags = self._base_flags() | L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0)
+        rflags = self._base_flags() | L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0) | \
+            (L.F_BUMP_CTR if device_ctr else 0)
         L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(self.obs), self.num_envs,
                                    self.env_id_offset, self.seed, self._ctr, None, 0, rflags, self._stream()), "rs_reset")
 
@@ -420,16 +429,22 @@ class RadSearch:
                     self._graphs[(p, first)] = self._capture(p, first)
 
     def _capture(self, p: int, first: bool):
-        """Capture {[zero list p] -> rs_step -> rs_reset(list) -> bump the device step counter} once; replayed per step."""
+        """Capture {rs_step -> rs_reset(list), whose last CTA bumps the device step counter} once; replayed per step."""
         dev = self.device
-        L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")   # load the kernel before capture
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(cap):
-            with torch.cuda.graph(g, stream=cap):
-                self._launch_step_sequence(self._act_buf, p, False, True, first)
-                L.check(self._lib.rs_bump_ctr(C.byref(self._st), self._stream()), "rs_bump_ctr")
+        # the region holds two kernel launches and nothing else; "relaxed" + no cyclic GC inside it, so that a finalizer of
+        # some unrelated object (say another env's graphs being destroyed) cannot invalidate the capture
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="relaxed"):
+                    self._launch_step_sequence(self._act_buf, p, False, True, first)
+        finally:
+            if gc_was_on:
+                gc.enable()
         self._ctr_dev_val = -1                           # capture does not execute; force a refresh before the replay
         return g
 

@@ -91,6 +91,7 @@ class EmuEnv:
         self.st_mean = np.zeros((A, n), np.float64)
         self.st_m2 = np.zeros((A, n), np.float64)
         self.raw_count = np.zeros((n, A), np.float32)
+        self.ticket = np.zeros(1, np.uint32)
         self.st = L.RsState(*[_vp(getattr(self, f)) for f, _ in L.RsState._fields_])
         self.obs = np.zeros((n, A, 11), np.float32)
         self.final_obs = np.zeros((n, A, 11), np.float32)

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layout_and_version(lib):
     assert lib.rs_version() == 2
     assert lib.rs_sizeof_config() == C.sizeof(L.RsConfig) == 52
-    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 208
+    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 216
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):

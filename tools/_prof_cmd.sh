@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-RS_PERIOD=4 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench13.log 2>&1; tail -c 1500 gpurun_out/bench13.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 8 -c 1 -f -o gpurun_out/prof_step_v10 \
+    python bench.py --steps 12 --warmup 3 --no-cpu-baseline --streams 1 > gpurun_out/ncu_step_v10.log 2>&1; echo "ncu step rc=$?"
