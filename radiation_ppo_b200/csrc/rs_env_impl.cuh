@@ -69,6 +69,15 @@ __device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx
 
 __device__ __forceinline__ double dist_int(int dx, int dy) { return sqrt((double)(dx * dx + dy * dy)); }
 
+// the same test as a real function: the step kernel calls it from three places (hint, pair, fall-back walk) and its
+// instruction footprint, not its call overhead, is what costs there (the kernel is instruction-fetch limited)
+__device__ __noinline__ bool visible_call(const int4 *rects, int stride, int num_obs, int px, int py, int qx, int qy) {
+    EnvView e;
+    e.rects = Col<int4>{const_cast<int4 *>(rects), stride};
+    e.num_obs = num_obs;
+    return visible(e, px, py, qx, qy);
+}
+
 // Straightforward form (used by the reset path): direct segment if visible, else min over corners.
 __device__ __forceinline__ double shortest_path(const EnvView &e, int px, int py) {
     if (visible(e, px, py, e.sx, e.sy)) return dist_int(px - e.sx, py - e.sy);
@@ -136,7 +145,10 @@ __device__ __forceinline__ uint32_t sp_seed_and_mask(const EnvView &e, const dou
         const int4 r = e.rects[hint >> 2];
         const int cx = corner_x(r, hint & 3), cy = corner_y(r, hint & 3);
         const double ds = drow[hint];
-        if (ds < inf && visible(e, px, py, cx, cy)) { best = ds + dist_int(px - cx, py - cy); besti = hint; }
+        if (ds < inf && visible_call(e.rects.p, e.rects.stride, e.num_obs, px, py, cx, cy)) {
+            best = ds + dist_int(px - cx, py - cy);
+            besti = hint;
+        }
     }
     uint32_t mask = 0u;
     for (int k = 0; k < e.num_obs; k++) {
@@ -167,7 +179,8 @@ __device__ __forceinline__ double sp_corner_candidate(const EnvView &e, const do
     const int4 r = e.rects[c >> 2];
     const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
     const double cand = drow[c] + dist_int(px - cx, py - cy);
-    return (cand < best && visible(e, px, py, cx, cy)) ? cand : __longlong_as_double(0x7ff0000000000000LL);
+    return (cand < best && visible_call(e.rects.p, e.rects.stride, e.num_obs, px, py, cx, cy))
+               ? cand : __longlong_as_double(0x7ff0000000000000LL);
 }
 
 __device__ __forceinline__ double shortest_path_pruned(const EnvView &e, const double *drow, int px, int py,
@@ -344,6 +357,70 @@ __device__ __forceinline__ void sensors_rects(const EnvView &e, int px, int py, 
         const float f2 = (float)max(best_d2[d], 1);
         const float v = (110.0f - f2 * rsqrtf(f2)) * (1.0f / 110.0f);
         if (best_d2[d] != -2) out[d] = best_d2[d] < 0 ? 0.0f : (best_d2[d] == 0 ? 1.0f : v);
+    }
+}
+
+// The same, direction-major like the reference's own loop (R:1186-1217) and NOT unrolled over the directions: an eighth
+// of the instruction footprint, for the step kernel (which is instruction-fetch limited).  The eight values go straight
+// to the observation row (shared memory).
+__device__ __forceinline__ void sensors_rects_row(const EnvView &e, int px, int py, int cand, float *row8,
+                                                  uint32_t &status) {
+    unsigned long long hits = 0ull;                  // 8 bits per rectangle (obs_idx_ls R:1190)
+    int ones = 0;
+#pragma unroll 1
+    for (int d = 0; d < 8; d++) {
+        const int sx = step_dx(d), sy = step_dy(d);
+        int inter = 0, dmin = -1, todo = cand;
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int4 r = e.rects[k];
+            int hk = 0;
+            // edge order R:1000-1006: (p0,p1) left, (p0,p3) bottom, (p2,p1) top, (p2,p3) right
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                bool hit;
+                int d2;
+                if (s == 0 || s == 3) {
+                    const int c = (s == 0) ? r.x : r.z;
+                    hit = ray_hits_vedge(px, py, sx, sy, c, r.y, r.w);
+                    const int ddx = px - c, ddy = clampdist(py, r.y, r.w);
+                    d2 = ddx * ddx + ddy * ddy;
+                } else {
+                    const int c = (s == 1) ? r.y : r.w;
+                    hit = ray_hits_vedge(py, px, sy, sx, c, r.x, r.z);      // transposed
+                    const int ddy = py - c, ddx = clampdist(px, r.x, r.z);
+                    d2 = ddx * ddx + ddy * ddy;
+                }
+                if (inter < 2 && hit) {
+                    dmin = (dmin < 0 || d2 < dmin) ? d2 : dmin;
+                    inter++;
+                    hk++;
+                }
+            }
+            hits += (unsigned long long)hk << (8 * k);
+        }
+        ones += (dmin == 0);
+        const float f2 = (float)max(dmin, 1);
+        const float v = (110.0f - f2 * rsqrtf(f2)) * (1.0f / 110.0f);
+        row8[d] = dmin < 0 ? 0.0f : (dmin == 0 ? 1.0f : v);
+    }
+    if (ones > 3) {
+        // max(zip(obs_idx_ls, self.poly)) R:1222-1226: most hits, ties -> lexicographically largest vertex list
+        int hits_best = -1, best_k = 0;
+        for (int k = 0; k < e.num_obs; k++) {
+            const int hk = (int)((hits >> (8 * k)) & 0xffull);
+            bool take = hk > hits_best;
+            if (!take && hk == hits_best) {
+                const int4 a = e.rects[k], b = e.rects[best_k];
+                take = (a.x != b.x) ? (a.x > b.x) : ((a.y != b.y) ? (a.y > b.y) : ((a.w != b.w) ? (a.w > b.w) : (a.z > b.z)));
+            }
+            if (take) { hits_best = hk; best_k = k; }
+        }
+        float out[8];
+        correct_coords(px, py, e.rects[best_k], out, status);
+#pragma unroll
+        for (int d = 0; d < 8; d++) row8[d] = out[d];
     }
 }
 

@@ -57,74 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
         : "memory");
 }
 
-struct RowDesc {
-    void *s;            // shared-memory row
-    void *g;            // the same row in HBM
-    uint32_t full;      // bytes of a full tile row
-    uint32_t valid;     // bytes of this tile's row (partial last tile)
+// One row of the tile: `bpe` bytes per environment, contiguous over the environments of the tile both in HBM (at
+// g + n0 * bpe) and in shared memory (at smem + off).  The host fills the table once per launch (rs_step), so the kernel's
+// staging loops are a table walk instead of per-row address arithmetic.
+struct RowEnt {
+    unsigned long long g;   // HBM address of the row's element for env 0 of this rank (0 = row absent)
+    uint32_t off;           // byte offset inside the CTA's dynamic shared memory
+    uint32_t bpe;           // bytes per environment
 };
-
-// state rows read by the step: 0 src, 1 rad, 2 meta, 3 actions, 4.. rects[k], then det / best / aflags (/ running
-// count statistics when RsConfig.standardize) per agent
-__device__ __forceinline__ int rows_per_agent(const rs::Tile &T) { return T.stm ? 5 : 3; }
-__device__ __forceinline__ int n_rows_in(const rs::Tile &T) { return 4 + T.K + rows_per_agent(T) * T.A; }
-__device__ __forceinline__ RowDesc row_in(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
-                                          int valid) {
-    const int E = T.E, A = T.A, K = T.K;
-    const size_t N = (size_t)a.n_env;
-    RowDesc r{nullptr, nullptr, 0u, 0u};
-    if (i == 0) r = RowDesc{T.src, S.src + 2 * (size_t)n0, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-    else if (i == 1) r = RowDesc{T.rad, S.rad + 2 * (size_t)n0, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-    else if (i == 2) r = RowDesc{T.meta, S.meta + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u};
-    else if (i == 3) {
-        if (a.actions)
-            r = RowDesc{const_cast<int *>(T.act), const_cast<int32_t *>(a.actions) + (size_t)n0 * A, (uint32_t)(E * A) * 4u,
-                        (uint32_t)(valid * A) * 4u};
-    } else if (i < 4 + K) {
-        const int k = i - 4;
-        r = RowDesc{T.rects + k * E, S.rects + ((size_t)k * N + n0) * 4, (uint32_t)E * 16u, (uint32_t)valid * 16u};
-    } else {
-        const int rpa = rows_per_agent(T), j = i - 4 - K, ag = j / rpa, w = j - rpa * ag;
-        const size_t off = (size_t)ag * N + n0;
-        if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-        else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-        else if (w == 2) r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
-        else if (w == 3) r = RowDesc{T.stm + ag * E, S.st_mean + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-        else r = RowDesc{T.stq + ag * E, S.st_m2 + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-    }
-    return r;
-}
-
-// rows written by the step: 0 meta, 1 obs, 2 reward, 3 team_reward, 4 done, 5 info, 6 ended, 7 raw counts, then
-// det / best / aflags (/ running count statistics) per agent
-__device__ __forceinline__ int n_rows_out(const rs::Tile &T) { return 8 + rows_per_agent(T) * T.A; }
-__device__ __forceinline__ RowDesc row_out(const rs::Tile &T, const RsState &S, const rs::StepArgs &a, int i, int n0,
-                                           int valid) {
-    const int E = T.E, A = T.A;
-    const size_t N = (size_t)a.n_env;
-    const uint32_t uE = (uint32_t)(E * A), uV = (uint32_t)(valid * A);
-    RowDesc r{nullptr, nullptr, 0u, 0u};
-    switch (i) {
-        case 0: r = RowDesc{T.meta, S.meta + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u}; break;
-        case 1: r = RowDesc{T.obs, a.obs + (size_t)n0 * A * RS_OBS_DIM, uE * RS_OBS_DIM * 4u, uV * RS_OBS_DIM * 4u}; break;
-        case 2: if (a.reward) r = RowDesc{T.reward, a.reward + (size_t)n0 * A, uE * 4u, uV * 4u}; break;
-        case 3: if (a.team_reward) r = RowDesc{T.team, a.team_reward + n0, (uint32_t)E * 4u, (uint32_t)valid * 4u}; break;
-        case 4: if (a.done) r = RowDesc{T.done, a.done + (size_t)n0 * A, uE, uV}; break;
-        case 5: if (a.info) r = RowDesc{T.info, a.info + (size_t)n0 * A, uE, uV}; break;
-        case 6: if (a.ended) r = RowDesc{T.ended, a.ended + n0, (uint32_t)E, (uint32_t)valid}; break;
-        case 7: if (T.raw && S.raw_count) r = RowDesc{T.raw, S.raw_count + (size_t)n0 * A, uE * 4u, uV * 4u}; break;
-        default: {
-            const int rpa = rows_per_agent(T), j = i - 8, ag = j / rpa, w = j - rpa * ag;
-            const size_t off = (size_t)ag * N + n0;
-            if (w == 0) r = RowDesc{T.det + ag * E, S.det + 2 * off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-            else if (w == 1) r = RowDesc{T.best + ag * E, S.best + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-            else if (w == 2) r = RowDesc{T.af + ag * E, S.aflags + off, (uint32_t)E * 4u, (uint32_t)valid * 4u};
-            else if (w == 3) r = RowDesc{T.stm + ag * E, S.st_mean + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-            else r = RowDesc{T.stq + ag * E, S.st_m2 + off, (uint32_t)E * 8u, (uint32_t)valid * 8u};
-        }
-    }
-    return r;
-}
+constexpr int kMaxRowsIn = 4 + RS_MAX_K + 5 * RS_MAX_A, kMaxRowsOut = 8 + 5 * RS_MAX_A;
+struct TileRows {
+    int n_in, n_out;
+    RowEnt in[kMaxRowsIn], out[kMaxRowsOut];
+};
 
 // warp-aggregated append of unit u to a shared-memory work list (whole warps call this)
 __device__ __forceinline__ void list_push(bool flag, int u, uint16_t *list, int *count) {
@@ -141,7 +86,8 @@ template <bool kFast, int E, int kOcc>
 __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
                                                          const __grid_constant__ rs::StepArgs a,
-                                                         const __grid_constant__ rs::TileLayout L, int bulk_ok,
+                                                         const __grid_constant__ rs::TileLayout L,
+                                                         const __grid_constant__ TileRows R, int bulk_ok,
                                                          uint32_t tx_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int A = P.n_agents, K = P.k_max, U = E * A;
@@ -156,7 +102,6 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
 
     // ---- stage the tile ------------------------------------------------------------------------------------------
     if (tid < 4) counters[tid] = 0;
-    const int nin = n_rows_in(T);
     if (bulk) {
         if (tid == 0) {
             mbar_init(mbar, 1);
@@ -164,19 +109,20 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
         }
         if (tid < 32) {
             __syncwarp();
-            for (int i = tid; i < nin; i += 32) {
-                const RowDesc r = row_in(T, S, a, i, n0, valid);
-                if (r.full) bulk_g2s(r.s, r.g, r.full, mbar);
+            for (int i = tid; i < R.n_in; i += 32) {
+                const RowEnt r = R.in[i];
+                bulk_g2s(smem + r.off, reinterpret_cast<const void *>(r.g + (unsigned long long)n0 * r.bpe),
+                         (uint32_t)E * r.bpe, mbar);
             }
         }
         __syncthreads();                                    // the barrier object is initialised for everybody
         mbar_wait(mbar, 0);
     } else {
-        for (int i = 0; i < nin; i++) {
-            const RowDesc r = row_in(T, S, a, i, n0, valid);
-            const uint32_t *g = reinterpret_cast<const uint32_t *>(r.g);
-            uint32_t *s = reinterpret_cast<uint32_t *>(r.s);
-            for (uint32_t w = tid; w < r.valid / 4u; w += kBlock) s[w] = g[w];
+        for (int i = 0; i < R.n_in; i++) {
+            const RowEnt r = R.in[i];
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(r.g + (unsigned long long)n0 * r.bpe);
+            uint32_t *s = reinterpret_cast<uint32_t *>(smem + r.off);
+            for (uint32_t w = tid; w < (uint32_t)valid * r.bpe / 4u; w += kBlock) s[w] = g[w];
         }
         __syncthreads();
     }
@@ -199,12 +145,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     {
         const int cb = counters[0], cd = counters[1], cp = counters[2];
         int off = 0;
-        if (P.tune & 2) {
-            for (int base = 0; base < cb; base += kBlock) {
-                const int j = base + ((tid - off) & (kBlock - 1));
-                if (j < cb) rs::phase_path(S, T, n0, lists[j]);
-            }
-        } else {
+        {
             // shortest path, flattened: (1) seed + marking pass per unit, the marked corners appended as (unit, corner)
             // pairs to a tile-wide list (warp-aggregated reservation; the reward / team rows serve as scratch until
             // phase_commit writes them); (2) one pair per thread: candidate, visibility, 64-bit atomicMin on the unit's
@@ -305,28 +246,28 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     }
 
     // ---- write the tile back ----------------------------------------------------------------------------------------
-    const int nout = n_rows_out(T);
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
         __syncthreads();
         if (tid < 32) {
-            for (int i = tid; i < nout; i += 32) {
-                const RowDesc r = row_out(T, S, a, i, n0, valid);
-                if (r.full) bulk_s2g(r.g, r.s, r.full);
+            for (int i = tid; i < R.n_out; i += 32) {
+                const RowEnt r = R.out[i];
+                bulk_s2g(reinterpret_cast<void *>(r.g + (unsigned long long)n0 * r.bpe), smem + r.off, (uint32_t)E * r.bpe);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released once it has been read
         }
     } else {
-        for (int i = 0; i < nout; i++) {
-            const RowDesc r = row_out(T, S, a, i, n0, valid);
-            const uint8_t *s = reinterpret_cast<const uint8_t *>(r.s);
-            uint8_t *g = reinterpret_cast<uint8_t *>(r.g);
-            if ((r.valid & 3u) == 0 && (reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
-                for (uint32_t w = tid; w < r.valid / 4u; w += kBlock)
+        for (int i = 0; i < R.n_out; i++) {
+            const RowEnt r = R.out[i];
+            const uint8_t *s = smem + r.off;
+            uint8_t *g = reinterpret_cast<uint8_t *>(r.g + (unsigned long long)n0 * r.bpe);
+            const uint32_t nb = (uint32_t)valid * r.bpe;
+            if ((nb & 3u) == 0 && (reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
+                for (uint32_t w = tid; w < nb / 4u; w += kBlock)
                     reinterpret_cast<uint32_t *>(g)[w] = reinterpret_cast<const uint32_t *>(s)[w];
             } else {
-                for (uint32_t w = tid; w < r.valid; w += kBlock) g[w] = s[w];
+                for (uint32_t w = tid; w < nb; w += kBlock) g[w] = s[w];
             }
         }
     }
@@ -460,9 +401,44 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     const int grid = (n_env + E - 1) / E;
     const rs::TileLayout L = rs::make_layout(E, A, K, kBlock, cfg->standardize);
     const size_t smem = (size_t)L.total;
+    // the tile's rows: state rows read (src, rad, meta, actions, rects[k], then det / best / aflags / running count
+    // statistics per agent) and rows written (meta, obs, reward, team_reward, done, info, ended, raw counts, then the
+    // per-agent state rows)
+    TileRows R;
+    R.n_in = R.n_out = 0;
+    const size_t Nn = (size_t)n_env;
+    auto add = [](RowEnt *tab, int &cnt, const void *g, int off, int bpe) {
+        if (g) tab[cnt++] = RowEnt{(unsigned long long)reinterpret_cast<uintptr_t>(g), (uint32_t)off, (uint32_t)bpe};
+    };
+    add(R.in, R.n_in, st->src, L.src, 8);
+    add(R.in, R.n_in, st->rad, L.rad, 8);
+    add(R.in, R.n_in, st->meta, L.meta, 4);
+    add(R.in, R.n_in, actions, L.act, A * 4);
+    for (int k = 0; k < K; k++) add(R.in, R.n_in, st->rects + (size_t)k * Nn * 4, L.rects + k * E * 16, 16);
+    add(R.out, R.n_out, st->meta, L.meta, 4);
+    add(R.out, R.n_out, obs, L.obs, A * RS_OBS_DIM * 4);
+    add(R.out, R.n_out, reward, L.reward, A * 4);
+    add(R.out, R.n_out, team_reward, L.team, 4);
+    add(R.out, R.n_out, done, L.done, A);
+    add(R.out, R.n_out, info, L.info, A);
+    add(R.out, R.n_out, ended, L.ended, 1);
+    if (cfg->standardize) add(R.out, R.n_out, st->raw_count, L.raw, A * 4);
+    for (int ag = 0; ag < A; ag++) {
+        for (int dir = 0; dir < 2; dir++) {
+            RowEnt *tab = dir ? R.out : R.in;
+            int &cnt = dir ? R.n_out : R.n_in;
+            add(tab, cnt, st->det + ((size_t)ag * Nn) * 2, L.det + ag * E * 8, 8);
+            add(tab, cnt, st->best + (size_t)ag * Nn, L.best + ag * E * 8, 8);
+            add(tab, cnt, st->aflags + (size_t)ag * Nn, L.af + ag * E * 4, 4);
+            if (cfg->standardize) {
+                add(tab, cnt, st->st_mean + (size_t)ag * Nn, L.stm + ag * E * 8, 8);
+                add(tab, cnt, st->st_m2 + (size_t)ag * Nn, L.stq + ag * E * 8, 8);
+            }
+        }
+    }
     // bytes of one full tile's state rows (what the bulk copies of a CTA deliver to its mbarrier)
-    const uint32_t tx_bytes = (uint32_t)(E * (8 + 8 + 4) + (actions ? E * A * 4 : 0) + K * E * 16 + A * E * (8 + 8 + 4) +
-                                         (cfg->standardize ? A * E * 16 : 0));
+    uint32_t tx_bytes = 0;
+    for (int i = 0; i < R.n_in; i++) tx_bytes += (uint32_t)E * R.in[i].bpe;
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
     // bulk-async tile copies need 16-byte aligned rows: every array base (the tile offsets are multiples of 32 elements)
     const int bulk_ok = aligned16(st->src) && aligned16(st->rad) && aligned16(st->rects) && aligned16(st->meta) &&
@@ -476,7 +452,7 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     do {                                                                                                            \
         if (smem > 48 * 1024)                                                                                       \
             cudaFuncSetAttribute(step_kernel<FAST, TE, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        step_kernel<FAST, TE, OCC><<<grid, kBlock, smem, s>>>(P, *st, a, L, bulk_ok, tx_bytes);                     \
+        step_kernel<FAST, TE, OCC><<<grid, kBlock, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                     \
     } while (0)
     if (E == 128) {
         if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6); else RS_LAUNCH_STEP(true, 128, 8); }

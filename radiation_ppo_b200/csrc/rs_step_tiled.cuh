@@ -337,12 +337,8 @@ __device__ __forceinline__ void phase_sense(const RsState &S, const Tile &T, int
     const int ag = u / E, t = u - ag * E, n = n0 + t;
     const EnvView e = tile_env(T, S, t, n);
     const int2 det = T.ndet[u];
-    float s[8];
     uint32_t status = 0;
-    sensors_rects(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, s, status);
-    float *row = T.obs + (t * A + ag) * RS_OBS_DIM;
-#pragma unroll
-    for (int d = 0; d < 8; d++) row[3 + d] = s[d];
+    sensors_rects_row(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, T.obs + (t * A + ag) * RS_OBS_DIM + 3, status);
     raise_status(S, n, status);
 }
 
