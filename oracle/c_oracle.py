@@ -262,6 +262,45 @@ class Standardizer:
         return np.array([s.std for s in self.s])
 
 
+class MapsOracle:
+    """One MapsBuffer of the reference (RADTEAM_core.py:394-932) restated in C (oracle/maps_oracle.c)."""
+
+    MAP_NAMES = ("prediction", "location", "others", "readings", "visits", "obstacles", "combined")
+
+    def __init__(self, n_agents: int, steps_per_episode: int = 120, dims=(27, 27), resolution_accuracy: float = 22.0):
+        L = lib()
+        L.orc_maps_new.restype = C.c_void_p
+        L.orc_maps_data.restype = C.POINTER(C.c_float)
+        L.orc_maps_status.restype = C.c_uint32
+        self.dims, self.A = tuple(dims), int(n_agents)
+        self._h = C.c_void_p(L.orc_maps_new(C.c_int32(dims[0]), C.c_int32(dims[1]), C.c_int32(n_agents),
+                                            C.c_int32(steps_per_episode), C.c_double(resolution_accuracy)))
+
+    def __del__(self):
+        try:
+            lib().orc_maps_free(self._h)
+        except Exception:
+            pass
+
+    def reset(self):
+        lib().orc_maps_reset(self._h)
+
+    def observation_to_map(self, obs, agent_id: int, pred) -> np.ndarray:
+        """obs [A, 11] float64, pred (x, y) deflated -> the seven maps [7, X, Y] float32 (a copy)."""
+        o = np.ascontiguousarray(obs, dtype=np.float64).reshape(self.A, OBS_DIM)
+        p = (C.c_double * 2)(float(pred[0]), float(pred[1]))
+        lib().orc_maps_observation_to_map(self._h, _p(o), C.c_int32(agent_id), p)
+        return self.maps()
+
+    def maps(self) -> np.ndarray:
+        ptr = lib().orc_maps_data(self._h)
+        return np.ctypeslib.as_array(ptr, shape=(7, *self.dims)).copy()
+
+    @property
+    def status(self) -> int:
+        return int(lib().orc_maps_status(self._h))
+
+
 def gae(rew, val, path_end, boot, gamma=0.99, lam=0.90, threads=0):
     """Batched P:391-423 over [T, N] float32 arrays -> (adv, ret) float32."""
     rew = np.ascontiguousarray(rew, dtype=np.float32)

@@ -125,6 +125,29 @@ typedef struct {
 double orc_stat_update_standardize(OrcStat *s, double x, int32_t mode /* 1 RAD-TEAM rule, 2 StatBuff + clip 8 */);
 void orc_stat_reset(OrcStat *s);
 
+/* RAD-TEAM map observation: one MapsBuffer (RADTEAM_core.py:394-932), see oracle/maps_oracle.c */
+typedef struct {
+    int32_t dim_x, dim_y, n_agents, base;
+    double ra;                        /* resolution_accuracy                                   */
+    float *maps;                      /* [7][dim_x][dim_y]: prediction, location, others, readings, visits, obstacles, combined */
+    int32_t *shadow;                  /* [dim_x][dim_y] visit_counts_shadow                    */
+    int32_t *log_cell;                /* sample table of the IntensityEstimator: cell of reading i */
+    double *log_val;                  /*                                         value of reading i */
+    int32_t log_len, log_cap;
+    int32_t last_cell[ORC_MAX_A];     /* tools.last_coords (-1 = none)                         */
+    int32_t last_pred;                /* tools.last_prediction (-1 = none)                     */
+    double std_mean, std_m2, std_std; /* tools.standardizer                                    */
+    int32_t std_count;
+    uint32_t status;                  /* 1 agent cell outside the map, 2 sample table full, 4 prediction outside the map */
+} OrcMaps;
+OrcMaps *orc_maps_new(int32_t dim_x, int32_t dim_y, int32_t n_agents, int32_t steps_per_episode,
+                      double resolution_accuracy);
+void orc_maps_free(OrcMaps *m);
+void orc_maps_reset(OrcMaps *m);
+void orc_maps_observation_to_map(OrcMaps *m, const double *obs /* [A][11] */, int32_t id, const double pred[2]);
+const float *orc_maps_data(const OrcMaps *m);
+uint32_t orc_maps_status(const OrcMaps *m);
+
 int32_t orc_sizeof_env(void);
 int32_t orc_sizeof_out(void);
 

@@ -146,3 +146,28 @@ def test_oracle_standardizer_reproduces_reference_classes(mode):
         np.testing.assert_array_equal(st.mean[live], g["mean" + sfx][live, t])
         np.testing.assert_array_equal(st.m2[live], g["m2_" + sfx][live, t])
         np.testing.assert_array_equal(st.std[live], g["std" + sfx][live, t])
+
+
+MAPS_FILES = {"ref_maps_a1": 1, "ref_maps_a4": 4, "ref_maps_a2_idle": 2}
+
+
+@pytest.mark.parametrize("name", list(MAPS_FILES))
+def test_oracle_maps_reproduce_reference_mapsbuffer(name):
+    """oracle/maps_oracle.c against the reference's MapsBuffer.observation_to_map (RADTEAM_core.py:532-616) run on
+    oracle-env rollouts by tools/make_golden.py: all seven float32 maps of every agent's buffer after every call,
+    bit for bit (location / others / combined / prediction counts, median-of-samples readings through the running
+    standardiser, log-scale visit counts, obstacle detections), including the bootstrap call and reset at episode ends."""
+    g = pu.load_golden(name)
+    A = MAPS_FILES[name]
+    bufs = [co.MapsOracle(A, 120, tuple(g["dims"]), float(g["ra"])) for _ in range(A)]
+    seen_multi = 0
+    for t in range(len(g["obs"])):
+        for i in range(A):
+            got = bufs[i].observation_to_map(g["obs"][t], i, g["pred"][t, i])
+            np.testing.assert_array_equal(got, g["maps"][t, i], err_msg=f"{name} call {t} agent {i}")
+            assert bufs[i].status == 0
+        seen_multi += int((g["maps"][t, 0, 6] > 1).any())
+        if g["reset_after"][t]:
+            for b in bufs:
+                b.reset()
+    assert g["reset_after"].sum() >= 1 and (A == 1 or seen_multi > 0)

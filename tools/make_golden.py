@@ -13,6 +13,9 @@
   ref_standardize.npz StatisticStandardization (RADTEAM_core.py:188-277) and StatBuff (test_environment/core.py:55-79)
                       run over count sequences in the caller's order update(x); standardize(x): z-scores and the
                       running mean / M2 / std after every reading.
+  ref_maps_*.npz      MapsBuffer.observation_to_map (RADTEAM_core.py:394-932): one reference MapsBuffer per agent fed
+                      with the observation dicts of an oracle-env rollout (float64) and random source predictions;
+                      the seven maps of every agent's buffer after every call, and the reset points.
 """
 from __future__ import annotations
 
@@ -85,6 +88,8 @@ def main():
         make_scenarios()
     if want("standardize"):
         make_standardize()
+    if want("maps"):
+        make_maps()
 
 
 def make_gae():
@@ -176,6 +181,70 @@ def make_scenarios():
             sc[f"obs{k}_{key}"] = v
     np.savez_compressed(os.path.join(OUT, "scenarios_v4.npz"), **sc)
     print("scenarios done")
+
+
+def make_maps():
+    import importlib
+    import warnings
+
+    from oracle import c_oracle as co
+    from oracle.ref_env import _prepare_path
+
+    _prepare_path()
+    core = importlib.import_module("algos.multiagent.NeuralNetworkCores.RADTEAM_core")
+    scale = 1 / 2200.0
+    ra = core.calculate_resolution_accuracy(resolution_multiplier=0.01, scale=scale)
+    offset = scale * 500.0                                   # enforce_boundaries: RADTEAM_core.py:1738-1739
+    for name, A, T, idle, ml, seed in (("ref_maps_a1", 1, 130, 0.05, 40, 3), ("ref_maps_a4", 4, 90, 0.15, 30, 4),
+                                      ("ref_maps_a2_idle", 2, 80, 0.7, 80, 5)):
+        rng = np.random.default_rng(seed)
+        ob = co.OracleBatch(1, co.default_config(n_agents=A, obstruction_count=4, enforce=1, max_ep_len=ml), seed=seed)
+        ob.reset()
+        bufs = [core.MapsBuffer(observation_dimension=11, steps_per_episode=120, number_of_agents=A, grid_bounds=(1, 1),
+                                resolution_accuracy=ra, offset=offset, resolution_multiplier=0.01) for _ in range(A)]
+        assert bufs[0].map_dimensions == (27, 27)
+        obs_seq, pred_seq, reset_seq, maps_seq = [], [], [], []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for t in range(T):
+                obs = ob.outs["obs"][0, :A].copy()                       # float64 [A, 11], the env's observation dict
+                pred = rng.uniform(0.0, 1.2, size=(A, 2))
+                d = {i: obs[i].copy() for i in range(A)}
+                stacks = [np.stack(bufs[i].observation_to_map(d, i, (float(pred[i, 0]), float(pred[i, 1])))) for i in range(A)]
+                obs_seq.append(obs); pred_seq.append(pred); maps_seq.append(np.stack(stacks).astype(np.float32))
+                acts = rng.integers(0, 8, size=(1, A))
+                acts[rng.random((1, A)) < idle] = 8
+                ob.step(acts, t + 1)
+                e = ob.envs
+                ended = bool(e["done"][0] == 1 or e["ep_len"][0] == ml)
+                reset_seq.append(ended)
+                if ended:
+                    # the bootstrap call on the final observation (train.py:476-480), then reset_agent (train.py:536-538)
+                    fobs = ob.outs["obs"][0, :A].copy()
+                    fpred = rng.uniform(0.0, 1.2, size=(A, 2))
+                    fd = {i: fobs[i].copy() for i in range(A)}
+                    fst = [np.stack(bufs[i].observation_to_map(fd, i, (float(fpred[i, 0]), float(fpred[i, 1])))) for i in range(A)]
+                    obs_seq.append(fobs); pred_seq.append(fpred); maps_seq.append(np.stack(fst).astype(np.float32))
+                    reset_seq.append(2)                                   # 2 = this record is a bootstrap call; reset follows
+                    for b in bufs:
+                        b.reset()
+                    ob.reset(mask=np.ones(1), new_obstacles=np.zeros(1))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), obs=np.stack(obs_seq), pred=np.stack(pred_seq),
+                            reset_after=_reset_flags(reset_seq),
+                            maps=np.stack(maps_seq), ra=np.float64(ra), dims=np.array([27, 27]))
+        print(name, len(obs_seq), "calls", flush=True)
+
+
+def _reset_flags(reset_seq):
+    """One flag per recorded call: 0 = nothing follows, 1 = the buffers are reset after this call (episode ended and this
+    was the bootstrap call)."""
+    out = []
+    for r in reset_seq:
+        if r == 2:
+            out.append(1)
+        else:
+            out.append(0)
+    return np.array(out, np.int32)
 
 
 def make_standardize():
