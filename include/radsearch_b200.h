@@ -178,6 +178,51 @@ int rs_adv_stats(const float *x, int64_t n, const double *center, double *stats,
 /* x[i] = (x[i] - *mean) / *std   (device doubles)                                                     P:446 */
 int rs_adv_normalize(float *x, int64_t n, const double *mean, const double *std, void *stream);
 
+/* ---- RAD-TEAM map observation ---------------------------------------------------------------------
+ * MapsBuffer.observation_to_map (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py:532-616 with its helpers :101-182
+ * IntensityEstimator, :188-277 StatisticStandardization, :322-365 log-scale normalisation, :692-932 map updates) for
+ * every agent's buffer of every environment, on persistent dense map stacks updated in place; MapsBuffer.reset
+ * (:513-523) for the environments that start a new episode.  Module switches as shipped (PFGRU on, simple / radiation
+ * normalisation off). */
+#define RS_MS_CELL_RANGE 1u      /* an agent's grid cell lies outside the map (the reference raises IndexError)          */
+#define RS_MS_LOG_FULL 2u        /* more readings in an episode than log_cap: the call's readings were not recorded      */
+#define RS_MS_PRED_RANGE 4u      /* a source prediction lies outside the map (the reference raises IndexError)           */
+
+typedef struct RsMapsConfig {
+    int32_t n_agents;            /* A                                                                    :437      */
+    int32_t dim_x, dim_y;        /* map_dimensions (27 x 27 with enforced boundaries, 147 x 147 without) :60-66    */
+    int32_t base;                /* (steps_per_episode + 1) * A: base of the visit-count normalisation   :500      */
+    int32_t log_cap;             /* readings an episode can record per environment (>= base + A)                   */
+    int32_t use_prediction;      /* PFGRU: maintain the source prediction map                            :39       */
+    double resolution_accuracy;  /* resolution_multiplier / scale (22.0)                                 :69-70    */
+    double scale;                /* the environment's coordinate scale 1 / search_area_max  rad_search_env.py:435  */
+} RsMapsConfig;
+
+typedef struct RsMapsState {     /* caller-owned device memory; X = dim_x, Y = dim_y, cell = x * Y + y              */
+    float *actor;                /* [N][A][6][X][Y] per buffer: prediction, own location, others, readings, visits, obstacles :1799-1823 */
+    float *critic;               /* [N][4][X][Y]    combined locations, readings, visits, obstacles (same in all A buffers) :1825-1832 */
+    uint16_t *shadow;            /* [N][X][Y]       visit_counts_shadow (steps by 2)                     :464      */
+    uint16_t *log_cell;          /* [N][log_cap]    sample table of the IntensityEstimator: cell of reading i (0xffff = none) */
+    float *log_val;              /* [N][log_cap]                                                value of reading i  */
+    int32_t *log_len;            /* [N]                                                                             */
+    int32_t *last_cell;          /* [N][A]          tools.last_coords (-1 = none)                        :369      */
+    int32_t *last_pred;          /* [N][A]          tools.last_prediction of buffer a (-1 = none)        :371      */
+    double *std;                 /* [N][2]          tools.standardizer: mean, M2                         :198-200  */
+    int32_t *std_count;          /* [N]                                                                  :207      */
+    const float *visit_lut;      /* [log_cap + 1]   normalize_incremental_logscale(2 i, base, 2) for i = 0..log_cap :356-360 */
+    uint32_t *status;            /* [N]             RS_MS_* bits                                                    */
+} RsMapsState;
+
+/* observation_to_map for all A buffers of the selected environments (mask[N] u8, NULL = all).  obs[N][A][11] f32 as
+ * written by rs_step / rs_reset (raw counts); loc_pred[N][A][2] f32 = the source location predicted for agent a's
+ * buffer in scaled coordinates (NULL or NaN = none). */
+int rs_maps_update(const RsMapsConfig *cfg, const RsMapsState *st, const float *obs, const float *loc_pred,
+                   const uint8_t *mask, int32_t n_env, void *stream);
+/* MapsBuffer.reset for the selected environments (mask NULL = all). */
+int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t n_env, void *stream);
+int rs_sizeof_maps_config(void);
+int rs_sizeof_maps_state(void);
+
 const char *rs_last_error(void);
 int rs_version(void);
 /* sizeof checks for the binding */

@@ -10,6 +10,7 @@ from .envs.rad_search_env import HostStepBuffers, RadSearch, StepResult
 from .ppo_buffer import (BatchedPPOBuffer, PPOBuffer, advantage_statistics, combined_shape, gae_advantages,
                          normalize_advantages_)
 from .dist import shard_range
+from .maps_buffer import BatchedMapsBuffer, MapsBuffer
 
 __all__ = ["RadSearch", "StepResult", "HostStepBuffers", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
-           "normalize_advantages_", "combined_shape", "shard_range", "RadSearchLibraryError", "_lib"]
+           "normalize_advantages_", "combined_shape", "shard_range", "BatchedMapsBuffer", "MapsBuffer", "RadSearchLibraryError", "_lib"]

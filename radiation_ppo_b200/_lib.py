@@ -17,8 +17,10 @@ ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, 
 
 EXPORTS = [
     "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
-    "rs_version", "rs_sizeof_config", "rs_sizeof_state",
+    "rs_version", "rs_sizeof_config", "rs_sizeof_state", "rs_maps_update", "rs_maps_reset", "rs_sizeof_maps_config",
+    "rs_sizeof_maps_state",
 ]
+MS_CELL_RANGE, MS_LOG_FULL, MS_PRED_RANGE = 1, 2, 4
 
 
 class RsConfig(C.Structure):
@@ -40,6 +42,25 @@ class RsState(C.Structure):
         "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count",
         "epi", "nx_src", "nx_det", "nx_rad", "nx_best", "nx_dsrc", "nx_obs", "nx_seq", "refill_list", "refill_count",
         "ctr_dev", "st_mean", "st_m2", "raw_count", "ticket")]
+
+
+class RsMapsConfig(C.Structure):
+    _fields_ = [
+        ("n_agents", C.c_int32),
+        ("dim_x", C.c_int32),
+        ("dim_y", C.c_int32),
+        ("base", C.c_int32),
+        ("log_cap", C.c_int32),
+        ("use_prediction", C.c_int32),
+        ("resolution_accuracy", C.c_double),
+        ("scale", C.c_double),
+    ]
+
+
+class RsMapsState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "actor", "critic", "shadow", "log_cell", "log_val", "log_len", "last_cell", "last_pred", "std", "std_count",
+        "visit_lut", "status")]
 
 
 class RadSearchLibraryError(RuntimeError):
@@ -78,6 +99,13 @@ def declare(lib, prefix="rs_"):
         lib.rs_adv_normalize.argtypes = [vp, i64, vp, vp, vp]
         lib.rs_bump_ctr.restype = i32
         lib.rs_bump_ctr.argtypes = [stp, vp]
+        mcp, msp = C.POINTER(RsMapsConfig), C.POINTER(RsMapsState)
+        lib.rs_maps_update.restype = i32
+        lib.rs_maps_update.argtypes = [mcp, msp, vp, vp, vp, i32, vp]
+        lib.rs_maps_reset.restype = i32
+        lib.rs_maps_reset.argtypes = [mcp, msp, vp, i32, vp]
+        lib.rs_sizeof_maps_config.restype = i32
+        lib.rs_sizeof_maps_state.restype = i32
         lib.rs_last_error.restype = C.c_char_p
         lib.rs_version.restype = i32
         lib.rs_sizeof_config.restype = i32
@@ -97,7 +125,8 @@ def load():
         if missing:
             raise RadSearchLibraryError(f"{LIB_PATH} lacks symbols {missing}")
         declare(lib)
-        if lib.rs_sizeof_config() != C.sizeof(RsConfig) or lib.rs_sizeof_state() != C.sizeof(RsState):
+        if lib.rs_sizeof_config() != C.sizeof(RsConfig) or lib.rs_sizeof_state() != C.sizeof(RsState) or \
+                lib.rs_sizeof_maps_config() != C.sizeof(RsMapsConfig) or lib.rs_sizeof_maps_state() != C.sizeof(RsMapsState):
             raise RadSearchLibraryError("struct layout mismatch between _lib.py and libradsearch_b200.so")
         _lib = lib
     return _lib

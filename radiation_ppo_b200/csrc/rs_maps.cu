@@ -1,0 +1,270 @@
+// RAD-TEAM map observation on the device: MapsBuffer.observation_to_map for every agent's buffer of
+// every environment in one launch, on PERSISTENT dense map stacks in HBM that are updated sparsely in place.
+// M: = /root/reference/algos/multiagent/NeuralNetworkCores/RADTEAM_core.py
+//   observation_to_map M:532-616, _inflate_coordinates M:692-715, _update_* M:748-932, IntensityEstimator M:101-182,
+//   StatisticStandardization M:188-277, normalize_incremental_logscale M:322-365, reset / _clear_maps M:513-530, 618-667
+//
+// The reference keeps one MapsBuffer per agent and feeds each of them the SAME observation dict every step, so the
+// readings / visit-count / obstacle / combined-location maps, the sample table and the running standardiser are
+// identical in the A buffers of an environment: they are computed once per environment and written to the agents'
+// actor stacks and to the (shared) critic stack.  Only the agent's own location, the others' locations and the source
+// prediction differ per buffer.
+//
+// One warp per environment.  Per call and environment the work is a scan of the episode's sample table (<= (T+1)*A
+// readings, 6 bytes each), a rank selection among the samples of the visited cells and ~6*A*A scattered 4-byte stores:
+// latency bound, not bandwidth bound; the dense stacks (29 KB per agent at 27x27) are never rewritten, the policy's
+// convolutions read them where they lie.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/radsearch_b200.h"
+#include "rs_error.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBlock = 32 * kWarpsPerBlock;
+
+__device__ __forceinline__ int cell_of(const RsMapsConfig &c, double vx, double vy) {
+    // int(v * resolution_accuracy) M:704-713, then numpy indexing: negative indices wrap once
+    int cx = (int)(vx * c.resolution_accuracy), cy = (int)(vy * c.resolution_accuracy);
+    if (cx < 0) cx += c.dim_x;
+    if (cy < 0) cy += c.dim_y;
+    if (cx < 0 || cy < 0 || cx >= c.dim_x || cy >= c.dim_y) return -1;
+    return cx * c.dim_y + cy;
+}
+
+__global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_constant__ RsMapsConfig c,
+                                                             const __grid_constant__ RsMapsState S, const float *obs,
+                                                             const float *loc_pred, const uint8_t *mask, int n_env) {
+    extern __shared__ float scratch_all[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + w;
+    if (n >= n_env || (mask && !mask[n])) return;                          // whole warps leave together
+    float *scratch = scratch_all + (size_t)w * c.log_cap;
+    const int A = c.n_agents, XY = c.dim_x * c.dim_y;
+    uint32_t status = 0;
+
+    // ---- this call's observations: lane a holds agent a -----------------------------------------------------------
+    int my_cell = -1, my_pred = -1;
+    float my_count = 0.0f, my_obst = 0.0f;
+    bool my_has_obst = false, pred_given = false;
+    if (lane < A) {
+        const float *o = obs + ((size_t)n * A + lane) * RS_OBS_DIM;
+        my_count = o[0];
+        // the env writes x * scale rounded to fp32; the reference's float64 observation is recovered from the lattice
+        // coordinate (exact: the fp32 error is 1e-4 of a lattice step)
+        const double x = rint((double)o[1] / c.scale), y = rint((double)o[2] / c.scale);
+        my_cell = cell_of(c, x * c.scale, y * c.scale);
+        if (my_cell < 0) status |= RS_MS_CELL_RANGE;
+#pragma unroll
+        for (int d = 3; d < RS_OBS_DIM; d++) {                             // M:929-932: the last non-zero detection wins
+            const float v = o[d];
+            if (v != 0.0f) { my_obst = v; my_has_obst = true; }
+        }
+        if (c.use_prediction && loc_pred) {
+            const float px = loc_pred[((size_t)n * A + lane) * 2], py = loc_pred[((size_t)n * A + lane) * 2 + 1];
+            if (px == px && py == py) {                                    // NaN = no prediction for this buffer
+                pred_given = true;
+                my_pred = cell_of(c, (double)px, (double)py);
+                if (my_pred < 0) status |= RS_MS_PRED_RANGE;
+            }
+        }
+    }
+
+    // ---- M:541-545: every agent's reading joins the sample table before any estimate -----------------------------------
+    uint16_t *log_cell = S.log_cell + (size_t)n * c.log_cap;
+    float *log_val = S.log_val + (size_t)n * c.log_cap;
+    int len = S.log_len[n];
+    if (len + A <= c.log_cap) {
+        if (lane < A) {
+            log_cell[len + lane] = (uint16_t)(my_cell < 0 ? 0xffff : my_cell);
+            log_val[len + lane] = my_count;
+        }
+        len += A;
+    } else {
+        status |= RS_MS_LOG_FULL;
+    }
+    __syncwarp();
+
+    double mean = S.std[2 * (size_t)n], m2 = S.std[2 * (size_t)n + 1];
+    int cnt = S.std_count[n];
+    float *actor = S.actor + ((size_t)n * A + (lane < A ? lane : 0)) * 6 * XY;   // lane a' owns buffer a'
+    float *critic = S.critic + (size_t)n * 4 * XY;
+    uint16_t *shadow = S.shadow + (size_t)n * XY;
+
+    // ---- source prediction map of buffer a' (PFGRU) M:564-568, 748-766 --------------------------------------------------
+    if (pred_given) {
+        const int last = S.last_pred[(size_t)n * A + lane];
+        if (last >= 0) actor[last] -= 1.0f;
+        if (my_pred >= 0) actor[my_pred] = 1.0f;       // outside the map (the reference raises): old mark cleared, none set
+        S.last_pred[(size_t)n * A + lane] = my_pred;
+    }
+
+    // ---- agents in dict order M:547-604 ---------------------------------------------------------------------------------
+    for (int a = 0; a < A; a++) {
+        const int cc = __shfl_sync(0xffffffffu, my_cell, a);
+        if (cc < 0) continue;
+        const float obst = __shfl_sync(0xffffffffu, my_obst, a);
+        const bool has_obst = __shfl_sync(0xffffffffu, (int)my_has_obst, a) != 0;
+        const int last = S.last_cell[(size_t)n * A + a];
+
+        // median of the samples of this cell (IntensityEstimator.get_estimate M:160-167): compact them, then select by rank
+        int m = 0;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            const bool hit = i < len && log_cell[i] == (uint16_t)cc;
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (hit) scratch[m + __popc(b & ((1u << lane) - 1u))] = log_val[i];
+            m += __popc(b);
+        }
+        __syncwarp();
+        const int k1 = (m - 1) >> 1, k2 = m >> 1;
+        float r1 = -1.0f, r2 = -1.0f;                                       // readings are >= 0
+        for (int i = lane; i < m; i += 32) {
+            const float v = scratch[i];
+            int rank = 0;
+            for (int j = 0; j < m; j++) {
+                const float u = scratch[j];
+                rank += (u < v) || (u == v && j < i);
+            }
+            if (rank == k1) r1 = v;
+            if (rank == k2) r2 = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+            r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        }
+        __syncwarp();                                                       // scratch is reused by the next agent
+        const double est = ((double)r1 + (double)r2) / 2.0;                 // statistics.median
+
+        // StatisticStandardization.update + standardize M:215-265 (same numbers on every lane)
+        cnt += 1;
+        double sd = 1.0;
+        if (cnt == 1) mean = est;
+        else {
+            const double mean_new = mean + (est - mean) / (double)cnt;
+            m2 = m2 + (est - mean) * (est - mean_new);
+            mean = mean_new;
+            sd = fmax(sqrt(m2 / (double)(cnt - 1)), 1.0);
+        }
+        const float z = (float)((est - mean) / sd);
+
+        // visit counts M:886-916: the shadow counter steps by 2; normalised value from the host's table (math.log)
+        const int cur = shadow[cc];
+        const float vis = S.visit_lut[cur >> 1];
+        __syncwarp();
+        if (lane == 0) shadow[cc] = (uint16_t)(cur + 2);
+
+        if (lane < A) {
+            // location maps of buffer a' = lane M:570-588, 768-848
+            float *loc = actor + (lane == a ? 1 : 2) * XY;
+            if (last >= 0) loc[last] -= 1.0f;
+            if (lane == a) loc[cc] = 1.0f;
+            else loc[cc] += 1.0f;
+            actor[3 * XY + cc] = z;                                         // readings map M:884
+            actor[4 * XY + cc] = vis;                                       // visit counts map M:906
+            if (has_obst) actor[5 * XY + cc] = obst;                        // obstacles map M:929-932
+        }
+        if (lane == 0) {                                                    // the critic's stack (same in every buffer)
+            if (last >= 0) critic[last] -= 1.0f;                            // combined locations M:786-810
+            critic[cc] += 1.0f;
+            critic[XY + cc] = z;
+            critic[2 * XY + cc] = vis;
+            if (has_obst) critic[3 * XY + cc] = obst;
+            S.last_cell[(size_t)n * A + a] = cc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        S.log_len[n] = len;
+        S.std[2 * (size_t)n] = mean;
+        S.std[2 * (size_t)n + 1] = m2;
+        S.std_count[n] = cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(0xffffffffu, status, o);
+    if (lane == 0 && status) S.status[n] |= status;
+}
+
+// MapsBuffer.reset M:513-523 (+ ConversionTools.reset M:378-385) for the selected environments: one warp zeroes the
+// environment's stacks with 16-byte stores
+__global__ void __launch_bounds__(kBlock) maps_reset_kernel(const __grid_constant__ RsMapsConfig c,
+                                                            const __grid_constant__ RsMapsState S, const uint8_t *mask,
+                                                            int n_env) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * kWarpsPerBlock + w;
+    if (n >= n_env || (mask && !mask[n])) return;
+    const int A = c.n_agents, XY = c.dim_x * c.dim_y;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        float *p = S.actor + (size_t)n * A * 6 * XY;
+        const size_t cnt = (size_t)A * 6 * XY;
+        if ((cnt & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0)
+            for (size_t i = lane; i < cnt / 4; i += 32) reinterpret_cast<float4 *>(p)[i] = z4;
+        else
+            for (size_t i = lane; i < cnt; i += 32) p[i] = 0.0f;
+    }
+    {
+        float *p = S.critic + (size_t)n * 4 * XY;
+        const size_t cnt = (size_t)4 * XY;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+            for (size_t i = lane; i < cnt / 4; i += 32) reinterpret_cast<float4 *>(p)[i] = z4;
+        else
+            for (size_t i = lane; i < cnt; i += 32) p[i] = 0.0f;
+    }
+    for (int i = lane; i < XY; i += 32) S.shadow[(size_t)n * XY + i] = 0;
+    if (lane < A) {
+        S.last_cell[(size_t)n * A + lane] = -1;
+        S.last_pred[(size_t)n * A + lane] = -1;
+    }
+    if (lane == 0) {
+        S.log_len[n] = 0;
+        S.std[2 * (size_t)n] = 0.0;
+        S.std[2 * (size_t)n + 1] = 0.0;
+        S.std_count[n] = 0;
+    }
+}
+
+int check_maps(const RsMapsConfig *c, const RsMapsState *s, int32_t n_env) {
+    if (!c || !s) return rs_set_error("maps cfg/state is NULL");
+    if (n_env <= 0) return rs_set_error("n_env must be positive");
+    if (c->n_agents < 1 || c->n_agents > RS_MAX_A) return rs_set_error("n_agents out of range [1, 8]");
+    if (c->dim_x < 1 || c->dim_y < 1 || (int64_t)c->dim_x * c->dim_y > 65535) return rs_set_error("map dimensions out of range");
+    if (c->log_cap < c->n_agents || c->log_cap > 8192) return rs_set_error("log_cap out of range");
+    if (c->base < 2) return rs_set_error("base must be >= 2");
+    if (!(c->resolution_accuracy > 0) || !(c->scale > 0)) return rs_set_error("resolution_accuracy / scale must be positive");
+    if (!s->actor || !s->critic || !s->shadow || !s->log_cell || !s->log_val || !s->log_len || !s->last_cell ||
+        !s->last_pred || !s->std || !s->std_count || !s->visit_lut || !s->status)
+        return rs_set_error("RsMapsState has NULL members");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rs_maps_update(const RsMapsConfig *cfg, const RsMapsState *st, const float *obs, const float *loc_pred,
+                   const uint8_t *mask, int32_t n_env, void *stream) {
+    if (int rc = check_maps(cfg, st, n_env)) return rc;
+    if (!obs) return rs_set_error("obs is NULL");
+    const int grid = (n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t smem = (size_t)kWarpsPerBlock * cfg->log_cap * sizeof(float);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(maps_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    maps_update_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, obs, loc_pred, mask, n_env);
+    return (int)cudaGetLastError();
+}
+
+int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t n_env, void *stream) {
+    if (int rc = check_maps(cfg, st, n_env)) return rc;
+    const int grid = (n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    maps_reset_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, mask, n_env);
+    return (int)cudaGetLastError();
+}
+
+int rs_sizeof_maps_config(void) { return (int)sizeof(RsMapsConfig); }
+int rs_sizeof_maps_state(void) { return (int)sizeof(RsMapsState); }
+
+}  // extern "C"
