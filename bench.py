@@ -295,6 +295,42 @@ def main():
     gae_gbs = GAE_BYTES_PER_ELEM * T * N / (gae_ms / 1e3) / 1e9
     del rew, val, end, boot, adv, ret
 
+    # ---- RAD-TEAM pipeline of BASELINE configs[3]: 16,384 envs x 4 agents, env step -> shared map observation ---------
+    maps_line = None
+    if world == 1:
+        Nm, Am, Tm = 16384, 4, 120
+        menv = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, number_agents=Am, num_envs=Nm, seed=4,
+                            device=dev, auto_reset=True, fast_poisson=fast)
+        mb = rp.BatchedMapsBuffer(Nm, Am, 120, environment_scale=menv.scale, device=dev)
+        macts = torch.randint(0, 8, (8, Nm, Am), generator=g, device=dev, dtype=torch.int32)
+        mpred = torch.rand(Nm, Am, 2, generator=g, device=dev)
+
+        def maps_step(i):
+            mb.update(menv.obs, mpred)
+            menv.step_batch(macts[i % 8])
+            mb.reset(mask=(menv.ended & 4) != 0)
+
+        for i in range(20):
+            maps_step(i)
+        torch.cuda.synchronize()
+        mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Tm)]
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(Tm):
+            mev[i][0].record()
+            mb.update(menv.obs, mpred)
+            mev[i][1].record()
+            menv.step_batch(macts[i % 8])
+            mb.reset(mask=(menv.ended & 4) != 0)
+        p1.record()
+        torch.cuda.synchronize()
+        upd_ms = sorted(a.elapsed_time(b) for a, b in mev)[Tm // 2]
+        maps_line = {"workload": f"{Nm} envs x {Am} agents, 27x27 maps, env step + rs_maps_update + rs_maps_reset (BASELINE configs[3])",
+                     "update_ms": upd_ms, "agent_map_updates_per_s": Nm * Am / (upd_ms / 1e3),
+                     "pipeline_env_steps_per_s": Nm * Tm / (p0.elapsed_time(p1) / 1e3),
+                     "maps_status_flags": int(mb.status.sum().item())}
+        del menv, mb
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----------------
     # RadSearch.step_host: pinned host actions -> device, step + auto-reset, ALL step outputs -> pinned host in one
     # transfer, on the env batch's own stream.  `e2e`: the R env batches of the ring are driven round-robin, the host
@@ -364,6 +400,7 @@ def main():
                             f"done/info/ended flags) -> pinned host in one copy; value = {R} env batches round-robin on "
                             "their own streams (host waits for a batch's previous results before sending its next "
                             "actions); sync_value = host waits after every step"},
+            "maps": maps_line,
             "gpu_launches": int((2 + 1 / rp.RadSearch.PREFETCH_PERIOD) * K) if not args.no_prefetch else 2 * K, "clocks": clocks, "status_flags_raised": status,
         }
         if not args.no_cpu_baseline and world == 1:

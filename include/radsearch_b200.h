@@ -178,6 +178,19 @@ int rs_adv_stats(const float *x, int64_t n, const double *center, double *stats,
 /* x[i] = (x[i] - *mean) / *std   (device doubles)                                                     P:446 */
 int rs_adv_normalize(float *x, int64_t n, const double *mean, const double *std, void *stream);
 
+/* ---- batched PPOBuffer.get (P:425-502) -----------------------------------------------------------
+ * packed[n*T + t][0..D+5] = [obs[t][n][0..D-1], adv, ret, logp, act, source_tar x, y]: the rows of the reference's
+ * np.hstack (P:456-465) in episode-major order -- column n of the rollout is one env's trajectory buffer, so every
+ * episode is one contiguous slice of `packed` (P:468-486).  obs [T][N][D], adv/ret/logp/act [T][N], src [T][N][2]
+ * (nullable: zeros), all f32. */
+int rs_pack_rollout(const float *obs, const float *adv, const float *ret, const float *logp, const float *act,
+                    const float *src, float *packed, int32_t T, int32_t N, int32_t D, void *stream);
+/* Episode segmentation of the [T][N] rollout (a trajectory ends where path_end != 0 and at t = T-1).  Two passes:
+ * ep_offset == NULL -> ep_count[n] = trajectories of column n; then, with ep_offset[n] = exclusive prefix sum of
+ * ep_count, ep_start[e] = first row of episode e in `packed` (n*T + t_first) and ep_len[e], in (column, time) order. */
+int rs_episode_table(const uint8_t *path_end, int32_t T, int32_t N, int32_t *ep_count, const int32_t *ep_offset,
+                     int32_t *ep_start, int32_t *ep_len, void *stream);
+
 /* ---- RAD-TEAM map observation ---------------------------------------------------------------------
  * MapsBuffer.observation_to_map (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py:532-616 with its helpers :101-182
  * IntensityEstimator, :188-277 StatisticStandardization, :322-365 log-scale normalisation, :692-932 map updates) for

@@ -11,6 +11,7 @@ from .ppo_buffer import (BatchedPPOBuffer, PPOBuffer, advantage_statistics, comb
                          normalize_advantages_)
 from .dist import shard_range
 from .maps_buffer import BatchedMapsBuffer, MapsBuffer
+from .evaluate import MonteCarloEvaluator, MonteCarloResults, uniform_policy
 
 __all__ = ["RadSearch", "StepResult", "HostStepBuffers", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
-           "normalize_advantages_", "combined_shape", "shard_range", "BatchedMapsBuffer", "MapsBuffer", "RadSearchLibraryError", "_lib"]
+           "normalize_advantages_", "combined_shape", "shard_range", "BatchedMapsBuffer", "MapsBuffer", "MonteCarloEvaluator", "MonteCarloResults", "uniform_policy", "RadSearchLibraryError", "_lib"]

@@ -256,11 +256,40 @@ class BatchedPPOBuffer:
         gae_advantages(self.rew_buf, self.val_buf, self.end_buf, self.boot_buf, self.gamma, self.lam, self.adv_buf,
                        self.ret_buf, self.stats, variant)
 
-    def get(self, group=None) -> Dict[str, torch.Tensor]:
+    def pack_episodes(self):
+        """The reference's `ep_form` (P:456-486) for the whole buffer: `packed` [N*T, D+6] float32 holds the rows
+        [obs | adv | ret | logp | act | source_tar] episode-major (column n's steps at rows n*T .. n*T+T-1), and
+        (`ep_start`, `ep_len`) int32 [E] describe every trajectory as the slice packed[ep_start[e] : ep_start[e] +
+        ep_len[e]], in (column, time) order.  Two kernel launches + one prefix sum; no per-episode host loop."""
+        lib = L.load()
+        T, N, D = self.T, self.N, self.D
+        packed = torch.empty(N * T, D + 6, dtype=torch.float32, device=self.device)
+        ep_count = torch.empty(N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.rs_pack_rollout(_ptr(self.obs_buf), _ptr(self.adv_buf), _ptr(self.ret_buf), _ptr(self.logp_buf),
+                                        _ptr(self.act_buf), _ptr(self.source_tar), _ptr(packed), T, N, D,
+                                        _stream(self.device)), "rs_pack_rollout")
+            L.check(lib.rs_episode_table(_ptr(self.end_buf), T, N, _ptr(ep_count), None, None, None,
+                                         _stream(self.device)), "rs_episode_table")
+            incl = torch.cumsum(ep_count, 0, dtype=torch.int32)
+            offset = (incl - ep_count).contiguous()
+            n_ep = int(incl[-1].item())
+            ep_start = torch.empty(n_ep, dtype=torch.int32, device=self.device)
+            ep_len = torch.empty(n_ep, dtype=torch.int32, device=self.device)
+            L.check(lib.rs_episode_table(_ptr(self.end_buf), T, N, _ptr(ep_count), _ptr(offset), _ptr(ep_start),
+                                         _ptr(ep_len), _stream(self.device)), "rs_episode_table")
+        return packed, ep_start, ep_len
+
+    def get(self, group=None, episodes: bool = False) -> Dict[str, torch.Tensor]:
+        """P:425-502 for the batched buffer: global (all-rank) advantage normalisation, flat views of the step data, and
+        with ``episodes=True`` the episode-major `packed` rows with their (`ep_start`, `ep_len`) table (pack_episodes)."""
         assert self.ptr == self.T
         mean, std = advantage_statistics(self.adv_buf, group=group)
         normalize_advantages_(self.adv_buf, mean.float().double(), std.float().double())
         self.quick_reset()
         f = lambda x: x.reshape(self.T * self.N, *x.shape[2:])                 # noqa: E731
-        return dict(obs=f(self.obs_buf), act=f(self.act_buf), ret=f(self.ret_buf), adv=f(self.adv_buf),
-                    logp=f(self.logp_buf), src=f(self.source_tar), end=self.end_buf, adv_mean=mean, adv_std=std)
+        out = dict(obs=f(self.obs_buf), act=f(self.act_buf), ret=f(self.ret_buf), adv=f(self.adv_buf),
+                   logp=f(self.logp_buf), src=f(self.source_tar), end=self.end_buf, adv_mean=mean, adv_std=std)
+        if episodes:
+            out["packed"], out["ep_start"], out["ep_len"] = self.pack_episodes()
+        return out

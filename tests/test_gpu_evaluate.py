@@ -1,0 +1,64 @@
+"""GPU test (pytest -m gpu) of the batched Monte-Carlo evaluation driver (radiation_ppo_b200/evaluate.py)
+against the oracle played the reference's way: one scenario, one run at a time, until done or the timeout
+(evaluate.py:333-475)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from tests import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+import radiation_ppo_b200 as rp  # noqa: E402
+
+
+@pytest.mark.parametrize("k,A", [(5, 1), (3, 2)])
+def test_monte_carlo_evaluator_matches_oracle_episodes(k, A):
+    sc = pu.load_golden("scenarios_v4")
+    S, R, T = 48, 5, 120
+    arr = {key: sc[f"obs{k}_{key}"][:S] for key in ("src", "det", "intensity", "bkg", "rects", "num_obs")}
+    ev = rp.MonteCarloEvaluator(scenarios=arr, montecarlo_runs=R, steps_per_episode=T, obstruction_count=k, seed=123,
+                                enforce_grid_boundaries=True, number_agents=A)
+    N = S * R
+    rng = np.random.default_rng(k)
+    table = rng.integers(0, 8, size=(T, N, A)).astype(np.int32)
+    # bias the walk towards the source so that a good share of the runs succeeds
+    src = np.repeat(arr["src"], R, axis=0).astype(np.float64) / 2200.0
+    dirs = np.array([[-1, 0], [-1, 1], [0, 1], [1, 1], [1, 0], [1, -1], [0, -1], [-1, -1]], np.float64)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    tab_dev = torch.as_tensor(table, device=ev.env.device)
+    src_dev = torch.as_tensor(src, dtype=torch.float32, device=ev.env.device)
+    dirs_dev = torch.as_tensor(dirs, dtype=torch.float32, device=ev.env.device)
+    log = []
+
+    def policy(obs, t):
+        # greedy towards the source on even steps (float32 arithmetic on the device), table action on odd steps
+        to = src_dev[:, None, :] - obs[:, :, 1:3]
+        greedy = (to @ dirs_dev.T).argmax(dim=2).to(torch.int32)
+        a = torch.where(torch.tensor(t % 2 == 0, device=obs.device), greedy, tab_dev[t])
+        log.append(a.cpu().numpy())
+        return a
+
+    res = ev.run(policy)
+    # the oracle, the reference's way
+    ob = co.OracleBatch(N, co.default_config(n_agents=A, obstruction_count=k, enforce=1), seed=123)
+    rep = {key: np.repeat(v, R, axis=0) for key, v in arr.items()}
+    ob.load_scenarios(rep["src"], rep["det"], rep["intensity"], rep["bkg"], rep["rects"], rep["num_obs"])
+    active = np.ones(N, bool); success = np.zeros(N, bool); length = np.zeros(N, np.int32); ret = np.zeros(N)
+    ctr0 = ev.env._ctr - len(log)
+    for t in range(len(log)):
+        ob.step(log[t], ctr0 + t + 1)
+        team = ob.outs["team_reward"].astype(np.float32).astype(np.float64)
+        ret += np.where(active, team, 0.0)
+        length += active
+        term = (ob.outs["done"][:, :A] != 0).any(axis=1) & active
+        success |= term
+        active &= ~term
+    np.testing.assert_array_equal(res.success.cpu().numpy().reshape(-1), success)
+    np.testing.assert_array_equal(res.episode_length.cpu().numpy().reshape(-1), length)
+    np.testing.assert_allclose(res.episode_return.cpu().numpy().reshape(-1), ret, rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(res.success_counter.cpu().numpy(), success.reshape(S, R).sum(1))
+    assert 0.1 < success.mean() < 1.0 and res.completed_runs == R
+    s = res.summary()
+    assert s["success_rate"] == pytest.approx(success.mean())

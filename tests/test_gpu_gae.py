@@ -200,3 +200,39 @@ def test_batched_buffer_end_to_end_against_oracle():
     m, s = a0.astype(np.float64).mean(), a0.astype(np.float64).std()
     np.testing.assert_allclose(data["adv"].cpu().numpy().reshape(T, N), (a0 - np.float32(m)) / np.float32(s), rtol=1e-6, atol=1e-6)
     assert data["obs"].shape == (T * N, 11) and buf.ptr == 0
+
+
+def test_batched_get_packs_the_reference_episode_tensors():
+    """BatchedPPOBuffer.get(episodes=True) (rs_pack_rollout + rs_episode_table) against the `ep_form` tensors of the
+    reference's PPOBuffer.get (P:425-502), one reference buffer per column (tests/golden/ref_get_epform.npz):
+    row layout [obs | adv | ret | logp | act | source_tar], episode order and lengths, bit-exact (the advantage column is
+    checked in the single-column buffers, where the reference's single-rank normalisation is the batched one)."""
+    g = pu.load_golden("ref_get_epform")
+    T, N, _ = g["obs"].shape
+    d = dev()
+
+    def fill(cols):
+        buf = rp.BatchedPPOBuffer(11, T, len(cols))
+        tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=d)          # noqa: E731
+        for t in range(T):
+            buf.store_batch(tt(g["obs"][t, cols]), tt(g["act"][t, cols]), tt(g["rew"][t, cols]), tt(g["val"][t, cols]),
+                            tt(g["logp"][t, cols]), src=tt(g["src"][t, cols]), end=tt(g["end"][t, cols]),
+                            boot=tt(g["boot"][t, cols]))
+        buf.finish_paths(variant=1)
+        return buf
+
+    data = fill(list(range(N))).get(episodes=True)
+    packed = data["packed"].cpu().numpy().reshape(N, T, 17)
+    np.testing.assert_array_equal(packed[:, :, :11], g["ep_rows"][:, :, :11])
+    np.testing.assert_array_equal(packed[:, :, 12:], g["ep_rows"][:, :, 12:])
+    es, el = data["ep_start"].cpu().numpy(), data["ep_len"].cpu().numpy()
+    want_len = np.concatenate([g["ep_lens"][n][g["ep_lens"][n] > 0] for n in range(N)])
+    want_start = np.concatenate([n * T + np.concatenate([[0], np.cumsum(g["ep_lens"][n][g["ep_lens"][n] > 0])[:-1]])
+                                 for n in range(N)])
+    np.testing.assert_array_equal(el, want_len)
+    np.testing.assert_array_equal(es, want_start)
+    for n in (0, 3):                                       # single column = the reference's single-rank buffer
+        one = fill([n]).get(episodes=True)
+        p1 = one["packed"].cpu().numpy()
+        np.testing.assert_allclose(p1[:, 11], g["ep_rows"][n][:, 11], rtol=2e-6, atol=2e-6)
+        np.testing.assert_array_equal(np.delete(p1, 11, axis=1), np.delete(g["ep_rows"][n], 11, axis=1))

@@ -90,6 +90,8 @@ def main():
         make_standardize()
     if want("maps"):
         make_maps()
+    if want("get"):
+        make_get()
 
 
 def make_gae():
@@ -181,6 +183,47 @@ def make_scenarios():
             sc[f"obs{k}_{key}"] = v
     np.savez_compressed(os.path.join(OUT, "scenarios_v4.npz"), **sc)
     print("scenarios done")
+
+
+def make_get():
+    """PPOBuffer.get() (P:425-502): one reference buffer per column; the rows of its `ep_form` tensors and their lengths."""
+    ppo = load_reference_ppo()
+    rng = np.random.default_rng(11)
+    T, N = 72, 8
+    g = dict(obs=rng.normal(size=(T, N, 11)).astype(np.float32), act=rng.integers(0, 8, (T, N)).astype(np.float32),
+             rew=(-0.5 * rng.uniform(0, 1.5, (T, N))).astype(np.float32), val=rng.normal(size=(T, N)).astype(np.float32),
+             logp=rng.normal(size=(T, N)).astype(np.float32), src=rng.uniform(0, 2200, (T, N, 2)).astype(np.float32),
+             end=np.zeros((T, N), np.uint8), boot=np.zeros((T, N), np.float32))
+    rows, lens, advs = [], [], []
+    for n in range(N):
+        buf = ppo.PPOBuffer(observation_dimension=11, max_size=T, max_episode_length=120, number_agents=1)
+        t = 0
+        while t < T:
+            e = min(T, t + int(rng.integers(1, 30))) - 1
+            g["end"][e, n] = 1
+            g["boot"][e, n] = 0.0 if rng.random() < 0.4 else np.float32(rng.normal())
+            t = e + 1
+        start = 0
+        for t in range(T):
+            buf.store(obs=g["obs"][t, n], act=g["act"][t, n], rew=g["rew"][t, n], val=g["val"][t, n], logp=g["logp"][t, n],
+                      src=g["src"][t, n], full_observation={}, heatmap_stacks=None, terminal=False)
+            if g["end"][t, n]:
+                buf.GAE_advantage_and_rewardsToGO(float(g["boot"][t, n]))
+                # train.py:493-503 stores the length of episodes that are over; an epoch cut-off leaves the tail to get()
+                if t < T - 1 or n % 2 == 0:
+                    buf.store_episode_length(t + 1 - start)
+                start = t + 1
+        data = buf.get()
+        ep = [e[0].numpy() for e in data["ep_form"]]
+        rows.append(np.concatenate(ep, axis=0))
+        ln = [len(e) for e in ep]
+        lens.append(np.array(ln + [0] * (T - len(ln)), np.int32))
+        advs.append(data["adv"].numpy())
+    g["ep_rows"] = np.stack(rows)           # [N, T, 17]
+    g["ep_lens"] = np.stack(lens)           # [N, T] zero padded
+    g["adv_norm"] = np.stack(advs, axis=1)  # [T, N] per-column (single rank) normalisation
+    np.savez_compressed(os.path.join(OUT, "ref_get_epform.npz"), **g)
+    print("ref_get_epform done", flush=True)
 
 
 def make_maps():
