@@ -214,7 +214,6 @@ typedef struct RsMapsConfig {
 typedef struct RsMapsState {     /* caller-owned device memory; X = dim_x, Y = dim_y, cell = x * Y + y              */
     float *actor;                /* [N][A][6][X][Y] per buffer: prediction, own location, others, readings, visits, obstacles :1799-1823 */
     float *critic;               /* [N][4][X][Y]    combined locations, readings, visits, obstacles (same in all A buffers) :1825-1832 */
-    uint16_t *shadow;            /* [N][X][Y]       visit_counts_shadow (steps by 2)                     :464      */
     uint16_t *log_cell;          /* [N][log_cap]    sample table of the IntensityEstimator: cell of reading i (0xffff = none) */
     float *log_val;              /* [N][log_cap]                                                value of reading i  */
     int32_t *log_len;            /* [N]                                                                             */
@@ -223,6 +222,7 @@ typedef struct RsMapsState {     /* caller-owned device memory; X = dim_x, Y = d
     double *std;                 /* [N][2]          tools.standardizer: mean, M2                         :198-200  */
     int32_t *std_count;          /* [N]                                                                  :207      */
     const float *visit_lut;      /* [log_cap + 1]   normalize_incremental_logscale(2 i, base, 2) for i = 0..log_cap :356-360 */
+                                 /*                 (the shadow counter :464 is 2 x the cell's samples recorded so far)      */
     uint32_t *status;            /* [N]             RS_MS_* bits                                                    */
 } RsMapsState;
 

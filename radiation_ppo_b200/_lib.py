@@ -59,7 +59,7 @@ class RsMapsConfig(C.Structure):
 
 class RsMapsState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "actor", "critic", "shadow", "log_cell", "log_val", "log_len", "last_cell", "last_pred", "std", "std_count",
+        "actor", "critic", "log_cell", "log_val", "log_len", "last_cell", "last_pred", "std", "std_count",
         "visit_lut", "status")]
 
 

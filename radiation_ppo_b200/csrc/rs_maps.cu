@@ -10,10 +10,13 @@
 // actor stacks and to the (shared) critic stack.  Only the agent's own location, the others' locations and the source
 // prediction differ per buffer.
 //
-// One warp per environment.  Per call and environment the work is a scan of the episode's sample table (<= (T+1)*A
-// readings, 6 bytes each), a rank selection among the samples of the visited cells and ~6*A*A scattered 4-byte stores:
-// latency bound, not bandwidth bound; the dense stacks (29 KB per agent at 27x27) are never rewritten, the policy's
-// convolutions read them where they lie.
+// One warp per environment.  Per call and environment the work is: the episode's sample table (<= (T+1)*A readings, 6
+// bytes each) staged into shared memory, per agent a compaction + rank selection among the samples of its cell, and
+// ~6*A*A scattered 4-byte STORES -- the location counts are recomputed from the agents' recorded cells and the visit
+// counter from the sample table, so no map is ever read back.  Bound by latency and by the scattered 32-byte-sector
+// traffic of those stores (per-cell chains instead of the table scan were tried: fewer instructions, one more dependent
+// load, slower); the dense stacks (29 KB per agent at 27x27) are never rewritten, the policy's convolutions read them
+// where they lie.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -37,13 +40,34 @@ __device__ __forceinline__ int cell_of(const RsMapsConfig &c, double vx, double 
 __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_constant__ RsMapsConfig c,
                                                              const __grid_constant__ RsMapsState S, const float *obs,
                                                              const float *loc_pred, const uint8_t *mask, int n_env) {
-    extern __shared__ float scratch_all[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * kWarpsPerBlock + w;
     if (n >= n_env || (mask && !mask[n])) return;                          // whole warps leave together
-    float *scratch = scratch_all + (size_t)w * c.log_cap;
+    // per warp: the episode's sample table (values, cells) and the compaction scratch
+    float *s_val = reinterpret_cast<float *>(smem_raw) + (size_t)w * 2 * c.log_cap;
+    float *scratch = s_val + c.log_cap;
+    uint16_t *s_cell = reinterpret_cast<uint16_t *>(reinterpret_cast<float *>(smem_raw) + (size_t)kWarpsPerBlock * 2 * c.log_cap) +
+                       (size_t)w * c.log_cap;
     const int A = c.n_agents, XY = c.dim_x * c.dim_y;
     uint32_t status = 0;
+
+    // ---- everything the call reads from HBM is requested up front (one round of latency) ------------------------------
+    uint16_t *log_cell = S.log_cell + (size_t)n * c.log_cap;
+    float *log_val = S.log_val + (size_t)n * c.log_cap;
+    int len = S.log_len[n];
+    double mean = S.std[2 * (size_t)n], m2 = S.std[2 * (size_t)n + 1];
+    int cnt = S.std_count[n];
+    int rec = -1, last_pred = -1;                                           // lane b: tools.last_coords[b] / buffer b's last prediction
+    if (lane < A) {
+        rec = S.last_cell[(size_t)n * A + lane];
+        last_pred = S.last_pred[(size_t)n * A + lane];
+    }
+#pragma unroll 4
+    for (int i = lane; i < len; i += 32) {
+        s_cell[i] = log_cell[i];
+        s_val[i] = log_val[i];
+    }
 
     // ---- this call's observations: lane a holds agent a -----------------------------------------------------------
     int my_cell = -1, my_pred = -1;
@@ -73,13 +97,13 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
     }
 
     // ---- M:541-545: every agent's reading joins the sample table before any estimate -----------------------------------
-    uint16_t *log_cell = S.log_cell + (size_t)n * c.log_cap;
-    float *log_val = S.log_val + (size_t)n * c.log_cap;
-    int len = S.log_len[n];
     if (len + A <= c.log_cap) {
         if (lane < A) {
-            log_cell[len + lane] = (uint16_t)(my_cell < 0 ? 0xffff : my_cell);
+            const uint16_t cell16 = (uint16_t)(my_cell < 0 ? 0xffff : my_cell);
+            log_cell[len + lane] = cell16;
             log_val[len + lane] = my_count;
+            s_cell[len + lane] = cell16;
+            s_val[len + lane] = my_count;
         }
         len += A;
     } else {
@@ -87,35 +111,34 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
     }
     __syncwarp();
 
-    double mean = S.std[2 * (size_t)n], m2 = S.std[2 * (size_t)n + 1];
-    int cnt = S.std_count[n];
     float *actor = S.actor + ((size_t)n * A + (lane < A ? lane : 0)) * 6 * XY;   // lane a' owns buffer a'
     float *critic = S.critic + (size_t)n * 4 * XY;
-    uint16_t *shadow = S.shadow + (size_t)n * XY;
 
-    // ---- source prediction map of buffer a' (PFGRU) M:564-568, 748-766 --------------------------------------------------
+    // ---- source prediction map of buffer a' (PFGRU) M:564-568, 748-766: the old mark (a 1) goes, the new one is set ------
     if (pred_given) {
-        const int last = S.last_pred[(size_t)n * A + lane];
-        if (last >= 0) actor[last] -= 1.0f;
+        if (last_pred >= 0 && last_pred != my_pred) actor[last_pred] = 0.0f;
         if (my_pred >= 0) actor[my_pred] = 1.0f;       // outside the map (the reference raises): old mark cleared, none set
         S.last_pred[(size_t)n * A + lane] = my_pred;
     }
 
     // ---- agents in dict order M:547-604 ---------------------------------------------------------------------------------
+    // The location maps hold small integer counts that are functions of the recorded cells (lane b: rec), so their new
+    // values are computed from those instead of read-modify-written: the loop issues stores only.
     for (int a = 0; a < A; a++) {
         const int cc = __shfl_sync(0xffffffffu, my_cell, a);
         if (cc < 0) continue;
         const float obst = __shfl_sync(0xffffffffu, my_obst, a);
         const bool has_obst = __shfl_sync(0xffffffffu, (int)my_has_obst, a) != 0;
-        const int last = S.last_cell[(size_t)n * A + a];
+        const int last = __shfl_sync(0xffffffffu, rec, a);
+        if (lane == a) rec = cc;
 
         // median of the samples of this cell (IntensityEstimator.get_estimate M:160-167): compact them, then select by rank
         int m = 0;
         for (int i0 = 0; i0 < len; i0 += 32) {
             const int i = i0 + lane;
-            const bool hit = i < len && log_cell[i] == (uint16_t)cc;
+            const bool hit = i < len && s_cell[i] == (uint16_t)cc;
             const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (hit) scratch[m + __popc(b & ((1u << lane) - 1u))] = log_val[i];
+            if (hit) scratch[m + __popc(b & ((1u << lane) - 1u))] = s_val[i];
             m += __popc(b);
         }
         __syncwarp();
@@ -151,32 +174,35 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
         }
         const float z = (float)((est - mean) / sd);
 
-        // visit counts M:886-916: the shadow counter steps by 2; normalised value from the host's table (math.log)
-        const int cur = shadow[cc];
-        const float vis = S.visit_lut[cur >> 1];
-        __syncwarp();
-        if (lane == 0) shadow[cc] = (uint16_t)(cur + 2);
+        // visit counts M:886-916: the shadow counter (2 per earlier visit of the cell) equals twice the number of the cell's
+        // samples recorded before this agent's turn: all of them minus this call's readings of agents a..A-1 there
+        const int later = __popc(__ballot_sync(0xffffffffu, lane < A && lane >= a && my_cell == cc));
+        const float vis = S.visit_lut[max(m - later, 0)];
 
+        // agents recorded at the old / new cell after this move
+        const int n_cc = __popc(__ballot_sync(0xffffffffu, lane < A && rec == cc));
+        const int n_last = __popc(__ballot_sync(0xffffffffu, lane < A && last >= 0 && rec == last));
         if (lane < A) {
-            // location maps of buffer a' = lane M:570-588, 768-848
-            float *loc = actor + (lane == a ? 1 : 2) * XY;
-            if (last >= 0) loc[last] -= 1.0f;
-            if (lane == a) loc[cc] = 1.0f;
-            else loc[cc] += 1.0f;
+            if (lane == a) {                                                // own location map M:812-830
+                if (last >= 0 && last != cc) actor[XY + last] = 0.0f;
+                actor[XY + cc] = 1.0f;
+            } else {                                                        // others' locations M:832-848: agents != a'
+                if (last >= 0) actor[2 * XY + last] = (float)(n_last - (rec == last));
+                actor[2 * XY + cc] = (float)(n_cc - (rec == cc));
+            }
             actor[3 * XY + cc] = z;                                         // readings map M:884
             actor[4 * XY + cc] = vis;                                       // visit counts map M:906
             if (has_obst) actor[5 * XY + cc] = obst;                        // obstacles map M:929-932
         }
         if (lane == 0) {                                                    // the critic's stack (same in every buffer)
-            if (last >= 0) critic[last] -= 1.0f;                            // combined locations M:786-810
-            critic[cc] += 1.0f;
+            if (last >= 0) critic[last] = (float)n_last;                    // combined locations M:786-810
+            critic[cc] = (float)n_cc;
             critic[XY + cc] = z;
             critic[2 * XY + cc] = vis;
             if (has_obst) critic[3 * XY + cc] = obst;
-            S.last_cell[(size_t)n * A + a] = cc;
         }
-        __syncwarp();
     }
+    if (lane < A) S.last_cell[(size_t)n * A + lane] = rec;
     if (lane == 0) {
         S.log_len[n] = len;
         S.std[2 * (size_t)n] = mean;
@@ -214,7 +240,6 @@ __global__ void __launch_bounds__(kBlock) maps_reset_kernel(const __grid_constan
         else
             for (size_t i = lane; i < cnt; i += 32) p[i] = 0.0f;
     }
-    for (int i = lane; i < XY; i += 32) S.shadow[(size_t)n * XY + i] = 0;
     if (lane < A) {
         S.last_cell[(size_t)n * A + lane] = -1;
         S.last_pred[(size_t)n * A + lane] = -1;
@@ -235,7 +260,7 @@ int check_maps(const RsMapsConfig *c, const RsMapsState *s, int32_t n_env) {
     if (c->log_cap < c->n_agents || c->log_cap > 8192) return rs_set_error("log_cap out of range");
     if (c->base < 2) return rs_set_error("base must be >= 2");
     if (!(c->resolution_accuracy > 0) || !(c->scale > 0)) return rs_set_error("resolution_accuracy / scale must be positive");
-    if (!s->actor || !s->critic || !s->shadow || !s->log_cell || !s->log_val || !s->log_len || !s->last_cell ||
+    if (!s->actor || !s->critic || !s->log_cell || !s->log_val || !s->log_len || !s->last_cell ||
         !s->last_pred || !s->std || !s->std_count || !s->visit_lut || !s->status)
         return rs_set_error("RsMapsState has NULL members");
     return 0;
@@ -250,7 +275,7 @@ int rs_maps_update(const RsMapsConfig *cfg, const RsMapsState *st, const float *
     if (int rc = check_maps(cfg, st, n_env)) return rc;
     if (!obs) return rs_set_error("obs is NULL");
     const int grid = (n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const size_t smem = (size_t)kWarpsPerBlock * cfg->log_cap * sizeof(float);
+    const size_t smem = (size_t)kWarpsPerBlock * cfg->log_cap * (2 * sizeof(float) + sizeof(uint16_t)) + 16;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(maps_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     maps_update_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, obs, loc_pred, mask, n_env);

@@ -71,7 +71,6 @@ class BatchedMapsBuffer:
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)     # noqa: E731
         self.actor_maps = z(N, A, 6, X, Y)
         self.critic_maps = z(N, 4, X, Y)
-        self._shadow = z(N, X, Y, dt=torch.int16)
         self._log_cell, self._log_val, self._log_len = z(N, cap, dt=torch.int16), z(N, cap), z(N, dt=torch.int32)
         self._last_cell = torch.full((N, A), -1, dtype=torch.int32, device=dev)
         self._last_pred = torch.full((N, A), -1, dtype=torch.int32, device=dev)
@@ -82,7 +81,7 @@ class BatchedMapsBuffer:
         self._visit_lut = torch.tensor(np.asarray(lut, dtype=np.float64).astype(np.float32), device=dev)
         self.status = z(N, dt=torch.int32)
         self._st = L.RsMapsState(*[t.data_ptr() for t in (
-            self.actor_maps, self.critic_maps, self._shadow, self._log_cell, self._log_val, self._log_len,
+            self.actor_maps, self.critic_maps, self._log_cell, self._log_val, self._log_len,
             self._last_cell, self._last_pred, self._std, self._std_count, self._visit_lut, self.status)])
 
     def _stream(self):

@@ -36,7 +36,7 @@ def test_struct_layout_and_version(lib):
     assert lib.rs_sizeof_config() == C.sizeof(L.RsConfig) == 52
     assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 216
     assert lib.rs_sizeof_maps_config() == C.sizeof(L.RsMapsConfig) == 40
-    assert lib.rs_sizeof_maps_state() == C.sizeof(L.RsMapsState) == 96
+    assert lib.rs_sizeof_maps_state() == C.sizeof(L.RsMapsState) == 88
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):
