@@ -392,7 +392,7 @@ def main():
                          "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_ms,
                          "kernel_env_steps_per_s": N / (k_ms / 1e3)},
             "gae": {"T": T, "N": N, "ms": gae_ms, "achieved": gae_gbs, "peak": peak, "unit": "GB/s", "frac": gae_gbs / peak,
-                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_cols_kernel<8,7>",
+                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_tile_kernel<128,8,3> (bulk-async tiles, per-column fp64 recurrence)",
                     "traffic": measured_traffic("gae_cols_kernel", N) if T == 480 else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "sync_value": e2e_vals["sync"],

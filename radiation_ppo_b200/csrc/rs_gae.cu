@@ -90,6 +90,237 @@ __global__ void __launch_bounds__(kColsBlock, MINB) gae_cols_kernel(const float 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// variant 6: the same per-column recurrence (same operation order: bit-identical to variant 1) fed by the copy engine.
+// A CTA owns 128 columns; the [U rows][128 columns] tiles of rew / val / path_end travel HBM -> shared memory as
+// bulk-async copies (cp.async.bulk + mbarrier, one 512-byte / 128-byte run per row) through a ring of S stages issued S
+// chunks ahead, so the threads spend their instructions on the fp64 chain instead of on address arithmetic and on
+// holding loads in registers; the (rare) bootstrap values of a chunk are requested one chunk ahead, as soon as its
+// path_end flags have landed, instead of inside the dependent chain.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t g_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     g_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(g_smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t *mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GAE_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GAE_WAIT_DONE;\n"
+        "bra GAE_WAIT_LOOP;\n"
+        "GAE_WAIT_DONE:\n"
+        "}\n" ::"r"(g_smem_u32(mbar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int C, int U, int S, int MINB>
+__global__ void __launch_bounds__(C, MINB) gae_tile_kernel(const float *__restrict__ rew, const float *__restrict__ val,
+                                                                    const uint8_t *__restrict__ pe, const float *__restrict__ boot,
+                                                                    float *__restrict__ adv, float *__restrict__ ret, int T, int N,
+                                                                    double gamma, double gl, double *stats) {
+    __shared__ __align__(128) float s_rew[S][U][C];
+    __shared__ __align__(128) float s_val[S][U][C];
+    __shared__ __align__(128) uint8_t s_pe[S][U][C];
+    __shared__ __align__(8) uint64_t full[S];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * C, n = n0 + tid;
+    const int chunks = (T + U - 1) / U;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(full + s)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // chunk c = steps T-1-c*U .. T-1-c*U-(U-1) (row j of the tile = step T-1-c*U-j), rows below step 0 are absent
+    auto issue = [&](int c) {
+        const int st = c % S, t_hi = T - 1 - c * U, rows = min(U, t_hi + 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(full + st)),
+                     "r"((uint32_t)rows * (uint32_t)(C * 9))
+                     : "memory");
+        for (int j = 0; j < rows; j++) {
+            const size_t g = (size_t)(t_hi - j) * N + n0;
+            g_bulk_g2s(&s_rew[st][j][0], rew + g, C * 4, full + st);
+            g_bulk_g2s(&s_val[st][j][0], val + g, C * 4, full + st);
+            g_bulk_g2s(&s_pe[st][j][0], pe + g, C, full + st);
+        }
+    };
+    if (tid == 0)
+        for (int c = 0; c < S && c < chunks; c++) issue(c);
+
+    double nv = 0.0, na = 0.0, nr = 0.0, s1 = 0.0, s2 = 0.0;
+    float bc[U], bn[U];
+    // bootstrap values of chunk 0 (every column ends at T-1)
+    g_mbar_wait(full + 0, 0);
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int t = T - 1 - j;
+        bc[j] = 0.0f;
+        if (t >= 0 && (s_pe[0][j][tid] || t == T - 1)) bc[j] = __ldcs(boot + (size_t)t * N + n);
+    }
+    for (int c = 0; c < chunks; c++) {
+        const int st = c % S, t_hi = T - 1 - c * U;
+        if (c + 1 < chunks) {                           // the next chunk has landed long ago: ask for its bootstrap values
+            const int sn = (c + 1) % S;
+            g_mbar_wait(full + sn, (uint32_t)((c + 1) / S) & 1u);
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int t = t_hi - U - j;
+                bn[j] = 0.0f;
+                if (t >= 0 && s_pe[sn][j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t_hi - j;
+            if (t >= 0) {
+                if (s_pe[st][j][tid] || t == T - 1) {
+                    const double b = (double)bc[j];
+                    nv = b; na = 0.0; nr = b;
+                }
+                const double rr = (double)s_rew[st][j][tid], vv = (double)s_val[st][j][tid];
+                const double delta = (rr + gamma * nv) - vv;
+                const double a = delta + gl * na;
+                const double g = rr + gamma * nr;
+                const float af = (float)a;
+                const size_t i = (size_t)t * N + n;
+                __stcs(adv + i, af);
+                __stcs(ret + i, (float)g);
+                s1 += (double)af;
+                s2 += (double)af * (double)af;
+                nv = vv; na = a; nr = g;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) bc[j] = bn[j];
+        __syncthreads();                                // everybody is done with stage st: refill it
+        if (tid == 0 && c + S < chunks) issue(c + S);
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats, s1);
+            atomicAdd(stats + 1, s2);
+        }
+    }
+}
+
+// variant 8: variant 6/7 with a producer warp.  Warp 4 only refills stages (it waits on the stage's `empty` barrier, which
+// the 128 consumer threads arrive on when they are done reading it), so no CTA-wide barrier sits in the consumers' loop
+// and the four consumer warps drift apart by up to S chunks.
+template <int U, int S, int MINB>
+__global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(const float *__restrict__ rew, const float *__restrict__ val,
+                                                                           const uint8_t *__restrict__ pe, const float *__restrict__ boot,
+                                                                           float *__restrict__ adv, float *__restrict__ ret, int T, int N,
+                                                                           double gamma, double gl, double *stats) {
+    __shared__ __align__(128) float s_rew[S][U][kColsBlock];
+    __shared__ __align__(128) float s_val[S][U][kColsBlock];
+    __shared__ __align__(128) uint8_t s_pe[S][U][kColsBlock];
+    __shared__ __align__(8) uint64_t full[S], empty[S];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * kColsBlock, n = n0 + tid;
+    const int chunks = (T + U - 1) / U;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(full + s)), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(empty + s)), "r"(kColsBlock) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= kColsBlock) {                            // ---- producer warp: lane j moves row j of the tile --------------
+        const int lane = tid - kColsBlock;
+        for (int c = 0; c < chunks; c++) {
+            const int st = c % S, t_hi = T - 1 - c * U, rows = min(U, t_hi + 1);
+            if (c >= S) g_mbar_wait(empty + st, (uint32_t)(c / S - 1) & 1u);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(full + st)),
+                             "r"((uint32_t)rows * (uint32_t)(kColsBlock * 9))
+                             : "memory");
+            __syncwarp();
+            if (lane < rows) {
+                const size_t g = (size_t)(t_hi - lane) * N + n0;
+                g_bulk_g2s(&s_rew[st][lane][0], rew + g, kColsBlock * 4, full + st);
+                g_bulk_g2s(&s_val[st][lane][0], val + g, kColsBlock * 4, full + st);
+                g_bulk_g2s(&s_pe[st][lane][0], pe + g, kColsBlock, full + st);
+            }
+        }
+        return;
+    }
+    double nv = 0.0, na = 0.0, nr = 0.0, s1 = 0.0, s2 = 0.0;
+    float bc[U], bn[U];
+    g_mbar_wait(full + 0, 0);
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int t = T - 1 - j;
+        bc[j] = 0.0f;
+        if (t >= 0 && (s_pe[0][j][tid] || t == T - 1)) bc[j] = __ldcs(boot + (size_t)t * N + n);
+    }
+    for (int c = 0; c < chunks; c++) {
+        const int st = c % S, t_hi = T - 1 - c * U;
+        if (c + 1 < chunks) {
+            const int sn = (c + 1) % S;
+            g_mbar_wait(full + sn, (uint32_t)((c + 1) / S) & 1u);
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int t = t_hi - U - j;
+                bn[j] = 0.0f;
+                if (t >= 0 && s_pe[sn][j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
+            }
+        }
+        float rj[U], vj[U];
+        uint8_t ej[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) { rj[j] = s_rew[st][j][tid]; vj[j] = s_val[st][j][tid]; ej[j] = s_pe[st][j][tid]; }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(empty + st)) : "memory");   // stage read
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t_hi - j;
+            if (t >= 0) {
+                if (ej[j] || t == T - 1) {
+                    const double b = (double)bc[j];
+                    nv = b; na = 0.0; nr = b;
+                }
+                const double rr = (double)rj[j], vv = (double)vj[j];
+                const double delta = (rr + gamma * nv) - vv;
+                const double a = delta + gl * na;
+                const double g = rr + gamma * nr;
+                const float af = (float)a;
+                const size_t i = (size_t)t * N + n;
+                __stcs(adv + i, af);
+                __stcs(ret + i, (float)g);
+                s1 += (double)af;
+                s2 += (double)af * (double)af;
+                nv = vv; na = a; nr = g;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) bc[j] = bn[j];
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats, s1);
+            atomicAdd(stats + 1, s2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // variant 2 (small N): a CTA stages an 8-column tile [T][8] in shared memory with full-sector loads; warp w owns column
 // w and its 32 lanes split T into contiguous chunks.  Each lane folds its chunk into the affine map
 // x_start = B + M * x_after, the maps are combined across lanes with a warp-shuffle (Kogge-Stone) suffix scan, and a
@@ -271,7 +502,27 @@ int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const fl
         const int grid = (N + kColsBlock - 1) / kColsBlock;
         // 16 loads in flight per array when there are few columns; 8 (<= 72 registers, 7 CTAs per SM) when the columns
         // would otherwise not all be resident in one wave (N = 131072: 886 threads per SM)
-        if (variant == 5)
+        const bool tile_ok = (N % kColsBlock) == 0 && ((reinterpret_cast<uintptr_t>(rew) | reinterpret_cast<uintptr_t>(val) |
+                                                        reinterpret_cast<uintptr_t>(path_end)) & 15) == 0;
+        if (variant >= 6 && variant <= 10 && !tile_ok) return rs_set_error("rs_gae: variant 6 needs N % 128 == 0 and 16-byte aligned arrays");
+        // auto: the copy-engine variants whenever the tiles are whole and fill the GPU (measured on B200, T = 480:
+        // N = 131072 -> 4.9 TB/s with the plain ring, N = 65536 -> 3.4 TB/s with the producer warp; register-pipelined
+        // loads 3.9 / 2.7 TB/s)
+        if (variant == 0 || variant == 1) {
+            if (tile_ok && (long long)N >= 148LL * 128 * 4) variant = 7;
+            else if (tile_ok && (long long)N >= 148LL * 128 * 2) variant = 8;
+        }
+        if (variant == 6)
+            gae_tile_kernel<128, 4, 4, 8><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 7)
+            gae_tile_kernel<128, 8, 3, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 10)
+            gae_tile_kernel<64, 8, 3, 14><<<N / 64, 64, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 8)
+            gae_tile_ws_kernel<8, 3, 7><<<grid, kColsBlock + 32, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 9)
+            gae_tile_ws_kernel<4, 6, 7><<<grid, kColsBlock + 32, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 5)
             gae_cols_kernel<4, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 3 || (variant != 4 && (long long)grid > 148LL * 4))
             gae_cols_kernel<8, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);

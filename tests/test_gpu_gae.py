@@ -33,6 +33,19 @@ def test_gae_thread_per_column_is_bit_exact(T, N):
     np.testing.assert_allclose(st, [a0.astype(np.float64).sum(), (a0.astype(np.float64) ** 2).sum()], rtol=1e-12)
 
 
+@pytest.mark.parametrize("variant", [6, 7, 8, 9, 10])
+@pytest.mark.parametrize("T,N", [(480, 1024), (96, 128), (481, 4096), (7, 256), (1, 128), (33, 384), (3, 128), (12, 128)])
+def test_gae_copy_engine_tiles_are_bit_exact(T, N, variant):
+    """variant 6 / 7: the per-column recurrence fed by bulk-async tile copies (N % 128 == 0); same operation order as
+    variant 1, hence bit-identical to the reference recurrence, incl. T not a multiple of the tile height."""
+    rew, val, end, boot = pu.synthetic_rollout(T, N, seed=T + N, max_ep=min(120, T))
+    a0, r0 = co.gae(rew, val, end, boot)
+    a1, r1, st = run_gae(rew, val, end, boot, variant=variant, stats=True)
+    np.testing.assert_array_equal(a1, a0)
+    np.testing.assert_array_equal(r1, r0)
+    np.testing.assert_allclose(st, [a0.astype(np.float64).sum(), (a0.astype(np.float64) ** 2).sum()], rtol=1e-12)
+
+
 @pytest.mark.parametrize("T,N", [(480, 1024), (96, 24), (480, 1021), (7, 3), (1, 1), (33, 9), (1000, 64)])
 def test_gae_warp_scan_within_tolerance(T, N):
     """fp32 outputs within 1e-5 relative of the reference recurrence (the scan re-associates the fp64 sums)."""
