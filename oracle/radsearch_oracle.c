@@ -303,6 +303,12 @@ double orc_shortest_path(const OrcEnv *e, const int32_t det[2]) {
     }
     node[m][0] = det[0]; node[m][1] = det[1]; m++;
     if (node[0][0] == det[0] && node[0][1] == det[1]) return 0.0;
+    /* mutually visible (grazing corners allowed): VisiLibity returns the direct segment, whose length can differ by an
+     * ulp from the sum over a corner that lies exactly on it */
+    if (visible_pts(e, node[0], det)) {
+        double dx = (double)node[0][0] - det[0], dy = (double)node[0][1] - det[1];
+        return sqrt(dx * dx + dy * dy);
+    }
     double dist[4 * ORC_MAX_K + 2];
     int fin[4 * ORC_MAX_K + 2];
     for (int i = 0; i < m; i++) { dist[i] = INFINITY; fin[i] = 0; }

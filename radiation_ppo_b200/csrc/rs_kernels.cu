@@ -82,6 +82,44 @@ __device__ __forceinline__ void list_push(bool flag, int u, uint16_t *list, int 
     if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)u;
 }
 
+// Shortest path, first half, for unit u (-1: this thread has none; whole warps call this): seed + corner marking, then the
+// marked corners are appended as (unit, corner) pairs to the tile-wide list (warp-aggregated reservation).  A warp whose
+// pairs do not fit walks its corners itself.
+__device__ __forceinline__ void seed_and_push(const RsState &S, const rs::Tile &T, int n0, int u, uint16_t *pairs,
+                                              int pair_cap, int *pair_count) {
+    const int lane = threadIdx.x & 31;
+    uint32_t mask = 0u;
+    int besti = -1;
+    double best = 0.0;
+    if (u >= 0) mask = rs::phase_path_seed(S, T, n0, u, best, besti);
+    const int n = __popc(mask);
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, pre, 31);
+    int wbase = 0;
+    if (lane == 31 && tot) wbase = atomicAdd(pair_count, tot);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    const bool fits = wbase + tot <= pair_cap;
+    if (!fits)                                                // reserved but unused slots inside the list
+        for (int i = wbase + lane; i < min(pair_cap, wbase + tot); i += 32) pairs[i] = 0xffffu;
+    if (u >= 0) {
+        if (fits) {
+            rs::phase_path_finish(T, u, best, besti);
+            int pos = wbase + pre - n;
+            while (mask) {
+                pairs[pos++] = (uint16_t)((u << 5) | (__ffs(mask) - 1));
+                mask &= mask - 1;
+            }
+        } else {
+            rs::phase_path_walk(S, T, n0, u, mask, best, besti);
+        }
+    }
+}
+
 template <bool kFast, int E, int kOcc>
 __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
@@ -130,12 +168,17 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     // a new refill list starts with this step: only the reset kernel that follows appends to it
     if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
 
+    const bool merged = (P.tune & 4) != 0;
     // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
     for (int u0 = 0; u0 < U; u0 += kBlock) {
         const int u = u0 + tid;
         int uf = 0;
         if (u < U && (u % E) < valid) uf = rs::phase_move<kFast>(P, S, a, T, n0, u, step_ctr);
-        list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
+        // RS_TUNE bit 2: most units need the shortest path (92 % at 5 obstructions), so the seed pass runs right here, in
+        // the thread that just moved the unit, instead of through list B and one more CTA barrier
+        if (merged) seed_and_push(S, T, n0, (uf & rs::UF_NEED_B) ? u : -1, reinterpret_cast<uint16_t *>(T.reward),
+                                  (L.done - L.reward) / 2, counters + 3);
+        else list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
         list_push(uf & rs::UF_NEED_D, u, lists + U, counters + 1);
         list_push(uf & rs::UF_NEED_P, u, lists + 2 * U, counters + 2);
     }
@@ -153,44 +196,12 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             uint16_t *pairs = reinterpret_cast<uint16_t *>(T.reward);
             const int pair_cap = (L.done - L.reward) / 2;
             int *pair_count = counters + 3;                               // idle until phase_commit
-            const int lane = tid & 31;
-            for (int base = 0; base < cb; base += kBlock) {
-                const int j = base + tid;
-                uint32_t mask = 0u;
-                int u = -1, besti = -1;
-                double best = 0.0;
-                if (j < cb) {
-                    u = lists[j];
-                    mask = rs::phase_path_seed(S, T, n0, u, best, besti);
+            if (!merged)
+                for (int base = 0; base < cb; base += kBlock) {
+                    const int j = base + tid;
+                    seed_and_push(S, T, n0, j < cb ? (int)lists[j] : -1, pairs, pair_cap, pair_count);
                 }
-                const int n = __popc(mask);
-                int pre = n;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, pre, o);
-                    if (lane >= o) pre += v;
-                }
-                const int tot = __shfl_sync(0xffffffffu, pre, 31);
-                int wbase = 0;
-                if (lane == 31 && tot) wbase = atomicAdd(pair_count, tot);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                const bool fits = wbase + tot <= pair_cap;
-                if (!fits)                                                // reserved but unused slots inside the list
-                    for (int i = wbase + lane; i < min(pair_cap, wbase + tot); i += 32) pairs[i] = 0xffffu;
-                if (u >= 0) {
-                    if (fits) {
-                        rs::phase_path_finish(T, u, best, besti);
-                        int pos = wbase + pre - n;
-                        while (mask) {
-                            pairs[pos++] = (uint16_t)((u << 5) | (__ffs(mask) - 1));
-                            mask &= mask - 1;
-                        }
-                    } else {
-                        rs::phase_path_walk(S, T, n0, u, mask, best, besti);
-                    }
-                }
-            }
-            __syncthreads();
+            if (!merged) __syncthreads();
             const int np = min(*pair_count, pair_cap);
             unsigned long long *spbits = reinterpret_cast<unsigned long long *>(T.sp);
             for (int j = tid; j < np; j += kBlock) {

@@ -28,7 +28,8 @@ def make_pair(n, A=1, oc=5, enforce=True, seed=11, env_id0=3, max_ep_len=120, **
 
 @pytest.mark.parametrize("n,A,oc,enforce,T,idle", [(1024, 1, 5, True, 130, 0.0), (1024, 1, -1, False, 100, 0.0),
                                                    (512, 4, 5, True, 90, 0.15), (256, 1, 0, True, 40, 0.0),
-                                                   (300, 2, 7, True, 70, 0.1), (37, 1, 3, False, 50, 0.0)])
+                                                   (300, 2, 7, True, 70, 0.1), (37, 1, 3, False, 50, 0.0),
+                                                   (480, 3, 4, True, 80, 0.1), (96, 5, 2, True, 40, 0.2), (50, 8, 3, True, 30, 0.1)])
 def test_rollout_matches_oracle(n, A, oc, enforce, T, idle):
     env, ob = make_pair(n, A, oc, enforce, seed=100 + n)
     v = pu.GpuView(env)
@@ -353,14 +354,15 @@ def test_step_host_matches_step_batch(graph):
     assert hbs[0].d2h_bytes >= n * (44 + 4 + 4 + 3) and hbs[0].h2d_bytes == n * 4
 
 
-@pytest.mark.parametrize("mode,A,fast_path", [(1, 1, False), (2, 1, False), (1, 4, False), (1, 1, True)])
-def test_fused_count_standardizer_matches_callers_order(mode, A, fast_path):
+@pytest.mark.parametrize("mode,A,fast_path,n", [(1, 1, False, 2048), (2, 1, False, 2048), (1, 4, False, 2048),
+                                                (1, 1, True, 2048), (1, 1, False, 37), (2, 3, False, 101), (2, 3, False, 2048)])
+def test_fused_count_standardizer_matches_callers_order(mode, A, fast_path, n):
     """RsConfig.standardize: the count channel leaves rs_step / rs_reset as the per-episode running
     z-score the RAD-A2C caller computes with StatisticStandardization (RADTEAM_core.py:188-277; mode 2: StatBuff of
     test_environment/core.py:55-79 + clip 8) in train.py's order; the oracle restatement is pinned on the reference
     classes (tests/golden/ref_standardize.npz).  Bar: the float64 z-score rounded to fp32, bit for bit; running mean and
     M2 bit for bit; raw counts unchanged.  fast_path = prefetch + CUDA-graph replay (adopted resets)."""
-    n, T, ML = 2048, 100, 30
+    T, ML = 100, 30
     kw = dict(prefetch=True, use_cuda_graph=True) if fast_path else {}
     env, ob = make_pair(n, A, 4, True, seed=31, max_ep_len=ML, auto_reset=True, standardize=mode, **kw)
     so = pu.StandardizedOracle(ob, mode)

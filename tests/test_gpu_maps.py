@@ -106,3 +106,39 @@ def test_maps_kernel_matches_oracle_on_env_rollouts(N, A, T):
                     for b in oracles[n]:
                         b.reset()
     assert int(mb.status.sum()) == 0
+
+
+def test_maps_unenforced_boundaries_147_grid_and_status_flags():
+    """enforce_grid_boundaries=False: the 147 x 147 maps of RADTEAM_core.py:1740-1746; detectors that leave the search area
+    to the low side get negative inflated coordinates, which numpy's indexing wraps once (the oracle restates that);
+    predictions outside the map raise in the reference and are flagged here."""
+    import radiation_ppo_b200.maps_buffer as mbm
+
+    N, A, T = 256, 2, 60
+    env = rp.RadSearch(obstruction_count=2, enforce_grid_boundaries=False, number_agents=A, num_envs=N, seed=3)
+    ra = mbm.calculate_resolution_accuracy(0.01, env.scale)
+    offset = env.scale * (500.0 + 120 * 100.0)
+    mb = rp.BatchedMapsBuffer(N, A, 120, resolution_accuracy=ra, offset=offset, environment_scale=env.scale)
+    assert mb.map_dimensions == (147, 147)
+    oracles = {n: [co.MapsOracle(A, 120, (147, 147), ra) for _ in range(A)] for n in range(0, N, 16)}
+    rng = np.random.default_rng(2)
+    wrapped = 0
+    for t in range(T):
+        pred = torch.as_tensor(rng.uniform(0, 1.0, size=(N, A, 2)).astype(np.float32), device="cuda")
+        actor, critic = mb.update(env.obs, pred)
+        a, c = actor.cpu().numpy(), critic.cpu().numpy()
+        o = env.obs.cpu().numpy().astype(np.float64)
+        for n, bufs in oracles.items():
+            o64 = o[n].copy()
+            o64[:, 1:3] = np.rint(o[n, :, 1:3] / env.scale) * env.scale
+            wrapped += int((o64[:, 1:3] < 0).any())
+            for i in range(A):
+                want = bufs[i].observation_to_map(o64, i, (float(pred[n, i, 0]), float(pred[n, i, 1])))
+                np.testing.assert_array_equal(stacks_to_seven(a[n], c[n], i), want)
+        # walk down-left so that some detectors cross x < 0 / y < 0
+        acts = torch.as_tensor(rng.choice([0, 6, 7, 7], size=(N, A)), dtype=torch.int32, device="cuda")
+        env.step_batch(acts)
+    assert wrapped > 0 and int(mb.status.sum()) == 0
+    bad = torch.full((N, A, 2), 9.0, device="cuda")                   # 9.0 * 22 = 198 > 147: outside the map
+    mb.update(env.obs, bad)
+    assert bool(((mb.status & 4) != 0).all())

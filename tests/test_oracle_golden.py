@@ -171,3 +171,44 @@ def test_oracle_maps_reproduce_reference_mapsbuffer(name):
             for b in bufs:
                 b.reset()
     assert g["reset_after"].sum() >= 1 and (A == 1 or seen_multi > 0)
+
+
+def test_shortest_path_through_a_grazed_corner_is_the_direct_segment():
+    """Source, an obstruction corner and the detector on one line: the two points are mutually visible (a grazed corner
+    does not block), so `shortest_path` is the direct segment (the exact-arithmetic visilibity restatement the reference
+    runs on, oracle/shims/visilibity.py), not the 1-ulp different sum over the corner.  Found by the GPU rollouts
+    (env 524 of a 2048-env, 3-agent run): C oracle, kernel logic (host emulation) and the shim must agree bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims"))
+    try:
+        import visilibity as vis
+    finally:
+        sys.path.pop(0)
+    from tests.emu.harness import EmuEnv, make_config
+
+    src = np.array([[437, 1730]])
+    rects = np.array([[[1924, 1843, 2273, 2051], [1803, 917, 2177, 1269], [1362, 201, 1851, 700], [865, 1612, 1136, 2034]]])
+    rng = np.random.default_rng(0)
+    dets = [[1721, 1376]] + [[int(x), int(y)] for x, y in rng.integers(200, 2200, size=(40, 2))]
+    # more collinear probes: points on the ray source -> corner (865, 1612), beyond the corner
+    for k in range(2, 6):
+        dets.append([437 + k * 428 // 2 * 2 // 2, 1730 - k * 118 // 1])
+    polys = [vis.Polygon([vis.Point(0, 0), vis.Point(2700, 0), vis.Point(2700, 2700), vis.Point(0, 2700)])]
+    for r in rects[0]:
+        x0, y0, x1, y1 = (float(v) for v in r)
+        polys.append(vis.Polygon([vis.Point(x0, y0), vis.Point(x0, y1), vis.Point(x1, y1), vis.Point(x1, y0)]))
+    world = vis.Environment(polys)
+    em = EmuEnv(1, make_config(n_agents=1, obstruction_count=4, enforce=True), seed=1)
+    ob = co.OracleBatch(1, co.default_config(n_agents=1, obstruction_count=4, enforce=1))
+    checked = 0
+    for det in dets:
+        if any(r[0] <= det[0] <= r[2] and r[1] <= det[1] <= r[3] for r in rects[0]):
+            continue
+        em.load_scenarios(src, np.array([det]), np.array([5000000]), np.array([20]), rects, np.array([4]))
+        ob.load_scenarios(src, np.array([det]), [5000000], [20], rects, [4])
+        want = world.shortest_path(vis.Point(float(src[0, 0]), float(src[0, 1])), vis.Point(float(det[0]), float(det[1])),
+                                   None, 1e-7).length()
+        assert ob.shortest_path(0, det) == want, det
+        assert em.query_sp(np.array([det]), 0)[0] == want and em.query_sp(np.array([det]), 1)[0] == want, det
+        checked += 1
+    assert checked > 30
