@@ -391,3 +391,47 @@ def test_fused_count_standardizer_matches_callers_order(mode, A, fast_path, n):
         np.testing.assert_array_equal(env._st_m2.cpu().numpy().T, so.st.m2.reshape(n, A))
     pu.compare_state(pu.GpuView(env), ob, A)
     assert big > 0
+
+
+@pytest.mark.parametrize("n,A,oc,enforce,T,fast_path", [(16384, 1, 5, True, 240, True), (8192, 4, -1, True, 130, False),
+                                                        (8192, 2, 7, False, 130, False), (4096, 8, 3, True, 60, False)])
+def test_soak_rollout_with_auto_reset_matches_oracle(n, A, oc, enforce, T, fast_path):
+    """Millions of env-steps against the oracle (every output of every step: observations, rewards, done / info / ended
+    flags, final observations, full state after the resets), to catch rare geometric coincidences (a grazed corner on the
+    source line was found this way).  fast_path = prefetched resets + CUDA-graph replay."""
+    ML = 120
+    kw = dict(prefetch=True, use_cuda_graph=True) if fast_path else {}
+    env, ob = make_pair(n, A, oc, enforce, seed=4242 + n + A, max_ep_len=ML, auto_reset=True, **kw)
+    rng = np.random.default_rng(n + A)
+    g = torch.Generator(device=env.device).manual_seed(1)
+    stagger = torch.randint(0, ML, (n,), generator=g, device=env.device, dtype=torch.int32)
+    env._meta.add_(stagger << 16)                                    # stagger the episodes like a long-running rollout
+    ob.envs["ep_len"] = stagger.cpu().numpy()
+    resets = 0
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 9 if A > 1 else 8, size=(n, A))
+        epoch_end = t == T // 2
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device), epoch_end=epoch_end)
+        ob.step(acts, env._ctr)
+        e, o = ob.envs, ob.outs
+        terminal, timeout = e["done"] == 1, e["ep_len"] == ML
+        want = terminal * 1 | timeout * 2 | ((terminal | timeout | epoch_end) * 4)
+        mask = (want & 4) != 0
+        final = o["obs"][:, :A].copy()
+        rew, done = o["reward"][:, :A].astype(np.float32).copy(), o["done"][:, :A].copy()
+        team = o["team_reward"].astype(np.float32).copy()
+        info_ref = (e["oob"][:, :A] | (e["blocked"][:, :A] * 2) | (e["collision"][:, :A] * 4) | (e["los_blocked"][:, :A] * 8)).copy()
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.full(n, epoch_end))
+        v = pu.GpuView(env)
+        np.testing.assert_array_equal(v.ended, want)
+        np.testing.assert_array_equal(v.reward, rew)
+        np.testing.assert_array_equal(v.team_reward, team)
+        np.testing.assert_array_equal(v.done, done)
+        np.testing.assert_array_equal(v.info & 15, info_ref)
+        pu.compare_obs(v.final_obs, final, sel=np.where(mask)[0])
+        pu.compare_obs(v.obs, np.where(mask[:, None, None], o["obs"][:, :A], final))
+        pu.compare_state(v, ob, A)
+        np.testing.assert_array_equal(v.ep_len, e["ep_len"])
+        resets += int(mask.sum())
+    assert resets > n
