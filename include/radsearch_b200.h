@@ -238,6 +238,10 @@ int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t 
 int rs_sizeof_maps_config(void);
 int rs_sizeof_maps_state(void);
 
+/* Debugging aid: with the environment variable RS_TUNE bit 3 set, rs_step's thread 0 of each of the first 2048 CTAs
+ * stamps clock64 at 8 phase boundaries; this copies [n_cta][12] stamps to the host (synchronises the device). */
+int rs_debug_timeline(long long *host_out, int n_cta);
+
 const char *rs_last_error(void);
 int rs_version(void);
 /* sizeof checks for the binding */

@@ -18,7 +18,7 @@ ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, 
 EXPORTS = [
     "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
     "rs_version", "rs_sizeof_config", "rs_sizeof_state", "rs_maps_update", "rs_maps_reset", "rs_sizeof_maps_config",
-    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table",
+    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table", "rs_debug_timeline",
 ]
 MS_CELL_RANGE, MS_LOG_FULL, MS_PRED_RANGE = 1, 2, 4
 
@@ -108,6 +108,8 @@ def declare(lib, prefix="rs_"):
         lib.rs_pack_rollout.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.rs_episode_table.restype = i32
         lib.rs_episode_table.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+        lib.rs_debug_timeline.restype = i32
+        lib.rs_debug_timeline.argtypes = [vp, i32]
         lib.rs_sizeof_maps_config.restype = i32
         lib.rs_sizeof_maps_state.restype = i32
         lib.rs_last_error.restype = C.c_char_p

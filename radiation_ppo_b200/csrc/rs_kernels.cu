@@ -120,6 +120,22 @@ __device__ __forceinline__ void seed_and_push(const RsState &S, const rs::Tile &
     }
 }
 
+// RS_TUNE bit 3: thread 0 of the first 2048 CTAs stamps clock64 at the phase boundaries (rs_debug_timeline reads them back)
+__device__ long long g_timeline[2048][12];
+__device__ __forceinline__ long long rs_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RS_STAMP(i)                                                                                       \
+    do {                                                                                                  \
+        if ((P.tune & 8) && tid == 0 && blockIdx.x < 2048) {                                              \
+            g_timeline[blockIdx.x][i] = clock64();                                                        \
+            if ((i) == 0) g_timeline[blockIdx.x][8] = rs_globaltimer();                                   \
+            if ((i) == 7) g_timeline[blockIdx.x][9] = rs_globaltimer();                                   \
+        }                                                                                                 \
+    } while (0)
+
 template <bool kFast, int E, int kOcc>
 __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     const int A = P.n_agents, K = P.k_max, U = E * A;
     const rs::Tile T = rs::carve_tile(smem, L, E, A, K, a.actions != nullptr);
     uint16_t *lists = reinterpret_cast<uint16_t *>(smem + L.lists);     // [3][U]: B, D, P
-    int *counters = reinterpret_cast<int *>(smem + L.counters);         // B, D, P, scheduled
+    int *counters = reinterpret_cast<int *>(smem + L.counters);         // B, D, P, scheduled, pairs
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.mbar);
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
@@ -139,7 +155,8 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     const bool bulk = bulk_ok && valid == E;
 
     // ---- stage the tile ------------------------------------------------------------------------------------------
-    if (tid < 4) counters[tid] = 0;
+    RS_STAMP(0);
+    if (tid < 8) counters[tid] = 0;
     if (bulk) {
         if (tid == 0) {
             mbar_init(mbar, 1);
@@ -164,6 +181,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
         }
         __syncthreads();
     }
+    RS_STAMP(1);
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
     // a new refill list starts with this step: only the reset kernel that follows appends to it
     if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
@@ -177,13 +195,14 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
         // RS_TUNE bit 2: most units need the shortest path (92 % at 5 obstructions), so the seed pass runs right here, in
         // the thread that just moved the unit, instead of through list B and one more CTA barrier
         if (merged) seed_and_push(S, T, n0, (uf & rs::UF_NEED_B) ? u : -1, reinterpret_cast<uint16_t *>(T.reward),
-                                  (L.done - L.reward) / 2, counters + 3);
+                                  (L.done - L.reward) / 2, counters + 4);
         else list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
         list_push(uf & rs::UF_NEED_D, u, lists + U, counters + 1);
         list_push(uf & rs::UF_NEED_P, u, lists + 2 * U, counters + 2);
     }
     __syncthreads();
 
+    RS_STAMP(2);
     // ---- compacted phases: list j starts at the first warp the previous lists left idle -----------------------------------
     {
         const int cb = counters[0], cd = counters[1], cp = counters[2];
@@ -195,13 +214,14 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             // running minimum (positive doubles order like their bit patterns); (3) the winners record the hint.
             uint16_t *pairs = reinterpret_cast<uint16_t *>(T.reward);
             const int pair_cap = (L.done - L.reward) / 2;
-            int *pair_count = counters + 3;                               // idle until phase_commit
+            int *pair_count = counters + 4;
             if (!merged)
                 for (int base = 0; base < cb; base += kBlock) {
                     const int j = base + tid;
                     seed_and_push(S, T, n0, j < cb ? (int)lists[j] : -1, pairs, pair_cap, pair_count);
                 }
             if (!merged) __syncthreads();
+            RS_STAMP(3);
             const int np = min(*pair_count, pair_cap);
             unsigned long long *spbits = reinterpret_cast<unsigned long long *>(T.sp);
             for (int j = tid; j < np; j += kBlock) {
@@ -211,33 +231,32 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
                 const double cur = *reinterpret_cast<volatile double *>(T.sp + u);
                 const double cand = rs::phase_path_pair(S, T, n0, u, c, cur);
                 if (cand < cur) {
-                    atomicMin(spbits + u, (unsigned long long)__double_as_longlong(cand));
-                    pairs[j] = (uint16_t)(pr | 0x8000u);                   // a visible improver: may be the new hint
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(cand);
+                    atomicMin(spbits + u, bits);
+                    // the corner of the smallest candidate (up to the last 5 mantissa bits: it only seeds the next search)
+                    atomicMin(T.hkey + u, (bits & ~31ull) | (unsigned long long)c);
                 }
             }
-            __syncthreads();
-            for (int j = tid; j < np; j += kBlock) {
-                const uint32_t pr = pairs[j];
-                if (pr == 0xffffu || !(pr & 0x8000u)) continue;
-                const int u = (int)((pr & 0x7fffu) >> 5), c = (int)(pr & 31u);
-                if (rs::phase_path_pair_value(S, T, n0, u, c) == T.sp[u]) T.af[u] = (T.af[u] & ~(31 << 25)) | (c << 25);
-            }
-            if (tid == 0) *pair_count = 0;
+            RS_STAMP(4);
         }
-        off = (off + ((cb + 31) & ~31)) & (kBlock - 1);
-        for (int base = 0; base < cd; base += kBlock) {
+        // timing experiments (RS_TUNE bits 4 / 5: skip the sensor / Poisson-retry lists; results are then wrong)
+        const int cd_ = (P.tune & 16) ? 0 : cd, cp_ = (P.tune & 32) ? 0 : cp;
+        off = 0;
+        for (int base = 0; base < cd_; base += kBlock) {
             const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cd) rs::phase_sense(S, T, n0, lists[U + j]);
+            if (j < cd_) rs::phase_sense(S, T, n0, lists[U + j]);
         }
-        off = (off + ((cd + 31) & ~31)) & (kBlock - 1);
-        for (int base = 0; base < cp; base += kBlock) {
+        off = (off + ((cd_ + 31) & ~31)) & (kBlock - 1);
+        for (int base = 0; base < cp_; base += kBlock) {
             const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cp) rs::phase_count<kFast>(P, S, a, T, n0, lists[2 * U + j], step_ctr);
+            if (j < cp_) rs::phase_count<kFast>(P, S, a, T, n0, lists[2 * U + j], step_ctr);
         }
     }
     __syncthreads();
 
+    RS_STAMP(5);
     // ---- phase_commit: every environment; CTA-aggregated append to the reset work list ---------------------------------
+
     for (int t0 = 0; t0 < E; t0 += kBlock) {
         const int t = t0 + tid;
         bool sched = false;
@@ -256,6 +275,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
         }
     }
 
+    RS_STAMP(6);
     // ---- write the tile back ----------------------------------------------------------------------------------------
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
@@ -282,6 +302,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             }
         }
     }
+    RS_STAMP(7);
 }
 
 // end of a captured step: advance the device step counter and empty the reset list for the next replay
@@ -574,6 +595,13 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
     if (smem > 48 * 1024) cudaFuncSetAttribute(sp_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sp_query_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
     return (int)cudaGetLastError();
+}
+
+int rs_debug_timeline(long long *host_out, int n_cta) {          // debugging aid (RS_TUNE bit 3), synchronises the device
+    if (!host_out || n_cta < 1 || n_cta > 2048) return rs_set_error("rs_debug_timeline: bad arguments");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 12 * n_cta);
+    return (int)e;
 }
 
 const char *rs_last_error(void) { return g_err; }

@@ -47,11 +47,12 @@ struct Tile {
     int2 *ndet;           // [U] position after take_action (committed by phase_commit: other agents' proposals are
                           //     computed from the old positions, R:645-648)
     double *sp;           // [U] shortest-path length
+    unsigned long long *hkey;   // [U] (candidate bits & ~31) | corner of the best improving pair (~0: none): next step's hint
     int *uflag;           // [U] UF_* | sensor candidate rectangles << 16
 };
 
 struct TileLayout {       // byte offsets of the arrays above inside the CTA's dynamic shared memory (all 16-aligned)
-    int rects, src, rad, meta, det, best, af, act, obs, reward, team, done, info, ended, ndet, sp, uflag, lists,
+    int rects, src, rad, meta, det, best, af, act, obs, reward, team, done, info, ended, ndet, sp, hkey, uflag, lists,
         counters, mbar, stm, stq, raw, total;
 };
 
@@ -77,9 +78,10 @@ __host__ __device__ inline TileLayout make_layout(int E, int A, int K, int threa
     L.ended = o;   o += align16(E);
     L.ndet = o;    o += align16(U * 8);
     L.sp = o;      o += align16(U * 8);
+    L.hkey = o;    o += align16(U * 8);
     L.uflag = o;   o += align16(U * 4);
     L.lists = o;   o += align16(3 * U * 2);
-    L.counters = o; o += 16;
+    L.counters = o; o += 32;
     L.mbar = o;    o += 16;
     L.stm = L.stq = L.raw = -1;                   // the default configuration keeps its footprint (8 CTAs per SM)
     if (standardize) {
@@ -110,6 +112,7 @@ __host__ __device__ inline Tile carve_tile(unsigned char *base, const TileLayout
     T.ended = base + L.ended;
     T.ndet = reinterpret_cast<int2 *>(base + L.ndet);
     T.sp = reinterpret_cast<double *>(base + L.sp);
+    T.hkey = reinterpret_cast<unsigned long long *>(base + L.hkey);
     T.uflag = reinterpret_cast<int *>(base + L.uflag);
     T.stm = L.stm >= 0 ? reinterpret_cast<double *>(base + L.stm) : nullptr;
     T.stq = L.stq >= 0 ? reinterpret_cast<double *>(base + L.stq) : nullptr;
@@ -281,6 +284,7 @@ __device__ __forceinline__ void phase_path(const RsState &S, const Tile &T, int 
     int af = T.af[u];
     int hint = (af >> 25) & 31;
     T.sp[u] = shortest_path_pruned(e, e.dsrc.p, det.x, det.y, hint);
+    T.hkey[u] = ~0ull;
     T.af[u] = (af & ~(31 << 25)) | (hint << 25);
 }
 
@@ -297,6 +301,7 @@ __device__ __forceinline__ uint32_t phase_path_seed(const RsState &S, const Tile
 }
 __device__ __forceinline__ void phase_path_finish(const Tile &T, int u, double best, int besti) {
     T.sp[u] = best;
+    T.hkey[u] = ~0ull;
     if (besti >= 0) T.af[u] = (T.af[u] & ~(31 << 25)) | (besti << 25);
 }
 // the rest of the per-thread walk (units whose pairs did not fit into the tile's pair list)
@@ -338,7 +343,13 @@ __device__ __forceinline__ void phase_sense(const RsState &S, const Tile &T, int
     const EnvView e = tile_env(T, S, t, n);
     const int2 det = T.ndet[u];
     uint32_t status = 0;
-    sensors_rects_row(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, T.obs + (t * A + ag) * RS_OBS_DIM + 3, status);
+    // rectangle-major and unrolled over the eight directions: eight independent dependency chains per thread (the
+    // direction-major loop has an eighth of the code but runs them one after the other: +3.5k cycles per CTA, measured)
+    float sv[8];
+    sensors_rects(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, sv, status);
+    float *row = T.obs + (t * A + ag) * RS_OBS_DIM + 3;
+#pragma unroll
+    for (int d = 0; d < 8; d++) row[d] = sv[d];
     raise_status(S, n, status);
 }
 
@@ -376,7 +387,11 @@ __device__ __forceinline__ bool phase_commit(const Params &P, const RsState &S, 
         const int2 det = T.ndet[u];
         const double sp = T.sp[u];
         double best = T.best[u];
-        const int af = T.af[u];
+        int af = T.af[u];
+        if (uf & UF_NEED_B) {                                           // the pair phase's best improving corner: next hint
+            const unsigned long long hk = T.hkey[u];
+            if (hk != ~0ull) { af = (af & ~(31 << 25)) | ((int)(hk & 31ull) << 25); T.af[u] = af; }
+        }
         const int action = T.act ? T.act[t * A + ag] : -1;
         float *row = T.obs + (t * A + ag) * RS_OBS_DIM;
         bool blocked_los = (uf & UF_BLOCKED_RAW) != 0;

@@ -1,11 +1,11 @@
-"""Ad-hoc timings on the GPU box (CUDA events): GAE variants, sparse / bulk reset latency.  Not part of the product."""
-import sys, os, json, time
+"""Ad-hoc timings on the GPU box (CUDA events).  Not part of the product."""
+import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import radiation_ppo_b200 as rp
 
 dev = torch.device("cuda:0")
-def timeit(fn, n=10, warm=3):
+def timeit(fn, n=20, warm=5):
     for _ in range(warm): fn()
     torch.cuda.synchronize()
     ts = []
@@ -15,26 +15,22 @@ def timeit(fn, n=10, warm=3):
     ts.sort(); return ts[len(ts)//2]
 
 out = {}
-for N in (65536, 131072):
-    T = 480
+for (N, A) in ((16384, 4), (16384, 1), (65536, 1), (131072, 1), (32768, 2)):
+    env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, number_agents=A, num_envs=N, seed=4, auto_reset=True, fast_poisson=True)
     g = torch.Generator(device=dev).manual_seed(1)
-    rew = -0.5 * torch.rand(T, N, generator=g, device=dev) * 1.5
-    val = torch.randn(T, N, generator=g, device=dev)
-    end = (torch.rand(T, N, generator=g, device=dev) < 0.01).to(torch.uint8); end[T-1] = 1
-    boot = torch.randn(T, N, generator=g, device=dev) * end
-    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
-    for v in (3, 7, 8, 10, 1):
-        if v == 2 and N > 65536: continue
-        ms = timeit(lambda: rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=v))
-        out[f"gae_N{N}_v{v}"] = dict(ms=ms, gbs=17 * T * N / ms / 1e6)
-    del rew, val, end, boot, adv, ret
-print(json.dumps(out, indent=1)); sys.exit(0)
-N = 131072
-env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, num_envs=N, seed=2, auto_reset=True, fast_poisson=True)
-for frac, name in ((1/120, "sparse"), (1/16, "mid"), (1.0, "bulk")):
-    mask = (torch.rand(N, device=dev) < frac)
-    out[f"reset_{name}_{int(mask.sum())}"] = timeit(lambda: env.reset_batch(mask=mask), n=5, warm=2)
-out["reset_bulk_newobs"] = timeit(lambda: env.reset_batch(new_obstacles=True), n=3, warm=1)
-acts = torch.randint(0, 8, (N, 1), device=dev, dtype=torch.int32)
-out["step_only_ms"] = timeit(lambda: env.step_batch(acts, auto_reset=False), n=20, warm=5)
+    env._meta.add_(torch.randint(0, 120, (N,), generator=g, device=dev, dtype=torch.int32) << 16)
+    acts = torch.randint(0, 8, (N, A), generator=g, device=dev, dtype=torch.int32)
+    for _ in range(30): env.step_batch(acts)
+    out[f"step+reset_N{N}_A{A}_us"] = 1e3 * timeit(lambda: env.step_batch(acts))
+    out[f"step_only_N{N}_A{A}_us"] = 1e3 * timeit(lambda: env.step_batch(acts, auto_reset=False))
+    if A == 4:
+        mb = rp.BatchedMapsBuffer(N, A, 120, environment_scale=env.scale)
+        pred = torch.rand(N, A, 2, device=dev)
+        for _ in range(60):
+            mb.update(env.obs, pred); env.step_batch(acts); mb.reset(mask=(env.ended & 4) != 0)
+        out["maps_update_us"] = 1e3 * timeit(lambda: mb.update(env.obs, pred))
+        m = (env.ended & 4) != 0
+        out["maps_reset_masked_us"] = 1e3 * timeit(lambda: mb.reset(mask=m))
+        out["mask_op_us"] = 1e3 * timeit(lambda: (env.ended & 4) != 0)
+    del env
 print(json.dumps(out, indent=1))
