@@ -206,7 +206,6 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     // ---- compacted phases: list j starts at the first warp the previous lists left idle -----------------------------------
     {
         const int cb = counters[0], cd = counters[1], cp = counters[2];
-        int off = 0;
         {
             // shortest path, flattened: (1) seed + marking pass per unit, the marked corners appended as (unit, corner)
             // pairs to a tile-wide list (warp-aggregated reservation; the reward / team rows serve as scratch until
@@ -224,32 +223,42 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             RS_STAMP(3);
             const int np = min(*pair_count, pair_cap);
             unsigned long long *spbits = reinterpret_cast<unsigned long long *>(T.sp);
-            for (int j = tid; j < np; j += kBlock) {
-                const uint32_t pr = pairs[j];
-                if (pr == 0xffffu) continue;
-                const int u = (int)(pr >> 5), c = (int)(pr & 31u);
-                const double cur = *reinterpret_cast<volatile double *>(T.sp + u);
-                const double cand = rs::phase_path_pair(S, T, n0, u, c, cur);
-                if (cand < cur) {
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(cand);
-                    atomicMin(spbits + u, bits);
-                    // the corner of the smallest candidate (up to the last 5 mantissa bits: it only seeds the next search)
-                    atomicMin(T.hkey + u, (bits & ~31ull) | (unsigned long long)c);
+            // One pool of work for the rest of the phase, fetched by the warps 32 items at a time: first the Poisson
+            // retries (few units, the longest dependent chains), then the sensor units, then the (unit, corner) pairs
+            // (many, short: they fill the gaps).  No warp waits at a barrier while another walks a list alone.
+            // (RS_TUNE bits 4 / 5 skip the sensor / retry lists: timing experiments, the results are then wrong.)
+            const int cd_ = (P.tune & 16) ? 0 : cd, cp_ = (P.tune & 32) ? 0 : cp;
+            const int chP = (cp_ + 31) >> 5, chD = (cd_ + 31) >> 5, chB = (np + 31) >> 5;
+            const int lane = tid & 31;
+            for (;;) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(counters + 5, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= chP + chD + chB) break;
+                if (c < chP) {
+                    const int j = 32 * c + lane;
+                    if (j < cp_) rs::phase_count<kFast>(P, S, a, T, n0, lists[2 * U + j], step_ctr);
+                } else if (c < chP + chD) {
+                    const int j = 32 * (c - chP) + lane;
+                    if (j < cd_) rs::phase_sense(S, T, n0, lists[U + j]);
+                } else {
+                    const int j = 32 * (c - chP - chD) + lane;
+                    const uint32_t pr = j < np ? pairs[j] : 0xffffu;
+                    if (pr != 0xffffu) {
+                        const int u = (int)(pr >> 5), cc = (int)(pr & 31u);
+                        const double cur = *reinterpret_cast<volatile double *>(T.sp + u);
+                        const double cand = rs::phase_path_pair(S, T, n0, u, cc, cur);
+                        if (cand < cur) {
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(cand);
+                            atomicMin(spbits + u, bits);
+                            // the corner of the smallest candidate (up to the last 5 mantissa bits: it only seeds the
+                            // next search)
+                            atomicMin(T.hkey + u, (bits & ~31ull) | (unsigned long long)cc);
+                        }
+                    }
                 }
             }
             RS_STAMP(4);
-        }
-        // timing experiments (RS_TUNE bits 4 / 5: skip the sensor / Poisson-retry lists; results are then wrong)
-        const int cd_ = (P.tune & 16) ? 0 : cd, cp_ = (P.tune & 32) ? 0 : cp;
-        off = 0;
-        for (int base = 0; base < cd_; base += kBlock) {
-            const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cd_) rs::phase_sense(S, T, n0, lists[U + j]);
-        }
-        off = (off + ((cd_ + 31) & ~31)) & (kBlock - 1);
-        for (int base = 0; base < cp_; base += kBlock) {
-            const int j = base + ((tid - off) & (kBlock - 1));
-            if (j < cp_) rs::phase_count<kFast>(P, S, a, T, n0, lists[2 * U + j], step_ctr);
         }
     }
     __syncthreads();

@@ -1,1 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_env.py -m gpu -x -q 2>&1 | tail -3
+RS_TUNE=8 python tools/phase_timeline.py 131072 2>/dev/null | head -9
+timeout 300 python bench.py --no-cpu-baseline --steps 4000 > gpurun_out/bench_v28.log 2>&1; echo "rc=$?"; python - <<PY
+import json
+for l in open("gpurun_out/bench_v28.log"):
+    if l.startswith("{"):
+        d=json.loads(l); print("value %.4g"%d["value"], "ms/step %.4f"%d["ms_per_step"], "kernel_ms %.4f"%d["roofline"]["kernel_ms"], "frac %.4f"%d["roofline"]["frac"])
+PY
