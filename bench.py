@@ -308,7 +308,7 @@ def main():
         def maps_step(i):
             mb.update(menv.obs, mpred)
             menv.step_batch(macts[i % 8])
-            mb.reset(mask=(menv.ended & 4) != 0)
+            mb.reset(mask=menv.ended, mask_bits=4)
 
         for i in range(20):
             maps_step(i)
@@ -321,7 +321,7 @@ def main():
             mb.update(menv.obs, mpred)
             mev[i][1].record()
             menv.step_batch(macts[i % 8])
-            mb.reset(mask=(menv.ended & 4) != 0)
+            mb.reset(mask=menv.ended, mask_bits=4)
         p1.record()
         torch.cuda.synchronize()
         upd_ms = sorted(a.elapsed_time(b) for a, b in mev)[Tm // 2]

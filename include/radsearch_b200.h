@@ -228,13 +228,16 @@ typedef struct RsMapsState {     /* caller-owned device memory; X = dim_x, Y = d
     uint32_t *status;            /* [N]             RS_MS_* bits                                                    */
 } RsMapsState;
 
-/* observation_to_map for all A buffers of the selected environments (mask[N] u8, NULL = all).  obs[N][A][11] f32 as
+/* observation_to_map for all A buffers of the selected environments: mask[N] u8 (NULL = all), env n is selected when
+ * mask[n] & mask_bits != 0 (mask_bits 0 = any non-zero byte; pass rs_step's ended[] with RS_E_RESET to follow the env's
+ * auto-resets without an intermediate mask).  obs[N][A][11] f32 as
  * written by rs_step / rs_reset (raw counts); loc_pred[N][A][2] f32 = the source location predicted for agent a's
  * buffer in scaled coordinates (NULL or NaN = none). */
 int rs_maps_update(const RsMapsConfig *cfg, const RsMapsState *st, const float *obs, const float *loc_pred,
-                   const uint8_t *mask, int32_t n_env, void *stream);
+                   const uint8_t *mask, int32_t mask_bits, int32_t n_env, void *stream);
 /* MapsBuffer.reset for the selected environments (mask NULL = all). */
-int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t n_env, void *stream);
+int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t mask_bits, int32_t n_env,
+                  void *stream);
 int rs_sizeof_maps_config(void);
 int rs_sizeof_maps_state(void);
 

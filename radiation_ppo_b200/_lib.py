@@ -101,9 +101,9 @@ def declare(lib, prefix="rs_"):
         lib.rs_bump_ctr.argtypes = [stp, vp]
         mcp, msp = C.POINTER(RsMapsConfig), C.POINTER(RsMapsState)
         lib.rs_maps_update.restype = i32
-        lib.rs_maps_update.argtypes = [mcp, msp, vp, vp, vp, i32, vp]
+        lib.rs_maps_update.argtypes = [mcp, msp, vp, vp, vp, i32, i32, vp]
         lib.rs_maps_reset.restype = i32
-        lib.rs_maps_reset.argtypes = [mcp, msp, vp, i32, vp]
+        lib.rs_maps_reset.argtypes = [mcp, msp, vp, i32, i32, vp]
         lib.rs_pack_rollout.restype = i32
         lib.rs_pack_rollout.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.rs_episode_table.restype = i32

@@ -39,11 +39,12 @@ __device__ __forceinline__ int cell_of(const RsMapsConfig &c, double vx, double 
 
 __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_constant__ RsMapsConfig c,
                                                              const __grid_constant__ RsMapsState S, const float *obs,
-                                                             const float *loc_pred, const uint8_t *mask, int n_env) {
+                                                             const float *loc_pred, const uint8_t *mask, int mask_bits,
+                                                             int n_env) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * kWarpsPerBlock + w;
-    if (n >= n_env || (mask && !mask[n])) return;                          // whole warps leave together
+    if (n >= n_env || (mask && !(mask[n] & mask_bits))) return;            // whole warps leave together
     // per warp: the episode's sample table (values, cells) and the compaction scratch
     float *s_val = reinterpret_cast<float *>(smem_raw) + (size_t)w * 2 * c.log_cap;
     float *scratch = s_val + c.log_cap;
@@ -218,10 +219,10 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
 // environment's stacks with 16-byte stores
 __global__ void __launch_bounds__(kBlock) maps_reset_kernel(const __grid_constant__ RsMapsConfig c,
                                                             const __grid_constant__ RsMapsState S, const uint8_t *mask,
-                                                            int n_env) {
+                                                            int mask_bits, int n_env) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * kWarpsPerBlock + w;
-    if (n >= n_env || (mask && !mask[n])) return;
+    if (n >= n_env || (mask && !(mask[n] & mask_bits))) return;
     const int A = c.n_agents, XY = c.dim_x * c.dim_y;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     {
@@ -271,21 +272,24 @@ int check_maps(const RsMapsConfig *c, const RsMapsState *s, int32_t n_env) {
 extern "C" {
 
 int rs_maps_update(const RsMapsConfig *cfg, const RsMapsState *st, const float *obs, const float *loc_pred,
-                   const uint8_t *mask, int32_t n_env, void *stream) {
+                   const uint8_t *mask, int32_t mask_bits, int32_t n_env, void *stream) {
     if (int rc = check_maps(cfg, st, n_env)) return rc;
     if (!obs) return rs_set_error("obs is NULL");
     const int grid = (n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const size_t smem = (size_t)kWarpsPerBlock * cfg->log_cap * (2 * sizeof(float) + sizeof(uint16_t)) + 16;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(maps_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    maps_update_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, obs, loc_pred, mask, n_env);
+    maps_update_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, obs, loc_pred, mask,
+                                                                                  mask_bits ? mask_bits : 0xff, n_env);
     return (int)cudaGetLastError();
 }
 
-int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t n_env, void *stream) {
+int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t *mask, int32_t mask_bits, int32_t n_env,
+                  void *stream) {
     if (int rc = check_maps(cfg, st, n_env)) return rc;
     const int grid = (n_env + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    maps_reset_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, mask, n_env);
+    maps_reset_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, mask, mask_bits ? mask_bits : 0xff,
+                                                                              n_env);
     return (int)cudaGetLastError();
 }
 

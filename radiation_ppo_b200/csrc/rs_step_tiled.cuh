@@ -343,13 +343,7 @@ __device__ __forceinline__ void phase_sense(const RsState &S, const Tile &T, int
     const EnvView e = tile_env(T, S, t, n);
     const int2 det = T.ndet[u];
     uint32_t status = 0;
-    // rectangle-major and unrolled over the eight directions: eight independent dependency chains per thread (the
-    // direction-major loop has an eighth of the code but runs them one after the other: +3.5k cycles per CTA, measured)
-    float sv[8];
-    sensors_rects(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, sv, status);
-    float *row = T.obs + (t * A + ag) * RS_OBS_DIM + 3;
-#pragma unroll
-    for (int d = 0; d < 8; d++) row[d] = sv[d];
+    sensors_rects_row(e, det.x, det.y, (T.uflag[u] >> 16) & 0xff, T.obs + (t * A + ag) * RS_OBS_DIM + 3, status);
     raise_status(S, n, status);
 }
 

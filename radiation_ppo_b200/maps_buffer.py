@@ -87,26 +87,35 @@ class BatchedMapsBuffer:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _mask(self, mask: Optional[torch.Tensor]):
+        if mask is None:
+            return None
+        if mask.dtype == torch.uint8 and mask.device == self.device and mask.is_contiguous():
+            return mask                                   # e.g. the env's `ended` tensor itself, with mask_bits
+        return mask.to(device=self.device, dtype=torch.uint8).contiguous()
+
     def update(self, obs: torch.Tensor, loc_prediction: Optional[torch.Tensor] = None,
-               mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+               mask: Optional[torch.Tensor] = None, mask_bits: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """observation_to_map for every agent's buffer of the selected envs.  obs: float32 CUDA [N, A, 11] (the env's
         observation tensor, raw counts); loc_prediction: float32 [N, A, 2] scaled source predictions of each agent's
-        PFGRU (None / NaN rows = none).  Returns (actor stacks [N, A, 6, X, Y], critic stacks [N, 4, X, Y])."""
+        PFGRU (None / NaN rows = none); mask: uint8 / bool [N] selects envs (mask[n] & mask_bits, 0 = any non-zero), e.g.
+        ``mask=env.ended, mask_bits=4`` for the envs the step just reset.  Returns (actor stacks [N, A, 6, X, Y], critic
+        stacks [N, 4, X, Y])."""
         o = obs.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, self.number_of_agents, L.OBS_DIM).contiguous()
         p = None if loc_prediction is None else loc_prediction.to(device=self.device, dtype=torch.float32).reshape(
             self.num_envs, self.number_of_agents, 2).contiguous()
-        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        m = self._mask(mask)
         with torch.cuda.device(self.device):
             L.check(self._lib.rs_maps_update(C.byref(self._cfg), C.byref(self._st), _ptr(o), _ptr(p), _ptr(m),
-                                             self.num_envs, self._stream()), "rs_maps_update")
+                                             int(mask_bits), self.num_envs, self._stream()), "rs_maps_update")
         return self.actor_maps, self.critic_maps
 
-    def reset(self, mask: Optional[torch.Tensor] = None) -> None:
-        """MapsBuffer.reset (M:513-523) for the selected envs (all when mask is None)."""
-        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+    def reset(self, mask: Optional[torch.Tensor] = None, mask_bits: int = 0) -> None:
+        """MapsBuffer.reset (M:513-523) for the selected envs (all when mask is None; see update for mask_bits)."""
+        m = self._mask(mask)
         with torch.cuda.device(self.device):
-            L.check(self._lib.rs_maps_reset(C.byref(self._cfg), C.byref(self._st), _ptr(m), self.num_envs,
-                                            self._stream()), "rs_maps_reset")
+            L.check(self._lib.rs_maps_reset(C.byref(self._cfg), C.byref(self._st), _ptr(m), int(mask_bits),
+                                            self.num_envs, self._stream()), "rs_maps_reset")
 
 
 class MapsBuffer:

@@ -48,9 +48,9 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert rc < 0 and b"n_agents" in lib.rs_last_error()
     assert lib.rs_gae(None, None, None, None, None, None, 1, 1, 0.99, 0.9, None, 0, None) < 0
     mc, ms = L.RsMapsConfig(), L.RsMapsState()
-    assert lib.rs_maps_update(C.byref(mc), C.byref(ms), None, None, None, 8, None) < 0 and b"n_agents" in lib.rs_last_error()
+    assert lib.rs_maps_update(C.byref(mc), C.byref(ms), None, None, None, 0, 8, None) < 0 and b"n_agents" in lib.rs_last_error()
     mc.n_agents, mc.dim_x, mc.dim_y, mc.base, mc.log_cap, mc.resolution_accuracy, mc.scale = 2, 27, 27, 242, 246, 22.0, 1 / 2200
-    assert lib.rs_maps_reset(C.byref(mc), C.byref(ms), None, 8, None) < 0 and b"NULL" in lib.rs_last_error()
+    assert lib.rs_maps_reset(C.byref(mc), C.byref(ms), None, 0, 8, None) < 0 and b"NULL" in lib.rs_last_error()
 
 
 def test_product_has_no_cpu_fallback():

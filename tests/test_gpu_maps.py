@@ -100,7 +100,7 @@ def test_maps_kernel_matches_oracle_on_env_rollouts(N, A, T):
         if bool(ended.any()):
             pred = torch.rand(N, A, 2, generator=gen, device="cuda") * 1.2
             check(env.final_obs, pred, mask=ended)                   # bootstrap call (train.py:476-480)
-            mb.reset(mask=ended)
+            mb.reset(mask=env.ended, mask_bits=4)                    # the env's ended[] with RS_E_RESET, no torch op
             for n in sample:
                 if bool(ended[n]):
                     for b in oracles[n]:
