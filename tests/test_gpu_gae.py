@@ -249,3 +249,67 @@ def test_batched_get_packs_the_reference_episode_tensors():
         p1 = one["packed"].cpu().numpy()
         np.testing.assert_allclose(p1[:, 11], g["ep_rows"][n][:, 11], rtol=2e-6, atol=2e-6)
         np.testing.assert_array_equal(np.delete(p1, 11, axis=1), np.delete(g["ep_rows"][n], 11, axis=1))
+
+
+def test_rollout_to_advantages_pipeline_matches_oracle():
+    """BASELINE configs[2] as a parity case (scaled to what the oracle replays in seconds): a batched rollout with
+    auto-reset feeds BatchedPPOBuffer.store_batch with the caller rules of train.py:446-491 (path end on terminal /
+    timeout / epoch end; bootstrap V(last observation) unless terminal), then one rs_gae launch, the global advantage
+    normalisation and the episode packing -- against the oracle env stepped the reference's way and the oracle GAE."""
+    N, T, ML = 4096, 160, 40
+    env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, num_envs=N, seed=99, steps_per_episode=ML,
+                       auto_reset=True, prefetch=True, use_cuda_graph=True)
+    ob = co.OracleBatch(N, co.default_config(obstruction_count=5, enforce=1, max_ep_len=ML), seed=99)
+    ob.reset()
+    d = env.device
+    buf = rp.BatchedPPOBuffer(11, T, N)
+    rng = np.random.default_rng(5)
+    w = torch.as_tensor(rng.normal(size=11).astype(np.float32), device=d)
+
+    def value_fn(obs):                                   # a fixed "critic": any deterministic function of the observation
+        x = obs.reshape(-1, 11).clone()
+        x[:, 0] = torch.log1p(x[:, 0]) * 0.1
+        return torch.tanh(x @ w)
+
+    rew_o = np.zeros((T, N), np.float32); val_o = np.zeros((T, N), np.float32)
+    end_o = np.zeros((T, N), np.uint8); boot_o = np.zeros((T, N), np.float32)
+    obs = env.obs.clone()
+    for t in range(T):
+        acts = rng.integers(0, 8, size=(N, 1))
+        val = value_fn(obs)
+        val_o[t] = value_fn(torch.as_tensor(ob.outs["obs"][:, :1].astype(np.float32), device=d)).cpu().numpy()
+        epoch_end = t == T - 1
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=d), epoch_end=epoch_end)
+        ended = env.ended
+        path_end = (ended & 4) != 0
+        terminal = (ended & 1) != 0
+        # bootstrap with V(last observation of the episode) unless the episode ended in a terminal state (train.py:462-487)
+        boot = torch.where(path_end & ~terminal, value_fn(env.final_obs), torch.zeros(N, device=d))
+        buf.store_batch(obs, torch.as_tensor(acts[:, 0], dtype=torch.float32, device=d), env.reward[:, 0], val,
+                        torch.zeros(N, device=d), end=path_end, boot=boot)
+        obs = env.obs.clone()
+        # the oracle, the reference's way
+        ob.step(acts, env._ctr)
+        e = ob.envs
+        term_o, timeout_o = e["done"] == 1, e["ep_len"] == ML
+        pe = term_o | timeout_o | epoch_end
+        rew_o[t] = ob.outs["reward"][:, 0].astype(np.float32)
+        end_o[t] = pe
+        fin = torch.as_tensor(ob.outs["obs"][:, :1].astype(np.float32), device=d)
+        boot_o[t] = np.where(pe & ~term_o, value_fn(fin).cpu().numpy(), 0.0)
+        if pe.any():
+            ob.reset(mask=pe, new_obstacles=np.full(N, epoch_end))
+    np.testing.assert_array_equal(buf.rew_buf.cpu().numpy(), rew_o)
+    np.testing.assert_array_equal(buf.end_buf.cpu().numpy(), end_o)
+    np.testing.assert_allclose(buf.val_buf.cpu().numpy(), val_o, rtol=1e-5, atol=1e-6)     # fp32 matmul on sensors within 1e-5
+    np.testing.assert_allclose(buf.boot_buf.cpu().numpy(), boot_o, rtol=1e-5, atol=1e-6)
+    buf.finish_paths()
+    a0, r0 = co.gae(buf.rew_buf.cpu().numpy(), buf.val_buf.cpu().numpy(), end_o, buf.boot_buf.cpu().numpy())
+    np.testing.assert_array_equal(buf.adv_buf.cpu().numpy(), a0)
+    np.testing.assert_array_equal(buf.ret_buf.cpu().numpy(), r0)
+    data = buf.get(episodes=True)
+    es, el = data["ep_start"].cpu().numpy(), data["ep_len"].cpu().numpy()
+    assert el.sum() == T * N and (el <= ML).all() and len(el) == int(end_o.sum())
+    packed = data["packed"].cpu().numpy().reshape(N, T, 17)
+    np.testing.assert_array_equal(packed[:, :, 12], r0.T)
+    assert end_o.sum() > 4 * N

@@ -1,1 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 4000 --warmup 100 > gpurun_out/bench_v30_g4.log 2>&1; echo "g4 rc=$?"; tail -c 2500 gpurun_out/bench_v30_g4.log | head -c 300
+timeout 900 python -m pytest tests/test_gpu_gae.py -m gpu -x -q -k pipeline 2>&1 | grep -v "^E    " | tail -30
