@@ -435,3 +435,28 @@ def test_soak_rollout_with_auto_reset_matches_oracle(n, A, oc, enforce, T, fast_
         np.testing.assert_array_equal(v.ep_len, e["ep_len"])
         resets += int(mask.sum())
     assert resets > n
+
+
+def test_results_do_not_depend_on_how_envs_are_sharded():
+    """rank r owns the contiguous global env ids shard_range(total, r, world) and keys its Philox streams with
+    them, so the shards of a 3-rank job reproduce the single-rank batch bit for bit (states, observations, rewards,
+    reset points) -- no collective on the data path."""
+    total, T = 1000, 70
+    kw = dict(obstruction_count=-1, enforce_grid_boundaries=True, number_agents=2, seed=17, steps_per_episode=25,
+              auto_reset=True)
+    full = rp.RadSearch(num_envs=total, **kw)
+    shards = []
+    for r in range(3):
+        lo, hi = rp.shard_range(total, r, 3)
+        shards.append((lo, hi, rp.RadSearch(num_envs=hi - lo, env_id_offset=lo, **kw)))
+    rng = np.random.default_rng(8)
+    for t in range(T):
+        acts = torch.as_tensor(rng.integers(0, 9, size=(total, 2)), dtype=torch.int32, device=full.device)
+        full.step_batch(acts, epoch_end=(t == 40))
+        for lo, hi, e in shards:
+            e.step_batch(acts[lo:hi], epoch_end=(t == 40))
+            for name in ("obs", "reward", "team_reward", "done_flags", "info_flags", "ended", "final_obs"):
+                np.testing.assert_array_equal(getattr(e, name).cpu().numpy(), getattr(full, name)[lo:hi].cpu().numpy(), err_msg=name)
+            np.testing.assert_array_equal(e._det.cpu().numpy(), full._det[:, lo:hi].cpu().numpy())
+            np.testing.assert_array_equal(e._src.cpu().numpy(), full._src[lo:hi].cpu().numpy())
+            np.testing.assert_array_equal(e._rects.cpu().numpy(), full._rects[:, lo:hi].cpu().numpy())
