@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import gc
+import os
 import weakref
 from typing import Any, Dict, NamedTuple, Optional, Sequence, Tuple, Union
 
@@ -251,7 +252,7 @@ class RadSearch:
         ptrs.append(self._ticket)
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
         self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
-        self._side = torch.cuda.Stream(device=dev, priority=int(__import__('os').environ.get('RS_SIDE_PRIO', '-1'))) if self.prefetch else None
+        self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("RS_SIDE_PRIO", "-1"))) if self.prefetch else None
         self._ev_main = torch.cuda.Event()
         self._ev_side = [torch.cuda.Event(), torch.cuda.Event()]
         self._pending = [False, False]      # list holds envs waiting for rs_prepare
@@ -344,7 +345,7 @@ class RadSearch:
     # list on a high-priority side stream while block b+1 runs.  An episode lasts >= 9 steps (source and detector
     # start >= 1000 apart, a step is <= 100.4, the goal radius is 110), so the next scenario is back in place in time;
     # if it ever is not, the env simply takes the synchronous reset path -- the resulting state is the same.
-    PREFETCH_PERIOD = int(__import__('os').environ.get('RS_PERIOD', '4'))
+    PREFETCH_PERIOD = int(os.environ.get("RS_PERIOD", "4"))
 
     def _quiesce_prefetch(self) -> None:
         """Make the main stream wait for any rs_prepare in flight and forget pending refill lists (the envs in them
