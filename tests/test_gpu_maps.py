@@ -142,3 +142,40 @@ def test_maps_unenforced_boundaries_147_grid_and_status_flags():
     bad = torch.full((N, A, 2), 9.0, device="cuda")                   # 9.0 * 22 = 198 > 147: outside the map
     mb.update(env.obs, bad)
     assert bool(((mb.status & 4) != 0).all())
+
+
+def test_reference_unit_test_scenario_observation_to_map():
+    """The scenario of the reference's own unit test (unit_tests/test_RADTEAM_core.py:576-704: three agents, two calls),
+    through the reference-style MapsBuffer interface.  That test predates the source-prediction map (it indexes a six-map
+    stack); the assertions are the same, with the stack order of the shipped code (RADTEAM_core.py:606-616)."""
+    maps = rp.MapsBuffer(observation_dimension=11, steps_per_episode=120, number_of_agents=3)
+    ra = maps.resolution_accuracy
+
+    def deflate(c):                                       # MapsBuffer._deflate_coordinates (RADTEAM_core.py:717-746)
+        return (float(c[0] / ra), float(c[1] / ra))
+
+    def call(count, c01, c2):
+        s1, s2 = deflate(c01), deflate(c2)
+        obs = {0: np.array([count, s1[0], s1[1], 0., 0., 0., 0.1, 0., 0., 0., 0.], dtype=np.float32),
+               1: np.array([count, s1[0], s1[1], 0., 0., 0., 0.1, 0., 0., 0., 0.], dtype=np.float32),
+               2: np.array([count, s2[0], s2[1], 0., 0., 0., 0.1, 0., 0., 0., 0.], dtype=np.float32)}
+        return maps.observation_to_map(obs, 0, (0.5, 0.5))
+
+    pred, loc, others, readings, visits, obstacles, combo = call(1000.0, (0, 1), (0, 2))
+    assert pred[11][11] == 1.0 and pred.sum() == 1.0
+    assert loc[0][1] == 1.0 and np.delete(loc.ravel(), 1).max() == 0.0
+    assert others[0][1] == 1.0 and others[0][2] == 1.0 and others.sum() == 2.0
+    assert readings.max() == 0.0                          # first readings standardise to 0
+    assert visits[0][1] > visits[0][2] > 0.0              # two agents visited (0, 1), one visited (0, 2)
+    assert obstacles[0][1] == np.float32(0.1) and obstacles[0][2] == np.float32(0.1)
+    assert combo[0][1] == 2.0 and combo[0][2] == 1.0 and combo.sum() == 3.0
+
+    pred, loc, others, readings, visits, obstacles, combo = call(5000.0, (0, 3), (0, 4))
+    assert loc[0][1] == 0.0 and loc[0][3] == 1.0
+    assert others[0][1] == 0.0 and others[0][2] == 0.0 and others[0][3] == 1.0 and others[0][4] == 1.0
+    assert readings[0][3] > 0.0 and readings[0][4] > 0.0
+    assert all(visits[0][k] > 0.0 for k in (1, 2, 3, 4))
+    assert all(obstacles[0][k] > 0.0 for k in (1, 2, 3, 4))
+    assert combo[0][1] == 0.0 and combo[0][2] == 0.0 and combo[0][3] == 2.0 and combo[0][4] == 1.0
+    maps.reset()
+    assert all(float(np.abs(m).sum()) == 0.0 for m in call(0.0, (5, 5), (5, 5))[3:4])      # readings: a zero count -> z = 0
