@@ -136,8 +136,8 @@ __device__ __forceinline__ long long rs_globaltimer() {
         }                                                                                                 \
     } while (0)
 
-template <bool kFast, int E, int kOcc>
-__global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constant__ rs::Params P,
+template <bool kFast, int E, int kOcc, int TB>
+__global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
                                                          const __grid_constant__ rs::StepArgs a,
                                                          const __grid_constant__ rs::TileLayout L,
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             const RowEnt r = R.in[i];
             const uint32_t *g = reinterpret_cast<const uint32_t *>(r.g + (unsigned long long)n0 * r.bpe);
             uint32_t *s = reinterpret_cast<uint32_t *>(smem + r.off);
-            for (uint32_t w = tid; w < (uint32_t)valid * r.bpe / 4u; w += kBlock) s[w] = g[w];
+            for (uint32_t w = tid; w < (uint32_t)valid * r.bpe / 4u; w += TB) s[w] = g[w];
         }
         __syncthreads();
     }
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
 
     const bool merged = (P.tune & 4) != 0;
     // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
-    for (int u0 = 0; u0 < U; u0 += kBlock) {
+    for (int u0 = 0; u0 < U; u0 += TB) {
         const int u = u0 + tid;
         int uf = 0;
         if (u < U && (u % E) < valid) uf = rs::phase_move<kFast>(P, S, a, T, n0, u, step_ctr);
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             const int pair_cap = (L.done - L.reward) / 2;
             int *pair_count = counters + 4;
             if (!merged)
-                for (int base = 0; base < cb; base += kBlock) {
+                for (int base = 0; base < cb; base += TB) {
                     const int j = base + tid;
                     seed_and_push(S, T, n0, j < cb ? (int)lists[j] : -1, pairs, pair_cap, pair_count);
                 }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
     RS_STAMP(5);
     // ---- phase_commit: every environment; CTA-aggregated append to the reset work list ---------------------------------
 
-    for (int t0 = 0; t0 < E; t0 += kBlock) {
+    for (int t0 = 0; t0 < E; t0 += TB) {
         const int t = t0 + tid;
         bool sched = false;
         if (t < valid) sched = rs::phase_commit<kFast>(P, S, a, T, n0, t, step_ctr);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             __shared__ int s_base;
             if (tid == 0) s_base = atomicAdd(S.reset_count, cs);
             __syncthreads();
-            for (int j = tid; j < cs; j += kBlock) S.reset_list[s_base + j] = n0 + lists[j];
+            for (int j = tid; j < cs; j += TB) S.reset_list[s_base + j] = n0 + lists[j];
         }
     }
 
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(kBlock, kOcc) step_kernel(const __grid_constan
             uint8_t *g = reinterpret_cast<uint8_t *>(r.g + (unsigned long long)n0 * r.bpe);
             const uint32_t nb = (uint32_t)valid * r.bpe;
             if ((nb & 3u) == 0 && (reinterpret_cast<uintptr_t>(g) & 3u) == 0) {
-                for (uint32_t w = tid; w < nb / 4u; w += kBlock)
+                for (uint32_t w = tid; w < nb / 4u; w += TB)
                     reinterpret_cast<uint32_t *>(g)[w] = reinterpret_cast<const uint32_t *>(s)[w];
             } else {
-                for (uint32_t w = tid; w < nb; w += kBlock) g[w] = s[w];
+                for (uint32_t w = tid; w < nb; w += TB) g[w] = s[w];
             }
         }
     }
@@ -438,9 +438,15 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags; a.parity = parity;
-    const int E = step_tile_envs(cfg->n_agents), A = cfg->n_agents, K = cfg->k_max;
+    static const int occ_env = getenv("RS_STEP_OCC") ? atoi(getenv("RS_STEP_OCC")) : 0;      // tuning switch
+    const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    const int A = cfg->n_agents, K = cfg->k_max;
+    // single agent, fast sampler: 256-env tiles on 256 threads (4 CTAs per SM) once they fill the GPU -- half as many
+    // tile loads / barriers / work-pool rounds per env as 128-env tiles: +3.5 % env-steps/s at 131072 envs (measured)
+    const bool wide = A == 1 && fast && (occ_env == 4 || (occ_env == 0 && (long long)n_env >= 148LL * 256 * 2));
+    const int E = wide ? 256 : step_tile_envs(cfg->n_agents);
     const int grid = (n_env + E - 1) / E;
-    const rs::TileLayout L = rs::make_layout(E, A, K, kBlock, cfg->standardize);
+    const rs::TileLayout L = rs::make_layout(E, A, K, E == 256 ? 256 : kBlock, cfg->standardize);
     const size_t smem = (size_t)L.total;
     // the tile's rows: state rows read (src, rad, meta, actions, rects[k], then det / best / aflags / running count
     // statistics per agent) and rows written (meta, obs, reward, team_reward, done, info, ended, raw counts, then the
@@ -480,7 +486,6 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     // bytes of one full tile's state rows (what the bulk copies of a CTA deliver to its mbarrier)
     uint32_t tx_bytes = 0;
     for (int i = 0; i < R.n_in; i++) tx_bytes += (uint32_t)E * R.in[i].bpe;
-    const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
     // bulk-async tile copies need 16-byte aligned rows: every array base (the tile offsets are multiples of 32 elements)
     const int bulk_ok = aligned16(st->src) && aligned16(st->rad) && aligned16(st->rects) && aligned16(st->meta) &&
                         aligned16(st->det) && aligned16(st->best) && aligned16(st->aflags) && aligned16(actions) &&
@@ -488,18 +493,18 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
                         aligned16(info) && aligned16(ended) && aligned16(st->st_mean) && aligned16(st->st_m2) &&
                         aligned16(st->raw_count) &&
                         (cfg->n_agents == 1 || n_env % 4 == 0);        // per-agent rows start at multiples of N elements
-    static const int occ_env = getenv("RS_STEP_OCC") ? atoi(getenv("RS_STEP_OCC")) : 0;      // tuning switch
-#define RS_LAUNCH_STEP(FAST, TE, OCC)                                                                               \
-    do {                                                                                                            \
-        if (smem > 48 * 1024)                                                                                       \
-            cudaFuncSetAttribute(step_kernel<FAST, TE, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        step_kernel<FAST, TE, OCC><<<grid, kBlock, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                     \
+#define RS_LAUNCH_STEP(FAST, TE, OCC, TB)                                                                              \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024)                                                                                             \
+            cudaFuncSetAttribute(step_kernel<FAST, TE, OCC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        step_kernel<FAST, TE, OCC, TB><<<grid, TB, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                        \
     } while (0)
-    if (E == 128) {
-        if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6); else RS_LAUNCH_STEP(true, 128, 8); }
-        else RS_LAUNCH_STEP(false, 128, 6);
-    } else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64, 6); else RS_LAUNCH_STEP(false, 64, 6); }
-    else { if (fast) RS_LAUNCH_STEP(true, 32, 6); else RS_LAUNCH_STEP(false, 32, 6); }
+    if (E == 256) RS_LAUNCH_STEP(true, 256, 4, 256);
+    else if (E == 128) {
+        if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6, 128); else RS_LAUNCH_STEP(true, 128, 8, 128); }
+        else RS_LAUNCH_STEP(false, 128, 6, 128);
+    } else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64, 6, 128); else RS_LAUNCH_STEP(false, 64, 6, 128); }
+    else { if (fast) RS_LAUNCH_STEP(true, 32, 6, 128); else RS_LAUNCH_STEP(false, 32, 6, 128); }
 #undef RS_LAUNCH_STEP
     return (int)cudaGetLastError();
 }

@@ -460,3 +460,34 @@ def test_results_do_not_depend_on_how_envs_are_sharded():
             np.testing.assert_array_equal(e._det.cpu().numpy(), full._det[:, lo:hi].cpu().numpy())
             np.testing.assert_array_equal(e._src.cpu().numpy(), full._src[lo:hi].cpu().numpy())
             np.testing.assert_array_equal(e._rects.cpu().numpy(), full._rects[:, lo:hi].cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [4096, 76032])
+def test_fast_sampler_kernel_variants_match_oracle_except_counts(n):
+    """fast_poisson=True selects other instantiations of the step kernel (64-register, 8 CTAs per SM; 256-env tiles on 256
+    threads from 75776 envs up -- the ones bench.py times).  Everything but the Poisson counts (KS-tested elsewhere) must
+    still equal the oracle bit for bit: positions, flags, shortest paths, rewards, termination, resets, sensors."""
+    ML, T = 60, 90
+    env, ob = make_pair(n, 1, 5, True, seed=2024, max_ep_len=ML, auto_reset=True, fast_poisson=True, prefetch=True,
+                        use_cuda_graph=True)
+    rng = np.random.default_rng(n)
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 8, size=(n, 1))
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+        ob.step(acts, env._ctr)
+        e, o = ob.envs, ob.outs
+        mask = (e["done"] == 1) | (e["ep_len"] == ML)
+        final = o["obs"][:, :1].copy()
+        rew, done = o["reward"][:, :1].astype(np.float32).copy(), o["done"][:, :1].copy()
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.zeros(n))
+        v = pu.GpuView(env)
+        np.testing.assert_array_equal(v.reward, rew)
+        np.testing.assert_array_equal(v.done, done)
+        np.testing.assert_array_equal((v.ended & 4) != 0, mask)
+        nxt = np.where(mask[:, None, None], o["obs"][:, :1], final).astype(np.float32)
+        np.testing.assert_array_equal(v.obs[:, :, 1:3], nxt[:, :, 1:3])
+        np.testing.assert_allclose(v.obs[:, :, 3:], nxt[:, :, 3:], rtol=1e-5, atol=0)
+        np.testing.assert_allclose(v.final_obs[mask][:, :, 3:], final[mask][:, :, 3:].astype(np.float32), rtol=1e-5, atol=0)
+        assert (v.obs[:, :, 0] >= 0).all()
+        pu.compare_state(v, ob, 1)
