@@ -444,9 +444,9 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     // single agent, fast sampler: 256-env tiles on 256 threads (4 CTAs per SM) once they fill the GPU -- half as many
     // tile loads / barriers / work-pool rounds per env as 128-env tiles: +3.5 % env-steps/s at 131072 envs (measured)
     const bool wide = A == 1 && fast && (occ_env == 4 || (occ_env == 0 && (long long)n_env >= 148LL * 256 * 2));
-    const int E = wide ? 256 : step_tile_envs(cfg->n_agents);
+    const int E = (occ_env == 2 && A == 1 && fast) ? 512 : (wide ? 256 : step_tile_envs(cfg->n_agents));
     const int grid = (n_env + E - 1) / E;
-    const rs::TileLayout L = rs::make_layout(E, A, K, E == 256 ? 256 : kBlock, cfg->standardize);
+    const rs::TileLayout L = rs::make_layout(E, A, K, E > 128 ? E : kBlock, cfg->standardize);
     const size_t smem = (size_t)L.total;
     // the tile's rows: state rows read (src, rad, meta, actions, rects[k], then det / best / aflags / running count
     // statistics per agent) and rows written (meta, obs, reward, team_reward, done, info, ended, raw counts, then the
@@ -499,7 +499,8 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
             cudaFuncSetAttribute(step_kernel<FAST, TE, OCC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         step_kernel<FAST, TE, OCC, TB><<<grid, TB, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                        \
     } while (0)
-    if (E == 256) RS_LAUNCH_STEP(true, 256, 4, 256);
+    if (E == 512) RS_LAUNCH_STEP(true, 512, 2, 512);
+    else if (E == 256) RS_LAUNCH_STEP(true, 256, 4, 256);
     else if (E == 128) {
         if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6, 128); else RS_LAUNCH_STEP(true, 128, 8, 128); }
         else RS_LAUNCH_STEP(false, 128, 6, 128);
