@@ -140,6 +140,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="synchronous reset kernel after every step")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
+    ap.add_argument("--episode-steps", type=int, default=120, help="steps_per_episode (120 = the reference's; a huge value "
+                    "shows the throughput without resets)")
     ap.add_argument("--streams", type=int, default=0,
                     help="CUDA streams the ring's env batches are spread over (0 = one per batch; 1 = serialised)")
     args = ap.parse_args()
@@ -167,10 +169,11 @@ def main():
     for r in range(R):
         e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=dev,
                          env_id_offset=(rank * R + r) * N, auto_reset=True, fast_poisson=fast,
+                         steps_per_episode=args.episode_steps,
                          prefetch=not args.no_prefetch, use_cuda_graph=not (args.no_graph or args.no_prefetch))
         # stagger the episodes: steady state of a training run (about 1/120 of the envs finish at every step)
         g = torch.Generator(device=dev).manual_seed(1000 + rank * R + r)
-        e._meta.add_(torch.randint(0, 120, (N,), generator=g, device=dev, dtype=torch.int32) << 16)
+        e._meta.add_(torch.randint(0, min(args.episode_steps, 120), (N,), generator=g, device=dev, dtype=torch.int32) << 16)
         torch.cuda.synchronize()
         e.capture_graphs()
         envs.append(e)
@@ -378,7 +381,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": f"RadSearch env step + auto-reset, {N} envs/GPU (BASELINE configs[4]), 5 obstructions, "
-                                   "enforced boundaries, 1 agent, uniform random actions, staggered 120-step episodes",
+                                   f"enforced boundaries, 1 agent, uniform random actions, staggered {args.episode_steps}-step episodes",
                        "envs_per_gpu": N, "obstructions": K_OBS, "poisson": "fp32-acceptance PTRS" if fast else "numpy-exact PTRS",
                        "l2": f"ring of {R} env batches ({state_mb:.0f} MB of state) cycled: every step reads its state from HBM",
                        "resets": ("next episodes prefetched by rs_prepare on a parallel graph branch / side stream"

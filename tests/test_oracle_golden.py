@@ -212,3 +212,63 @@ def test_shortest_path_through_a_grazed_corner_is_the_direct_segment():
         assert em.query_sp(np.array([det]), 0)[0] == want and em.query_sp(np.array([det]), 1)[0] == want, det
         checked += 1
     assert checked > 30
+
+
+def test_shortest_path_c_oracle_vs_exact_shim_random_and_collinear():
+    """orc_shortest_path and the kernel's pruned search (host emulation) against the exact-arithmetic visilibity
+    restatement on random obstruction sets, with detectors drawn at random AND placed on lines through the source and
+    obstruction corners (grazing / collinear cases, where a 1-ulp slip is possible): bit-exact path lengths."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims"))
+    try:
+        import visilibity as vis
+    finally:
+        sys.path.pop(0)
+    from tests.emu.harness import EmuEnv, make_config
+
+    rng = np.random.default_rng(123)
+    checked = collinear = 0
+    for case in range(10):
+        K = int(rng.integers(1, 6))
+        # obstructions the way create_obs draws them (R:948-1011), rejected when they touch
+        rects = []
+        while len(rects) < K:
+            x, y = int(rng.integers(200, 1980)), int(rng.integers(200, 1980))
+            w, h = int(rng.integers(200, 500)), int(rng.integers(200, 500))
+            r = [x, y, x + w, y + h]
+            if all(r[2] < q[0] - 1 or q[2] < r[0] - 1 or r[3] < q[1] - 1 or q[3] < r[1] - 1 for q in rects):
+                rects.append(r)
+        rects_a = np.zeros((1, 5, 4), np.int64); rects_a[0, :K] = rects
+        inside = lambda p: any(r[0] <= p[0] <= r[2] and r[1] <= p[1] <= r[3] for r in rects)      # noqa: E731
+        while True:
+            src = [int(v) for v in rng.integers(200, 2200, 2)]
+            if not inside(src):
+                break
+        dets = [[int(v) for v in rng.integers(200, 2200, 2)] for _ in range(8)]
+        for r in rects:                                   # points on the ray source -> corner, beyond the corner
+            for cx, cy in ((r[0], r[1]), (r[0], r[3]), (r[2], r[3]), (r[2], r[1])):
+                dx, dy = cx - src[0], cy - src[1]
+                g = int(np.gcd(abs(dx), abs(dy))) or 1
+                for mult in (1, 2, 5):
+                    p = [cx + mult * dx // g, cy + mult * dy // g]
+                    if 0 <= p[0] <= 2700 and 0 <= p[1] <= 2700:
+                        dets.append(p); collinear += 1
+        polys = [vis.Polygon([vis.Point(0, 0), vis.Point(2700, 0), vis.Point(2700, 2700), vis.Point(0, 2700)])]
+        for r in rects:
+            x0, y0, x1, y1 = (float(v) for v in r)
+            polys.append(vis.Polygon([vis.Point(x0, y0), vis.Point(x0, y1), vis.Point(x1, y1), vis.Point(x1, y0)]))
+        world = vis.Environment(polys)
+        em = EmuEnv(1, make_config(n_agents=1, obstruction_count=K, enforce=True, k_max=5), seed=1)
+        ob = co.OracleBatch(1, co.default_config(n_agents=1, obstruction_count=K, enforce=1))
+        for det in dets:
+            if inside(det) or det == src:
+                continue
+            em.load_scenarios(np.array([src]), np.array([det]), np.array([5000000]), np.array([20]), rects_a, np.array([K]))
+            ob.load_scenarios(np.array([src]), np.array([det]), [5000000], [20], rects_a, [K])
+            want = world.shortest_path(vis.Point(float(src[0]), float(src[1])), vis.Point(float(det[0]), float(det[1])),
+                                       None, 1e-7).length()
+            assert ob.shortest_path(0, det) == want, (case, src, det, rects)
+            assert em.query_sp(np.array([det]), 0)[0] == want, (case, src, det, rects)
+            assert em.query_sp(np.array([det]), 1)[0] == want, (case, src, det, rects)
+            checked += 1
+    assert checked > 150 and collinear > 50
