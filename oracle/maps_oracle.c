@@ -5,7 +5,7 @@
  * methods M:748-932, IntensityEstimator M:101-182 (median of the samples of a grid cell), StatisticStandardization
  * M:188-277, Normalizer.normalize_incremental_logscale M:322-365, MapsBuffer.reset / _clear_maps M:513-530, 618-667.
  * Module switches as shipped: PFGRU = True (M:39), SIMPLE_NORMALIZATION = False (M:58), NORMALIZE_RADIATION = False
- * (M:59).  Pinned against the reference class itself: tests/golden/ref_maps_*.npz (tools/make_golden.py maps).
+ * (M:59).  Pinned against the reference class itself: tests/golden/ref_maps_*.npz (tests/golden/make_golden.py maps).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may link or call this.
  */

@@ -6,7 +6,7 @@ import stubs in oracle/shims (gym, matplotlib) and the exact-arithmetic `visilib
 `ray` / `mpi4py` stubs.
 
 /root/reference only exists in the build container; on the GPU box these loaders raise and the tests that need
-them skip -- the committed vectors under tests/golden/ (made by tools/make_golden.py with these loaders) stand in.
+them skip -- the committed vectors under tests/golden/ (made by tests/golden/make_golden.py with these loaders) stand in.
 Nothing in the product package imports this file.
 """
 from __future__ import annotations

@@ -1,5 +1,5 @@
 """Generates the committed fixtures under tests/golden/ by running the UNMODIFIED reference from /root/reference
-(through oracle/shims) in the build container.  Re-run: `python tools/make_golden.py` (takes a few minutes).
+(through oracle/shims) in the build container.  Re-run: `python tests/golden/make_golden.py` (takes a few minutes).
 
   ref_steps_*.npz     per-call records of RadSearch.reset()/step(): full pre-state, actions, the uniforms numpy's
                       poisson consumed, and every output (observation, rewards, done, info, new state).
@@ -24,11 +24,11 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle.ref_env import REFERENCE_ROOT, load_reference_env, load_reference_ppo  # noqa: E402
-from tools.ref_harness import record_episodes, record_probes  # noqa: E402
+from tests.golden.ref_harness import record_episodes, record_probes  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 PRE_KEYS = ["src", "det", "intensity", "bkg", "rects", "num_obs", "best", "iter_count", "done", "oob_count", "blocked",
@@ -57,7 +57,7 @@ def pack(recs):
 
 
 def main():
-    only = set(sys.argv[1:])          # e.g. `python tools/make_golden.py gae` regenerates one group
+    only = set(sys.argv[1:])          # e.g. `python tests/golden/make_golden.py gae` regenerates one group
     want = lambda grp: not only or grp in only      # noqa: E731
     os.makedirs(OUT, exist_ok=True)
     m = load_reference_env()
@@ -149,7 +149,7 @@ def make_gae():
 
 def make_reset_stats(m):
     # ---- reset marginals ----------------------------------------------------------------------------------------
-    from tools.ref_harness import rect_of
+    from tests.golden.ref_harness import rect_of
 
     env = m.RadSearch(obstruction_count=-1, np_random=np.random.default_rng(99), enforce_grid_boundaries=True)
     rows = []

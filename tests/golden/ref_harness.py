@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- drives the unmodified reference RadSearch (through oracle/shims) and records
 trajectories: state before each call, actions, the uniforms numpy's poisson consumed, and every output.
 
-Used by tools/make_golden.py (writes tests/golden/*.npz) and by tests/test_oracle_vs_reference.py (container only).
+Used by tests/golden/make_golden.py (writes tests/golden/*.npz) and by tests/test_oracle_vs_reference.py (container only).
 """
 from __future__ import annotations
 

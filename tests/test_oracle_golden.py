@@ -1,5 +1,5 @@
 """CPU tests: the oracle (oracle/radsearch_oracle.c) against the golden vectors recorded from the unmodified reference
-(tools/make_golden.py), numpy's own poisson, Python's round, the Philox known-answer vectors and scipy's lfilter."""
+(tests/golden/make_golden.py), numpy's own poisson, Python's round, the Philox known-answer vectors and scipy's lfilter."""
 import copy
 
 import numpy as np
@@ -134,7 +134,7 @@ def test_oracle_reset_distribution_matches_reference():
 def test_oracle_standardizer_reproduces_reference_classes(mode):
     """oracle/radsearch_oracle.c::orc_stat_update_standardize against StatisticStandardization (RADTEAM_core.py:188-277,
     mode 1) and StatBuff + np.clip(.., -8, 8) (algos/test_environment/core.py:55-79, ppo.py:502, mode 2), recorded from
-    the reference classes by tools/make_golden.py: z-scores, running mean, M2 and std bit for bit in float64."""
+    the reference classes by tests/golden/make_golden.py: z-scores, running mean, M2 and std bit for bit in float64."""
     g = pu.load_golden("ref_standardize")
     S = len(g["length"])
     st = co.Standardizer(S, mode)
@@ -154,7 +154,7 @@ MAPS_FILES = {"ref_maps_a1": 1, "ref_maps_a4": 4, "ref_maps_a2_idle": 2}
 @pytest.mark.parametrize("name", list(MAPS_FILES))
 def test_oracle_maps_reproduce_reference_mapsbuffer(name):
     """oracle/maps_oracle.c against the reference's MapsBuffer.observation_to_map (RADTEAM_core.py:532-616) run on
-    oracle-env rollouts by tools/make_golden.py: all seven float32 maps of every agent's buffer after every call,
+    oracle-env rollouts by tests/golden/make_golden.py: all seven float32 maps of every agent's buffer after every call,
     bit for bit (location / others / combined / prediction counts, median-of-samples readings through the running
     standardiser, log-scale visit counts, obstacle detections), including the bootstrap call and reset at episode ends."""
     g = pu.load_golden(name)
