@@ -508,6 +508,17 @@ class RadSearch:
         self.epoch_end = False
         return self.obs
 
+    def scenario_arrays(self) -> Dict[str, np.ndarray]:
+        """The current scenario of every env (source, agent 0's detector, intensities, obstructions) as the arrays of
+        scenario_io.scenario_arrays: what create_envs (algos/test_environment/eval/test_env_gen.py:13-24) saves after
+        env.reset().  With scenario_io.to_env_dict / save_test_env_dict this writes the reference's test-environment files
+        from one batched reset instead of one gym.make + reset per scenario."""
+        K = self._cfg.k_max
+        return dict(src=self._src.cpu().numpy().astype(np.int32), det=self._det[0].cpu().numpy().astype(np.int32),
+                    intensity=self._rad[:, 0].cpu().numpy().astype(np.int32), bkg=self._rad[:, 1].cpu().numpy().astype(np.int32),
+                    rects=self._rects[:max(K, 1)].permute(1, 0, 2).contiguous().cpu().numpy().astype(np.int32),
+                    num_obs=(self._meta & 0xFF).cpu().numpy().astype(np.int32))
+
     def shortest_path_to(self, points: torch.Tensor, variant: int = 0) -> torch.Tensor:
         """Shortest-path length from each env's source to points[n] (int tensor [N, 2]) around its obstructions
         (world.shortest_path(...).length(), R:491-493) -> float64 tensor [N]."""

@@ -62,3 +62,31 @@ def test_monte_carlo_evaluator_matches_oracle_episodes(k, A):
     assert 0.1 < success.mean() < 1.0 and res.completed_runs == R
     s = res.summary()
     assert s["success_rate"] == pytest.approx(success.mean())
+
+
+def test_batched_reset_writes_reference_test_environment_files(tmp_path):
+    """create_envs / create_envs_snr (algos/test_environment/eval/test_env_gen.py:13-69) from ONE batched reset: the
+    sampled scenarios leave as the reference's joblib dict, come back through the loader, and drive the evaluator; the
+    oracle loaded with the same file agrees with the GPU env bit for bit."""
+    from radiation_ppo_b200 import scenario_io as sio
+
+    n, k = 4000, 3
+    env = rp.RadSearch(obstruction_count=k, enforce_grid_boundaries=True, num_envs=n, seed=21)
+    arr = env.scenario_arrays()
+    assert (arr["num_obs"] == k).all() and (np.linalg.norm(arr["src"] - arr["det"], axis=1) >= 1000).all()
+    idx = sio.select_by_snr(arr, 40, "none")
+    picked = {key: v[idx] for key, v in arr.items()}
+    path = str(tmp_path / f"test_env_dict_obs{k}")
+    sio.save_test_env_dict(path, sio.to_env_dict(picked))
+    d = sio.load_test_env_dict(path)
+    assert len(d) == 40 and len(d["env_0"][4]) == k
+    ev = rp.MonteCarloEvaluator(env_dict=d, montecarlo_runs=3, steps_per_episode=30, obstruction_count=k, seed=5,
+                                enforce_grid_boundaries=True)
+    res = ev.run(rp.uniform_policy(0))
+    assert res.episode_length.shape == (40, 3) and int(res.episode_length.max()) <= 30
+    ob = co.OracleBatch(40, co.default_config(obstruction_count=k, enforce=1))
+    back = sio.scenario_arrays(d, k_max=k, with_obstacles=True)
+    ob.load_scenarios(back["src"], back["det"], back["intensity"], back["bkg"], back["rects"], back["num_obs"])
+    env2 = rp.RadSearch(obstruction_count=k, enforce_grid_boundaries=True, num_envs=40, seed=5)
+    env2.load_scenarios(**back)
+    np.testing.assert_array_equal(env2._best[0].cpu().numpy(), [ob.shortest_path(i, back["det"][i]) for i in range(40)])
