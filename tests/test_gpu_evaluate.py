@@ -90,3 +90,47 @@ def test_batched_reset_writes_reference_test_environment_files(tmp_path):
     env2 = rp.RadSearch(obstruction_count=k, enforce_grid_boundaries=True, num_envs=40, seed=5)
     env2.load_scenarios(**back)
     np.testing.assert_array_equal(env2._best[0].cpu().numpy(), [ob.shortest_path(i, back["det"][i]) for i in range(40)])
+
+
+def test_episode_stats_follow_the_training_loops_bookkeeping():
+    """radiation_ppo_b200.EpisodeStats against the per-env bookkeeping of train.py:359-527 done in numpy on an oracle
+    rollout: EpRet / EpLen of the episodes that ended by terminal or timeout (not by the epoch cut), DoneCount, OutOfBound."""
+    N, A, T, ML = 1024, 2, 90, 20
+    env = rp.RadSearch(obstruction_count=2, enforce_grid_boundaries=True, number_agents=A, num_envs=N, seed=12,
+                       steps_per_episode=ML, auto_reset=True)
+    ob = co.OracleBatch(N, co.default_config(n_agents=A, obstruction_count=2, enforce=1, max_ep_len=ML), seed=12)
+    ob.reset()
+    st = rp.EpisodeStats(N, A, env.device)
+    rng = np.random.default_rng(4)
+    ep_ret = np.zeros(N); ep_len = np.zeros(N, np.int64)
+    rets, lens, done_cnt, oob_cnt = [], [], np.zeros(A), np.zeros(A)
+    src = None
+    for t in range(T):
+        # walk towards the lower-left wall now and then so that out-of-bounds events occur
+        acts = np.where(rng.random((N, A)) < 0.3, 7, rng.integers(0, 8, size=(N, A)))
+        epoch_end = t == T - 1
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device), epoch_end=epoch_end)
+        st.update(env.reward, env.team_reward, env.done_flags, env.info_flags, env.ended)
+        ob.step(acts, env._ctr)
+        e, o = ob.envs, ob.outs
+        ep_ret += o["team_reward"].astype(np.float32).astype(np.float64)
+        ep_len += 1
+        done_cnt += (o["done"][:, :A] != 0).sum(0)
+        oob_cnt += (e["oob"][:, :A] != 0).sum(0)
+        over = (e["done"] == 1) | (e["ep_len"] == ML)
+        rets += list(ep_ret[over]); lens += list(ep_len[over])
+        mask = over | epoch_end
+        ep_ret[mask] = 0; ep_len[mask] = 0
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.full(N, epoch_end))
+    s = {k: v.cpu().numpy() for k, v in st.epoch_summary().items()}
+    rets, lens = np.array(rets), np.array(lens)
+    assert s["Episodes"][0] == len(rets) > N
+    np.testing.assert_allclose(s["AverageEpRet"], rets.mean(), rtol=1e-12)
+    np.testing.assert_allclose(s["StdEpRet"], rets.std(), rtol=1e-9)
+    np.testing.assert_allclose(s["MinEpRet"], rets.min(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s["MaxEpRet"], rets.max(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s["EpLen"], lens.mean(), rtol=1e-12)
+    np.testing.assert_array_equal(s["DoneCount"], done_cnt)
+    np.testing.assert_array_equal(s["OutOfBound"], oob_cnt)
+    assert oob_cnt.sum() > 0 and float(st._acc.abs().sum()) == 0.0
