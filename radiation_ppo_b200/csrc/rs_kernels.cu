@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
             // One pool of work for the rest of the phase, fetched by the warps 32 items at a time: first the Poisson
             // retries (few units, the longest dependent chains), then the sensor units, then the (unit, corner) pairs
             // (many, short: they fill the gaps).  No warp waits at a barrier while another walks a list alone.
-            // (RS_TUNE bits 4 / 5 skip the sensor / retry lists: timing experiments, the results are then wrong.)
-            const int cd_ = (P.tune & 16) ? 0 : cd, cp_ = (P.tune & 32) ? 0 : cp;
+            const int cd_ = cd, cp_ = cp;
             const int chP = (cp_ + 31) >> 5, chD = (cd_ + 31) >> 5, chB = (np + 31) >> 5;
             const int lane = tid & 31;
             for (;;) {
