@@ -399,8 +399,8 @@ def main():
                     "traffic": measured_traffic("gae_cols_kernel", N) if T == 480 else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "sync_value": e2e_vals["sync"],
-                    "note": f"RadSearch.step_host: pinned host actions -> device, step+reset, all outputs (obs, rewards, "
-                            f"done/info/ended flags) -> pinned host in one copy; value = {R} env batches round-robin on "
+                    "note": f"RadSearch.step_host: pinned host actions -> device, step+reset, all outputs (obs, reward, "
+                            f"done/info/ended flags; 51 B per env) -> pinned host in one copy; value = {R} env batches round-robin on "
                             "their own streams (host waits for a batch's previous results before sending its next "
                             "actions); sync_value = host waits after every step"},
             "maps": maps_line,

@@ -82,12 +82,18 @@ class HostStepBuffers:
 
     def __init__(self, env: "RadSearch"):
         self.actions = torch.zeros((env.num_envs, env.number_agents), dtype=torch.int32).pin_memory()
-        self.flat = torch.zeros(env._out_flat.numel(), dtype=torch.uint8).pin_memory()
+        # with one agent the team reward IS the agent's reward (R:661-665): it stays on the device and `team_reward` is a
+        # view of `reward` here -- 4 of 55 bytes per env-step less on the PCIe link that bounds this path
+        self.nbytes = env._out_host_bytes
+        self.flat = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
         for name, shape, dt, o, nbytes in env._out_layout:
-            setattr(self, name, self.flat[o:o + nbytes].view(dt).view(*shape))
+            if o + nbytes <= self.nbytes:
+                setattr(self, name, self.flat[o:o + nbytes].view(dt).view(*shape))
+        if not hasattr(self, "team_reward"):
+            self.team_reward = self.reward.view(env.num_envs)
         self.event = torch.cuda.Event()
         self.h2d_bytes = self.actions.numel() * 4
-        self.d2h_bytes = self.flat.numel()
+        self.d2h_bytes = self.nbytes
 
     def wait(self) -> "HostStepBuffers":
         self.event.synchronize()
@@ -263,14 +269,15 @@ class RadSearch:
         # step outputs: views into ONE flat allocation (256-byte aligned segments) so that a host consumer gets them with
         # a single device->host copy (step_host)
         segs = [("obs", (N, A, L.OBS_DIM), torch.float32), ("reward", (N, A), torch.float32),
-                ("team_reward", (N,), torch.float32), ("done_flags", (N, A), torch.uint8),
-                ("info_flags", (N, A), torch.uint8), ("ended", (N,), torch.uint8)]
+                ("done_flags", (N, A), torch.uint8), ("info_flags", (N, A), torch.uint8), ("ended", (N,), torch.uint8),
+                ("team_reward", (N,), torch.float32)]        # last: not sent to the host when A == 1 (it equals reward)
         self._out_layout, off = [], 0
         for name, shape, dt in segs:
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
             self._out_layout.append((name, shape, dt, off, nbytes))
             off += (nbytes + 255) // 256 * 256
         self._out_flat = torch.zeros(off, dtype=torch.uint8, device=dev)
+        self._out_host_bytes = self._out_layout[-1][3] if A == 1 else off
         for name, shape, dt, o, nbytes in self._out_layout:
             setattr(self, name, self._out_flat[o:o + nbytes].view(dt).view(*shape))
         self.final_obs = z(N, A, L.OBS_DIM, dt=torch.float32)
@@ -473,7 +480,7 @@ class RadSearch:
             else:
                 acts = h_act.to(self.device, non_blocking=True)
             self.step_batch(acts, epoch_end=epoch_end)
-            hb.flat.copy_(self._out_flat, non_blocking=True)
+            hb.flat.copy_(self._out_flat[:hb.nbytes], non_blocking=True)
             hb.event.record(self._host_stream)
         return hb
 

@@ -351,7 +351,8 @@ def test_step_host_matches_step_batch(graph):
             hb = hbs[r].wait()
             for name in ("obs", "reward", "team_reward", "done_flags", "info_flags", "ended"):
                 np.testing.assert_array_equal(getattr(hb, name).numpy(), getattr(ref[r], name).cpu().numpy(), err_msg=name)
-    assert hbs[0].d2h_bytes >= n * (44 + 4 + 4 + 3) and hbs[0].h2d_bytes == n * 4
+    # one agent: obs 44 + reward 4 + done / info / ended 3 bytes per env (the team reward equals the reward and is a host view)
+    assert n * (44 + 4 + 3) <= hbs[0].d2h_bytes < n * (44 + 4 + 4 + 3) and hbs[0].h2d_bytes == n * 4
 
 
 @pytest.mark.parametrize("mode,A,fast_path,n", [(1, 1, False, 2048), (2, 1, False, 2048), (1, 4, False, 2048),
