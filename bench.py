@@ -106,7 +106,7 @@ def run_reference(args):
     from oracle import c_oracle as co
 
     cores = os.cpu_count() or 1
-    n = 4096
+    n = 16384                    # per step: enough envs per thread for the OpenMP loop to run at its best rate
     ob = co.OracleBatch(n, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=cores)
     ob.reset()
     ctr = 1
