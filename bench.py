@@ -408,6 +408,22 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
+            # GAE on the host cores: the oracle's per-column float64 recurrence (the reference's lfilter arithmetic), OpenMP
+            import numpy as np
+            from oracle import c_oracle as co
+            Tg, Ng = T_EPOCH, 16384
+            rg = np.random.default_rng(0)
+            c_rew = (-0.5 * rg.uniform(0, 1.5, (Tg, Ng))).astype(np.float32)
+            c_val = rg.normal(size=(Tg, Ng)).astype(np.float32)
+            c_end = (rg.random((Tg, Ng)) < 0.01).astype(np.uint8); c_end[-1] = 1
+            c_boot = (rg.normal(size=(Tg, Ng)) * c_end).astype(np.float32)
+            co.gae(c_rew, c_val, c_end, c_boot, threads=cores)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                co.gae(c_rew, c_val, c_end, c_boot, threads=cores)
+            dtg = (time.perf_counter() - t0) / 3
+            line["gae"]["cpu_baseline"] = {"value": GAE_BYTES_PER_ELEM * Tg * Ng / dtg / 1e9, "unit": "GB/s", "cores": cores,
+                                           "kind": "port", "sample": f"[{Tg}, {Ng}] rollout, oracle orc_gae (OpenMP over columns)"}
             v1, dt1, _ = cpu_baseline(256, 60, cores)                 # calibrate
             n_s = max(256, min(16384, int(256 * 12.0 / max(dt1, 1e-3)) // 256 * 256))
             v, dt, _ = cpu_baseline(n_s, 60, cores)
