@@ -109,21 +109,22 @@ def run_reference(args):
     n = 16384                    # per step: enough envs per thread for the OpenMP loop to run at its best rate
     ob = co.OracleBatch(n, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=cores)
     ob.reset()
+    inner = 8                    # one reference step = 16384 envs x 8 steps = 131072 env-steps, the GPU arm's units per step
     ctr = 1
     for _ in range(args.warmup):
-        ob.rollout(1, ctr, epoch_end_last=False); ctr += 1
+        ob.rollout(inner, ctr, epoch_end_last=False); ctr += inner
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ob.rollout(1, ctr, epoch_end_last=False); ctr += 1
+        ob.rollout(inner, ctr, epoch_end_last=False); ctr += inner
     dt = time.perf_counter() - t0
-    v = n * args.steps / dt
+    v = n * inner * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": "RadSearch env step, 5 obstructions, enforced boundaries, random actions, auto-reset; "
-                                   f"bounded sample of {n} envs per step (of 131072 per GPU)"},
+                                   f"one step = {n} envs x {inner} steps = {n * inner} env-steps (the GPU arm's units per step)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n} envs x {args.steps} steps, oracle/radsearch_oracle.c (scalar per-env loop, OpenMP)"},
+                             "sample": f"{n} envs x {inner * args.steps} steps, oracle/radsearch_oracle.c (scalar per-env loop, OpenMP)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
