@@ -109,8 +109,13 @@ def run_reference(args):
     n = 16384                    # per step: enough envs per thread for the OpenMP loop to run at its best rate
     ob = co.OracleBatch(n, co.default_config(obstruction_count=K_OBS, enforce=1), seed=2, threads=cores)
     ob.reset()
-    inner = 8                    # one reference step = 16384 envs x 8 steps = 131072 env-steps, the GPU arm's units per step
-    ctr = 1
+    # one reference step = 16384 envs x `inner` steps: 8 (= 131072 env-steps, the GPU arm's units per step) unless the
+    # requested number of steps would then run for more than ~90 s on these cores
+    t0 = time.perf_counter()
+    ob.rollout(2, 1, epoch_end_last=False)
+    rate = 2 * n / (time.perf_counter() - t0)
+    inner = int(max(1, min(8, rate * 90.0 / max(args.steps + args.warmup, 1) / n)))
+    ctr = 3
     for _ in range(args.warmup):
         ob.rollout(inner, ctr, epoch_end_last=False); ctr += inner
     t0 = time.perf_counter()
