@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--ring", type=int, default=4, help="env batches cycled so that each step's state comes from HBM")
     ap.add_argument("--exact-poisson", action="store_true", help="fp64 numpy-exact PTRS acceptance instead of fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident throughput and the step-kernel timing only "
+                    "(what the ncu passes replay)")
     ap.add_argument("--no-prefetch", action="store_true", help="synchronous reset kernel after every step")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
     ap.add_argument("--episode-steps", type=int, default=120, help="steps_per_episode (120 = the reference's; a huge value "
@@ -282,6 +284,14 @@ def main():
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / Kr
     peak, peak_src = measured_peak_gbs()
     achieved = BYTES_PER_ENV_STEP * N / (k_ms / 1e3) / 1e9
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": total_ms / K, "kernel_ms": k_ms,
+                              "frac": achieved / peak}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- GAE over the [T, N] rollout buffer ("GAE GB/s vs HBM peak") -------------------------------------------------
     T = T_EPOCH

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RS_VERSION 2
+#define RS_VERSION 3
 #define RS_OBS_DIM 11            /* [count, x/2200, y/2200, 8 proximity sensors]            R:591-593 */
 #define RS_MAX_K 8               /* obstruction slots (env allows 0..7)                     R:317     */
 #define RS_MAX_A 8               /* agents per environment                                            */
@@ -119,6 +119,10 @@ typedef struct RsState {
     double *st_m2;               /* [A][N]    aggregated squared distance from the mean   RADTEAM_core.py:200         */
     float *raw_count;            /* [N][A]    the unstandardised count of the last observation (output, nullable)     */
     uint32_t *ticket;            /* [1]       CTA completion counter of rs_reset (RS_F_BUMP_CTR), zero between launches   */
+    float *dsf;                  /* [N][4K]   dsrc rounded DOWN to float (written by rs_reset / rs_load_scenarios with dsrc):  */
+                                 /*           the single-agent step kernel prunes the shortest-path search on this table and   */
+                                 /*           reads dsrc itself only for the corners that survive (k_max > 0)                  */
+    float *nx_dsf;               /* [N][4K]   the same for the prefetched episode (with nx_dsrc)                              */
 } RsState;
 
 /* One environment step for n_env environments (all agents).  actions[N][A] in 0..8 (8 = idle), or NULL for the
@@ -240,10 +244,6 @@ int rs_maps_reset(const RsMapsConfig *cfg, const RsMapsState *st, const uint8_t 
                   void *stream);
 int rs_sizeof_maps_config(void);
 int rs_sizeof_maps_state(void);
-
-/* Debugging aid: with the environment variable RS_TUNE bit 3 set, rs_step's thread 0 of each of the first 2048 CTAs
- * stamps clock64 at 8 phase boundaries; this copies [n_cta][12] stamps to the host (synchronises the device). */
-int rs_debug_timeline(long long *host_out, int n_cta);
 
 const char *rs_last_error(void);
 int rs_version(void);

@@ -18,7 +18,7 @@ ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, 
 EXPORTS = [
     "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
     "rs_version", "rs_sizeof_config", "rs_sizeof_state", "rs_maps_update", "rs_maps_reset", "rs_sizeof_maps_config",
-    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table", "rs_debug_timeline",
+    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table",
 ]
 MS_CELL_RANGE, MS_LOG_FULL, MS_PRED_RANGE = 1, 2, 4
 
@@ -41,7 +41,7 @@ class RsState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "src", "rad", "rects", "meta", "det", "best", "aflags", "dsrc", "vis", "status", "reset_list", "reset_count",
         "epi", "nx_src", "nx_det", "nx_rad", "nx_best", "nx_dsrc", "nx_obs", "nx_seq", "refill_list", "refill_count",
-        "ctr_dev", "st_mean", "st_m2", "raw_count", "ticket")]
+        "ctr_dev", "st_mean", "st_m2", "raw_count", "ticket", "dsf", "nx_dsf")]
 
 
 class RsMapsConfig(C.Structure):
@@ -108,8 +108,6 @@ def declare(lib, prefix="rs_"):
         lib.rs_pack_rollout.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.rs_episode_table.restype = i32
         lib.rs_episode_table.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
-        lib.rs_debug_timeline.restype = i32
-        lib.rs_debug_timeline.argtypes = [vp, i32]
         lib.rs_sizeof_maps_config.restype = i32
         lib.rs_sizeof_maps_state.restype = i32
         lib.rs_last_error.restype = C.c_char_p

@@ -18,8 +18,8 @@ struct Params {
     int sx0, sy0, sx1, sy1;       // search area R:393-420
     int lo, hi;                   // observation_area
     int enforce, n_agents, obstruction_count, count_law, max_ep_len, k_max, standardize;
-    int tune;                     // RS_TUNE experiment bits (rs_step reads the environment variable once); 0 = default
     double max_dist;              // R:423-425
+    double inv_max_dist;          // 1 / max_dist rounded to nearest (div_const in rs_step1.cuh)
     double inv_scale;             // 1 / search_area[2][1]  R:435
 };
 
@@ -31,9 +31,9 @@ __host__ __device__ inline Params make_params(const RsConfig &c) {
     p.enforce = c.enforce; p.n_agents = c.n_agents; p.obstruction_count = c.obstruction_count;
     p.count_law = c.count_law; p.max_ep_len = c.max_ep_len; p.k_max = c.k_max;
     p.standardize = c.standardize;
-    p.tune = 0;
     const double dy = (double)(p.sy1 - p.sy0);
     p.max_dist = sqrt(dy * dy);
+    p.inv_max_dist = 1.0 / p.max_dist;
     p.inv_scale = 1.0 / (double)p.sy1;
     return p;
 }
@@ -671,7 +671,10 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
             {                                           // the prefetched source-distance row (env-major, 4K doubles)
                 const int nc0 = 4 * (S.meta[n] & 0xff);
                 const size_t row = (size_t)n * 4 * P.k_max;
-                for (int c = lane; c < nc0; c += nl) S.dsrc[row + c] = S.nx_dsrc[row + c];
+                for (int c = lane; c < nc0; c += nl) {
+                    S.dsrc[row + c] = S.nx_dsrc[row + c];
+                    S.dsf[row + c] = S.nx_dsf[row + c];
+                }
             }
             if (lane == 0) {
                 const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
@@ -800,9 +803,11 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     source_segment(e, detx, dety, direct, blocked_raw);
     // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
     double *dsrc_out = (prepare ? S.nx_dsrc : S.dsrc) + (size_t)n * 4 * P.k_max;
+    float *dsf_out = (prepare ? S.nx_dsf : S.dsf) + (size_t)n * 4 * P.k_max;     // lower bounds for the marking pass
     for (int c = lane; c < nc; c += nl) {
         const double ds = w_dsrc[c];
         dsrc_out[c] = ds;
+        dsf_out[c] = __double2float_rd(ds);
         const int4 r = w_rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         double cand = inf;

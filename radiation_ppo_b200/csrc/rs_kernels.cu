@@ -3,10 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
-#include "rs_step_tiled.cuh"
+#include "rs_step1.cuh"
 #include "rs_error.h"
 
 namespace {
@@ -120,22 +119,6 @@ __device__ __forceinline__ void seed_and_push(const RsState &S, const rs::Tile &
     }
 }
 
-// RS_TUNE bit 3: thread 0 of the first 2048 CTAs stamps clock64 at the phase boundaries (rs_debug_timeline reads them back)
-__device__ long long g_timeline[2048][12];
-__device__ __forceinline__ long long rs_globaltimer() {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define RS_STAMP(i)                                                                                       \
-    do {                                                                                                  \
-        if ((P.tune & 8) && tid == 0 && blockIdx.x < 2048) {                                              \
-            g_timeline[blockIdx.x][i] = clock64();                                                        \
-            if ((i) == 0) g_timeline[blockIdx.x][8] = rs_globaltimer();                                   \
-            if ((i) == 7) g_timeline[blockIdx.x][9] = rs_globaltimer();                                   \
-        }                                                                                                 \
-    } while (0)
-
 template <bool kFast, int E, int kOcc, int TB>
 __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ rs::Params P,
                                                          const __grid_constant__ RsState S,
@@ -155,7 +138,6 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
     const bool bulk = bulk_ok && valid == E;
 
     // ---- stage the tile ------------------------------------------------------------------------------------------
-    RS_STAMP(0);
     if (tid < 8) counters[tid] = 0;
     if (bulk) {
         if (tid == 0) {
@@ -181,28 +163,20 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
         }
         __syncthreads();
     }
-    RS_STAMP(1);
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
     // a new refill list starts with this step: only the reset kernel that follows appends to it
     if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
 
-    const bool merged = (P.tune & 4) != 0;
     // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
     for (int u0 = 0; u0 < U; u0 += TB) {
         const int u = u0 + tid;
         int uf = 0;
         if (u < U && (u % E) < valid) uf = rs::phase_move<kFast>(P, S, a, T, n0, u, step_ctr);
-        // RS_TUNE bit 2: most units need the shortest path (92 % at 5 obstructions), so the seed pass runs right here, in
-        // the thread that just moved the unit, instead of through list B and one more CTA barrier
-        if (merged) seed_and_push(S, T, n0, (uf & rs::UF_NEED_B) ? u : -1, reinterpret_cast<uint16_t *>(T.reward),
-                                  (L.done - L.reward) / 2, counters + 4);
-        else list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
+        list_push(uf & rs::UF_NEED_B, u, lists, counters + 0);
         list_push(uf & rs::UF_NEED_D, u, lists + U, counters + 1);
         list_push(uf & rs::UF_NEED_P, u, lists + 2 * U, counters + 2);
     }
     __syncthreads();
-
-    RS_STAMP(2);
     // ---- compacted phases: list j starts at the first warp the previous lists left idle -----------------------------------
     {
         const int cb = counters[0], cd = counters[1], cp = counters[2];
@@ -214,13 +188,11 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
             uint16_t *pairs = reinterpret_cast<uint16_t *>(T.reward);
             const int pair_cap = (L.done - L.reward) / 2;
             int *pair_count = counters + 4;
-            if (!merged)
-                for (int base = 0; base < cb; base += TB) {
-                    const int j = base + tid;
-                    seed_and_push(S, T, n0, j < cb ? (int)lists[j] : -1, pairs, pair_cap, pair_count);
-                }
-            if (!merged) __syncthreads();
-            RS_STAMP(3);
+            for (int base = 0; base < cb; base += TB) {
+                const int j = base + tid;
+                seed_and_push(S, T, n0, j < cb ? (int)lists[j] : -1, pairs, pair_cap, pair_count);
+            }
+            __syncthreads();
             const int np = min(*pair_count, pair_cap);
             unsigned long long *spbits = reinterpret_cast<unsigned long long *>(T.sp);
             // One pool of work for the rest of the phase, fetched by the warps 32 items at a time: first the Poisson
@@ -257,12 +229,9 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
                     }
                 }
             }
-            RS_STAMP(4);
         }
     }
     __syncthreads();
-
-    RS_STAMP(5);
     // ---- phase_commit: every environment; CTA-aggregated append to the reset work list ---------------------------------
 
     for (int t0 = 0; t0 < E; t0 += TB) {
@@ -282,8 +251,6 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
             for (int j = tid; j < cs; j += TB) S.reset_list[s_base + j] = n0 + lists[j];
         }
     }
-
-    RS_STAMP(6);
     // ---- write the tile back ----------------------------------------------------------------------------------------
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
@@ -310,7 +277,171 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
             }
         }
     }
-    RS_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-agent step kernel (rs_step1.cuh): one thread per environment, warp-autonomous.  A CTA of TB threads owns TB
+// consecutive environments.  Thread 0 starts bulk-async copies (cp.async.bulk, one mbarrier) of the tile's rectangle rows
+// [k][TB] and of its block of the float source-distance table [TB][4K] into shared memory -- the two tables that lanes
+// read for each other's environments or index dynamically; every other state row goes straight from HBM into the
+// owning thread's registers with coalesced loads, and the unit's Philox block is computed while both are in flight.
+// After the one CTA barrier that publishes the mbarrier, warps never meet again: the front half (move, segment to the
+// source, shortest path, Poisson draw) is straight-line per-lane code, the ray casts are (unit, direction) items of the
+// warp, the reset work list is appended with one atomic per warp, state and scalar outputs leave as coalesced stores and
+// the observation rows through a shared-memory staging block as 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kFast, int KMAX, int TB, int kOcc>
+__global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__ rs::Params P,
+                                                          const __grid_constant__ RsState S,
+                                                          const __grid_constant__ rs::StepArgs a, int bulk_ok) {
+    constexpr int KS = KMAX > 0 ? KMAX : 1;
+    __shared__ __align__(16) int4 s_rects[KS * TB];
+    __shared__ __align__(16) float s_dsf[TB * 4 * KS];
+    __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
+    __shared__ uint8_t s_list[TB];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
+    const int n0 = blockIdx.x * TB;
+    const int n = n0 + tid;
+    const bool live = n < a.n_env;
+    const int K = KMAX > 0 ? P.k_max : 0;
+    const size_t N = (size_t)a.n_env;
+    const bool bulk = KMAX > 0 && bulk_ok && n0 + TB <= a.n_env;
+    if (bulk && tid == 0) {
+        mbar_init(&s_mbar, 1);
+        mbar_expect_tx(&s_mbar, (uint32_t)(2 * K * 16 * TB));
+        for (int k = 0; k < K; k++)
+            bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar);
+        bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar);
+    }
+    // scalar state rows: coalesced, straight into registers
+    int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
+    int meta = 0, action = -1, af = 0;
+    double best = 0.0, stm = 0.0, stq = 0.0;
+    if (live) {
+        src = reinterpret_cast<const int2 *>(S.src)[n];
+        rad = reinterpret_cast<const int2 *>(S.rad)[n];
+        det = reinterpret_cast<const int2 *>(S.det)[n];
+        meta = S.meta[n];
+        af = S.aflags[n];
+        best = S.best[n];
+        if (a.actions) action = a.actions[n];
+        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
+    }
+    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
+    // a new refill list starts with this step: only the reset kernel that follows appends to it
+    if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
+    uint32_t x[4] = {0u, 0u, 0u, 0u};
+    if (kFast)      // needs nothing from memory: runs while the tile is in flight
+        rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), x);
+    if (bulk) {
+        __syncthreads();                                    // the barrier object is initialised for everybody
+        mbar_wait(&s_mbar, 0);
+    } else if (KMAX > 0) {
+        if (live) {
+            for (int k = 0; k < K; k++) s_rects[k * TB + tid] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+            for (int k = 0; k < K; k++)
+                reinterpret_cast<float4 *>(s_dsf)[tid * K + k] = reinterpret_cast<const float4 *>(S.dsf)[(size_t)n * K + k];
+        }
+        __syncwarp();
+    }
+    float *row = s_obs + tid * RS_OBS_DIM;
+#pragma unroll
+    for (int d = 0; d < 8; d++) row[3 + d] = 0.0f;
+    rs::Unit1 o;
+    o.det = det; o.af = af; o.uf = 0; o.sp = 0.0; o.blocked_los = false; o.count = 0.0f; o.status = 0u;
+    if (live) o = rs::unit1_front<kFast, KMAX>(P, S, a, s_rects + tid, TB, s_dsf + tid * 4 * K, n, src, rad, meta, action, det,
+                                               af, step_ctr, x);
+    // ---- obstruction_sensors: (unit, direction) items of the warp ---------------------------------------------------------
+    const unsigned need = __ballot_sync(0xffffffffu, (o.uf & rs::UF_NEED_D) != 0);
+    if (need) {
+        uint8_t *wl = s_list + w0;
+        if ((need >> lane) & 1u) wl[__popc(need & ((1u << lane) - 1u))] = (uint8_t)lane;
+        __syncwarp();
+        const int cnt = __popc(need);
+        for (int base = 0; base < 8 * cnt; base += 32) {
+            const int item = base + lane, j = item >> 3, d = item & 7;
+            const bool valid = j < cnt;
+            const int owner = valid ? (int)wl[j] : 0;
+            const int px = __shfl_sync(0xffffffffu, o.det.x, owner), py = __shfl_sync(0xffffffffu, o.det.y, owner);
+            const int ufo = __shfl_sync(0xffffffffu, o.uf, owner), nob = __shfl_sync(0xffffffffu, meta, owner) & 0xff;
+            const int4 *col = s_rects + w0 + owner;
+            unsigned long long hits = 0ull;
+            int dmin = -1;
+            if (valid) dmin = rs::sense_dir1(col, TB, (ufo >> 16) & 0xff, px, py, d, hits);
+            float v = rs::sense_value(dmin);
+            // the detector stands on an obstruction edge when more than three of its rays read exactly 1.0: R:1219-1226
+            const unsigned zero = __ballot_sync(0xffffffffu, valid && dmin == 0);
+            const bool fix = __popc((zero >> (lane & 24)) & 0xffu) > 3;
+            if (__any_sync(0xffffffffu, fix)) {
+#pragma unroll
+                for (int s = 1; s < 8; s <<= 1) hits += __shfl_xor_sync(0xffffffffu, hits, s);
+                if (fix) {
+                    float out[8];
+                    uint32_t st = 0u;
+                    rs::correct_coords(px, py, col[rs::sense_correct_rect(col, TB, nob, hits) * TB], out, st);
+                    v = out[0];
+#pragma unroll
+                    for (int i = 1; i < 8; i++) v = d == i ? out[i] : v;
+                    if (d == 0) rs::raise_status(S, n0 + w0 + owner, st);
+                }
+            }
+            if (valid) s_obs[(w0 + owner) * RS_OBS_DIM + 3 + d] = v;
+        }
+        __syncwarp();
+    }
+    // ---- commit: reward, terminal, caller rules, state and scalar outputs (coalesced) --------------------------------------
+    bool sched = false;
+    if (live) {
+        uint32_t status = o.status;
+        float raw = 0.0f;
+        const rs::Commit1 c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw,
+                                               status);
+        S.meta[n] = c.meta;
+        reinterpret_cast<int2 *>(S.det)[n] = o.det;
+        S.best[n] = c.best;
+        S.aflags[n] = o.af;
+        if (P.standardize) {
+            S.st_mean[n] = stm;
+            S.st_m2[n] = stq;
+            if (S.raw_count) S.raw_count[n] = raw;
+        }
+        if (a.reward) a.reward[n] = c.reward;
+        if (a.team_reward) a.team_reward[n] = c.reward;                 // one agent: the team reward is its reward R:661-665
+        if (a.done) a.done[n] = (uint8_t)c.done;
+        if (a.info) a.info[n] = (uint8_t)c.info;
+        if (a.ended) a.ended[n] = (uint8_t)c.ended;
+        sched = c.scheduled;
+        if (sched && a.final_obs) {
+#pragma unroll
+            for (int i = 0; i < RS_OBS_DIM; i++) a.final_obs[(size_t)n * RS_OBS_DIM + i] = row[i];
+        }
+        rs::raise_status(S, n, status);
+    }
+    {   // reset work list: one atomic per warp
+        const unsigned m = __ballot_sync(0xffffffffu, sched);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(S.reset_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sched) S.reset_list[base + __popc(m & ((1u << lane) - 1u))] = n;
+        }
+    }
+    __syncwarp();
+    // ---- observation rows: the warp's 32 rows are one contiguous run of 352 floats in shared memory and in HBM --------------
+    {
+        const int nw = n0 + w0;                             // first environment of this warp
+        const float *sw = s_obs + w0 * RS_OBS_DIM;
+        float *g = a.obs + (size_t)nw * RS_OBS_DIM;
+        if (bulk_ok && nw + 32 <= a.n_env) {
+            for (int i = lane; i < 32 * RS_OBS_DIM / 4; i += 32)
+                reinterpret_cast<float4 *>(g)[i] = reinterpret_cast<const float4 *>(sw)[i];
+        } else {
+            const int rows = min(32, a.n_env - nw);
+            for (int i = lane; i < rows * RS_OBS_DIM; i += 32) g[i] = sw[i];
+        }
+    }
 }
 
 // end of a captured step: advance the device step counter and empty the reset list for the next replay
@@ -373,7 +504,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, 
 
 int check_prefetch(const RsConfig *cfg, const RsState *st) {
     if (!st->nx_src || !st->nx_det || !st->nx_rad || !st->nx_best || !st->nx_obs || !st->nx_seq || !st->refill_list ||
-        !st->refill_count || (cfg->k_max > 0 && !st->nx_dsrc))
+        !st->refill_count || (cfg->k_max > 0 && (!st->nx_dsrc || !st->nx_dsf)))
         return fail("prefetch needs the RsState.nx_* / refill_* buffers");
     return 0;
 }
@@ -390,14 +521,14 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
     if (cfg->bbox[2] - cfg->obs_area[1] <= cfg->bbox[0] + cfg->obs_area[0]) return fail("empty search area");
     if (!st->src || !st->rad || !st->meta || !st->det || !st->best || !st->aflags || !st->status || !st->epi)
         return fail("RsState has NULL members");
-    if (cfg->k_max > 0 && (!st->rects || !st->dsrc || !st->vis)) return fail("RsState obstruction tables are NULL");
+    if (cfg->k_max > 0 && (!st->rects || !st->dsrc || !st->vis || !st->dsf)) return fail("RsState obstruction tables are NULL");
     if (cfg->standardize < 0 || cfg->standardize > 2) return fail("standardize must be 0, 1 or 2");
     if (cfg->standardize && (!st->st_mean || !st->st_m2)) return fail("standardize needs RsState.st_mean / st_m2");
     return 0;
 }
 
-// envs per CTA of the step kernel: 128 threads cover 128 / 128 / 128 / 256 (env, agent) units
-int step_tile_envs(int n_agents) { return n_agents == 1 ? 128 : (n_agents == 2 ? 64 : 32); }
+// envs per CTA of the multi-agent tile kernel: 128 threads cover 128 / 96 / 128 / ... / 256 (env, agent) units
+int step_tile_envs(int n_agents) { return n_agents == 2 ? 64 : 32; }
 size_t query_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * sizeof(int4); }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 size_t reset_smem(const RsConfig *cfg) {
@@ -431,21 +562,36 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
         if (e != cudaSuccess) return (int)e;
     }
     rs::Params P = rs::make_params(*cfg);
-    static const int tune_env = getenv("RS_TUNE") ? atoi(getenv("RS_TUNE")) : 0;                 // experiment switches
-    P.tune = tune_env;
     rs::StepArgs a;
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
     a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
     a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags; a.parity = parity;
-    static const int occ_env = getenv("RS_STEP_OCC") ? atoi(getenv("RS_STEP_OCC")) : 0;      // tuning switch
     const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
     const int A = cfg->n_agents, K = cfg->k_max;
-    // single agent, fast sampler: 256-env tiles on 256 threads (4 CTAs per SM) once they fill the GPU -- half as many
-    // tile loads / barriers / work-pool rounds per env as 128-env tiles: +3.5 % env-steps/s at 131072 envs (measured)
-    const bool wide = A == 1 && fast && (occ_env == 4 || (occ_env == 0 && (long long)n_env >= 148LL * 256 * 2));
-    const int E = (occ_env == 2 && A == 1 && fast) ? 512 : (wide ? 256 : step_tile_envs(cfg->n_agents));
+    if (A == 1) {
+        // one thread per environment (rs_step1.cuh); KMAX = the unroll bound of the per-rectangle loops
+        constexpr int TB = 128;
+        const int grid = (n_env + TB - 1) / TB;
+        // 16-byte alignment of what the bulk copies and the float4 stores touch (tile offsets are multiples of 128 envs)
+        const int bulk_ok = aligned16(st->rects) && aligned16(st->dsf) && aligned16(obs) && n_env % 4 == 0;
+#define RS_LAUNCH_STEP1(FAST, KM, OCC) step1_kernel<FAST, KM, TB, OCC><<<grid, TB, 0, s>>>(P, *st, a, bulk_ok)
+#define RS_LAUNCH_STEP1_K(KM, OCC)                                     \
+    do {                                                               \
+        if (fast) RS_LAUNCH_STEP1(true, KM, OCC);                      \
+        else RS_LAUNCH_STEP1(false, KM, OCC);                          \
+    } while (0)
+        if (K == 0) RS_LAUNCH_STEP1_K(0, 7);
+        else if (K <= 3) RS_LAUNCH_STEP1_K(3, 7);
+        else if (K <= 5) RS_LAUNCH_STEP1_K(5, 7);
+        else RS_LAUNCH_STEP1_K(8, 5);
+#undef RS_LAUNCH_STEP1_K
+#undef RS_LAUNCH_STEP1
+        return (int)cudaGetLastError();
+    }
+    // several agents per environment: the tile program (rs_step_tiled.cuh), 64 / 32 environments per CTA of 128 threads
+    const int E = step_tile_envs(cfg->n_agents);
     const int grid = (n_env + E - 1) / E;
-    const rs::TileLayout L = rs::make_layout(E, A, K, E > 128 ? E : kBlock, cfg->standardize);
+    const rs::TileLayout L = rs::make_layout(E, A, K, kBlock, cfg->standardize);
     const size_t smem = (size_t)L.total;
     // the tile's rows: state rows read (src, rad, meta, actions, rects[k], then det / best / aflags / running count
     // statistics per agent) and rows written (meta, obs, reward, team_reward, done, info, ended, raw counts, then the
@@ -490,21 +636,15 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
                         aligned16(st->det) && aligned16(st->best) && aligned16(st->aflags) && aligned16(actions) &&
                         aligned16(obs) && aligned16(reward) && aligned16(team_reward) && aligned16(done) &&
                         aligned16(info) && aligned16(ended) && aligned16(st->st_mean) && aligned16(st->st_m2) &&
-                        aligned16(st->raw_count) &&
-                        (cfg->n_agents == 1 || n_env % 4 == 0);        // per-agent rows start at multiples of N elements
-#define RS_LAUNCH_STEP(FAST, TE, OCC, TB)                                                                              \
+                        aligned16(st->raw_count) && n_env % 4 == 0;     // per-agent rows start at multiples of N elements
+#define RS_LAUNCH_STEP(FAST, TE)                                                                                          \
     do {                                                                                                                  \
         if (smem > 48 * 1024)                                                                                             \
-            cudaFuncSetAttribute(step_kernel<FAST, TE, OCC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        step_kernel<FAST, TE, OCC, TB><<<grid, TB, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                        \
+            cudaFuncSetAttribute(step_kernel<FAST, TE, 6, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        step_kernel<FAST, TE, 6, kBlock><<<grid, kBlock, smem, s>>>(P, *st, a, L, R, bulk_ok, tx_bytes);                  \
     } while (0)
-    if (E == 512) RS_LAUNCH_STEP(true, 512, 2, 512);
-    else if (E == 256) RS_LAUNCH_STEP(true, 256, 4, 256);
-    else if (E == 128) {
-        if (fast) { if (occ_env == 6) RS_LAUNCH_STEP(true, 128, 6, 128); else RS_LAUNCH_STEP(true, 128, 8, 128); }
-        else RS_LAUNCH_STEP(false, 128, 6, 128);
-    } else if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64, 6, 128); else RS_LAUNCH_STEP(false, 64, 6, 128); }
-    else { if (fast) RS_LAUNCH_STEP(true, 32, 6, 128); else RS_LAUNCH_STEP(false, 32, 6, 128); }
+    if (E == 64) { if (fast) RS_LAUNCH_STEP(true, 64); else RS_LAUNCH_STEP(false, 64); }
+    else { if (fast) RS_LAUNCH_STEP(true, 32); else RS_LAUNCH_STEP(false, 32); }
 #undef RS_LAUNCH_STEP
     return (int)cudaGetLastError();
 }
@@ -514,12 +654,10 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
     rs::Params P = rs::make_params(*cfg);
     int need = (a.n_env + 3) / 4;                       // one warp per env is the widest teaming
     int cap = kResetGrid;
-    static const int prep_nl_env = getenv("RS_PREPARE_NL") ? atoi(getenv("RS_PREPARE_NL")) : 1;      // tuning switches
-    static const int prep_grid_env = getenv("RS_PREPARE_GRID") ? atoi(getenv("RS_PREPARE_GRID")) : 148;
-    const int prepare_nl = (prep_nl_env == 8 || prep_nl_env == 32) ? prep_nl_env : 1;
+    const int prepare_nl = 1;                           // rs_prepare: one thread per environment (throughput, not latency)
     if (a.prepare) {                                    // kept small: it shares the GPU with rs_step
         need = (a.n_env + kBlock / prepare_nl - 1) / (kBlock / prepare_nl);
-        cap = prep_grid_env;
+        cap = 148;
     }
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
@@ -609,13 +747,6 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
     if (smem > 48 * 1024) cudaFuncSetAttribute(sp_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sp_query_kernel<<<grid, kBlock, smem, static_cast<cudaStream_t>(stream)>>>(P, *st, pts, out, n_env, variant);
     return (int)cudaGetLastError();
-}
-
-int rs_debug_timeline(long long *host_out, int n_cta) {          // debugging aid (RS_TUNE bit 3), synchronises the device
-    if (!host_out || n_cta < 1 || n_cta > 2048) return rs_set_error("rs_debug_timeline: bad arguments");
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 12 * n_cta);
-    return (int)e;
 }
 
 const char *rs_last_error(void) { return g_err; }

@@ -224,7 +224,7 @@ __device__ __forceinline__ int phase_move(const Params &P, const RsState &S, con
     else {
         uf |= UF_NEED_B;
 #ifndef RS_HOST_EMU
-        if (!(P.tune & 1)) {    // the env-major source-distance row (4K doubles) is wanted by phase_path: start it now
+        {                       // the env-major source-distance row (4K doubles) is wanted by phase_path: start it now
             const char *row = reinterpret_cast<const char *>(S.dsrc + (size_t)n * 4 * T.K);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
             if (T.K > 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));

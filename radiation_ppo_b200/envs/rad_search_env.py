@@ -256,6 +256,10 @@ class RadSearch:
             ptrs += [None] * 3
         self._ticket = z(1)
         ptrs.append(self._ticket)
+        # float lower bounds of dsrc (same rows): the single-agent step kernel prunes its shortest-path search on them
+        self._dsf = z(N, max(4 * K, 1), dt=torch.float32)
+        self._nx_dsf = z(N, max(4 * K, 1), dt=torch.float32) if self.prefetch else None
+        ptrs += [self._dsf, self._nx_dsf]
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
         self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
         self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("RS_SIDE_PRIO", "-1"))) if self.prefetch else None

@@ -17,6 +17,7 @@
 struct int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 using std::max;
@@ -35,6 +36,9 @@ static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 static inline float __double2float_rd(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
 static inline float __int2float_rd(int x) { float f = (float)x; if ((double)f > (double)x) f = nextafterf(f, -INFINITY); return f; }
 static inline float __fsqrt_rd(float v) { float f = sqrtf(v); if ((double)f * (double)f > (double)v) f = nextafterf(f, -INFINITY); return f; }
+static inline float __double2float_ru(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
+static inline float __fsub_ru(float a, float b) { return __double2float_ru((double)a - (double)b); }
+static inline float __fmul_ru(float a, float b) { return __double2float_ru((double)a * (double)b); }
 static inline float __fadd_rd(float a, float b) { return __double2float_rd((double)a + (double)b); }
 static inline float rsqrtf(float v) { return 1.0f / sqrtf(v); }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }

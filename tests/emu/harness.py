@@ -22,6 +22,8 @@ def build_emu(force=False):
     srcs = [os.path.join(HERE, "rs_emu.cpp"), os.path.join(HERE, "cuda_host_shim.h"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_env_impl.cuh"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_step_tiled.cuh"),
+            os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_step1.cuh"),
+            os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_poisson_alias.h"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_device.cuh"),
             os.path.join(ROOT, "include", "radsearch_b200.h")]
     if force or not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(s) for s in srcs):
@@ -37,6 +39,12 @@ def emu():
     global _emu
     if _emu is None:
         _emu = L.declare(C.CDLL(build_emu()), prefix="emu_")
+        _emu.emu_step1.restype = _emu.emu_step.restype
+        _emu.emu_step1.argtypes = _emu.emu_step.argtypes
+        _emu.emu_div_const_mismatches.restype = C.c_longlong
+        _emu.emu_div_const_mismatches.argtypes = [C.c_void_p, C.c_longlong, C.c_double]
+        _emu.emu_round2_fast.restype = _emu.emu_round2.restype = C.c_double
+        _emu.emu_round2_fast.argtypes = _emu.emu_round2.argtypes = [C.c_double]
     return _emu
 
 
@@ -61,8 +69,9 @@ def _vp(a):
 
 
 class EmuEnv:
-    def __init__(self, n, cfg, seed=0, env_id0=0):
-        self.n, self.cfg, self.seed, self.env_id0 = n, cfg, seed, env_id0
+    def __init__(self, n, cfg, seed=0, env_id0=0, tiled=False):
+        # tiled=True: single-agent steps go through the multi-agent tile program's phases instead of rs_step1.cuh
+        self.n, self.cfg, self.seed, self.env_id0, self.tiled = n, cfg, seed, env_id0, tiled
         A, K = cfg.n_agents, cfg.k_max
         self.A, self.K = A, K
         self.src = np.zeros((n, 2), np.int32)
@@ -92,6 +101,8 @@ class EmuEnv:
         self.st_m2 = np.zeros((A, n), np.float64)
         self.raw_count = np.zeros((n, A), np.float32)
         self.ticket = np.zeros(1, np.uint32)
+        self.dsf = np.zeros((n, max(4 * K, 1)), np.float32)
+        self.nx_dsf = np.zeros((n, max(4 * K, 1)), np.float32)
         self.st = L.RsState(*[_vp(getattr(self, f)) for f, _ in L.RsState._fields_])
         self.obs = np.zeros((n, A, 11), np.float32)
         self.final_obs = np.zeros((n, A, 11), np.float32)
@@ -104,7 +115,8 @@ class EmuEnv:
     def step(self, actions, step_ctr, uniforms=None, flags=0):
         a = None if actions is None else np.ascontiguousarray(actions, np.int32).reshape(self.n, self.A)
         u = None if uniforms is None else np.ascontiguousarray(uniforms, np.float64)
-        rc = emu().emu_step(C.byref(self.cfg), C.byref(self.st), _vp(a), _vp(self.obs), _vp(self.reward),
+        fn = emu().emu_step1 if (self.A == 1 and not self.tiled) else emu().emu_step
+        rc = fn(C.byref(self.cfg), C.byref(self.st), _vp(a), _vp(self.obs), _vp(self.reward),
                             _vp(self.team_reward), _vp(self.done), _vp(self.info), _vp(self.ended),
                             _vp(self.final_obs), self.n, self.env_id0, self.seed, step_ctr, _vp(u),
                             0 if u is None else u.shape[-1], flags)

@@ -2,9 +2,68 @@
 // the same C entry-point shapes as include/radsearch_b200.h, operating on host memory.  Used by
 // tests/test_kernel_logic_emu.py to compare the kernel logic with the oracle where no GPU exists.
 #define RS_HOST_EMU 1
-#include "../../radiation_ppo_b200/csrc/rs_step_tiled.cuh"
+#include "../../radiation_ppo_b200/csrc/rs_step1.cuh"
 
 #include <vector>
+
+// The single-agent kernel's per-unit code (rs_step1.cuh) for every environment in turn; the warp-level distribution of
+// the (unit, direction) sensor items is replayed as a plain loop over the eight directions.
+template <bool kFast, int KMAX>
+static void step1_env(const rs::Params &P, const RsState *st, const rs::StepArgs &a, int n, uint64_t step_ctr) {
+    const int K = P.k_max, N = a.n_env;
+    int4 rects[RS_MAX_K];
+    for (int k = 0; k < K; k++) rects[k] = reinterpret_cast<const int4 *>(st->rects)[(size_t)k * N + n];
+    alignas(16) float dsf[4 * RS_MAX_K];
+    for (int c = 0; c < 4 * K; c++) dsf[c] = st->dsf[(size_t)n * 4 * K + c];
+    const int2 src = reinterpret_cast<const int2 *>(st->src)[n], rad = reinterpret_cast<const int2 *>(st->rad)[n];
+    const int2 det = reinterpret_cast<const int2 *>(st->det)[n];
+    const int meta = st->meta[n], af = st->aflags[n];
+    const int action = a.actions ? a.actions[n] : -1;
+    double best = st->best[n], stm = 0.0, stq = 0.0;
+    if (P.standardize) { stm = st->st_mean[n]; stq = st->st_m2[n]; }
+    uint32_t x[4] = {0, 0, 0, 0};
+    if (kFast)
+        rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), x);
+    float row[RS_OBS_DIM] = {0};
+    const rs::Unit1 o = rs::unit1_front<kFast, KMAX>(P, *st, a, rects, 1, dsf, n, src, rad, meta, action, det, af, step_ctr, x);
+    uint32_t status = o.status;
+    if (o.uf & rs::UF_NEED_D) {
+        unsigned long long hits = 0ull;
+        int dmin[8], ones = 0;
+        for (int d = 0; d < 8; d++) {
+            dmin[d] = rs::sense_dir1(rects, 1, (o.uf >> 16) & 0xff, o.det.x, o.det.y, d, hits);
+            ones += dmin[d] == 0;
+            row[3 + d] = rs::sense_value(dmin[d]);
+        }
+        if (ones > 3) {
+            float out[8];
+            rs::correct_coords(o.det.x, o.det.y, rects[rs::sense_correct_rect(rects, 1, meta & 0xff, hits)], out, status);
+            for (int d = 0; d < 8; d++) row[3 + d] = out[d];
+        }
+    }
+    float raw = 0.0f;
+    const rs::Commit1 c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw, status);
+    st->meta[n] = c.meta;
+    reinterpret_cast<int2 *>(st->det)[n] = o.det;
+    st->best[n] = c.best;
+    st->aflags[n] = o.af;
+    if (P.standardize) {
+        st->st_mean[n] = stm; st->st_m2[n] = stq;
+        if (st->raw_count) st->raw_count[n] = raw;
+    }
+    for (int i = 0; i < RS_OBS_DIM; i++) a.obs[(size_t)n * RS_OBS_DIM + i] = row[i];
+    if (a.reward) a.reward[n] = c.reward;
+    if (a.team_reward) a.team_reward[n] = c.reward;
+    if (a.done) a.done[n] = (uint8_t)c.done;
+    if (a.info) a.info[n] = (uint8_t)c.info;
+    if (a.ended) a.ended[n] = (uint8_t)c.ended;
+    if (c.scheduled) {
+        if (a.final_obs) for (int i = 0; i < RS_OBS_DIM; i++) a.final_obs[(size_t)n * RS_OBS_DIM + i] = row[i];
+        st->reset_list[(*st->reset_count)++] = n;
+    }
+    if (status) st->status[n] |= status;
+}
 
 extern "C" {
 
@@ -74,6 +133,43 @@ int emu_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, flo
     }
     return 0;
 }
+
+int emu_step1(const RsConfig *cfg, const RsState *st, const int32_t *actions, float *obs, float *reward,
+              float *team_reward, uint8_t *done, uint8_t *info, uint8_t *ended, float *final_obs, int32_t n_env,
+              uint32_t env_id0, uint64_t seed, uint64_t step_ctr, const double *uniforms, int32_t n_uniforms,
+              int32_t flags) {
+    if (cfg->n_agents != 1) return -1;
+    rs::Params P = rs::make_params(*cfg);
+    rs::StepArgs a;
+    a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
+    a.done = done; a.info = info; a.ended = ended; a.n_env = n_env; a.env_id0 = env_id0; a.seed = seed;
+    a.step_ctr = step_ctr; a.uniforms = uniforms; a.n_uniforms = n_uniforms; a.flags = flags;
+    a.parity = (flags & RS_F_PARITY1) ? 1 : 0;
+    if (flags & RS_F_AUTO_RESET) *st->reset_count = 0;
+    const bool fast = (flags & RS_F_FAST_POISSON) && !uniforms;
+    const int K = cfg->k_max;
+    for (int n = 0; n < n_env; n++) {
+        // the same unroll bounds the GPU launch picks
+        if (K == 0) { if (fast) step1_env<true, 0>(P, st, a, n, step_ctr); else step1_env<false, 0>(P, st, a, n, step_ctr); }
+        else if (K <= 3) { if (fast) step1_env<true, 3>(P, st, a, n, step_ctr); else step1_env<false, 3>(P, st, a, n, step_ctr); }
+        else if (K <= 5) { if (fast) step1_env<true, 5>(P, st, a, n, step_ctr); else step1_env<false, 5>(P, st, a, n, step_ctr); }
+        else { if (fast) step1_env<true, 8>(P, st, a, n, step_ctr); else step1_env<false, 8>(P, st, a, n, step_ctr); }
+    }
+    return 0;
+}
+
+// x / d through the reciprocal (rs_step1.cuh::div_const) against the IEEE quotient: returns the number of mismatches
+long long emu_div_const_mismatches(const double *x, long long n, double d) {
+    const double rd = 1.0 / d;
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        const double q = rs::div_const(x[i], d, rd), w = x[i] / d;
+        bad += !(q == w || (q != q && w != w));
+    }
+    return bad;
+}
+double emu_round2_fast(double x) { return rs::round2_fast(x); }
+double emu_round2(double x) { return rs::round2(x); }
 
 // bit0: open segment meets the open rectangle, bit1: closed segment meets the closed rectangle (rs_device.cuh::seg_rect)
 int emu_seg_rect(int px, int py, int qx, int qy, int x0, int y0, int x1, int y1) {

@@ -32,9 +32,9 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_struct_layout_and_version(lib):
-    assert lib.rs_version() == 2
+    assert lib.rs_version() == 3
     assert lib.rs_sizeof_config() == C.sizeof(L.RsConfig) == 52
-    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 216
+    assert lib.rs_sizeof_state() == C.sizeof(L.RsState) == 232
     assert lib.rs_sizeof_maps_config() == C.sizeof(L.RsMapsConfig) == 40
     assert lib.rs_sizeof_maps_state() == C.sizeof(L.RsMapsState) == 88
 
