@@ -69,6 +69,8 @@ extern "C" {
 #define RS_ST_CORRECT_MISS 8u    /* correct_coords would never terminate (reference hangs)                         */
 #define RS_ST_WALL_ASSERT 16u    /* `assert dists[i] == 0.0` in obstruction_sensors would fire                     */
 #define RS_ST_COORD_RANGE 32u    /* |coordinate| > 16383: outside the exact-int32 geometry range                   */
+#define RS_ST_REFILL_OVERFLOW 64u /* more resets in one block of steps than a refill list holds (the env was not listed   */
+                                 /* and takes the synchronous reset path next time)                                     */
 
 /* Environment constants (dataclass fields R:320-390 that the hot path reads). */
 typedef struct RsConfig {

@@ -14,6 +14,7 @@ F_PREFETCH, F_REFILL_LIST, F_DEVICE_CTR, F_PARITY1, F_BUMP_CTR, F_ZERO_REFILL = 
 I_OOB, I_BLOCKED, I_COLLISION, I_LOS_BLOCKED, I_MOVED = 1, 2, 4, 8, 16
 E_TERMINAL, E_TIMEOUT, E_RESET = 1, 2, 4
 ST_REJECT_CAP, ST_LAMBDA_INF, ST_UNIFORMS_OUT, ST_CORRECT_MISS, ST_WALL_ASSERT, ST_COORD_RANGE = 1, 2, 4, 8, 16, 32
+ST_REFILL_OVERFLOW = 64
 
 EXPORTS = [
     "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",

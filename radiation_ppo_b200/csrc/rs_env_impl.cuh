@@ -705,8 +705,11 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
                 reinterpret_cast<int2 *>(S.rad)[n] = r0;
                 S.meta[n] = meta & 0xff;                                  // done = 0, ep_len = 0
                 S.epi[n] = ep_seq;
+                // an env is listed once per block of steps (episodes outlast a block: RadSearch refuses prefetch
+                // otherwise); the bound keeps a caller that breaks that rule from writing past its list
                 const int slot = atomicAdd(S.refill_count + a.parity, 1);
-                S.refill_list[(size_t)a.parity * N + slot] = n;
+                if (slot < N) S.refill_list[(size_t)a.parity * N + slot] = n;
+                else atomicOr(S.status + n, RS_ST_REFILL_OVERFLOW);
             }
             return;
         }
@@ -869,7 +872,8 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         }
     } else if (lane == 0 && a.parity >= 0 && S.refill_list) {
         const int slot = atomicAdd(S.refill_count + a.parity, 1);
-        S.refill_list[(size_t)a.parity * N + slot] = n;
+        if (slot < N) S.refill_list[(size_t)a.parity * N + slot] = n;
+        else status |= RS_ST_REFILL_OVERFLOW;
     }
     status |= g.status;
     if (status && lane == 0) S.status[n] |= status;

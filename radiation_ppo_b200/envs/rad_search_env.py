@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import ctypes as C
 import gc
-import os
 import weakref
 from typing import Any, Dict, NamedTuple, Optional, Sequence, Tuple, Union
 
@@ -174,7 +173,9 @@ class RadSearch:
         self.auto_reset = bool(auto_reset)
         self.fast_poisson = bool(fast_poisson)
         self.env_id_offset = int(env_id_offset)
-        self.prefetch = bool(prefetch) and self.auto_reset
+        # prefetch lists every env at most once per block of PREFETCH_PERIOD steps: episodes must outlast a block
+        # (terminal episodes always do: >= 9 steps; timeouts only if steps_per_episode allows it)
+        self.prefetch = bool(prefetch) and self.auto_reset and int(steps_per_episode) >= 2 * self.PREFETCH_PERIOD
         self.use_cuda_graph = bool(use_cuda_graph) and self.prefetch
         self.seed = int(seed) if seed is not None else int(self.np_random.integers(0, 2**63 - 1))
 
@@ -262,7 +263,7 @@ class RadSearch:
         ptrs += [self._dsf, self._nx_dsf]
         self._st = L.RsState(*[None if t is None else t.data_ptr() for t in ptrs])
         self._blk_par, self._blk_pos = 0, 0         # refill list of the current block of steps, position in the block
-        self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("RS_SIDE_PRIO", "-1"))) if self.prefetch else None
+        self._side = torch.cuda.Stream(device=dev, priority=-1) if self.prefetch else None
         self._ev_main = torch.cuda.Event()
         self._ev_side = [torch.cuda.Event(), torch.cuda.Event()]
         self._pending = [False, False]      # list holds envs waiting for rs_prepare
@@ -356,7 +357,7 @@ class RadSearch:
     # list on a high-priority side stream while block b+1 runs.  An episode lasts >= 9 steps (source and detector
     # start >= 1000 apart, a step is <= 100.4, the goal radius is 110), so the next scenario is back in place in time;
     # if it ever is not, the env simply takes the synchronous reset path -- the resulting state is the same.
-    PREFETCH_PERIOD = int(os.environ.get("RS_PERIOD", "4"))
+    PREFETCH_PERIOD = 4
 
     def _quiesce_prefetch(self) -> None:
         """Make the main stream wait for any rs_prepare in flight and forget pending refill lists (the envs in them

@@ -239,14 +239,20 @@ class BatchedPPOBuffer:
         self.rew_buf[t].copy_(rew.reshape(self.N))
         self.val_buf[t].copy_(val.reshape(self.N))
         self.logp_buf[t].copy_(logp.reshape(self.N))
+        # rows that are not supplied are cleared: rs_gae reads boot[t] wherever end[t] is set and at t = T-1, so a value
+        # left over from the previous epoch must never survive (the reference passes last_state_value on every call)
         if src is not None:
             self.source_tar[t].copy_(src.reshape(self.N, 2))
+        else:
+            self.source_tar[t].zero_()
         if end is not None:
             self.end_buf[t].copy_(end.reshape(self.N))
         else:
             self.end_buf[t].zero_()
         if boot is not None:
             self.boot_buf[t].copy_(boot.reshape(self.N))
+        else:
+            self.boot_buf[t].zero_()
         self.ptr += 1
 
     def finish_paths(self, variant: int = 0) -> None:

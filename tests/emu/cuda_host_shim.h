@@ -32,6 +32,7 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline void __threadfence() {}
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
 // round-down conversions used for the shortest-path lower bounds
 static inline float __double2float_rd(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
 static inline float __int2float_rd(int x) { float f = (float)x; if ((double)f > (double)x) f = nextafterf(f, -INFINITY); return f; }

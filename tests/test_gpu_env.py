@@ -329,6 +329,25 @@ def test_prefetched_resets_match_oracle(graph):
     pu.compare_state(pu.GpuView(env), ob, A)
 
 
+def test_prefetch_is_refused_for_episodes_shorter_than_a_block():
+    """An env is listed for refill once per block of PREFETCH_PERIOD steps: with 2-step episodes the prefetch machinery is
+    switched off (the results are those of the synchronous resets) instead of overrunning its lists."""
+    n, T, ML = 1024, 24, 2
+    env, ob = make_pair(n, 1, 5, True, seed=31, max_ep_len=ML, auto_reset=True, prefetch=True, use_cuda_graph=True)
+    assert not env.prefetch and not env.use_cuda_graph
+    rng = np.random.default_rng(1)
+    for t in range(T):
+        acts = rng.integers(0, 8, size=(n, 1))
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+        ob.step(acts, env._ctr)
+        e = ob.envs
+        mask = (e["done"] == 1) | (e["ep_len"] == ML)
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.zeros(n))
+        pu.compare_state(pu.GpuView(env), ob, 1)
+    assert int((env.status & L.ST_REFILL_OVERFLOW).sum()) == 0
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_step_host_matches_step_batch(graph):
     """RadSearch.step_host (pinned host actions in, one packed device->host copy out, the env's own stream) gives the

@@ -215,6 +215,31 @@ def test_batched_buffer_end_to_end_against_oracle():
     assert data["obs"].shape == (T * N, 11) and buf.ptr == 0
 
 
+def test_batched_buffer_second_epoch_without_bootstrap_rows_starts_clean():
+    """store_batch with boot / end / src omitted must not inherit the previous epoch's rows (rs_gae reads boot[T-1]
+    unconditionally): epoch 2, stored without boot, equals a fresh buffer fed the same data with boot = 0."""
+    T, N = 32, 128
+    d = dev()
+    rew, val, end, boot = pu.synthetic_rollout(T, N, seed=4, max_ep=12)
+    rew2, val2, _, _ = pu.synthetic_rollout(T, N, seed=5, max_ep=12)
+    z = torch.zeros(N, device=d)
+    buf = rp.BatchedPPOBuffer(11, T, N)
+    for t in range(T):                                               # epoch 1: every optional row filled with non-zeros
+        buf.store_batch(torch.zeros(N, 11, device=d), z, torch.as_tensor(rew[t], device=d), torch.as_tensor(val[t], device=d), z,
+                        src=torch.ones(N, 2, device=d), end=torch.as_tensor(end[t], device=d),
+                        boot=torch.as_tensor(boot[t], device=d) + 3.0)
+    buf.finish_paths(variant=1)
+    buf.get()
+    for t in range(T):                                               # epoch 2: no boot / end / src
+        buf.store_batch(torch.zeros(N, 11, device=d), z, torch.as_tensor(rew2[t], device=d), torch.as_tensor(val2[t], device=d), z)
+    buf.finish_paths(variant=1)
+    e0 = np.zeros((T, N), np.uint8); e0[-1] = 1
+    a0, r0 = co.gae(rew2, val2, e0, np.zeros((T, N), np.float32))
+    np.testing.assert_array_equal(buf.adv_buf.cpu().numpy(), a0)
+    np.testing.assert_array_equal(buf.ret_buf.cpu().numpy(), r0)
+    assert float(buf.source_tar.abs().sum()) == 0.0 and float(buf.boot_buf.abs().sum()) == 0.0
+
+
 def test_batched_get_packs_the_reference_episode_tensors():
     """BatchedPPOBuffer.get(episodes=True) (rs_pack_rollout + rs_episode_table) against the `ep_form` tensors of the
     reference's PPOBuffer.get (P:425-502), one reference buffer per column (tests/golden/ref_get_epform.npz):
