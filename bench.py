@@ -1,13 +1,32 @@
-"""bench.py -- RadSearch env-steps/s (5 obstructions) on N B200s of one node, plus GAE GB/s, roofline and CPU baseline.
+"""bench.py -- RadSearch env-steps/s (5 obstructions) on N B200s of one node, GAE GB/s, rooflines, the rollout pipeline,
+and the CPU baselines.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs-per-gpu E]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs-per-gpu E] [--legs a,b,...]
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one batched environment step of every env on every GPU: rs_step (all agents: move, collision, shortest
-path, LOS, expected counts, Philox+Poisson, 8 sensors, reward/terminal, caller rules) followed by rs_reset for the envs
-that finished (auto-reset).  Workload = BASELINE.json configs[4]: 131,072 envs per GPU, 5 obstructions, enforced
-boundaries, uniform random actions 0..7, episodes staggered so that ~1/120 of the envs reset at every step.
+A "step" is one batched environment step of every env on every GPU: rs_step (move, obstruction collision, line of sight,
+shortest path, expected counts, Philox + Poisson, 8 sensors, reward / terminal, caller rules) followed by rs_reset for the
+envs that finished (auto-reset).  Headline workload = BASELINE.json configs[4]: 131,072 envs per GPU, 5 obstructions,
+enforced boundaries, uniform random actions 0..7, episodes staggered so that ~1/120 of the envs reset at every step.
 Weak scaling: envs shard independently over ranks, no data-path collective.
+
+What the JSON line carries (rank 0 prints it):
+  value / ms_per_step   device-resident env-steps/s: the K-step window is run `reps` times, every window bracketed by a
+                        barrier + synchronize on both sides and timed with CUDA events, MAX over ranks per window, MEDIAN
+                        over the windows (min / max alongside)
+  roofline              the step kernel alone against the HBM roofline (algorithmic bytes SURVEY.md 8d)
+  exact_poisson         the same headline with the numpy-exact PTRS sampler instead of the KS-equivalent fast one
+  sweep                 BASELINE configs[1] (1,024 envs, 1-5 obstructions) and configs[2]'s size (65,536 envs): per-launch
+                        step-kernel time with L2 flushed in between, env-steps/s and roofline fraction
+  gae                   rs_gae over [480, N] for N = 1,024 / 65,536 / 131,072: GB/s at 17 B per element vs the HBM peak
+  pipeline              BASELINE configs[2]: 65,536 envs x T = 480, policy in the loop (stock PyTorch GRU(11 -> 24) + heads),
+                        the step kernel storing straight into the rollout buffer, GAE, get(episodes=True), one PPO update;
+                        with several ranks the section-8e collectives under NCCL, timed and checked
+  maps                  BASELINE configs[3]: 16,384 envs x 4 agents, env step + map observation
+  e2e                   the same metric through RadSearch.step_host with pinned HOST buffers, copies inside the timed region,
+                        next to the measured ceiling of the device->host link
+  cpu_baseline          the oracle's C port of the reference's per-env loop on the box's host cores (+ the reference's own
+                        Python, timed in the build container, as secondary keys)
 """
 from __future__ import annotations
 
@@ -29,6 +48,7 @@ K_OBS = 5
 BYTES_PER_ENV_STEP = 122 + 32 * K_OBS        # algorithmic bytes per env-step, single agent
 GAE_BYTES_PER_ELEM = 17                      # rew 4 + val 4 + path_end 1 + adv 4 + ret 4
 T_EPOCH = 480
+ALL_LEGS = ("exact", "sweep", "gae", "pipeline", "maps", "e2e", "cpu")
 
 
 def measured_traffic(kernel: str, n_env: int):
@@ -86,6 +106,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_baseline(n_envs: int, T: int, threads: int):
     """The oracle's scalar per-env loop (reference semantics, OpenMP over envs) on the host cores."""
     from oracle import c_oracle as co
@@ -96,6 +124,29 @@ def cpu_baseline(n_envs: int, T: int, threads: int):
     n, chk = ob.rollout(T, 1, epoch_end_last=False)
     dt = time.perf_counter() - t0
     return n / dt, dt, chk
+
+
+def gae_lfilter_baseline(T: int, n_cols: int):
+    """PPOBuffer.GAE_advantage_and_rewardsToGO's arithmetic (ppo.py:391-423: np.append, deltas, two scipy lfilter calls per
+    trajectory, discount_cumsum ppo.py:62-85) over the columns of a [T, n_cols] rollout, one process."""
+    import numpy as np
+    from tests import parity_util as pu
+
+    rew, val, end, boot = pu.synthetic_rollout(T, n_cols, seed=1, max_ep=120)
+    t0 = time.perf_counter()
+    pu.gae_numpy_reference(rew, val, end, boot)
+    dt = time.perf_counter() - t0
+    return GAE_BYTES_PER_ELEM * T * n_cols / dt / 1e9, dt
+
+
+def reference_python_record():
+    p = os.path.join(ROOT, "profiles", "r02_reference_python_baselines.json")
+    try:
+        d = json.load(open(p))
+        d["kind"] = "reference-python, timed in the build container by tools/time_reference_python.py (not on this box)"
+        return d
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -134,233 +185,541 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12000)
-    ap.add_argument("--warmup", type=int, default=240)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=131072)
-    ap.add_argument("--ring", type=int, default=4, help="env batches cycled so that each step's state comes from HBM")
-    ap.add_argument("--exact-poisson", action="store_true", help="fp64 numpy-exact PTRS acceptance instead of fp32")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="device-resident throughput and the step-kernel timing only "
-                    "(what the ncu passes replay)")
-    ap.add_argument("--no-prefetch", action="store_true", help="synchronous reset kernel after every step")
-    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
-    ap.add_argument("--episode-steps", type=int, default=120, help="steps_per_episode (120 = the reference's; a huge value "
-                    "shows the throughput without resets)")
-    ap.add_argument("--streams", type=int, default=0,
-                    help="CUDA streams the ring's env batches are spread over (0 = one per batch; 1 = serialised)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """What every leg needs: torch handles, rank info, helpers."""
 
-    import torch
-    import torch.distributed as dist
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    import radiation_ppo_b200 as rp
+        import radiation_ppo_b200 as rp
+        from radiation_ppo_b200 import _lib as L
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
-    N, K, W, R = args.envs_per_gpu, args.steps, max(args.warmup, 3), max(args.ring, 1)
-    fast = not args.exact_poisson
+        self.torch, self.dist, self.rp, self.L, self.args = torch, dist, rp, L, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local_rank}"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device(f"cuda:{self.local_rank}")
+        self.lib = L.load()
+        self.peak, self.peak_src = measured_peak_gbs()
+        self._flush = None
 
-    # ---- R independent env batches of N envs (global env ids: rank-major, then ring slot) --------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def flush_l2(self):
+        """Write a buffer twice the size of L2 (126 MB): what ran before is out of the cache."""
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self._flush.fill_(1)
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def make_ring(cx: Ctx, N: int, R: int, fast: bool, episode_steps: int, graph: bool = True, prefetch: bool = True):
+    torch, rp = cx.torch, cx.rp
     envs = []
     for r in range(R):
-        e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=dev,
-                         env_id_offset=(rank * R + r) * N, auto_reset=True, fast_poisson=fast,
-                         steps_per_episode=args.episode_steps,
-                         prefetch=not args.no_prefetch, use_cuda_graph=not (args.no_graph or args.no_prefetch))
+        e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=cx.dev,
+                         env_id_offset=(cx.rank * R + r) * N, auto_reset=True, fast_poisson=fast,
+                         steps_per_episode=episode_steps, prefetch=prefetch, use_cuda_graph=graph and prefetch)
         # stagger the episodes: steady state of a training run (about 1/120 of the envs finish at every step)
-        g = torch.Generator(device=dev).manual_seed(1000 + rank * R + r)
-        e._meta.add_(torch.randint(0, min(args.episode_steps, 120), (N,), generator=g, device=dev, dtype=torch.int32) << 16)
+        g = torch.Generator(device=cx.dev).manual_seed(1000 + cx.rank * R + r)
+        e._meta.add_(torch.randint(0, min(episode_steps, 120), (N,), generator=g, device=cx.dev, dtype=torch.int32) << 16)
         torch.cuda.synchronize()
         e.capture_graphs()
         envs.append(e)
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
-    n_act = 16
-    actions = torch.randint(0, 8, (n_act, N, 1), generator=g, device=dev, dtype=torch.int32)   # resident in HBM
-    state_mb = R * N * (BYTES_PER_ENV_STEP + 160 + 80) / 1e6
+    return envs
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    # The env batches of the ring are independent vector envs: batch r is stepped on its own stream, so that the short
-    # tail kernels of one batch (reset of finished envs, counter bump) and the drain of its step kernel's last CTAs
-    # overlap the step kernel of the next batch instead of idling the GPU.
-    n_streams = R if args.streams <= 0 else min(args.streams, R)
-    main_stream = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else [main_stream]
+def headline(cx: Ctx, envs, K: int, W: int, reps: int, sample_clocks: bool):
+    """Device-resident throughput of the ring of env batches: K steps per window, `reps` windows.  Batch r lives on its own
+    stream, so that the short tail kernels of one batch (reset of finished envs) and the drain of its step kernel's last
+    CTAs overlap the next batch's step kernel.  Whole blocks of PREFETCH_PERIOD steps are one CUDA-graph launch
+    (RadSearch.step_block); a K that is not a multiple of the period runs step by step."""
+    torch = cx.torch
+    R, N = len(envs), envs[0].num_envs
+    P = envs[0].PREFETCH_PERIOD
+    g = torch.Generator(device=cx.dev).manual_seed(7 + cx.rank)
+    n_act = 8
+    act_blocks = torch.randint(0, 8, (n_act, P, N, 1), generator=g, device=cx.dev, dtype=torch.int32)   # resident in HBM
+    main = torch.cuda.current_stream(cx.dev)
+    streams = [torch.cuda.Stream(device=cx.dev) for _ in range(R)] if R > 1 else [main]
+    use_blocks = envs[0].use_cuda_graph and K % P == 0
+    counter = [0]
 
-    def one_step(i):
-        with torch.cuda.stream(streams[(i % R) % n_streams]):
-            return envs[i % R].step_batch(actions[i % n_act], epoch_end=False)
-
-    def fork():
+    def window(k_steps):
         for st in streams:
-            st.wait_stream(main_stream)
-
-    def join():
+            st.wait_stream(main)
+        if use_blocks:
+            for _ in range(k_steps // P):
+                i = counter[0]; counter[0] += 1
+                with torch.cuda.stream(streams[i % R]):
+                    envs[i % R].step_block(act_blocks[i % n_act])
+        else:
+            for _ in range(k_steps):
+                i = counter[0]; counter[0] += 1
+                with torch.cuda.stream(streams[i % R]):
+                    envs[i % R].step_batch(act_blocks[i % n_act, i % P], epoch_end=False)
         for st in streams:
-            main_stream.wait_stream(st)
+            main.wait_stream(st)
 
-    # ---- device-resident throughput: `value` -----------------------------------------------------------------------
-    fork()
-    for i in range(W):
-        one_step(i)
-    join()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    window(-(-max(W, 3) // P) * P)                       # warm-up: at least W steps, whole blocks
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
+    if sample_clocks and cx.rank == 0:
         sampler.start()
-    # nvidia-smi samples every 100 ms: when the K timed steps last less than that, the same steps keep running (untimed)
-    # in front of the timed region so that the samples are taken under this very load
-    t_pre = time.perf_counter()
-    i_pre = 0
+    # nvidia-smi samples every 100 ms: the same windows keep running (untimed) for 0.6 s in front of the timed ones so that
+    # the clock samples are taken under this very load
+    t_pre, pre = time.perf_counter(), 0
     while time.perf_counter() - t_pre < 0.6:
-        fork()
-        for _ in range(200):
-            one_step(W + i_pre)
-            i_pre += 1
-        join()
+        for _ in range(8):
+            window(K)
+            pre += K
         torch.cuda.synchronize()
-    W0, W = W, W + i_pre
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    fork()
-    for i in range(K):
-        one_step(W + i)
-    join()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    value = N * world * K / (total_ms / 1e3)
+    times = []
+    for _ in range(reps):
+        cx.barrier()
+        e0, e1 = cx.event(), cx.event()
+        e0.record()
+        window(K)
+        e1.record()
+        cx.barrier()
+        times.append(e0.elapsed_time(e1))
+    clocks = sampler.stop() if (sample_clocks and cx.rank == 0) else None
+    times = cx.max_over_ranks(times)
+    med = median(times)
+    launches_per_step = (2 + 1.0 / P)
+    return {"ms": med, "ms_min": min(times), "ms_max": max(times), "reps": reps, "preroll_steps": pre,
+            "value": N * cx.world * K / (med / 1e3), "clocks": clocks, "launches": int(launches_per_step * K),
+            "graph_launches": (K // P) if use_blocks else K,
+            "mode": (f"one CUDA-graph launch per block of {P} steps" if use_blocks else "one CUDA-graph launch per step")
+            if envs[0].use_cuda_graph else "stream launches"}
 
-    # ---- roofline pass: CUDA events around the step kernel alone (same stream), averaged over K launches ------------
+
+def step_kernel_time(cx: Ctx, envs, groups: int, fast: bool):
+    """CUDA events around the step kernel alone, on the stream it is launched on.  `back_to_back`: one launch per batch of
+    the ring between an event pair (independent batches, same stream), time / launches; `single`: an event pair per
+    launch (adds the event overhead of an otherwise empty stream)."""
     import ctypes as C
-    from radiation_ppo_b200 import _lib as L
 
-    lib = L.load()
-    Kr = min(K, 480)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kr)]
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    torch, L, lib = cx.torch, cx.L, cx.lib
+    R, N = len(envs), envs[0].num_envs
+    g = torch.Generator(device=cx.dev).manual_seed(99 + cx.rank)
+    acts = torch.randint(0, 8, (4, N, 1), generator=g, device=cx.dev, dtype=torch.int32)
+    stream = C.c_void_p(torch.cuda.current_stream(cx.dev).cuda_stream)
     for e in envs:
         e._quiesce_prefetch()
     torch.cuda.synchronize()
     sflags = L.F_AUTO_RESET | L.F_DEVICE_CTR | (L.F_FAST_POISSON if fast else 0)     # DEVICE_CTR: no memset inside
-    for i in range(Kr):
-        e = envs[i % R]
-        a = actions[i % n_act]
+
+    def launch_step(e, a):
         e._ctr += 1
         e._ctr_dev.fill_(e._ctr)
         e._reset_count.zero_()
-        kev[i][0].record()
-        L.check(lib.rs_step(C.byref(e._cfg), C.byref(e._st), C.c_void_p(a.data_ptr()), C.c_void_p(e.obs.data_ptr()),
-                            C.c_void_p(e.reward.data_ptr()), C.c_void_p(e.team_reward.data_ptr()),
-                            C.c_void_p(e.done_flags.data_ptr()), C.c_void_p(e.info_flags.data_ptr()),
-                            C.c_void_p(e.ended.data_ptr()), C.c_void_p(e.final_obs.data_ptr()), N, e.env_id_offset,
-                            e.seed, e._ctr, None, 0, sflags, stream), "rs_step")
-        kev[i][1].record()
+        return lambda: L.check(lib.rs_step(
+            C.byref(e._cfg), C.byref(e._st), C.c_void_p(a.data_ptr()), C.c_void_p(e.obs.data_ptr()),
+            C.c_void_p(e.reward.data_ptr()), C.c_void_p(e.team_reward.data_ptr()), C.c_void_p(e.done_flags.data_ptr()),
+            C.c_void_p(e.info_flags.data_ptr()), C.c_void_p(e.ended.data_ptr()), C.c_void_p(e.final_obs.data_ptr()), N,
+            e.env_id_offset, e.seed, e._ctr, None, 0, sflags, stream), "rs_step")
+
+    def launch_reset(e):
         L.check(lib.rs_reset(C.byref(e._cfg), C.byref(e._st), None, None, C.c_void_p(e.obs.data_ptr()), N,
-                             e.env_id_offset, e.seed, e._ctr, None, 0,
-                             L.F_RESET_LIST | (L.F_FAST_POISSON if fast else 0), stream), "rs_reset")
+                             e.env_id_offset, e.seed, e._ctr, None, 0, L.F_RESET_LIST | (L.F_FAST_POISSON if fast else 0),
+                             stream), "rs_reset")
         e._ctr_dev_val = -1
+
+    b2b, single = [], []
+    for i in range(groups + 2):
+        fns = [launch_step(e, acts[(i + j) % 4]) for j, e in enumerate(envs)]
+        e0, e1 = cx.event(), cx.event()
+        e0.record()
+        for f in fns:
+            f()
+        e1.record()
+        for e in envs:
+            launch_reset(e)
+        if i >= 2:
+            b2b.append((e0, e1))
+    for i in range(groups):
+        e = envs[i % R]
+        f = launch_step(e, acts[i % 4])
+        e0, e1 = cx.event(), cx.event()
+        e0.record()
+        f()
+        e1.record()
+        launch_reset(e)
+        single.append((e0, e1))
     torch.cuda.synchronize()
-    k_ms = sum(a.elapsed_time(b) for a, b in kev) / Kr
-    peak, peak_src = measured_peak_gbs()
-    achieved = BYTES_PER_ENV_STEP * N / (k_ms / 1e3) / 1e9
+    t_b2b = [a.elapsed_time(b) / R for a, b in b2b]
+    t_single = [a.elapsed_time(b) for a, b in single]
+    return sum(t_b2b) / len(t_b2b), median(t_b2b), sum(t_single) / len(t_single)
 
-    if args.quick:
-        if rank == 0:
-            print(json.dumps({"quick": True, "value": value, "ms_per_step": total_ms / K, "kernel_ms": k_ms,
-                              "frac": achieved / peak}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    # ---- GAE over the [T, N] rollout buffer ("GAE GB/s vs HBM peak") -------------------------------------------------
+def sweep_leg(cx: Ctx, fast: bool):
+    """Per-launch step-kernel time at the smaller BASELINE sizes, L2 flushed before every timed launch."""
+    import ctypes as C
+
+    torch, L, lib, rp = cx.torch, cx.L, cx.lib, cx.rp
+    out = []
+    for N, oc, label in ((1024, -1, "BASELINE configs[1]: 1,024 envs, 1-5 obstructions"),
+                         (65536, K_OBS, "BASELINE configs[2] size: 65,536 envs, 5 obstructions")):
+        e = rp.RadSearch(obstruction_count=oc, enforce_grid_boundaries=True, num_envs=N, seed=3, device=cx.dev,
+                         auto_reset=True, fast_poisson=fast, steps_per_episode=120)
+        g = torch.Generator(device=cx.dev).manual_seed(5)
+        e._meta.add_(torch.randint(0, 120, (N,), generator=g, device=cx.dev, dtype=torch.int32) << 16)
+        acts = torch.randint(0, 8, (4, N, 1), generator=g, device=cx.dev, dtype=torch.int32)
+        for i in range(8):
+            e.step_batch(acts[i % 4])
+        stream = C.c_void_p(torch.cuda.current_stream(cx.dev).cuda_stream)
+        flags = L.F_AUTO_RESET | (L.F_FAST_POISSON if fast else 0)
+        evs = []
+        for i in range(24):
+            e._ctr += 1
+            e._reset_count.zero_()
+            cx.flush_l2()
+            e0, e1 = cx.event(), cx.event()
+            e0.record()
+            L.check(lib.rs_step(C.byref(e._cfg), C.byref(e._st), C.c_void_p(acts[i % 4].data_ptr()), C.c_void_p(e.obs.data_ptr()),
+                                C.c_void_p(e.reward.data_ptr()), C.c_void_p(e.team_reward.data_ptr()),
+                                C.c_void_p(e.done_flags.data_ptr()), C.c_void_p(e.info_flags.data_ptr()),
+                                C.c_void_p(e.ended.data_ptr()), C.c_void_p(e.final_obs.data_ptr()), N, e.env_id_offset,
+                                e.seed, e._ctr, None, 0, flags | L.F_DEVICE_CTR * 0, stream), "rs_step")
+            e1.record()
+            L.check(lib.rs_reset(C.byref(e._cfg), C.byref(e._st), None, None, C.c_void_p(e.obs.data_ptr()), N,
+                                 e.env_id_offset, e.seed, e._ctr, None, 0, L.F_RESET_LIST | (L.F_FAST_POISSON if fast else 0),
+                                 stream), "rs_reset")
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = median([a.elapsed_time(b) for a, b in evs[4:]])
+        nbytes = int((122 * N + 32 * (e._meta & 0xFF).sum().item()))
+        # rs_step with a host step counter clears the reset list with a 4-byte memset first: it is inside the event pair
+        out.append({"workload": label, "n_envs": N, "kernel_ms": ms, "env_steps_per_s": N / (ms / 1e3),
+                    "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9, "peak": cx.peak,
+                    "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / cx.peak, "l2": "flushed before every timed launch",
+                    "note": "latency-bound: fewer warps than the GPU holds" if N < 148 * 128 * 7 else ""})
+        del e
+    return out
+
+
+def gae_leg(cx: Ctx, sizes):
+    torch, rp = cx.torch, cx.rp
+    out = []
     T = T_EPOCH
-    rew = -0.5 * torch.rand(T, N, generator=g, device=dev) * 1.5
-    val = torch.randn(T, N, generator=g, device=dev)
-    end = (torch.rand(T, N, generator=g, device=dev) < 1 / 100).to(torch.uint8)
-    end[T - 1] = 1
-    boot = torch.randn(T, N, generator=g, device=dev) * end
-    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
-    for _ in range(3):
-        rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=1)
+    g = torch.Generator(device=cx.dev).manual_seed(11)
+    for N in sizes:
+        rew = -0.5 * torch.rand(T, N, generator=g, device=cx.dev) * 1.5
+        val = torch.randn(T, N, generator=g, device=cx.dev)
+        end = (torch.rand(T, N, generator=g, device=cx.dev) < 1 / 100).to(torch.uint8)
+        end[T - 1] = 1
+        boot = torch.randn(T, N, generator=g, device=cx.dev) * end
+        adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+        for _ in range(3):
+            rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=0)
+        evs = []
+        for _ in range(12):
+            cx.flush_l2()
+            a, b = cx.event(), cx.event()
+            a.record()
+            rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=0)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = median([a.elapsed_time(b) for a, b in evs])
+        gbs = GAE_BYTES_PER_ELEM * T * N / (ms / 1e3) / 1e9
+        out.append({"T": T, "N": N, "ms": ms, "achieved": gbs, "peak": cx.peak, "unit": "GB/s", "frac": gbs / cx.peak,
+                    "bytes_per_element": GAE_BYTES_PER_ELEM, "l2": "flushed before every timed launch",
+                    "traffic": measured_traffic("gae_tile_kernel", N)})
+        del rew, val, end, boot, adv, ret
+    return out
+
+
+class GruPolicy:
+    """Stock PyTorch actor-critic for the pipeline leg: GRUCell(11 -> 24), a categorical head over the 8 moves and a value
+    head (the shape of the reference's RAD-A2C core, algos/test_environment/core.py).  `act` / `value` run as captured CUDA
+    graphs on static buffers; everything inside them is torch's own kernels (cuBLAS GEMMs, elementwise)."""
+
+    def __init__(self, cx: Ctx, N: int, obs_dim: int = 11, hidden: int = 24, n_act: int = 8, final_obs=None):
+        torch = cx.torch
+        self.torch, self.N = torch, N
+        torch.manual_seed(0)
+        self.net = torch.nn.ModuleDict({"gru": torch.nn.GRUCell(obs_dim, hidden), "pi": torch.nn.Linear(hidden, n_act),
+                                        "v": torch.nn.Linear(hidden, 1)}).to(cx.dev)
+        self.h = torch.zeros(N, hidden, device=cx.dev)
+        self.obs_in = torch.zeros(N, obs_dim, device=cx.dev)
+        self.final_obs = final_obs
+        self.action = torch.zeros(N, dtype=torch.int32, device=cx.dev)
+        self.val = torch.zeros(N, device=cx.dev)
+        self.logp = torch.zeros(N, device=cx.dev)
+        self.v_next = torch.zeros(N, device=cx.dev)
+        self.g_act = self.g_val = None
+        self._capture(cx)
+
+    def _act_body(self):
+        torch = self.torch
+        with torch.no_grad():
+            h = self.net["gru"](self.obs_in, self.h)
+            self.h.copy_(h)
+            logits = self.net["pi"](h)
+            lp = torch.log_softmax(logits, dim=-1)
+            # Gumbel-max sampling: stays on the device and inside the graph
+            u = torch.rand_like(lp).clamp_(1e-10, 1.0)
+            a = (lp - torch.log(-torch.log(u))).argmax(dim=-1)
+            self.action.copy_(a)
+            self.logp.copy_(lp.gather(1, a[:, None]).squeeze(1))
+            self.val.copy_(self.net["v"](h).squeeze(1))
+
+    def _val_body(self):
+        torch = self.torch
+        with torch.no_grad():
+            h = self.net["gru"](self.final_obs, self.h)
+            self.v_next.copy_(self.net["v"](h).squeeze(1))
+
+    def _capture(self, cx):
+        torch = self.torch
+        s = torch.cuda.Stream(device=cx.dev)
+        s.wait_stream(torch.cuda.current_stream(cx.dev))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._act_body()
+                self._val_body()
+        torch.cuda.current_stream(cx.dev).wait_stream(s)
+        torch.cuda.synchronize()
+        self.g_act, self.g_val = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_act):
+            self._act_body()
+        with torch.cuda.graph(self.g_val):
+            self._val_body()
+        self.h.zero_()
+
+    def act(self, obs):
+        self.obs_in.copy_(obs)
+        self.g_act.replay()
+        return self.action, self.val, self.logp
+
+    def value(self, obs):
+        assert obs.data_ptr() == self.final_obs.data_ptr()
+        self.g_val.replay()
+        return self.v_next
+
+    def reset_state(self, mask):
+        if mask is None:
+            self.h.zero_()
+        else:
+            self.h.masked_fill_(mask[:, None], 0.0)
+
+
+def ppo_update(cx: Ctx, pol: GruPolicy, buf, data, opt, chunk: int = 16384, clip: float = 0.2):
+    """One PPO update over the epoch's rollout (clipped policy loss + value loss, P:1150-1281 in spirit): the GRU is re-run
+    over the T steps of every column with its state restarted where a path ended, gradients accumulated over column
+    chunks, averaged over ranks with ONE flattened all-reduce (dist.average_gradients = mpi_avg_grads), one Adam step."""
+    torch = cx.torch
+    from radiation_ppo_b200 import dist as rdist
+
+    T, N, D = buf.T, buf.N, buf.D
+    obs = data["obs"].view(T, N, D)
+    act = data["act"].view(T, N).long()
+    adv, ret, logp_old = data["adv"].view(T, N), data["ret"].view(T, N), data["logp"].view(T, N)
+    end = data["end"]
+    opt.zero_grad(set_to_none=True)
+    total = 0.0
+    for c0 in range(0, N, chunk):
+        sl = slice(c0, min(N, c0 + chunk))
+        h = torch.zeros(sl.stop - sl.start, pol.h.shape[1], device=cx.dev)
+        loss = 0.0
+        for t in range(T):
+            h = pol.net["gru"](obs[t, sl], h)
+            lp = torch.log_softmax(pol.net["pi"](h), dim=-1).gather(1, act[t, sl, None]).squeeze(1)
+            v = pol.net["v"](h).squeeze(1)
+            ratio = torch.exp(lp - logp_old[t, sl])
+            a = adv[t, sl]
+            loss = loss - torch.minimum(ratio * a, torch.clamp(ratio, 1 - clip, 1 + clip) * a).sum() \
+                + 0.5 * ((v - ret[t, sl]) ** 2).sum()
+            h = h * (end[t, sl] == 0)[:, None]
+        loss = loss / (T * N)
+        loss.backward()
+        total += float(loss.detach())
+    t0 = cx.event(); t1 = cx.event()
+    t0.record()
+    rdist.average_gradients(pol.net.parameters())
+    t1.record()
+    opt.step()
+    return total, (t0, t1)
+
+
+def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: int = 2, do_update: bool = True):
+    """BASELINE configs[2]: rollout (policy -> env step storing into the buffer -> bootstrap) x T, GAE, get(episodes=True),
+    one PPO update; train.py:321-571 with ppo.py:746 / 1150-1281 as the consumer."""
+    torch, rp = cx.torch, cx.rp
+    from radiation_ppo_b200 import dist as rdist
+
+    env = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=4, device=cx.dev,
+                       env_id_offset=cx.rank * N, auto_reset=True, fast_poisson=fast, steps_per_episode=120,
+                       prefetch=True, use_cuda_graph=False, standardize=1)
+    buf = rp.BatchedPPOBuffer(11, T, N, device=cx.dev)
+    pol = GruPolicy(cx, N, final_obs=env.final_obs.view(N, 11))
+    if cx.world > 1:
+        rdist.sync_params(pol.net)                                                   # train.py:250-256
+    stats = rp.EpisodeStats(N, 1, cx.dev)
+    col = rp.RolloutCollector(env, buf, pol, stats)
+    opt = torch.optim.Adam(pol.net.parameters(), lr=3e-4)
+    rec = []
+    for ep in range(epochs):
+        cx.barrier()
+        ev = [cx.event() for _ in range(6)]
+        ev[0].record()
+        col.collect()                                     # T steps + rs_gae
+        ev[1].record()
+        data = buf.get(episodes=True)                     # adv statistics (2 all-reduces) + normalise + pack + episode table
+        ev[2].record()
+        summ = stats.epoch_summary()                      # episode statistics: one sum + one min + one max all-reduce
+        ev[3].record()
+        loss, (g0, g1) = ppo_update(cx, pol, buf, data, opt) if do_update else (0.0, (ev[3], ev[3]))
+        ev[4].record()
+        cx.barrier()
+        ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        rec.append({"rollout_gae_ms": ms[0], "get_ms": ms[1], "episode_stats_ms": ms[2], "update_ms": ms[3],
+                    "grad_allreduce_us": 1e3 * g0.elapsed_time(g1), "loss": loss,
+                    "episodes": float(summ["Episodes"][0]), "avg_ep_ret": float(summ["AverageEpRet"][0]),
+                    "n_episodes_packed": int(data["ep_len"].numel())})
+    r = rec[-1]
+    tot = cx.max_over_ranks([r["rollout_gae_ms"], r["rollout_gae_ms"] + r["get_ms"] + r["episode_stats_ms"] + r["update_ms"]])
+    out = {"workload": f"{N} envs/GPU x T={T}, 5 obstructions, GRU(11->24) policy in the loop, count standardiser fused in the "
+                       "step kernel, step kernel stores into the rollout buffer (no store copies), GAE, get(episodes=True), "
+                       "1 PPO update (BASELINE configs[2])",
+           "rollout_env_steps_per_s": N * cx.world * T / (tot[0] / 1e3),
+           "pipeline_env_steps_per_s": N * cx.world * T / (tot[1] / 1e3),
+           "us_per_rollout_step": 1e3 * r["rollout_gae_ms"] / T, "stages_ms": r, "epochs_run": epochs,
+           "status_flags_raised": int((env.status & ~2).ne(0).sum().item())}
+    # ---- SURVEY 8e collectives on their own: timed over 20 calls each, results asserted -----------------------------------
+    if cx.world > 1:
+        dist = cx.dist
+        params = [p for p in pol.net.parameters()]
+        for p in params:
+            p.grad = torch.full_like(p, float(cx.rank + 1))
+        times = {}
+
+        def timeit(name, fn):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(20):
+                cx.barrier()
+                a, b = cx.event(), cx.event()
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(1e3 * a.elapsed_time(b))
+            times[name] = median(cx.max_over_ranks(ts))
+
+        def grads():
+            for p in params:
+                p.grad.fill_(float(cx.rank + 1))
+            rdist.average_gradients(params)
+        timeit("average_gradients_us", grads)
+        want = sum(range(1, cx.world + 1)) / cx.world
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, want)) for p in params), "average_gradients is wrong"
+        adv = buf.adv_buf
+        timeit("advantage_statistics_us", lambda: rp.advantage_statistics(adv))
+        mean, std = rp.advantage_statistics(adv)
+        gathered = [torch.zeros(2, dtype=torch.float64, device=cx.dev) for _ in range(cx.world)]
+        a64 = adv.double()
+        dist.all_gather(gathered, torch.stack([a64.sum(), (a64 * a64).sum()]))
+        s1 = sum(float(g[0]) for g in gathered); s2 = sum(float(g[1]) for g in gathered); n = adv.numel() * cx.world
+        assert abs(float(mean) - s1 / n) < 1e-9 and abs(float(std) - (s2 / n - (s1 / n) ** 2) ** 0.5) < 1e-6, "advantage_statistics is wrong"
+        st = {"a": torch.tensor(float(cx.rank), device=cx.dev), "b": torch.tensor(2.0, device=cx.dev)}
+        timeit("reduce_episode_stats_us", lambda: rdist.reduce_episode_stats(st))
+        red = rdist.reduce_episode_stats(st)
+        assert float(red["a"]) == sum(range(cx.world)) and float(red["b"]) == 2.0 * cx.world, "reduce_episode_stats is wrong"
+        timeit("sync_params_us", lambda: rdist.sync_params(pol.net))
+        times["flat_gradient_bytes"] = int(sum(p.numel() for p in params) * 4)
+        times["backend"] = "nccl"
+        times["checked"] = True
+        out["collectives_us"] = times
+    del env, buf, pol
+    return out
+
+
+def maps_leg(cx: Ctx, fast: bool):
+    """RAD-TEAM pipeline of BASELINE configs[3]: 16,384 envs x 4 agents, env step -> shared map observation."""
+    torch, rp = cx.torch, cx.rp
+    Nm, Am, Tm = 16384, 4, 120
+    g = torch.Generator(device=cx.dev).manual_seed(21)
+    menv = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, number_agents=Am, num_envs=Nm, seed=4,
+                        device=cx.dev, auto_reset=True, fast_poisson=fast, prefetch=True, use_cuda_graph=True)
+    mb = rp.BatchedMapsBuffer(Nm, Am, 120, environment_scale=menv.scale, device=cx.dev)
+    macts = torch.randint(0, 8, (8, Nm, Am), generator=g, device=cx.dev, dtype=torch.int32)
+    mpred = torch.rand(Nm, Am, 2, generator=g, device=cx.dev)
+
+    def maps_step(i):
+        mb.update(menv.obs, mpred)
+        menv.step_batch(macts[i % 8])
+        mb.reset(mask=menv.ended, mask_bits=4)
+
+    for i in range(24):
+        maps_step(i)
     torch.cuda.synchronize()
-    gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
-    for a, b in gev:
+    mev = []
+    p0, p1 = cx.event(), cx.event()
+    p0.record()
+    for i in range(Tm):
+        a, b = cx.event(), cx.event()
         a.record()
-        rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=1)
+        mb.update(menv.obs, mpred)
         b.record()
+        menv.step_batch(macts[i % 8])
+        mb.reset(mask=menv.ended, mask_bits=4)
+        mev.append((a, b))
+    p1.record()
     torch.cuda.synchronize()
-    gae_ms = sorted(a.elapsed_time(b) for a, b in gev)[len(gev) // 2]
-    gae_gbs = GAE_BYTES_PER_ELEM * T * N / (gae_ms / 1e3) / 1e9
-    del rew, val, end, boot, adv, ret
+    upd_ms = median([a.elapsed_time(b) for a, b in mev])
+    # algorithmic bytes of one rs_maps_update call (DESIGN.md section 3): per env 44 A obs + the episode's sample table scan
+    # (6 B per logged reading, (T/2 + 1) A on average) + 4 B x (6 A + 6) A scattered map stores
+    alg = Nm * (44 * Am + 6 * (Tm // 2 + 1) * Am + 4 * (6 * Am + 6) * Am)
+    traffic = measured_traffic("maps_update_kernel", Nm)
+    line = {"workload": f"{Nm} envs x {Am} agents, 27x27 maps, env step + rs_maps_update + rs_maps_reset (BASELINE configs[3])",
+            "update_ms": upd_ms, "agent_map_updates_per_s": Nm * Am / (upd_ms / 1e3),
+            "pipeline_env_steps_per_s": Nm * Tm / (p0.elapsed_time(p1) / 1e3),
+            "maps_status_flags": int(mb.status.sum().item()),
+            "roofline": {"bound": "hbm", "kernel": "maps_update_kernel", "algorithmic_bytes_per_launch": alg,
+                         "achieved": alg / (upd_ms / 1e3) / 1e9, "peak": cx.peak, "unit": "GB/s",
+                         "frac": alg / (upd_ms / 1e3) / 1e9 / cx.peak, "traffic": traffic,
+                         "traffic_over_algorithmic": (traffic / alg) if traffic else None}}
+    del menv, mb
+    return line
 
-    # ---- RAD-TEAM pipeline of BASELINE configs[3]: 16,384 envs x 4 agents, env step -> shared map observation ---------
-    maps_line = None
-    if world == 1:
-        Nm, Am, Tm = 16384, 4, 120
-        menv = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, number_agents=Am, num_envs=Nm, seed=4,
-                            device=dev, auto_reset=True, fast_poisson=fast)
-        mb = rp.BatchedMapsBuffer(Nm, Am, 120, environment_scale=menv.scale, device=dev)
-        macts = torch.randint(0, 8, (8, Nm, Am), generator=g, device=dev, dtype=torch.int32)
-        mpred = torch.rand(Nm, Am, 2, generator=g, device=dev)
 
-        def maps_step(i):
-            mb.update(menv.obs, mpred)
-            menv.step_batch(macts[i % 8])
-            mb.reset(mask=menv.ended, mask_bits=4)
-
-        for i in range(20):
-            maps_step(i)
-        torch.cuda.synchronize()
-        mev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Tm)]
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for i in range(Tm):
-            mev[i][0].record()
-            mb.update(menv.obs, mpred)
-            mev[i][1].record()
-            menv.step_batch(macts[i % 8])
-            mb.reset(mask=menv.ended, mask_bits=4)
-        p1.record()
-        torch.cuda.synchronize()
-        upd_ms = sorted(a.elapsed_time(b) for a, b in mev)[Tm // 2]
-        maps_line = {"workload": f"{Nm} envs x {Am} agents, 27x27 maps, env step + rs_maps_update + rs_maps_reset (BASELINE configs[3])",
-                     "update_ms": upd_ms, "agent_map_updates_per_s": Nm * Am / (upd_ms / 1e3),
-                     "pipeline_env_steps_per_s": Nm * Tm / (p0.elapsed_time(p1) / 1e3),
-                     "maps_status_flags": int(mb.status.sum().item())}
-        del menv, mb
-
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----------------
-    # RadSearch.step_host: pinned host actions -> device, step + auto-reset, ALL step outputs -> pinned host in one
-    # transfer, on the env batch's own stream.  `e2e`: the R env batches of the ring are driven round-robin, the host
-    # waiting for batch r's previous results before it sends batch r's next actions (an asynchronous vector-env loop:
-    # copies of one batch overlap the kernels of the others).  `e2e_sync`: one batch at a time, host waits every step.
+def e2e_leg(cx: Ctx, envs, K: int, W: int):
+    """End to end through the public API with HOST buffers (pinned), copies inside the timed region.
+    RadSearch.step_host: pinned host actions -> device, step + auto-reset, ALL step outputs -> pinned host in one transfer,
+    on the env batch's own stream.  `pipelined`: the R env batches of the ring are driven round-robin, the host waiting for
+    batch r's previous results before it sends batch r's next actions; `sync`: one batch at a time, host waits every step.
+    link: a bare pinned cudaMemcpyAsync device->host of the same bytes per rank, all ranks at once -- the ceiling of this
+    host's link for that transfer."""
+    torch = cx.torch
+    R, N = len(envs), envs[0].num_envs
+    n_act = 8
     h_act = torch.randint(0, 8, (n_act, N, 1), dtype=torch.int32).pin_memory()
     hbs = [e.host_buffers() for e in envs]
     torch.cuda.synchronize()
-    Ke = min(K, 480)
+    Ke = min(max(K, 40), 480)
 
-    def e2e_run(k0, k1, depth_all):
+    def run(k0, k1, depth_all):
         chk = 0
         for i in range(k0, k1):
             r = i % R
@@ -375,60 +734,153 @@ def main():
             hb.wait()
         return chk
 
-    e2e_vals = {}
+    vals = {}
     for name, depth_all in (("sync", False), ("pipelined", True)):
-        e2e_run(0, W, depth_all)
-        barrier()
+        run(0, max(W, 8), depth_all)
+        ts = []
+        for rep in range(5):
+            cx.barrier()
+            t0 = time.perf_counter()
+            run(W, W + Ke, depth_all)
+            cx.barrier()
+            ts.append(time.perf_counter() - t0)
+        ts = cx.max_over_ranks(ts)
+        vals[name] = N * cx.world * Ke / median(ts)
+    # the link: the same number of bytes, device -> pinned host, nothing else running, all ranks concurrently
+    nbytes = hbs[0].d2h_bytes
+    src = torch.empty(nbytes, dtype=torch.uint8, device=cx.dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    ts = []
+    for rep in range(5):
+        cx.barrier()
         t0 = time.perf_counter()
-        e2e_run(W, W + Ke, depth_all)
-        barrier()
-        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e_vals[name] = N * world * Ke / float(e2e_s.item())
-    # both drive RadSearch.step_host with host buffers; report the faster schedule (with many ranks on one host the
-    # pipelined one can lose to the synchronous one: more copies in flight than the host side can absorb)
-    e2e_mode = "pipelined" if e2e_vals["pipelined"] >= e2e_vals["sync"] else "sync"
-    e2e_value = e2e_vals[e2e_mode]
-    h2d, d2h = hbs[0].h2d_bytes, hbs[0].d2h_bytes
+        for _ in range(50):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        cx.barrier()
+        ts.append((time.perf_counter() - t0) / 50)
+    t_copy = median(cx.max_over_ranks(ts))
+    link_gbs = nbytes * cx.world / t_copy / 1e9
+    mode = "pipelined" if vals["pipelined"] >= vals["sync"] else "sync"
+    e2e_value = vals[mode]
+    per_env = (hbs[0].d2h_bytes + hbs[0].h2d_bytes) / N
+    return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hbs[0].h2d_bytes, "d2h_bytes_per_step": hbs[0].d2h_bytes,
+            "steps": Ke, "schedule": mode + " (the faster of the two schedules measured)", "sync_value": vals["sync"],
+            "pipelined_value": vals["pipelined"], "reps": 5,
+            "link_gbs": link_gbs, "link_env_steps_per_s": N * cx.world / t_copy,
+            "frac_of_link": e2e_value / (N * cx.world / t_copy),
+            "note": f"RadSearch.step_host: pinned host actions -> device, step+reset, all outputs (obs, reward, done/info/ended "
+                    f"flags; {per_env:.0f} B per env both ways) -> pinned host in one copy; link_gbs = bare pinned "
+                    f"cudaMemcpyAsync device->host of the same {nbytes} bytes per rank, all ranks concurrently (aggregate); "
+                    "frac_of_link = value / (envs per copy / copy time)"}
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--ring", type=int, default=4, help="env batches cycled so that each step's state comes from HBM")
+    ap.add_argument("--reps", type=int, default=0, help="timed windows (0: 50, fewer for long windows)")
+    ap.add_argument("--exact-poisson", action="store_true", help="fp64 numpy-exact PTRS acceptance as the headline sampler")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + step-kernel timing only (what the ncu passes replay)")
+    ap.add_argument("--legs", default=",".join(ALL_LEGS), help="comma list of " + ",".join(ALL_LEGS))
+    ap.add_argument("--no-prefetch", action="store_true", help="synchronous reset kernel after every step")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
+    ap.add_argument("--episode-steps", type=int, default=120, help="steps_per_episode (120 = the reference's; a huge value "
+                    "shows the throughput without resets)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    legs = set() if args.quick else {x for x in args.legs.split(",") if x}
+    if args.no_cpu_baseline:
+        legs.discard("cpu")
+
+    cx = Ctx(args)
+    torch = cx.torch
+    N, K, W, R = args.envs_per_gpu, args.steps, max(args.warmup, 3), max(args.ring, 1)
+    fast = not args.exact_poisson
+    reps = args.reps if args.reps > 0 else max(10, min(50, int(2.0e6 / max(K * 20, 1))))
+    graph, prefetch = not (args.no_graph or args.no_prefetch), not args.no_prefetch
+
+    envs = make_ring(cx, N, R, fast, args.episode_steps, graph, prefetch)
+    head = headline(cx, envs, K, W, reps, sample_clocks=True)
+    k_mean, k_med, k_single = step_kernel_time(cx, envs, 120, fast)
+    achieved = BYTES_PER_ENV_STEP * N / (k_mean / 1e3) / 1e9
+    state_mb = R * N * (BYTES_PER_ENV_STEP + 160 + 80 + 80) / 1e6
     status = int(sum(int((e.status & ~2).any()) for e in envs))
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W0, "preroll_steps": i_pre,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": f"RadSearch env step + auto-reset, {N} envs/GPU (BASELINE configs[4]), 5 obstructions, "
-                                   f"enforced boundaries, 1 agent, uniform random actions, staggered {args.episode_steps}-step episodes",
-                       "envs_per_gpu": N, "obstructions": K_OBS, "poisson": "fp32-acceptance PTRS" if fast else "numpy-exact PTRS",
-                       "l2": f"ring of {R} env batches ({state_mb:.0f} MB of state) cycled: every step reads its state from HBM",
-                       "resets": ("next episodes prefetched by rs_prepare on a parallel graph branch / side stream"
-                                  if not args.no_prefetch else "synchronous rs_reset after every step"),
-                       "launch": ("CUDA graph replay" if not (args.no_graph or args.no_prefetch) else "stream launches") +
-                                 f", ring batches on {n_streams} stream(s)",
-                       "parallelism": f"env-sharded x{world}, no data-path collective"},
-            "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic("step_kernel", N), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * N,
-                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_ms,
-                         "kernel_env_steps_per_s": N / (k_ms / 1e3)},
-            "gae": {"T": T, "N": N, "ms": gae_ms, "achieved": gae_gbs, "peak": peak, "unit": "GB/s", "frac": gae_gbs / peak,
-                    "bytes_per_element": GAE_BYTES_PER_ELEM, "kernel": "gae_tile_kernel<128,8,3> (bulk-async tiles, per-column fp64 recurrence)",
-                    "traffic": measured_traffic("gae_cols_kernel", N) if T == 480 else None},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "schedule": e2e_mode, "sync_value": e2e_vals["sync"],
-                    "pipelined_value": e2e_vals["pipelined"],
-                    "note": f"RadSearch.step_host: pinned host actions -> device, step+reset, all outputs (obs, reward, "
-                            f"done/info/ended flags; 51 B per env) -> pinned host in one copy; pipelined_value = {R} env batches "
-                            "round-robin on their own streams (host waits for a batch's previous results before sending its "
-                            "next actions); sync_value = host waits after every step; value = the faster of the two"},
-            "maps": maps_line,
-            "gpu_launches": int((2 + 1 / rp.RadSearch.PREFETCH_PERIOD) * K) if not args.no_prefetch else 2 * K, "clocks": clocks, "status_flags_raised": status,
-        }
-        if not args.no_cpu_baseline and world == 1:
+    if args.quick:
+        if cx.rank == 0:
+            print(json.dumps({"quick": True, "value": head["value"], "ms_per_step": head["ms"] / K, "kernel_ms": k_mean,
+                              "kernel_ms_single_launch": k_single, "frac": achieved / cx.peak}), flush=True)
+        if cx.world > 1:
+            cx.dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": cx.world, "steps": K, "warmup": W,
+        "ms_per_step": head["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64", "data": "synthetic",
+        "timing": {"reps": head["reps"], "window_ms_median": head["ms"], "window_ms_min": head["ms_min"],
+                   "window_ms_max": head["ms_max"], "preroll_steps": head["preroll_steps"],
+                   "rule": "every K-step window bracketed by barrier + synchronize, CUDA events, max over ranks, median over windows"},
+        "config": {"workload": f"RadSearch env step + auto-reset, {N} envs/GPU (BASELINE configs[4]), 5 obstructions, "
+                               f"enforced boundaries, 1 agent, uniform random actions, staggered {args.episode_steps}-step episodes",
+                   "envs_per_gpu": N, "obstructions": K_OBS,
+                   "poisson": ("alias table for blocked lines of sight + fp32-acceptance PTRS (KS-equivalent to numpy)" if fast
+                               else "numpy-exact PTRS"),
+                   "l2": f"ring of {R} env batches ({state_mb:.0f} MB of state) cycled: every step reads its state from HBM",
+                   "resets": ("next episodes prefetched by rs_prepare on a parallel graph branch / side stream"
+                              if prefetch else "synchronous rs_reset after every step"),
+                   "launch": head["mode"] + f", ring batches on {R} stream(s)",
+                   "parallelism": f"env-sharded x{cx.world}, no data-path collective"},
+        "roofline": {"bound": "hbm", "kernel": "step1_kernel", "achieved": achieved, "peak": cx.peak, "unit": "GB/s",
+                     "frac": achieved / cx.peak, "traffic": measured_traffic("step1_kernel", N), "peak_source": cx.peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * N,
+                     "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": k_mean, "kernel_ms_median": k_med,
+                     "kernel_ms_single_launch": k_single,
+                     "kernel_ms_rule": f"CUDA events around {R} back-to-back launches (one per ring batch, same stream) / {R}, "
+                                       "mean over 120 groups; single_launch = an event pair around every launch",
+                     "kernel_env_steps_per_s": N / (k_mean / 1e3)},
+        "gpu_launches": head["launches"], "graph_launches": head["graph_launches"], "clocks": head["clocks"],
+        "status_flags_raised": status,
+    }
+    if "exact" in legs and fast:
+        for e in envs:
+            e._quiesce_prefetch()
+        envs_x = make_ring(cx, N, 2, False, args.episode_steps, graph, prefetch)
+        hx = headline(cx, envs_x, K, W, max(10, reps // 2), sample_clocks=False)
+        kx_mean, _, kx_single = step_kernel_time(cx, envs_x, 40, False)
+        line["exact_poisson"] = {"value": hx["value"], "ms_per_step": hx["ms"] / K, "kernel_ms": kx_mean,
+                                 "frac": BYTES_PER_ENV_STEP * N / (kx_mean / 1e3) / 1e9 / cx.peak,
+                                 "sampler": "numpy-exact PTRS (bit-identical counts to the oracle on the shared Philox stream)",
+                                 "ring": 2}
+        line["exact_poisson_value"] = hx["value"]
+        del envs_x
+    if "e2e" in legs:
+        line["e2e"] = e2e_leg(cx, envs, K, W)
+    del envs
+    torch.cuda.empty_cache()
+    if "sweep" in legs and cx.world == 1:
+        line["sweep"] = sweep_leg(cx, fast)
+    if "gae" in legs:
+        gl = gae_leg(cx, (1024, 65536, 131072) if cx.world == 1 else (131072,))
+        line["gae"] = dict(gl[-1])
+        line["gae"]["kernel"] = "rs_gae variant 0 (bulk-async tiles, per-column fp64 recurrence; warp-scan form for small N)"
+        line["gae"]["sizes"] = gl
+    if "pipeline" in legs:
+        line["pipeline"] = pipeline_leg(cx, fast)
+    if "maps" in legs and cx.world == 1:
+        line["maps"] = maps_leg(cx, fast)
+    if cx.rank == 0:
+        if "cpu" in legs and cx.world == 1:
             cores = os.cpu_count() or 1
-            # GAE on the host cores: the oracle's per-column float64 recurrence (the reference's lfilter arithmetic), OpenMP
             import numpy as np
             from oracle import c_oracle as co
             Tg, Ng = T_EPOCH, 16384
@@ -442,17 +894,27 @@ def main():
             for _ in range(3):
                 co.gae(c_rew, c_val, c_end, c_boot, threads=cores)
             dtg = (time.perf_counter() - t0) / 3
-            line["gae"]["cpu_baseline"] = {"value": GAE_BYTES_PER_ELEM * Tg * Ng / dtg / 1e9, "unit": "GB/s", "cores": cores,
-                                           "kind": "port", "sample": f"[{Tg}, {Ng}] rollout, oracle orc_gae (OpenMP over columns)"}
+            if "gae" in line:
+                line["gae"]["cpu_baseline"] = {"value": GAE_BYTES_PER_ELEM * Tg * Ng / dtg / 1e9, "unit": "GB/s", "cores": cores,
+                                               "kind": "port", "sample": f"[{Tg}, {Ng}] rollout, oracle orc_gae (OpenMP over columns)"}
+                lf, lf_dt = gae_lfilter_baseline(Tg, 256)
+                line["gae"]["cpu_baseline_lfilter"] = {"value": lf, "unit": "GB/s", "cores": 1, "kind": "port (scipy.signal.lfilter "
+                                                       "per trajectory, the reference's arithmetic ppo.py:391-423)",
+                                                       "sample": f"[{Tg}, 256] rollout in {lf_dt:.2f}s, one process"}
             v1, dt1, _ = cpu_baseline(256, 60, cores)                 # calibrate
             n_s = max(256, min(16384, int(256 * 12.0 / max(dt1, 1e-3)) // 256 * 256))
             v, dt, _ = cpu_baseline(n_s, 60, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_s} envs x 60 steps in {dt:.1f}s, oracle/radsearch_oracle.c "
                                               "(scalar per-env loop with per-step Dijkstra, OpenMP over envs)"}
+            ref = reference_python_record()
+            if ref:
+                line["cpu_baseline_reference_python"] = ref
+        if "e2e" not in line:
+            line["e2e"] = None
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ from .dist import shard_range
 from .maps_buffer import BatchedMapsBuffer, MapsBuffer
 from .evaluate import MonteCarloEvaluator, MonteCarloResults, uniform_policy
 from .rollout_stats import EpisodeStats
+from .rollout import RolloutCollector
 
 __all__ = ["RadSearch", "StepResult", "HostStepBuffers", "PPOBuffer", "BatchedPPOBuffer", "gae_advantages", "advantage_statistics",
-           "normalize_advantages_", "combined_shape", "shard_range", "BatchedMapsBuffer", "MapsBuffer", "MonteCarloEvaluator", "MonteCarloResults", "uniform_policy", "EpisodeStats", "RadSearchLibraryError", "_lib"]
+           "normalize_advantages_", "combined_shape", "shard_range", "BatchedMapsBuffer", "MapsBuffer", "MonteCarloEvaluator", "MonteCarloResults", "uniform_policy", "EpisodeStats", "RolloutCollector", "RadSearchLibraryError", "_lib"]

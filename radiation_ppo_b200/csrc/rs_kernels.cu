@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     __shared__ __align__(16) float s_dsf[TB * 4 * KS];
     __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
     __shared__ uint8_t s_list[TB];
+    constexpr int kPairCap = 128;                           // (unit, corner) pairs of a warp: ~35 at 5 obstructions
+    __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
     __shared__ __align__(8) uint64_t s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
     const int n0 = blockIdx.x * TB;
@@ -328,6 +330,10 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         if (a.actions) action = a.actions[n];
         if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
     }
+    // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
+    const int hint = (af >> 25) & 31;
+    double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
+    if (KMAX > 0 && live && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
     // a new refill list starts with this step: only the reset kernel that follows appends to it
     if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
@@ -346,13 +352,79 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         }
         __syncwarp();
     }
+    // ---- take_action, segment to the source; for obstructed units the bound through last step's corner + marking pass -----
+    const int num_obs = meta & 0xff;
+    rs::Move1 mv;
+    mv.det = det; mv.af = af; mv.uf = 0; mv.d2 = 0; mv.direct = true; mv.blocked_raw = false; mv.status = 0u;
+    double best_sp = 0.0;
+    int besti = -1;
+    uint32_t marked = 0u;
+    if (live) {
+        mv = rs::unit1_move<KMAX>(P, s_rects + tid, TB, src, meta, action, det, af);
+        if (!mv.direct)
+            marked = rs::sp_hint_mark1<KMAX>(s_rects + tid, TB, num_obs, s_dsf + tid * 4 * K, mv.det.x, mv.det.y, hint, ds_hint,
+                                             best_sp, besti);
+    }
+    // ---- the marked corners of the warp as (unit, corner) pairs, one per lane: exact candidate + visibility ---------------
+    if (KMAX > 0 && __any_sync(0xffffffffu, marked != 0u)) {
+        const int cnt = __popc(marked);
+        int incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+        uint16_t *pl = s_pairs + (w0 >> 5) * kPairCap;
+        double *res = reinterpret_cast<double *>(s_obs + w0 * RS_OBS_DIM);      // the warp's staging block, free until commit
+        {
+            uint32_t m = marked;
+            int pos = off;
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < kPairCap) pl[pos] = (uint16_t)((lane << 5) | c);
+                pos++;
+            }
+        }
+        __syncwarp();
+        const int np = min(total, kPairCap);
+        for (int base = 0; base < np; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < np;
+            const int e = valid ? (int)pl[j] : 0, owner = e >> 5, c = e & 31;
+            const int px = __shfl_sync(0xffffffffu, mv.det.x, owner), py = __shfl_sync(0xffffffffu, mv.det.y, owner);
+            const int nob = __shfl_sync(0xffffffffu, num_obs, owner);
+            const double bo = __shfl_sync(0xffffffffu, best_sp, owner);
+            double ds = __longlong_as_double(0x7ff0000000000000LL);
+            if (valid) ds = S.dsrc[(size_t)(n0 + w0 + owner) * 4 * K + c];
+            const double v = rs::sp_pair1<KMAX>(s_rects + w0 + owner, TB, nob, px, py, c, ds, bo);
+            if (valid) res[j] = v;
+        }
+        __syncwarp();
+        {
+            uint32_t m = marked;
+            int pos = off;
+            while (m) {                                     // the unit's own pairs: keep the smallest
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                // pairs beyond the warp's list (never seen so far) are evaluated by their own thread
+                const double v = pos < kPairCap ? res[pos]
+                                                : rs::sp_pair1<KMAX>(s_rects + tid, TB, num_obs, mv.det.x, mv.det.y, c,
+                                                                     S.dsrc[(size_t)n * 4 * K + c], best_sp);
+                if (v < best_sp) { best_sp = v; besti = c; }
+                pos++;
+            }
+        }
+        __syncwarp();
+    }
     float *row = s_obs + tid * RS_OBS_DIM;
 #pragma unroll
     for (int d = 0; d < 8; d++) row[3 + d] = 0.0f;
     rs::Unit1 o;
     o.det = det; o.af = af; o.uf = 0; o.sp = 0.0; o.blocked_los = false; o.count = 0.0f; o.status = 0u;
-    if (live) o = rs::unit1_front<kFast, KMAX>(P, S, a, s_rects + tid, TB, s_dsf + tid * 4 * K, n, src, rad, meta, action, det,
-                                               af, step_ctr, x);
+    if (live) o = rs::unit1_measure<kFast>(P, a, mv, n, rad, best_sp, besti >= 0 ? besti : hint, step_ctr, x);
+    __syncwarp();
     // ---- obstruction_sensors: (unit, direction) items of the warp ---------------------------------------------------------
     const unsigned need = __ballot_sync(0xffffffffu, (o.uf & rs::UF_NEED_D) != 0);
     if (need) {

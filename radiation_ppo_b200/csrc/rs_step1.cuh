@@ -8,12 +8,12 @@
 //     in_obstruction, the detector->source segment, the visibility of the hint corner, the corner marking pass);
 //   * the shortest path keeps round 1's idea (upper bound through last step's best corner, then only corners that can
 //     still improve on it) but the marking pass now applies the EXACT improvement test in directed-rounding fp32
-//     (d^2 < (best - dsrc[c])^2 on a float lower bound of the per-episode table, RsState.dsf), so that almost no corner
-//     survives it and the survivors are walked by their own thread;
+//     (d^2 < (best - dsrc[c])^2 on a float lower bound of the per-episode table, RsState.dsf); about one corner per unit
+//     survives it, and the survivors of the whole warp are evaluated as (unit, corner) pairs, one per lane;
 //   * the Poisson draw is finished in place: RS_F_FAST_POISSON takes Poisson(bkg) -- 9 units in 10: the line of sight is
 //     blocked, R:498-502 -- from an alias table (rs_poisson_alias.h) and the rest from the fp32 PTRS sampler fed by the same
 //     Philox block; the numpy-exact sampler tries the squeeze first and calls the full sampler only where it fails;
-//   * the only cross-lane phase left are the 8-direction ray casts, as (unit, direction) work items of the warp.
+//   * the other cross-lane phase are the 8-direction ray casts, as (unit, direction) work items of the warp.
 //
 // Results are identical to the tile program's (and the oracle's): the integer geometry is the same code, the fp64
 // values are the same expressions in the same order.  The functions below are plain per-unit code, also compiled as
@@ -63,44 +63,50 @@ __device__ __forceinline__ bool in_obstruction1(const int4 *rects, int rstride, 
     return blocked;
 }
 
+// the near-corner clause of boundary_distance < 0.001 (see corner_grazes) as a call: it is needed for about one segment
+// in a thousand, and inlined it would keep four cross products alive through the whole rectangle loop
+__device__ __noinline__ bool graze_call(int px, int py, int qx, int qy, int4 r) {
+    int cr[4];
+    seg_rect(px, py, qx, qy, r, cr);
+    const int dx = qx - px, dy = qy - py;
+    return corner_grazes(px, py, dx, dy, dx * dx + dy * dy, r, cr);
+}
+
 // source_segment() of rs_env_impl.cuh without the box pre-filter and the per-lane rectangle list: every rectangle, every lane
 template <int KMAX>
 __device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, int num_obs, int px, int py, int sx, int sy,
                                                 bool &direct, bool &blocked) {
     const int dx = sx - px, dy = sy - py;
     const int l2 = dx * dx + dy * dy;
-    bool vis_ok = true, blk = false;
+    int acc = 0;                                            // bit 0: some open rectangle met, bit 1: some boundary within 0.001
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
         if (k < num_obs) {
             const int4 r = rects[k * rstride];
             int cr[4];
             const int h = seg_rect(px, py, sx, sy, r, cr);
-            vis_ok = vis_ok && !(h & 1);
-            bool b = (h & 2) && !(in_rect_open(px, py, r) && in_rect_open(sx, sy, r));
+            // (both end points strictly inside the rectangle: no boundary is met; the source never is, so test it first)
+            int b = h & 2;
+            if (b && in_rect_open(sx, sy, r) && in_rect_open(px, py, r)) b = 0;
             // near-corner clause (|cross| <= 3, |pq| > 1000): guarded by one unsigned minimum over the four cross products
             const unsigned g = min(min((unsigned)(cr[0] + 3), (unsigned)(cr[1] + 3)),
                                    min((unsigned)(cr[2] + 3), (unsigned)(cr[3] + 3)));
-            if (g <= 6u && !b && l2 > 1000000) b = corner_grazes(px, py, dx, dy, l2, r, cr);
-            blk = blk || b;
+            if (g <= 6u && !b && l2 > 1000000 && graze_call(px, py, sx, sy, r)) b = 2;
+            acc |= (h & 1) | b;
         }
     }
-    direct = vis_ok;
-    blocked = blk;
+    direct = !(acc & 1);
+    blocked = (acc & 2) != 0;
 }
 
 // visible() of rs_env_impl.cuh, unrolled and branch-free
 template <int KMAX>
 __device__ __forceinline__ bool visible1(const int4 *rects, int rstride, int num_obs, int px, int py, int qx, int qy) {
-    bool hit = false;
+    int hit = 0;
 #pragma unroll
     for (int k = 0; k < KMAX; k++)
-        if (k < num_obs) hit = hit || (seg_rect(px, py, qx, qy, rects[k * rstride]) & 1);
-    return !hit;
-}
-template <int KMAX>
-__device__ __noinline__ bool visible1_call(const int4 *rects, int rstride, int num_obs, int px, int py, int qx, int qy) {
-    return visible1<KMAX>(rects, rstride, num_obs, px, py, qx, qy);
+        if (k < num_obs) hit |= seg_rect(px, py, qx, qy, rects[k * rstride]);      // every rectangle: no lane leaves early
+    return !(hit & 1);
 }
 
 // Marking pass of the pruned shortest path: the corners that may still improve on the upper bound `best`.  A corner c
@@ -132,38 +138,39 @@ __device__ __forceinline__ uint32_t mark1(const int4 *rects, int rstride, int nu
     return mask;
 }
 
-// Shortest path source -> p around the rectangles for a unit whose source segment is obstructed; drow = the env's row of
-// RsState.dsrc (global memory: only the hint's and the surviving corners' entries are read), dsf = the float lower bounds
-// of the same row.  Exactly the value of shortest_path() / shortest_path_pruned().
+// Pruned shortest path source -> p for a unit whose source segment is obstructed, in two halves.
+// (1) sp_hint_mark1: the upper bound through the corner that was optimal at the previous step (`hint`; ds_hint = its
+//     dsrc entry, fetched by the caller ahead of time; any hint is allowed, it only seeds the bound), then the marking
+//     pass.  best / besti = the value through the hint (inf / -1 when it is unusable); returns the marked corners.
+// (2) sp_pair1, once per marked corner: its exact candidate if it beats `best` and is visible from p, else inf.
+// The minimum of best and the pair values is exactly shortest_path() / shortest_path_pruned() of rs_env_impl.cuh.
 template <int KMAX>
-__device__ __forceinline__ double shortest_path1(const int4 *rects, int rstride, int num_obs, const double *drow,
-                                                 const float *dsf, int px, int py, int &hint) {
+__device__ __forceinline__ uint32_t sp_hint_mark1(const int4 *rects, int rstride, int num_obs, const float *dsf, int px,
+                                                  int py, int hint, double ds_hint, double &best, int &besti) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int nc = 4 * num_obs;
-    double best = inf;
-    int besti = -1;
-    if (hint < nc) {
-        const int4 r = rects[(hint >> 2) * rstride];
-        const int cx = corner_x(r, hint & 3), cy = corner_y(r, hint & 3);
-        const double ds = drow[hint];
-        if (ds < inf && visible1<KMAX>(rects, rstride, num_obs, px, py, cx, cy)) {
-            best = ds + dist_int(px - cx, py - cy);
-            besti = hint;
-        }
-    }
-    const float bf = best < inf ? __fmul_ru(__double2float_ru(best), 1.000001f) : __int_as_float(0x7f800000);
+    // evaluated on every lane, usable or not: no branch around the root and the visibility test
+    const int hc = hint < nc ? hint : 0;
+    const int4 r = rects[(hc >> 2) * rstride];
+    const int cx = corner_x(r, hc & 3), cy = corner_y(r, hc & 3);
+    const bool vis = visible1<KMAX>(rects, rstride, num_obs, px, py, cx, cy);
+    const double cand = ds_hint + dist_int(px - cx, py - cy);
+    const bool ok = hint < nc && ds_hint < inf && vis;
+    best = ok ? cand : inf;
+    besti = ok ? hint : -1;
+    const float bf = ok ? __fmul_ru(__double2float_ru(cand), 1.000001f) : __int_as_float(0x7f800000);
     uint32_t mask = mark1<KMAX>(rects, rstride, num_obs, dsf, px, py, bf);
-    if (besti >= 0) mask &= ~(1u << besti);
-    while (mask) {
-        const int c = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int4 r = rects[(c >> 2) * rstride];
-        const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
-        const double cand = drow[c] + dist_int(px - cx, py - cy);
-        if (cand < best && visible1_call<KMAX>(rects, rstride, num_obs, px, py, cx, cy)) { best = cand; besti = c; }
-    }
-    if (besti >= 0) hint = besti;
-    return best;
+    if (ok) mask &= ~(1u << hint);
+    return mask;
+}
+template <int KMAX>
+__device__ __forceinline__ double sp_pair1(const int4 *rects, int rstride, int num_obs, int px, int py, int c, double ds,
+                                           double best) {
+    const int4 r = rects[(c >> 2) * rstride];
+    const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
+    const double cand = ds + dist_int(px - cx, py - cy);
+    const bool vis = visible1<KMAX>(rects, rstride, num_obs, px, py, cx, cy);
+    return (cand < best && vis) ? cand : __longlong_as_double(0x7ff0000000000000LL);
 }
 
 // RS_F_FAST_POISSON draw from the unit's first Philox block x[0..3] (counter block 0 of the stream poisson_f32 walks):
@@ -220,28 +227,27 @@ __device__ __forceinline__ long long count_exact1(const StepArgs &a, int n, uint
     return ok ? k : count_exact_retry(a, n, step_ctr, lam, status);
 }
 
-// What the front half of a step leaves in registers for the sensing and commit halves.
-struct Unit1 {
+// What take_action and the segment to the source leave in registers.
+struct Move1 {
     int2 det;            // position after take_action
-    int af;              // aflags with this step's changes (oob count, blocked bit, hint corner)
+    int af;              // aflags with this step's changes (oob count, blocked bit)
     int uf;              // UF_MOVED | UF_OOB | UF_NEED_D | sensor candidate rectangles << 16
-    double sp;           // shortest-path length
-    bool blocked_los;    // is_intersect R:1133-1146
-    float count;         // raw Poisson count
+    int d2;              // |det - src|^2
+    bool direct;         // source and detector see each other: the shortest path is the segment
+    bool blocked_raw;    // boundary_distance(segment, some rectangle) < 0.001 (R:1139-1141 without the isclose clause)
     uint32_t status;
 };
 
-// take_action, the detector -> source segment, the shortest path and the measurement of one unit.  rects / dsf: the unit's
-// rectangle column (element k at rects[k * rstride]) and float table row in shared memory; x = Philox block 0 (kFast).
-template <bool kFast, int KMAX>
-__device__ __forceinline__ Unit1 unit1_front(const Params &P, const RsState &S, const StepArgs &a, const int4 *rects,
-                                             int rstride, const float *dsf, int n, int2 src, int2 rad, int meta, int action,
-                                             int2 det, int af, uint64_t step_ctr, const uint32_t x[4]) {
-    Unit1 o;
+// take_action R:876-946 (one agent: no collision), the detector -> source segment, the sensor candidates.  rects: the
+// unit's rectangle column in shared memory (element k at rects[k * rstride]).
+template <int KMAX>
+__device__ __forceinline__ Move1 unit1_move(const Params &P, const int4 *rects, int rstride, int2 src, int meta, int action,
+                                            int2 det, int af) {
+    Move1 m;
     const int num_obs = meta & 0xff;
     int uf = 0;
     uint32_t status = 0;
-    if (action >= 0) {                                                  // take_action R:876-946 (one agent: no collision)
+    if (action >= 0) {
         const int tx = det.x + step_dx(action), ty = det.y + step_dy(action);
         bool roll = false;
         if (P.enforce) {
@@ -253,8 +259,7 @@ __device__ __forceinline__ Unit1 unit1_front(const Params &P, const RsState &S, 
         if (!roll) { det.x = tx; det.y = ty; uf |= UF_MOVED; }
     }
     if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
-    bool direct, blocked_raw;
-    source_segment1<KMAX>(rects, rstride, num_obs, det.x, det.y, src.x, src.y, direct, blocked_raw);
+    source_segment1<KMAX>(rects, rstride, num_obs, det.x, det.y, src.x, src.y, m.direct, m.blocked_raw);
     int cand = 0;                                                       // sensor candidates: a ray is at most 100 long
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
@@ -265,22 +270,40 @@ __device__ __forceinline__ Unit1 unit1_front(const Params &P, const RsState &S, 
     }
     if (cand) uf |= UF_NEED_D | (cand << 16);
     const int ddx = det.x - src.x, ddy = det.y - src.y;
-    const int d2 = ddx * ddx + ddy * ddy;
-    double sp, euc = 0.0;
+    m.d2 = ddx * ddx + ddy * ddy;
+    m.det = det; m.af = af; m.uf = uf; m.status = status;
+    return m;
+}
+
+// What the measurement leaves for the sensing and commit halves.
+struct Unit1 {
+    int2 det;
+    int af;              // aflags incl. the hint corner of the next step
+    int uf;
+    double sp;           // shortest-path length
+    bool blocked_los;    // is_intersect R:1133-1146
+    float count;         // raw Poisson count
+    uint32_t status;
+};
+
+// Shortest-path value -> line of sight -> expected counts -> Poisson draw.  sp_blocked / hint: the pruned search's result for
+// a unit whose segment is obstructed (ignored for direct units); x = Philox block 0 of the unit (kFast).
+template <bool kFast>
+__device__ __forceinline__ Unit1 unit1_measure(const Params &P, const StepArgs &a, const Move1 &m, int n, int2 rad,
+                                               double sp_blocked, int hint, uint64_t step_ctr, const uint32_t x[4]) {
+    Unit1 o;
+    uint32_t status = m.status;
     // euc is needed where it is the answer (direct), where it sets the expected count (line of sight free) and for the
-    // isclose leftover (euc <= 2); the other units -- most of them -- never take the root
-    const bool need_euc = direct || !blocked_raw || d2 <= 4;
-    if (need_euc) euc = sqrt((double)d2);
-    if (direct) sp = euc;
-    else {
-        int hint = (af >> 25) & 31;
-        sp = shortest_path1<KMAX>(rects, rstride, num_obs, S.dsrc + (size_t)n * 4 * P.k_max, dsf, det.x, det.y, hint);
-        af = (af & ~(31 << 25)) | (hint << 25);
-    }
+    // isclose leftover (euc <= 2, i.e. d2 <= 4); the other units -- most of them -- never take the root
+    double euc = 0.0;
+    if (m.direct || !m.blocked_raw || m.d2 <= 4) euc = sqrt((double)m.d2);
+    const double sp = m.direct ? euc : sp_blocked;
+    int af = m.af;
+    if (!m.direct) af = (af & ~(31 << 25)) | (hint << 25);
     // is_intersect R:1133-1146 = blocked_raw && !isclose(sqrt(euc), sp, abs_tol=0.1); the isclose clause can only hold for
     // euc <= 2 (see rs_step_tiled.cuh)
-    bool blocked_los = blocked_raw;
-    if (d2 <= 4) blocked_los = blocked_los && !isclose_quirk(euc, sp);
+    bool blocked_los = m.blocked_raw;
+    if (m.d2 <= 4) blocked_los = blocked_los && !isclose_quirk(euc, sp);
     EnvView e;
     e.intensity = rad.x; e.bkg = rad.y;
     long long k;
@@ -293,7 +316,7 @@ __device__ __forceinline__ Unit1 unit1_front(const Params &P, const RsState &S, 
         const double lam = unit_lambda(P, e, euc, blocked_los, status);
         k = count_exact1(a, n, step_ctr, lam, status);
     }
-    o.det = det; o.af = af; o.uf = uf; o.sp = sp; o.blocked_los = blocked_los; o.count = (float)k; o.status = status;
+    o.det = m.det; o.af = af; o.uf = m.uf; o.sp = sp; o.blocked_los = blocked_los; o.count = (float)k; o.status = status;
     return o;
 }
 

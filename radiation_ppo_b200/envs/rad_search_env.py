@@ -269,7 +269,10 @@ class RadSearch:
         self._pending = [False, False]      # list holds envs waiting for rs_prepare
         self._inflight = [False, False]     # an rs_prepare draining the list is running on the side stream
         self._graphs = {}
+        self._block_graphs = {}
+        self._refill_dirty = False
         self._act_buf = z(N, A)
+        self._act_block = z(self.PREFETCH_PERIOD, N, A) if self.use_cuda_graph else None
         self._ctr_dev_val = 0               # host mirror of *ctr_dev (graph replays advance both)
         # step outputs: views into ONE flat allocation (256-byte aligned segments) so that a host consumer gets them with
         # a single device->host copy (step_host)
@@ -322,34 +325,63 @@ class RadSearch:
                 self._launch_prepare(0, use_list=False)      # next episodes of everybody, against the current obstructions
         return self.obs
 
+    _OUT_SPEC = (("obs", "obs", torch.float32), ("reward", "reward", torch.float32),
+                 ("team_reward", "team_reward", torch.float32), ("done", "done_flags", torch.uint8),
+                 ("info", "info_flags", torch.uint8), ("ended", "ended", torch.uint8), ("final_obs", "final_obs", torch.float32))
+
+    def _outputs(self, out: Optional[Dict[str, torch.Tensor]]):
+        """The seven output tensors of a step: the env's own, or the caller's where `out` names one (same shape and dtype,
+        contiguous, on this device) -- e.g. the rows of a rollout buffer, so that the kernel stores straight into them."""
+        if not out:
+            return (self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended, self.final_obs)
+        unknown = set(out) - {k for k, _, _ in self._OUT_SPEC}
+        if unknown:
+            raise ValueError(f"unknown step outputs {sorted(unknown)}")
+        res = []
+        for key, attr, dt in self._OUT_SPEC:
+            own = getattr(self, attr)
+            t = out.get(key)
+            if t is None:
+                res.append(own)
+                continue
+            if t.dtype != dt or t.device != own.device or t.numel() != own.numel() or not t.is_contiguous():
+                raise ValueError(f"out[{key!r}] must be a contiguous {dt} tensor of {own.numel()} elements on {own.device}")
+            res.append(t)
+        return tuple(res)
+
     def step_batch(self, actions: Optional[torch.Tensor], epoch_end: bool = False,
-                   uniforms: Optional[torch.Tensor] = None, auto_reset: Optional[bool] = None):
+                   uniforms: Optional[torch.Tensor] = None, auto_reset: Optional[bool] = None,
+                   out: Optional[Dict[str, torch.Tensor]] = None):
         """One step for every env.  actions: int32 CUDA tensor [N] or [N, A] (None = the reference's step(None) probe).
         Returns (obs, reward, team_reward, done, info, ended); with auto-reset, envs that finished have already been
-        reset, `obs` holds their first observation and `final_obs` the last one of the finished episode."""
+        reset, `obs` holds their first observation and `final_obs` the last one of the finished episode.
+        out: tensors that receive the step's outputs instead of the env's own (keys obs, reward, team_reward, done, info,
+        ended, final_obs) -- BatchedPPOBuffer.step_outputs(t) hands out its rows this way, so a rollout needs no copies."""
         ar = self.auto_reset if auto_reset is None else auto_reset
         a = None
         if actions is not None:
             a = actions.to(device=self.device, dtype=torch.int32).reshape(self.num_envs, self.number_agents).contiguous()
         u = None if uniforms is None else uniforms.to(device=self.device, dtype=torch.float64).contiguous()
+        outs = self._outputs(out)
         self._ctr += 1
         if ar and self.prefetch and a is not None and u is None:
-            self._step_prefetch(a, epoch_end)
-            return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+            self._step_prefetch(a, epoch_end, outs if out else None)
+            return outs[:6]
         self._quiesce_prefetch()
+        o_obs, o_rew, o_team, o_done, o_info, o_ended, o_final = outs
         flags = self._base_flags() | (L.F_AUTO_RESET if ar else 0) | (L.F_EPOCH_END if (ar and epoch_end) else 0)
         with torch.cuda.device(self.device):
-            L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
-                                      _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
-                                      _ptr(self.ended), _ptr(self.final_obs) if ar else None, self.num_envs,
+            L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(o_obs), _ptr(o_rew),
+                                      _ptr(o_team), _ptr(o_done), _ptr(o_info),
+                                      _ptr(o_ended), _ptr(o_final) if ar else None, self.num_envs,
                                       self.env_id_offset, self.seed, self._ctr, _ptr(u),
                                       0 if u is None else u.shape[-1], flags, self._stream()), "rs_step")
             if ar:
                 rflags = self._base_flags() | L.F_RESET_LIST | (L.F_NEW_OBSTACLES if epoch_end else 0)
-                L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(self.obs),
+                L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(o_obs),
                                            self.num_envs, self.env_id_offset, self.seed, self._ctr, None, 0, rflags,
                                            self._stream()), "rs_reset")
-        return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+        return outs[:6]
 
     # ---- prefetch machinery -------------------------------------------------------------------------------------
     # Steps are grouped in blocks of PREFETCH_PERIOD (4: one rs_prepare launch must finish within a block); the envs that adopt their prefetched episode during block b are
@@ -366,31 +398,36 @@ class RadSearch:
             return
         if any(self._inflight):
             torch.cuda.current_stream(self.device).wait_stream(self._side)
+        if any(self._pending) or self._refill_dirty:
+            self._refill_count.zero_()              # nothing stale for an unconditional rs_prepare (block graphs) to redo
+            self._refill_dirty = False
         self._inflight = [False, False]
         self._pending = [False, False]
         self._blk_pos = 0
 
-    def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool, first: bool) -> None:
+    def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool, first: bool, outs=None) -> None:
         """rs_step (which starts refill list p when `first`) + rs_reset(list) on the current stream; with the device
         step counter the reset kernel's last CTA advances it (RS_F_BUMP_CTR): two launches per step."""
+        o_obs, o_rew, o_team, o_done, o_info, o_ended, o_final = outs if outs is not None else self._outputs(None)
         pf = L.F_PREFETCH | (L.F_PARITY1 if p else 0) | (L.F_DEVICE_CTR if device_ctr else 0)
         flags = self._base_flags() | L.F_AUTO_RESET | pf | (L.F_EPOCH_END if epoch_end else 0) | \
             (L.F_ZERO_REFILL if first else 0)
-        L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(self.obs), _ptr(self.reward),
-                                  _ptr(self.team_reward), _ptr(self.done_flags), _ptr(self.info_flags),
-                                  _ptr(self.ended), _ptr(self.final_obs), self.num_envs, self.env_id_offset, self.seed,
+        L.check(self._lib.rs_step(C.byref(self._cfg), C.byref(self._st), _ptr(a), _ptr(o_obs), _ptr(o_rew),
+                                  _ptr(o_team), _ptr(o_done), _ptr(o_info),
+                                  _ptr(o_ended), _ptr(o_final), self.num_envs, self.env_id_offset, self.seed,
                                   self._ctr, None, 0, flags, self._stream()), "rs_step")
         rflags = self._base_flags() | L.F_RESET_LIST | pf | (L.F_NEW_OBSTACLES if epoch_end else 0) | \
             (L.F_BUMP_CTR if device_ctr else 0)
-        L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(self.obs), self.num_envs,
+        L.check(self._lib.rs_reset(C.byref(self._cfg), C.byref(self._st), None, None, _ptr(o_obs), self.num_envs,
                                    self.env_id_offset, self.seed, self._ctr, None, 0, rflags, self._stream()), "rs_reset")
+        self._refill_dirty = True
 
     def _launch_prepare(self, p: int, use_list: bool = True) -> None:
         flags = self._base_flags() | (L.F_REFILL_LIST if use_list else 0) | (L.F_PARITY1 if p else 0)
         L.check(self._lib.rs_prepare(C.byref(self._cfg), C.byref(self._st), self.num_envs, self.env_id_offset, self.seed,
                                      flags, self._stream()), "rs_prepare")
 
-    def _step_prefetch(self, a: torch.Tensor, epoch_end: bool) -> None:
+    def _step_prefetch(self, a: torch.Tensor, epoch_end: bool, outs=None) -> None:
         dev = self.device
         main = torch.cuda.current_stream(dev)
         p, first = self._blk_par, self._blk_pos == 0
@@ -398,7 +435,7 @@ class RadSearch:
             if epoch_end:
                 # new obstructions for everybody: nothing may be preparing scenarios against the old ones
                 self._quiesce_prefetch()
-                self._launch_step_sequence(a, p, True, False, True)
+                self._launch_step_sequence(a, p, True, False, True, outs)
                 self._pending[p] = True                 # the reset pushed every env to list p
                 self._blk_par, self._blk_pos = p ^ 1, 0
                 return
@@ -413,7 +450,7 @@ class RadSearch:
                 if self._inflight[p]:                   # list p is about to be reused: its rs_prepare must be done
                     main.wait_event(self._ev_side[p])
                     self._inflight[p] = False
-            if self.use_cuda_graph:
+            if self.use_cuda_graph and outs is None:                     # (a captured graph stores to the env's own outputs)
                 if a.data_ptr() != self._act_buf.data_ptr():             # the caller may fill action_buffer in place
                     self._act_buf.copy_(a)
                 key = (p, first)
@@ -426,20 +463,91 @@ class RadSearch:
                 g.replay()
                 self._ctr_dev_val = self._ctr + 1
             else:
-                self._launch_step_sequence(a, p, False, False, first)
+                self._launch_step_sequence(a, p, False, False, first, outs)
             self._pending[p] = True
             self._blk_pos += 1
             if self._blk_pos == self.PREFETCH_PERIOD:
                 self._blk_par, self._blk_pos = p ^ 1, 0
 
     def capture_graphs(self) -> None:
-        """Capture the four step-graph variants (refill list 0/1 x first-step-of-block) ahead of time."""
+        """Capture the four step-graph variants (refill list 0/1 x first-step-of-block) and the two block graphs ahead of
+        time."""
         if not self.use_cuda_graph:
             return
         for p in (0, 1):
             for first in (False, True):
                 if (p, first) not in self._graphs:
                     self._graphs[(p, first)] = self._capture(p, first)
+            if p not in self._block_graphs:
+                self._block_graphs[p] = self._capture_block(p)
+
+    @property
+    def action_block(self) -> torch.Tensor:
+        """int32 [PREFETCH_PERIOD, N, A] device buffer step_block reads its actions from."""
+        return self._act_block
+
+    def step_block(self, actions: Optional[torch.Tensor] = None):
+        """PREFETCH_PERIOD consecutive steps (+ auto-resets) replayed as ONE CUDA graph: the 2 x PERIOD kernel launches
+        of the block on the current stream and, on a parallel branch, the rs_prepare that refills the next episodes of the
+        envs that finished during the previous block.  For callers that have the block's actions up front (open-loop
+        rollouts, Monte-Carlo evaluation with a scripted policy, throughput measurement): one graph launch per PERIOD steps
+        instead of one per step.  actions: int32 [PERIOD, N(, A)] (None: action_block was filled in place).  The outputs
+        left in obs / reward / ... are those of the block's last step.  Same results as PERIOD step_batch calls."""
+        if not self.use_cuda_graph:
+            raise ValueError("step_block needs auto_reset=True, prefetch=True, use_cuda_graph=True")
+        if self._blk_pos != 0:
+            raise ValueError("step_block must start at a block boundary (a multiple of PREFETCH_PERIOD steps since the "
+                             "last reset / epoch end)")
+        dev, P = self.device, self.PREFETCH_PERIOD
+        main = torch.cuda.current_stream(dev)
+        p = self._blk_par
+        with torch.cuda.device(dev):
+            if actions is not None and actions.data_ptr() != self._act_block.data_ptr():
+                self._act_block.copy_(actions.reshape(P, self.num_envs, self.number_agents))
+            if any(self._inflight):                     # a stream-launched rs_prepare: order it before the graph
+                main.wait_stream(self._side)
+                self._inflight = [False, False]
+            g = self._block_graphs.get(p)
+            if g is None:
+                g = self._block_graphs[p] = self._capture_block(p)
+            if self._ctr_dev_val != self._ctr + 1:
+                self._ctr_dev.fill_(self._ctr + 1)
+                self._reset_count.zero_()
+            g.replay()
+        self._ctr += P
+        self._ctr_dev_val = self._ctr + 1
+        self._pending[p], self._pending[p ^ 1] = True, False      # the graph's rs_prepare drained the other list
+        self._refill_dirty = True
+        self._blk_par = p ^ 1
+        return self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended
+
+    def _capture_block(self, p: int):
+        """{rs_prepare(list p^1) on a side branch || PERIOD x (rs_step -> rs_reset(list p))} captured once per parity."""
+        dev = self.device
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        ctr = self._ctr
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="relaxed"):
+                    fork.record(cap)
+                    self._side.wait_event(fork)
+                    with torch.cuda.stream(self._side):
+                        self._launch_prepare(p ^ 1)
+                        join.record(self._side)
+                    for i in range(self.PREFETCH_PERIOD):
+                        self._launch_step_sequence(self._act_block[i], p, False, True, i == 0)
+                    cap.wait_event(join)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        self._ctr = ctr
+        self._ctr_dev_val = -1
+        return g
 
     def _capture(self, p: int, first: bool):
         """Capture {rs_step -> rs_reset(list), whose last CTA bumps the device step counter} once; replayed per step."""

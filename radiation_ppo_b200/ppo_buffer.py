@@ -182,18 +182,15 @@ class PPOBuffer:
         mean, std = advantage_statistics(self.adv_buf)
         normalize_advantages_(self.adv_buf, mean.float().double(), std.float().double())
         self.quick_reset()
-        episode_len_size = number_episodes + int(total_episode_length != len(self.obs_buf))
-        stacked = torch.cat((self.obs_buf, self.adv_buf[:, None], self.ret_buf[:, None], self.logp_buf[:, None],
-                             self.act_buf[:, None], self.source_tar), dim=1)
-        episode_form: List[List[torch.Tensor]] = [[] for _ in range(episode_len_size)]
-        slice_b = slice_f = jj = 0
-        for ep_i in episode_lengths:
-            slice_f += ep_i
-            episode_form[jj].append(stacked[slice_b:slice_f].clone())
-            slice_b += ep_i
-            jj += 1
-        if slice_f != len(self.obs_buf):
-            episode_form[jj].append(stacked[slice_f:].clone())
+        # ep_form (P:456-486): one [len, D + 6] tensor of [obs | adv | ret | logp | act | source_tar] rows per recorded
+        # episode, plus the unfinished tail of the buffer when the recorded lengths do not cover it
+        rows = torch.cat((self.obs_buf, self.adv_buf[:, None], self.ret_buf[:, None], self.logp_buf[:, None],
+                          self.act_buf[:, None], self.source_tar), dim=1)
+        sizes = list(episode_lengths)
+        tail = rows.shape[0] - total_episode_length
+        if tail:
+            sizes.append(tail)
+        episode_form: List[List[torch.Tensor]] = [[piece.clone()] for piece in torch.split(rows, sizes, dim=0)]
         return dict(
             obs=self.obs_buf.clone(), act=self.act_buf.clone(), ret=self.ret_buf.clone(), adv=self.adv_buf.clone(),
             logp=self.logp_buf.clone(), loc_pred=self.obs_win_std.clone(),
@@ -218,7 +215,10 @@ class BatchedPPOBuffer:
         self.T, self.N, self.D = T, N, D
         self.gamma, self.lam = gamma, lam
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=self.device)   # noqa: E731
-        self.obs_buf = z(T, N, D)
+        # T + 1 observation rows: row t is what the policy saw at step t, row T the observation that follows the epoch's
+        # last step (it opens the next epoch).  A step kernel that is handed step_outputs(t) stores row t + 1 itself.
+        self._obs_store = z(T + 1, N, D)
+        self.obs_buf = self._obs_store[:T]
         self.act_buf = z(T, N)
         self.rew_buf, self.val_buf, self.logp_buf = z(T, N), z(T, N), z(T, N)
         self.adv_buf, self.ret_buf = z(T, N), z(T, N)
@@ -230,6 +230,32 @@ class BatchedPPOBuffer:
 
     def quick_reset(self) -> None:
         self.ptr = 0
+
+    # ---- zero-copy rollout (P:339-381 without the per-step copies): the env step and the policy write the rows ---------
+    def start_epoch(self, first_obs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Row 0 of the epoch: `first_obs` (the env's reset observation) or, when omitted, the observation that followed
+        the previous epoch's last step.  Returns the row (the policy's first input)."""
+        self.ptr = 0
+        self._obs_store[0].copy_(self._obs_store[self.T] if first_obs is None else first_obs.reshape(self.N, self.D))
+        return self._obs_store[0]
+
+    def step_outputs(self, t: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """What RadSearch.step_batch(..., out=) should fill for step t (default: the current one): the observation the
+        policy sees next -> obs row t + 1, the step's reward -> rew_buf[t], its path-end flags (rs_step's `ended` byte is
+        non-zero exactly where train.py:446-491 finishes a trajectory) -> end_buf[t]."""
+        t = self.ptr if t is None else t
+        assert 0 <= t < self.T
+        return {"obs": self._obs_store[t + 1], "reward": self.rew_buf[t], "ended": self.end_buf[t]}
+
+    def policy_rows(self, t: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """Rows of step t the policy side fills: obs (read), act / val / logp / boot / src (write)."""
+        t = self.ptr if t is None else t
+        return {"obs": self._obs_store[t], "act": self.act_buf[t], "val": self.val_buf[t], "logp": self.logp_buf[t],
+                "boot": self.boot_buf[t], "src": self.source_tar[t]}
+
+    def advance(self) -> None:
+        assert self.ptr < self.T
+        self.ptr += 1
 
     def store_batch(self, obs, act, rew, val, logp, src=None, end=None, boot=None) -> None:
         assert self.ptr < self.T

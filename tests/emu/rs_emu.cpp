@@ -26,7 +26,24 @@ static void step1_env(const rs::Params &P, const RsState *st, const rs::StepArgs
         rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
                           (uint32_t)(a.seed >> 32), x);
     float row[RS_OBS_DIM] = {0};
-    const rs::Unit1 o = rs::unit1_front<kFast, KMAX>(P, *st, a, rects, 1, dsf, n, src, rad, meta, action, det, af, step_ctr, x);
+    const int num_obs = meta & 0xff, hint = (af >> 25) & 31;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double *drow = st->dsrc + (size_t)n * 4 * K;
+    const rs::Move1 mv = rs::unit1_move<KMAX>(P, rects, 1, src, meta, action, det, af);
+    double best_sp = 0.0;
+    int besti = -1;
+    if (!mv.direct) {
+        const double ds_hint = hint < 4 * num_obs ? drow[hint] : inf;
+        uint32_t marked = rs::sp_hint_mark1<KMAX>(rects, 1, num_obs, dsf, mv.det.x, mv.det.y, hint, ds_hint, best_sp, besti);
+        const double best0 = best_sp;                  // every pair is judged against the hint's bound, as on the GPU
+        while (marked) {
+            const int c = __ffs(marked) - 1;
+            marked &= marked - 1;
+            const double v = rs::sp_pair1<KMAX>(rects, 1, num_obs, mv.det.x, mv.det.y, c, drow[c], best0);
+            if (v < best_sp) { best_sp = v; besti = c; }
+        }
+    }
+    const rs::Unit1 o = rs::unit1_measure<kFast>(P, a, mv, n, rad, best_sp, besti >= 0 ? besti : hint, step_ctr, x);
     uint32_t status = o.status;
     if (o.uf & rs::UF_NEED_D) {
         unsigned long long hits = 0ull;
