@@ -171,10 +171,10 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
 /* GAE-lambda advantages and rewards-to-go over a [T][N] rollout.  path_end[t][n] != 0 where the caller finished a
  * trajectory after step t; boot[t][n] = bootstrap value passed there (read only where path_end or t == T-1).
  * stats (nullable): double[2] device accumulators += {sum(adv), sum(adv^2)} (zero them first).
- * variant: 0 auto; 1 thread-per-column recurrence (bit-exact vs the reference; fed by bulk-async tile copies when
- * N % 128 == 0 and the arrays are 16-byte aligned, else by register-pipelined loads); 2 warp-shuffle scan along T;
- * 3/4/5 force the 8- / 16- / 4-deep register-pipelined instantiation, 6/7/10 the copy-engine tiles (4x4 / 8x3 stages of
- * 128 columns, 8x3 of 64 columns), 8/9 the producer-warp form (tuning). */
+ * variant: 0 auto; 1 thread-per-column recurrence in the reference's operation order (bit-exact vs scipy's lfilter), fed by
+ * bulk-async tile copies when N % 128 == 0 and the arrays are 16-byte aligned, else by register-pipelined loads; 2 warp-
+ * shuffle scan along T (small N; within 1e-5).  3 / 4 force the 8- / 16-deep register-pipelined form, 7 the 3-stage tile
+ * ring, 8 / 9 / 11 the producer-warp form with 3 x 8, 6 x 4 and 6 x 8 rows in flight -- all bit-identical to variant 1. */
 int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
            int32_t T, int32_t N, double gamma, double lam, double *stats, int32_t variant, void *stream);
 

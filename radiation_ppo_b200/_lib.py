@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libradsearch_b200.so")
+# RADSEARCH_B200_LIB: another build of the same library (e.g. one made with different -D tuning macros, see build.py)
+LIB_PATH = os.environ.get("RADSEARCH_B200_LIB") or os.path.join(HERE, "_C", "libradsearch_b200.so")
 
 OBS_DIM, MAX_K, MAX_A = 11, 8, 8
 F_AUTO_RESET, F_EPOCH_END, F_RESET_LIST, F_NEW_OBSTACLES, F_FAST_POISSON = 1, 2, 4, 8, 16

@@ -29,16 +29,21 @@ def _newest_source_mtime() -> float:
     return m
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
-        return LIB
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """defines / out: a variant build with -D tuning macros (e.g. RS_STEP1_OCC=8) written next to the shipped library;
+    load it with RADSEARCH_B200_LIB=<path> (measurement only: tools/gpu_variants.sh)."""
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_source_mtime():
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *( ["-Xptxas", "-v"] if verbose else []), "-o", LIB,
+    cmd = [nvcc, *NVCC_FLAGS, *( ["-Xptxas", "-v"] if verbose else []), *[f"-D{d}" for d in defines], "-o", out,
            *[os.path.join(SRC_DIR, s) for s in SOURCES]]
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=os.path.join(OUT_DIR, outs[0]) if outs else LIB))

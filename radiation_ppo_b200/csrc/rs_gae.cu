@@ -222,10 +222,15 @@ __global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(cons
                                                                            const uint8_t *__restrict__ pe, const float *__restrict__ boot,
                                                                            float *__restrict__ adv, float *__restrict__ ret, int T, int N,
                                                                            double gamma, double gl, double *stats) {
-    __shared__ __align__(128) float s_rew[S][U][kColsBlock];
-    __shared__ __align__(128) float s_val[S][U][kColsBlock];
-    __shared__ __align__(128) uint8_t s_pe[S][U][kColsBlock];
-    __shared__ __align__(8) uint64_t full[S], empty[S];
+    // dynamic shared memory (the 6-stage form needs 54 KB): [S][U][128] rew | val | path_end, then the barriers
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    typedef float (*TileF)[U][kColsBlock];
+    typedef uint8_t (*TileB)[U][kColsBlock];
+    TileF s_rew = reinterpret_cast<TileF>(ws_smem);
+    TileF s_val = reinterpret_cast<TileF>(ws_smem + sizeof(float) * S * U * kColsBlock);
+    TileB s_pe = reinterpret_cast<TileB>(ws_smem + 2 * sizeof(float) * S * U * kColsBlock);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ws_smem + 9 * S * U * kColsBlock);
+    uint64_t *empty = full + S;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * kColsBlock, n = n0 + tid;
     const int chunks = (T + U - 1) / U;
@@ -504,27 +509,25 @@ int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const fl
         // would otherwise not all be resident in one wave (N = 131072: 886 threads per SM)
         const bool tile_ok = (N % kColsBlock) == 0 && ((reinterpret_cast<uintptr_t>(rew) | reinterpret_cast<uintptr_t>(val) |
                                                         reinterpret_cast<uintptr_t>(path_end)) & 15) == 0;
-        if (variant >= 6 && variant <= 10 && !tile_ok) return rs_set_error("rs_gae: variant 6 needs N % 128 == 0 and 16-byte aligned arrays");
+        if (variant >= 7 && variant <= 11 && !tile_ok) return rs_set_error("rs_gae: the tile variants need N % 128 == 0 and 16-byte aligned arrays");
         // auto: the copy-engine variants whenever the tiles are whole and fill the GPU (measured on B200, T = 480:
         // N = 131072 -> 4.9 TB/s with the plain ring, N = 65536 -> 3.4 TB/s with the producer warp; register-pipelined
         // loads 3.9 / 2.7 TB/s)
         if (variant == 0 || variant == 1) {
             if (tile_ok && (long long)N >= 148LL * 128 * 4) variant = 7;
-            else if (tile_ok && N >= 16384) variant = 8;      // measured: 16384 -> 122 us (159), 32768 -> 132 us (171)
+            else if (tile_ok && N >= 16384) variant = 11;     // <= 4 CTAs per SM: twice the stages in flight per CTA
         }
-        if (variant == 6)
-            gae_tile_kernel<128, 4, 4, 8><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 7)
+        if (variant == 7)
             gae_tile_kernel<128, 8, 3, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 10)
-            gae_tile_kernel<64, 8, 3, 14><<<N / 64, 64, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 8)
-            gae_tile_ws_kernel<8, 3, 7><<<grid, kColsBlock + 32, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 9)
-            gae_tile_ws_kernel<4, 6, 7><<<grid, kColsBlock + 32, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 5)
-            gae_cols_kernel<4, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 3 || (variant != 4 && (long long)grid > 148LL * 4))
+            gae_tile_ws_kernel<8, 3, 7><<<grid, kColsBlock + 32, 9 * 3 * 8 * kColsBlock + 2 * 3 * 8, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 11) {
+            // 6 stages of 8 rows (54 KB of tiles per CTA, 4 CTAs per SM): mid-size rollouts (N < 75776 columns) do not fill
+            // the SMs with CTAs, so each CTA keeps more bytes in flight instead
+            constexpr int smem11 = 9 * 6 * 8 * kColsBlock + 2 * 6 * 8;
+            cudaFuncSetAttribute(gae_tile_ws_kernel<8, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem11);
+            gae_tile_ws_kernel<8, 6, 4><<<grid, kColsBlock + 32, smem11, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        } else if (variant == 3 || (variant != 4 && (long long)grid > 148LL * 4))
             gae_cols_kernel<8, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else
             gae_cols_kernel<16, 1><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);

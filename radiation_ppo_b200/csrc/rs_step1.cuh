@@ -78,6 +78,12 @@ __device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, 
                                                 bool &direct, bool &blocked) {
     const int dx = sx - px, dy = sy - py;
     const int l2 = dx * dx + dy * dy;
+    // rectangles that hold the source strictly inside (none in a valid scenario): there, a detector strictly inside the
+    // same rectangle meets no boundary
+    int src_in = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; k++)
+        if (k < num_obs && in_rect_open(sx, sy, rects[k * rstride])) src_in |= 1 << k;
     int acc = 0;                                            // bit 0: some open rectangle met, bit 1: some boundary within 0.001
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
@@ -85,9 +91,8 @@ __device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, 
             const int4 r = rects[k * rstride];
             int cr[4];
             const int h = seg_rect(px, py, sx, sy, r, cr);
-            // (both end points strictly inside the rectangle: no boundary is met; the source never is, so test it first)
             int b = h & 2;
-            if (b && in_rect_open(sx, sy, r) && in_rect_open(px, py, r)) b = 0;
+            if (src_in && ((src_in >> k) & 1) && in_rect_open(px, py, r)) b = 0;
             // near-corner clause (|cross| <= 3, |pq| > 1000): guarded by one unsigned minimum over the four cross products
             const unsigned g = min(min((unsigned)(cr[0] + 3), (unsigned)(cr[1] + 3)),
                                    min((unsigned)(cr[2] + 3), (unsigned)(cr[3] + 3)));
@@ -370,6 +375,21 @@ __device__ __forceinline__ int sense_dir1(const int4 *rects, int rstride, int ca
         hits += (unsigned long long)hk << (8 * k);
     }
     return dmin;
+}
+
+// can the ray of direction d from (px,py) touch any candidate rectangle at all?  (closed boxes: a superset of sense_dir1's hits)
+__device__ __forceinline__ bool sense_box1(const int4 *rects, int rstride, int cand, int px, int py, int d) {
+    const int sx = step_dx(d), sy = step_dy(d);
+    const int xlo = min(px, px + sx), xhi = max(px, px + sx), ylo = min(py, py + sy), yhi = max(py, py + sy);
+    bool any = false;
+    int todo = cand;
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4 r = rects[k * rstride];
+        any = any || (r.x <= xhi && xlo <= r.z && r.y <= yhi && ylo <= r.w);
+    }
+    return any;
 }
 
 // (110 - dist)/110 of a scored edge; 0 = no hit, exactly 1 on the edge (MUFU.RSQ, ~3e-7 relative, as sensors_rects_row)

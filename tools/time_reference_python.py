@@ -105,7 +105,8 @@ def _config1_epoch(seed=2):
             v, logp = float(vf(h)), float(dist.log_prob(a))
             nobs, rew, done, _ = env.step({0: int(a)})
             buf.store(obs=obs, act=int(a), rew=rew["individual_reward"][0], val=v, logp=logp,
-                      src=np.array(env.src_coords, dtype="float32"), terminal=False)
+                      src=np.array(env.src_coords, dtype="float32"), full_observation={0: obs}, heatmap_stacks=None,
+                      terminal=False)
             obs = nobs[0]
             in_ep += 1
             timeout, last = in_ep == 120, t == 479
@@ -127,7 +128,16 @@ def _config1_epoch(seed=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=20.0)
+    ap.add_argument("--only-config1", action="store_true", help="re-time the config-1 epoch and merge it into the existing file")
     args = ap.parse_args()
+    path = os.path.join(ROOT, "profiles", "r02_reference_python_baselines.json")
+    if args.only_config1:
+        out = json.load(open(path))
+        out["config1_epoch_s"] = _config1_epoch()
+        out["config1_env_steps_per_s"] = 480 / out["config1_epoch_s"]
+        json.dump(out, open(path, "w"), indent=1)
+        print("config1 epoch", out["config1_epoch_s"])
+        return
     P = os.cpu_count() or 1
     out = {"where": "build container (the reference cannot travel to the GPU box)", "cores": P,
            "python": sys.version.split()[0],
@@ -150,7 +160,6 @@ def main():
     out["config1_epoch_s"] = _config1_epoch()
     out["config1_env_steps_per_s"] = 480 / out["config1_epoch_s"]
     print("config1 epoch", out["config1_epoch_s"], flush=True)
-    path = os.path.join(ROOT, "profiles", "r02_reference_python_baselines.json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path)
 
