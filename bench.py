@@ -462,6 +462,7 @@ class GruPolicy:
         self.net = torch.nn.ModuleDict({"gru": torch.nn.GRUCell(obs_dim, hidden), "pi": torch.nn.Linear(hidden, n_act),
                                         "v": torch.nn.Linear(hidden, 1)}).to(cx.dev)
         self.h = torch.zeros(N, hidden, device=cx.dev)
+        self.hidden_state = self.h                       # restarted in place by rs_rollout_post (RolloutCollector)
         self.obs_in = torch.zeros(N, obs_dim, device=cx.dev)
         self.final_obs = final_obs
         self.action = torch.zeros(N, dtype=torch.int32, device=cx.dev)

@@ -93,7 +93,7 @@ typedef struct RsState {
     int32_t *src;                /* [N][2]    source x,y                                                        */
     int32_t *rad;                /* [N][2]    intensity, background                                             */
     int32_t *rects;              /* [K][N][4] x0,y0,x1,y1 (16-byte rows; slot k of env n at (k*N+n)*4)          */
-    int32_t *meta;               /* [N]       num_obs | done<<8 | ep_len<<16                      */
+    int32_t *meta;               /* [N]       num_obs | done<<8 | (rectangles holding the source strictly inside)<<9 | ep_len<<16 */
     int32_t *det;                /* [A][N][2] detector x,y                                                      */
     double *best;                /* [A][N]    Agent.prev_det_dist (running minimum of the shortest-path length)  */
     int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24                       */
@@ -198,6 +198,21 @@ int rs_pack_rollout(const float *obs, const float *adv, const float *ret, const 
  * ep_count, ep_start[e] = first row of episode e in `packed` (n*T + t_first) and ep_len[e], in (column, time) order. */
 int rs_episode_table(const uint8_t *path_end, int32_t T, int32_t N, int32_t *ep_count, const int32_t *ep_offset,
                      int32_t *ep_start, int32_t *ep_len, void *stream);
+
+/* ---- caller-side bookkeeping of a batched rollout (T:359-527), two elementwise launches per step ---
+ * rs_rollout_pre, before the env step of time t: act_row[n] = action[n], val_row / logp_row = the policy's state value and
+ * log-probability, src_row[n][2] = the source coordinates (nullable) -- row t of the rollout buffer (PPOBuffer.store P:339-381).
+ * rs_rollout_post, after it: boot_row[n] = v_next[n] where the trajectory was cut (ended & RS_E_TIMEOUT, or every env when
+ * last_step != 0), else 0 (T:462-487); hidden[n][0..hidden_dim) = 0 where ended != 0 and not last_step (T:509-511; nullable);
+ * episode statistics (nullable as a group): ep_return[n] += reward[n], ep_steps[n] += 1, acc[0..5] += {episodes over by a
+ * terminal state or the timeout, sum / sum of squares of their returns, sum of their lengths, done flags, out-of-bounds
+ * flags}, *ep_min / *ep_max = extreme returns, then return and length restart where a reset was scheduled (T:361-391,
+ * 493-535).  All arrays device, [n] unless noted. */
+int rs_rollout_pre(const int32_t *action, const float *val, const float *logp, const int32_t *src, float *act_row,
+                   float *val_row, float *logp_row, float *src_row, int32_t n, void *stream);
+int rs_rollout_post(const float *reward, const uint8_t *ended, const uint8_t *done, const uint8_t *info, const float *v_next,
+                    float *boot_row, float *hidden, int32_t hidden_dim, double *ep_return, int32_t *ep_steps, double *acc,
+                    double *ep_min, double *ep_max, int32_t n, int32_t last_step, void *stream);
 
 /* ---- RAD-TEAM map observation ---------------------------------------------------------------------
  * MapsBuffer.observation_to_map (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py:532-616 with its helpers :101-182

@@ -20,7 +20,7 @@ ST_REFILL_OVERFLOW = 64
 EXPORTS = [
     "rs_step", "rs_reset", "rs_prepare", "rs_bump_ctr", "rs_load_scenarios", "rs_query_shortest_path", "rs_gae", "rs_adv_stats", "rs_adv_normalize", "rs_last_error",
     "rs_version", "rs_sizeof_config", "rs_sizeof_state", "rs_maps_update", "rs_maps_reset", "rs_sizeof_maps_config",
-    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table",
+    "rs_sizeof_maps_state", "rs_pack_rollout", "rs_episode_table", "rs_rollout_pre", "rs_rollout_post",
 ]
 MS_CELL_RANGE, MS_LOG_FULL, MS_PRED_RANGE = 1, 2, 4
 
@@ -110,6 +110,10 @@ def declare(lib, prefix="rs_"):
         lib.rs_pack_rollout.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.rs_episode_table.restype = i32
         lib.rs_episode_table.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+        lib.rs_rollout_pre.restype = i32
+        lib.rs_rollout_pre.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.rs_rollout_post.restype = i32
+        lib.rs_rollout_post.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp]
         lib.rs_sizeof_maps_config.restype = i32
         lib.rs_sizeof_maps_state.restype = i32
         lib.rs_last_error.restype = C.c_char_p

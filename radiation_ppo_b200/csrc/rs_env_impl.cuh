@@ -831,7 +831,12 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         } else {
             reinterpret_cast<int2 *>(S.src)[n] = make_int2(e.sx, e.sy);
             reinterpret_cast<int2 *>(S.rad)[n] = make_int2(e.intensity, e.bkg);
-            S.meta[n] = e.num_obs;                                       // done = 0, ep_len = 0   R:739-740
+            // done = 0, ep_len = 0 R:739-740; bits 9..15: rectangles that hold the source strictly inside (an injected
+            // scenario may have them; the sampler rejects such sources R:1091-1129) -- see rs_step1.cuh::source_segment1
+            int src_in = 0;
+            if (inject)
+                for (int k = 0; k < e.num_obs && k < 7; k++) src_in |= (int)in_rect_open(e.sx, e.sy, w_rects[k]) << k;
+            S.meta[n] = e.num_obs | (src_in << 9);
             S.epi[n] = ep_seq;
         }
     }

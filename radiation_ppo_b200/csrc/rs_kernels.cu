@@ -289,8 +289,7 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
 // all 131072 environments of the headline workload resident in one wave).
 // After the one CTA barrier that publishes the mbarrier, warps never meet again:
 //   front      move, segment to the source, bound through last step's corner + marking pass: straight-line per-lane code
-//   pairs      every lane evaluates its first marked corner itself; the rest of the warp's marked corners are dealt out
-//              as (unit, corner) items, one per lane
+//   pairs      the marked corners of the whole warp are dealt out as (unit, corner) items, one per lane
 //   measure    line of sight, expected counts, Poisson draw
 //   sensors    (unit, direction) items of the warp: first the rays whose box meets a candidate rectangle are collected,
 //              then those are cast
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
                                                           const __grid_constant__ RsState S,
                                                           const __grid_constant__ rs::StepArgs a, int bulk_ok) {
     constexpr int KS = KMAX > 0 ? KMAX : 1;
-    constexpr int kPairCap = 96;                            // listed (unit, corner) pairs of a warp: ~13 at 5 obstructions
+    constexpr int kPairCap = 96;                            // (unit, corner) pairs of a warp: ~35 at 5 obstructions
     constexpr int kResBytes = kPairCap * 8;                 // pair results (doubles) at the start of the warp's slice
     constexpr int kSliceT = (kResBytes + 32 * RS_OBS_DIM * 4 + 31) / 32;     // bytes per thread: results + 32 obs rows
     constexpr int kDsfT = 16 * KS > kSliceT ? 16 * KS : ((kSliceT + 15) & ~15);
@@ -394,61 +393,53 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     // ---- pairs: the first marked corner by its own lane, the others of the warp as (unit, corner) items -------------------
     if (KMAX > 0 && __any_sync(0xffffffffu, marked != 0u)) {
         const double *drow = S.dsrc + (size_t)n * 4 * K;
-        if (marked) {
-            const int c = __ffs(marked) - 1;
-            marked &= marked - 1;
-            const double v = rs::sp_pair1<KMAX>(col, TB, num_obs, mv.det.x, mv.det.y, c, drow[c], best_sp);
-            if (v < best_sp) { best_sp = v; besti = c; }
-        }
-        if (__any_sync(0xffffffffu, marked != 0u)) {
-            const int cnt = __popc(marked);
-            int incl = cnt;
+        const int cnt = __popc(marked);
+        int incl = cnt;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= s) incl += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
-            {
-                uint32_t m = marked;
-                int pos = off;
-                while (m) {
-                    const int c = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (pos < kPairCap) items[pos] = (uint16_t)((lane << 5) | c);
-                    pos++;
-                }
-            }
-            __syncwarp();
-            const int np = min(total, kPairCap);
-            for (int base = 0; base < np; base += 32) {
-                const int j = base + lane;
-                const bool valid = j < np;
-                const int e = valid ? (int)items[j] : 0, owner = e >> 5, c = e & 31;
-                const int px = __shfl_sync(0xffffffffu, mv.det.x, owner), py = __shfl_sync(0xffffffffu, mv.det.y, owner);
-                const int nob = __shfl_sync(0xffffffffu, num_obs, owner);
-                const double bo = __shfl_sync(0xffffffffu, best_sp, owner);
-                double ds = __longlong_as_double(0x7ff0000000000000LL);
-                if (valid) ds = S.dsrc[(size_t)(n0 + w0 + owner) * 4 * K + c];
-                const double v = rs::sp_pair1<KMAX>(s_rects + w0 + owner, TB, nob, px, py, c, ds, bo);
-                if (valid) res[j] = v;
-            }
-            __syncwarp();
-            {
-                uint32_t m = marked;
-                int pos = off;
-                while (m) {                                 // the unit's own listed pairs: keep the smallest
-                    const int c = __ffs(m) - 1;
-                    m &= m - 1;
-                    // pairs beyond the warp's list are evaluated by their own thread
-                    const double v = pos < kPairCap ? res[pos]
-                                                    : rs::sp_pair1<KMAX>(col, TB, num_obs, mv.det.x, mv.det.y, c, drow[c], best_sp);
-                    if (v < best_sp) { best_sp = v; besti = c; }
-                    pos++;
-                }
-            }
-            __syncwarp();
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += v;
         }
+        const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+        {
+            uint32_t m = marked;
+            int pos = off;
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < kPairCap) items[pos] = (uint16_t)((lane << 5) | c);
+                pos++;
+            }
+        }
+        __syncwarp();
+        const int np = min(total, kPairCap);
+        for (int base = 0; base < np; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < np;
+            const int e = valid ? (int)items[j] : 0, owner = e >> 5, c = e & 31;
+            const int px = __shfl_sync(0xffffffffu, mv.det.x, owner), py = __shfl_sync(0xffffffffu, mv.det.y, owner);
+            const int nob = __shfl_sync(0xffffffffu, num_obs, owner);
+            const double bo = __shfl_sync(0xffffffffu, best_sp, owner);
+            double ds = __longlong_as_double(0x7ff0000000000000LL);
+            if (valid) ds = S.dsrc[(size_t)(n0 + w0 + owner) * 4 * K + c];
+            const double v = rs::sp_pair1<KMAX>(s_rects + w0 + owner, TB, nob, px, py, c, ds, bo);
+            if (valid) res[j] = v;
+        }
+        __syncwarp();
+        {
+            uint32_t m = marked;
+            int pos = off;
+            while (m) {                                     // the unit's own pairs: keep the smallest
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                // pairs beyond the warp's list (never seen so far) are evaluated by their own thread
+                const double v = pos < kPairCap ? res[pos]
+                                                : rs::sp_pair1<KMAX>(col, TB, num_obs, mv.det.x, mv.det.y, c, drow[c], best_sp);
+                if (v < best_sp) { best_sp = v; besti = c; }
+                pos++;
+            }
+        }
+        __syncwarp();
     }
     // ---- measure: line of sight, expected counts, Poisson draw -----------------------------------------------------------
     float *row = rows + lane * RS_OBS_DIM;
@@ -707,7 +698,10 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
     const int A = cfg->n_agents, K = cfg->k_max;
     if (A == 1) {
         // one thread per environment (rs_step1.cuh); KMAX = the unroll bound of the per-rectangle loops
-        constexpr int TB = 128;
+#ifndef RS_STEP1_TB
+#define RS_STEP1_TB 128
+#endif
+        constexpr int TB = RS_STEP1_TB;
         const int grid = (n_env + TB - 1) / TB;
         // 16-byte alignment of what the bulk copies and the float4 stores touch (tile offsets are multiples of 128 envs)
         const int bulk_ok = aligned16(st->rects) && aligned16(st->dsf) && aligned16(st->best) && aligned16(st->rad) &&

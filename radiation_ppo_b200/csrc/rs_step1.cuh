@@ -73,17 +73,13 @@ __device__ __noinline__ bool graze_call(int px, int py, int qx, int qy, int4 r) 
 }
 
 // source_segment() of rs_env_impl.cuh without the box pre-filter and the per-lane rectangle list: every rectangle, every lane
+// src_in: the rectangles that hold the source strictly inside (meta bits 9..15, set by rs_load_scenarios; never in a
+// sampled scenario): there, a detector strictly inside the same rectangle meets no boundary.
 template <int KMAX>
-__device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, int num_obs, int px, int py, int sx, int sy,
-                                                bool &direct, bool &blocked) {
+__device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, int num_obs, int src_in, int px, int py, int sx,
+                                                int sy, bool &direct, bool &blocked) {
     const int dx = sx - px, dy = sy - py;
     const int l2 = dx * dx + dy * dy;
-    // rectangles that hold the source strictly inside (none in a valid scenario): there, a detector strictly inside the
-    // same rectangle meets no boundary
-    int src_in = 0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++)
-        if (k < num_obs && in_rect_open(sx, sy, rects[k * rstride])) src_in |= 1 << k;
     int acc = 0;                                            // bit 0: some open rectangle met, bit 1: some boundary within 0.001
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
@@ -264,7 +260,7 @@ __device__ __forceinline__ Move1 unit1_move(const Params &P, const int4 *rects, 
         if (!roll) { det.x = tx; det.y = ty; uf |= UF_MOVED; }
     }
     if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
-    source_segment1<KMAX>(rects, rstride, num_obs, det.x, det.y, src.x, src.y, m.direct, m.blocked_raw);
+    source_segment1<KMAX>(rects, rstride, num_obs, (meta >> 9) & 0x7f, det.x, det.y, src.x, src.y, m.direct, m.blocked_raw);
     int cand = 0;                                                       // sensor candidates: a ray is at most 100 long
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
@@ -463,7 +459,7 @@ __device__ __forceinline__ Commit1 unit1_commit(const Params &P, const StepArgs 
         if (done || timeout || (a.flags & RS_F_EPOCH_END)) { ended |= RS_E_RESET; scheduled = true; }
     }
     c.reward = (float)reward; c.done = done; c.info = info; c.ended = ended; c.best = best; c.scheduled = scheduled;
-    c.meta = (meta & 0xff) | (done << 8) | (ep_len << 16);
+    c.meta = (meta & 0xfeff) | (done << 8) | (ep_len << 16);
     return c;
 }
 

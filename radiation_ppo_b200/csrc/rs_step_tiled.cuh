@@ -441,7 +441,7 @@ __device__ __forceinline__ bool phase_commit(const Params &P, const RsState &S, 
         }
     }
     T.ended[t] = (uint8_t)ended;
-    T.meta[t] = (meta & 0xff) | (done << 8) | (ep_len << 16);
+    T.meta[t] = (meta & 0xfeff) | (done << 8) | (ep_len << 16);      // bits 9..15: see rs_step1.cuh::source_segment1
     raise_status(S, n, status);
     return scheduled;
 }

@@ -15,6 +15,7 @@ The policy is the caller's (any torch module); this module only fixes the order 
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Protocol, Tuple
 
 import torch
@@ -34,7 +35,9 @@ class RolloutPolicy(Protocol):
         """State value f32 [N] of `obs` under the current recurrent state, without advancing it (T:470-477)."""
 
     def reset_state(self, mask: Optional[torch.Tensor]) -> None:
-        """Restart the recurrent state of the envs in `mask` (bool [N]; None = all) (T:326, 509-511)."""
+        """Restart the recurrent state of the envs in `mask` (bool [N]; None = all) (T:326, 509-511).  A policy that
+        exposes its state as `hidden_state` (float32 [N, H], contiguous) has it restarted in place by rs_rollout_post and
+        is only called with mask=None."""
 
 
 class RolloutCollector:
@@ -53,31 +56,33 @@ class RolloutCollector:
 
     def collect(self, gae_variant: int = 0) -> None:
         env, buf, pol = self.env, self.buf, self.policy
-        T = buf.T
+        T, N = buf.T, buf.N
+        lib = L.load()
+        stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())             # noqa: E731
         # the observation that opens the epoch: the env's reset observation the first time, afterwards the one that
         # followed the previous epoch's last step (already in the buffer's row T)
         buf.start_epoch(env.obs if self._first else None)
         self._first = False
         pol.reset_state(None)                                                        # T:326
-        src = env.num_envs > 1
+        hidden = getattr(pol, "hidden_state", None)                                  # [N, H] float32, restarted in place
+        st = self.stats.fused_args() if self.stats is not None else (None,) * 5
+        final_obs = env.final_obs.reshape(N, buf.D)
         for t in range(T):
             rows = buf.policy_rows(t)
             action, value, logp = pol.act(rows["obs"])
-            rows["act"].copy_(action)
-            rows["val"].copy_(value)
-            rows["logp"].copy_(logp)
-            if src:
-                rows["src"].copy_(env.src_coords)                                    # T:283-285, 416 (target of the PFGRU)
+            # row t of the buffer <- action, value, log-probability, source coordinates (T:416-428), one launch
+            L.check(lib.rs_rollout_pre(p(action), p(value), p(logp), p(env._src), p(rows["act"]), p(rows["val"]),
+                                       p(rows["logp"]), p(rows["src"]), N, stream), "rs_rollout_pre")
             last = t == T - 1
-            env.step_batch(action, epoch_end=last, out=buf.step_outputs(t))          # obs -> row t+1, reward / ended -> row t
-            ended = buf.end_buf[t]
-            # T:462-487: bootstrap where the trajectory was cut (timeout, or every env at the epoch's last step)
-            v_next = pol.value(env.final_obs.reshape(buf.N, buf.D))
-            cut = torch.ones_like(ended, dtype=torch.bool) if last else (ended & L.E_TIMEOUT) != 0
-            torch.where(cut, v_next, torch.zeros_like(v_next), out=rows["boot"])
-            if self.stats is not None:
-                self.stats.update(buf.rew_buf[t].view(buf.N, 1), buf.rew_buf[t], env.done_flags, env.info_flags, ended)
-            if not last:
-                pol.reset_state(ended != 0)                                          # T:509-511
+            outs = buf.step_outputs(t)
+            env.step_batch(action, epoch_end=last, out=outs)                         # obs -> row t+1, reward / ended -> row t
+            # T:462-487 bootstrap where the trajectory was cut, T:509-511 recurrent state, T:361-391 episode statistics
+            v_next = pol.value(final_obs)
+            L.check(lib.rs_rollout_post(p(outs["reward"]), p(outs["ended"]), p(env.done_flags), p(env.info_flags), p(v_next),
+                                        p(rows["boot"]), p(hidden), 0 if hidden is None else hidden.shape[1], p(st[0]),
+                                        p(st[1]), p(st[2]), p(st[3]), p(st[4]), N, int(last), stream), "rs_rollout_post")
+            if hidden is None and not last:
+                pol.reset_state(outs["ended"] != 0)                                  # T:509-511
             buf.advance()
         buf.finish_paths(variant=gae_variant)

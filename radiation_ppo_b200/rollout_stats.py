@@ -52,6 +52,13 @@ class EpisodeStats:
         self.episode_return.masked_fill_(reset[:, None], 0.0)
         self.steps_in_episode.masked_fill_(reset, 0)
 
+    def fused_args(self):
+        """Device pointers of the single-agent accumulators for rs_rollout_post (which does what `update` does, in the
+        same launch as the bootstrap rule): ep_return [N] f64, ep_steps [N] i32, acc [6] f64, min [1], max [1]."""
+        if self.A != 1 or self.team_mode == "competitive":
+            raise ValueError("the fused bookkeeping covers one agent per environment")
+        return (self.episode_return, self.steps_in_episode, self._acc, self._min, self._max)
+
     def epoch_summary(self, group=None, clear: bool = True) -> Dict[str, torch.Tensor]:
         """Per agent [A]: Episodes, AverageEpRet, StdEpRet (population), MinEpRet, MaxEpRet, EpLen (mean), DoneCount,
         OutOfBound -- over all envs of all ranks (sums all-reduced once, min / max once each)."""
