@@ -40,10 +40,11 @@ extern "C" {
 #define RS_F_RESET_LIST 4        /* rs_reset: reset the envs rs_step scheduled (RsState.reset_list / reset_count)  */
 #define RS_F_NEW_OBSTACLES 8     /* rs_reset: draw new obstructions for every env being reset (env.epoch_end)      */
 #define RS_F_FAST_POISSON 16     /* Philox path only: fp32 acceptance test in the PTRS sampler (KS-equivalent)     */
-#define RS_F_PREFETCH 32         /* rs_reset: an env whose next episode was prefetched (RsState.nx_*, rs_prepare)   */
-                                 /* adopts it with a few copies instead of recomputing it; every env reset is       */
-                                 /* appended to refill list `parity` (the caller zeroes refill_count[parity] when   */
-                                 /* it starts a list and drains it with rs_prepare)                                 */
+#define RS_F_PREFETCH 32         /* an env whose next episode was prefetched (RsState.nx_*, rs_prepare) adopts it    */
+                                 /* with a few copies instead of recomputing it: rs_step does so for the envs it     */
+                                 /* schedules (single agent), rs_reset for the envs of its work list; every env that  */
+                                 /* starts an episode is appended to refill list `parity` (RS_F_ZERO_REFILL starts a  */
+                                 /* list, rs_prepare drains it)                                                      */
 #define RS_F_REFILL_LIST 64      /* rs_prepare: prepare the envs of refill list `parity`; else all envs            */
 #define RS_F_DEVICE_CTR 128      /* read the step counter from RsState.ctr_dev (CUDA-graph replay); rs_bump_ctr     */
 #define RS_F_PARITY1 256         /* which of the two refill lists rs_step / rs_reset push to (rs_prepare drains)    */

@@ -164,8 +164,6 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
         __syncthreads();
     }
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
-    // a new refill list starts with this step: only the reset kernel that follows appends to it
-    if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
 
     // ---- phase_move: every unit; build the work lists ---------------------------------------------------------------
     for (int u0 = 0; u0 < U; u0 += TB) {
@@ -282,37 +280,25 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------------
 // Single-agent step kernel (rs_step1.cuh): one thread per environment, warp-autonomous.  A CTA of TB threads owns TB
 // consecutive environments.  Thread 0 starts bulk-async copies (cp.async.bulk, one mbarrier) of the tile's rectangle rows
-// [k][TB], of its block of the float source-distance table [TB][4K] and of the two state rows that are only needed at the
-// end of the step (best distance, intensities) into shared memory; the rows a thread needs at once (source, detector,
-// meta, flags, action) go straight from HBM into its registers with coalesced loads, and the unit's Philox block is
-// computed while both are in flight (and parked in shared memory: registers are the scarce resource, 72 per thread keep
-// all 131072 environments of the headline workload resident in one wave).
-// After the one CTA barrier that publishes the mbarrier, warps never meet again:
-//   front      move, segment to the source, bound through last step's corner + marking pass: straight-line per-lane code
-//   pairs      the marked corners of the whole warp are dealt out as (unit, corner) items, one per lane
-//   measure    line of sight, expected counts, Poisson draw
-//   sensors    (unit, direction) items of the warp: first the rays whose box meets a candidate rectangle are collected,
-//              then those are cast
-//   commit     reward, terminal, caller rules; state and scalar outputs leave as coalesced stores, the reset work list
-//              gets one atomic per warp, the observation rows go through a staging block as 16-byte stores.
-// The staging block and the pair results reuse the warp's slice of the float table, which is dead after the marking pass.
+// [k][TB] and of its block of the float source-distance table [TB][4K] into shared memory -- the two tables that lanes
+// read for each other's environments or index dynamically; every other state row goes straight from HBM into the
+// owning thread's registers with coalesced loads, and the unit's Philox block is computed while both are in flight.
+// After the one CTA barrier that publishes the mbarrier, warps never meet again: the front half (move, segment to the
+// source, shortest path, Poisson draw) is straight-line per-lane code, the ray casts are (unit, direction) items of the
+// warp, the reset work list is appended with one atomic per warp, state and scalar outputs leave as coalesced stores and
+// the observation rows through a shared-memory staging block as 16-byte stores.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool kFast, int KMAX, int TB, int kOcc>
 __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__ rs::Params P,
                                                           const __grid_constant__ RsState S,
                                                           const __grid_constant__ rs::StepArgs a, int bulk_ok) {
     constexpr int KS = KMAX > 0 ? KMAX : 1;
-    constexpr int kPairCap = 96;                            // (unit, corner) pairs of a warp: ~35 at 5 obstructions
-    constexpr int kResBytes = kPairCap * 8;                 // pair results (doubles) at the start of the warp's slice
-    constexpr int kSliceT = (kResBytes + 32 * RS_OBS_DIM * 4 + 31) / 32;     // bytes per thread: results + 32 obs rows
-    constexpr int kDsfT = 16 * KS > kSliceT ? 16 * KS : ((kSliceT + 15) & ~15);
     __shared__ __align__(16) int4 s_rects[KS * TB];
-    __shared__ __align__(16) unsigned char s_tab[TB * kDsfT];    // float table [TB][4K]; later results + obs rows per warp
-    __shared__ __align__(16) double s_best[TB];
-    __shared__ __align__(16) int2 s_rad[TB];
-    __shared__ uint32_t s_x[4 * TB];
-    __shared__ uint16_t s_items[(TB / 32) * kPairCap];
-    __shared__ __align__(4) uint8_t s_list[TB], s_ones[TB];
+    __shared__ __align__(16) float s_dsf[TB * 4 * KS];
+    __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
+    __shared__ uint8_t s_list[TB];
+    constexpr int kPairCap = 128;                           // (unit, corner) pairs of a warp: ~35 at 5 obstructions
+    __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
     __shared__ __align__(8) uint64_t s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
     const int n0 = blockIdx.x * TB;
@@ -320,79 +306,63 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     const bool live = n < a.n_env;
     const int K = KMAX > 0 ? P.k_max : 0;
     const size_t N = (size_t)a.n_env;
-    const bool bulk = bulk_ok && n0 + TB <= a.n_env;
+    const bool bulk = KMAX > 0 && bulk_ok && n0 + TB <= a.n_env;
     if (bulk && tid == 0) {
         mbar_init(&s_mbar, 1);
-        mbar_expect_tx(&s_mbar, (uint32_t)((2 * K + 1) * 16 * TB));
+        mbar_expect_tx(&s_mbar, (uint32_t)(2 * K * 16 * TB));
         for (int k = 0; k < K; k++)
             bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar);
-        if (K > 0)      // one copy per warp, to the start of the warp's own slice (which it reuses after the marking pass)
-            for (int w = 0; w < TB / 32; w++)
-                bulk_g2s(s_tab + w * 32 * kDsfT, S.dsf + (size_t)(n0 + 32 * w) * 4 * K, (uint32_t)(32 * 16 * K), &s_mbar);
-        bulk_g2s(s_best, S.best + n0, TB * 8, &s_mbar);
-        bulk_g2s(s_rad, S.rad + (size_t)n0 * 2, TB * 8, &s_mbar);
+        bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar);
     }
-    // the state rows a thread needs at once: coalesced, straight into registers
-    int2 src = make_int2(0, 0), det = make_int2(0, 0);
+    // scalar state rows: coalesced, straight into registers
+    int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
     int meta = 0, action = -1, af = 0;
+    double best = 0.0, stm = 0.0, stq = 0.0;
     if (live) {
         src = reinterpret_cast<const int2 *>(S.src)[n];
+        rad = reinterpret_cast<const int2 *>(S.rad)[n];
         det = reinterpret_cast<const int2 *>(S.det)[n];
         meta = S.meta[n];
         af = S.aflags[n];
+        best = S.best[n];
         if (a.actions) action = a.actions[n];
+        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
     }
-    const int num_obs = meta & 0xff;
     // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
     const int hint = (af >> 25) & 31;
     double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
-    if (KMAX > 0 && live && hint < 4 * num_obs) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
+    if (KMAX > 0 && live && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
     const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
-    // a new refill list starts with this step: only the reset kernel that follows appends to it
-    if ((a.flags & RS_F_ZERO_REFILL) && blockIdx.x == 0 && tid == 0) S.refill_count[a.parity] = 0;
-    if (kFast) {    // needs nothing from memory: runs while the tile is in flight; parked in shared memory until the draw
-        uint32_t x[4];
+    uint32_t x[4] = {0u, 0u, 0u, 0u};
+    if (kFast)      // needs nothing from memory: runs while the tile is in flight
         rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
                           (uint32_t)(a.seed >> 32), x);
-#pragma unroll
-        for (int i = 0; i < 4; i++) s_x[i * TB + tid] = x[i];
-    }
-    s_ones[tid] = 0;
     if (bulk) {
         __syncthreads();                                    // the barrier object is initialised for everybody
         mbar_wait(&s_mbar, 0);
-    } else {
+    } else if (KMAX > 0) {
         if (live) {
             for (int k = 0; k < K; k++) s_rects[k * TB + tid] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
             for (int k = 0; k < K; k++)
-                reinterpret_cast<float4 *>(s_tab + w0 * kDsfT + lane * 16 * K)[k] =
-                    reinterpret_cast<const float4 *>(S.dsf)[(size_t)n * K + k];
-            s_best[tid] = S.best[n];
-            s_rad[tid] = reinterpret_cast<const int2 *>(S.rad)[n];
+                reinterpret_cast<float4 *>(s_dsf)[tid * K + k] = reinterpret_cast<const float4 *>(S.dsf)[(size_t)n * K + k];
         }
         __syncwarp();
     }
-    const int4 *col = s_rects + tid;                        // this unit's rectangles: element k at col[k * TB]
-    // ---- front: take_action, segment to the source; for obstructed units the bound through last step's corner + marking --
+    // ---- take_action, segment to the source; for obstructed units the bound through last step's corner + marking pass -----
+    const int num_obs = meta & 0xff;
     rs::Move1 mv;
     mv.det = det; mv.af = af; mv.uf = 0; mv.d2 = 0; mv.direct = true; mv.blocked_raw = false; mv.status = 0u;
     double best_sp = 0.0;
     int besti = -1;
     uint32_t marked = 0u;
     if (live) {
-        mv = rs::unit1_move<KMAX>(P, col, TB, src, meta, action, det, af);
-        if (KMAX > 0 && !mv.direct)
-            marked = rs::sp_hint_mark1<KMAX>(col, TB, num_obs, reinterpret_cast<const float *>(s_tab + w0 * kDsfT + lane * 16 * K),
-                                             mv.det.x, mv.det.y, hint, ds_hint, best_sp, besti);
+        mv = rs::unit1_move<KMAX>(P, s_rects + tid, TB, src, meta, action, det, af);
+        if (!mv.direct)
+            marked = rs::sp_hint_mark1<KMAX>(s_rects + tid, TB, num_obs, s_dsf + tid * 4 * K, mv.det.x, mv.det.y, hint, ds_hint,
+                                             best_sp, besti);
     }
-    __syncwarp();                                           // the warp's slice of the float table is free from here on
-    unsigned char *slice = s_tab + w0 * kDsfT;
-    double *res = reinterpret_cast<double *>(slice);
-    float *rows = reinterpret_cast<float *>(slice + kResBytes);
-    uint16_t *items = s_items + (w0 >> 5) * kPairCap;
-    // ---- pairs: the first marked corner by its own lane, the others of the warp as (unit, corner) items -------------------
+    // ---- the marked corners of the warp as (unit, corner) pairs, one per lane: exact candidate + visibility ---------------
     if (KMAX > 0 && __any_sync(0xffffffffu, marked != 0u)) {
-        const double *drow = S.dsrc + (size_t)n * 4 * K;
         const int cnt = __popc(marked);
         int incl = cnt;
 #pragma unroll
@@ -401,13 +371,15 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             if (lane >= s) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+        uint16_t *pl = s_pairs + (w0 >> 5) * kPairCap;
+        double *res = reinterpret_cast<double *>(s_obs + w0 * RS_OBS_DIM);      // the warp's staging block, free until commit
         {
             uint32_t m = marked;
             int pos = off;
             while (m) {
                 const int c = __ffs(m) - 1;
                 m &= m - 1;
-                if (pos < kPairCap) items[pos] = (uint16_t)((lane << 5) | c);
+                if (pos < kPairCap) pl[pos] = (uint16_t)((lane << 5) | c);
                 pos++;
             }
         }
@@ -416,7 +388,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         for (int base = 0; base < np; base += 32) {
             const int j = base + lane;
             const bool valid = j < np;
-            const int e = valid ? (int)items[j] : 0, owner = e >> 5, c = e & 31;
+            const int e = valid ? (int)pl[j] : 0, owner = e >> 5, c = e & 31;
             const int px = __shfl_sync(0xffffffffu, mv.det.x, owner), py = __shfl_sync(0xffffffffu, mv.det.y, owner);
             const int nob = __shfl_sync(0xffffffffu, num_obs, owner);
             const double bo = __shfl_sync(0xffffffffu, best_sp, owner);
@@ -434,87 +406,56 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
                 m &= m - 1;
                 // pairs beyond the warp's list (never seen so far) are evaluated by their own thread
                 const double v = pos < kPairCap ? res[pos]
-                                                : rs::sp_pair1<KMAX>(col, TB, num_obs, mv.det.x, mv.det.y, c, drow[c], best_sp);
+                                                : rs::sp_pair1<KMAX>(s_rects + tid, TB, num_obs, mv.det.x, mv.det.y, c,
+                                                                     S.dsrc[(size_t)n * 4 * K + c], best_sp);
                 if (v < best_sp) { best_sp = v; besti = c; }
                 pos++;
             }
         }
         __syncwarp();
     }
-    // ---- measure: line of sight, expected counts, Poisson draw -----------------------------------------------------------
-    float *row = rows + lane * RS_OBS_DIM;
+    float *row = s_obs + tid * RS_OBS_DIM;
 #pragma unroll
     for (int d = 0; d < 8; d++) row[3 + d] = 0.0f;
     rs::Unit1 o;
     o.det = det; o.af = af; o.uf = 0; o.sp = 0.0; o.blocked_los = false; o.count = 0.0f; o.status = 0u;
-    if (live) {
-        uint32_t x[4] = {0u, 0u, 0u, 0u};
-        if (kFast) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) x[i] = s_x[i * TB + tid];
-        }
-        o = rs::unit1_measure<kFast>(P, a, mv, n, s_rad[tid], best_sp, besti >= 0 ? besti : hint, step_ctr, x);
-    }
+    if (live) o = rs::unit1_measure<kFast>(P, a, mv, n, rad, best_sp, besti >= 0 ? besti : hint, step_ctr, x);
     __syncwarp();
-    // ---- obstruction_sensors: (unit, direction) items of the warp --------------------------------------------------------
+    // ---- obstruction_sensors: (unit, direction) items of the warp ---------------------------------------------------------
     const unsigned need = __ballot_sync(0xffffffffu, (o.uf & rs::UF_NEED_D) != 0);
     if (need) {
         uint8_t *wl = s_list + w0;
         if ((need >> lane) & 1u) wl[__popc(need & ((1u << lane) - 1u))] = (uint8_t)lane;
         __syncwarp();
         const int cnt = __popc(need);
-        // pass 1: the rays whose bounding box meets one of the unit's candidate rectangles (a ray that misses all boxes
-        // scores nothing: its sensor stays 0)
-        int n_items = 0;
         for (int base = 0; base < 8 * cnt; base += 32) {
             const int item = base + lane, j = item >> 3, d = item & 7;
             const bool valid = j < cnt;
             const int owner = valid ? (int)wl[j] : 0;
             const int px = __shfl_sync(0xffffffffu, o.det.x, owner), py = __shfl_sync(0xffffffffu, o.det.y, owner);
-            const int ufo = __shfl_sync(0xffffffffu, o.uf, owner);
-            bool hitbox = false;
-            if (valid) hitbox = rs::sense_box1(s_rects + w0 + owner, TB, (ufo >> 16) & 0xff, px, py, d);
-            const unsigned hb = __ballot_sync(0xffffffffu, hitbox);
-            if (hitbox) {
-                const int pos = n_items + __popc(hb & ((1u << lane) - 1u));
-                if (pos < kPairCap) items[pos] = (uint16_t)((owner << 3) | d);
-            }
-            n_items += __popc(hb);
-        }
-        __syncwarp();
-        // pass 2: cast them
-        const int ni = min(n_items, kPairCap);
-        for (int base = 0; base < ni; base += 32) {
-            const int j = base + lane;
-            const bool valid = j < ni;
-            const int e = valid ? (int)items[j] : 0, owner = e >> 3, d = e & 7;
-            const int px = __shfl_sync(0xffffffffu, o.det.x, owner), py = __shfl_sync(0xffffffffu, o.det.y, owner);
-            const int ufo = __shfl_sync(0xffffffffu, o.uf, owner);
-            if (valid) {
-                unsigned long long hits = 0ull;
-                const int dmin = rs::sense_dir1(s_rects + w0 + owner, TB, (ufo >> 16) & 0xff, px, py, d, hits);
-                rows[owner * RS_OBS_DIM + 3 + d] = rs::sense_value(dmin);
-                if (dmin == 0) atomicAdd_block(reinterpret_cast<unsigned int *>(s_ones) + ((w0 + owner) >> 2),
-                                               1u << (8 * ((w0 + owner) & 3)));
-            }
-        }
-        __syncwarp();
-        // the detector stands on an obstruction edge when more than three of its rays read exactly 1.0 (R:1219-1226), and so
-        // does a unit whose items did not fit the list (never seen): the owner redoes its eight rays in the reference's order
-        if (((need >> lane) & 1u) && (s_ones[tid] > 3 || n_items > kPairCap)) {
+            const int ufo = __shfl_sync(0xffffffffu, o.uf, owner), nob = __shfl_sync(0xffffffffu, meta, owner) & 0xff;
+            const int4 *col = s_rects + w0 + owner;
             unsigned long long hits = 0ull;
-            int ones = 0;
-            for (int d = 0; d < 8; d++) {
-                const int dmin = rs::sense_dir1(col, TB, (o.uf >> 16) & 0xff, o.det.x, o.det.y, d, hits);
-                ones += dmin == 0;
-                row[3 + d] = rs::sense_value(dmin);
-            }
-            if (ones > 3) {
-                float out[8];
-                rs::correct_coords(o.det.x, o.det.y, col[rs::sense_correct_rect(col, TB, num_obs, hits) * TB], out, o.status);
+            int dmin = -1;
+            if (valid) dmin = rs::sense_dir1(col, TB, (ufo >> 16) & 0xff, px, py, d, hits);
+            float v = rs::sense_value(dmin);
+            // the detector stands on an obstruction edge when more than three of its rays read exactly 1.0: R:1219-1226
+            const unsigned zero = __ballot_sync(0xffffffffu, valid && dmin == 0);
+            const bool fix = __popc((zero >> (lane & 24)) & 0xffu) > 3;
+            if (__any_sync(0xffffffffu, fix)) {
 #pragma unroll
-                for (int d = 0; d < 8; d++) row[3 + d] = out[d];
+                for (int s = 1; s < 8; s <<= 1) hits += __shfl_xor_sync(0xffffffffu, hits, s);
+                if (fix) {
+                    float out[8];
+                    uint32_t st = 0u;
+                    rs::correct_coords(px, py, col[rs::sense_correct_rect(col, TB, nob, hits) * TB], out, st);
+                    v = out[0];
+#pragma unroll
+                    for (int i = 1; i < 8; i++) v = d == i ? out[i] : v;
+                    if (d == 0) rs::raise_status(S, n0 + w0 + owner, st);
+                }
             }
+            if (valid) s_obs[(w0 + owner) * RS_OBS_DIM + 3 + d] = v;
         }
         __syncwarp();
     }
@@ -523,19 +464,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     if (live) {
         uint32_t status = o.status;
         float raw = 0.0f;
-        double stm = 0.0, stq = 0.0;
-        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
-        const rs::Commit1 c = rs::unit1_commit(P, a, o, meta, action, s_best[tid], row, P.standardize ? &stm : nullptr, &stq, &raw,
-                                               status);
-        S.meta[n] = c.meta;
-        reinterpret_cast<int2 *>(S.det)[n] = o.det;
-        S.best[n] = c.best;
-        S.aflags[n] = o.af;
-        if (P.standardize) {
-            S.st_mean[n] = stm;
-            S.st_m2[n] = stq;
-            if (S.raw_count) S.raw_count[n] = raw;
-        }
+        const rs::Commit1 c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw, status);
         if (a.reward) a.reward[n] = c.reward;
         if (a.team_reward) a.team_reward[n] = c.reward;                 // one agent: the team reward is its reward R:661-665
         if (a.done) a.done[n] = (uint8_t)c.done;
@@ -545,6 +474,51 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         if (sched && a.final_obs) {
 #pragma unroll
             for (int i = 0; i < RS_OBS_DIM; i++) a.final_obs[(size_t)n * RS_OBS_DIM + i] = row[i];
+        }
+        // RS_F_PREFETCH: an env whose next episode rs_prepare has already computed (same seed, env, episode number and
+        // obstructions: nx_seq carries the episode number) starts it right here -- a few copies by the thread that has the
+        // env in hand -- and never reaches the reset kernel; the others go to the reset work list as before
+        bool adopted = false;
+        if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
+            const uint32_t ep_seq = S.epi[n] + 1u;
+            if (*reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n) == ep_seq) {
+                __threadfence();
+                adopted = true;
+                const size_t r0 = (size_t)n * 4 * K;
+                for (int c4 = 0; c4 < num_obs; c4++) {                  // source-distance rows of the new episode
+                    reinterpret_cast<double2 *>(S.dsrc + r0)[2 * c4] = reinterpret_cast<const double2 *>(S.nx_dsrc + r0)[2 * c4];
+                    reinterpret_cast<double2 *>(S.dsrc + r0)[2 * c4 + 1] = reinterpret_cast<const double2 *>(S.nx_dsrc + r0)[2 * c4 + 1];
+                    reinterpret_cast<float4 *>(S.dsf + r0)[c4] = reinterpret_cast<const float4 *>(S.nx_dsf + r0)[c4];
+                }
+                const float *nxo = S.nx_obs + (size_t)n * RS_OBS_DIM;
+#pragma unroll
+                for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[i];
+                if (P.standardize) {                                    // first reading of the episode: z = 0
+                    stm = (double)row[0]; stq = 0.0; raw = row[0]; row[0] = 0.0f;
+                }
+                reinterpret_cast<int2 *>(S.src)[n] = reinterpret_cast<const int2 *>(S.nx_src)[n];
+                reinterpret_cast<int2 *>(S.rad)[n] = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+                reinterpret_cast<int2 *>(S.det)[n] = reinterpret_cast<const int2 *>(S.nx_det)[n];
+                S.best[n] = S.nx_best[n];
+                S.aflags[n] = 0;
+                S.meta[n] = meta & 0xff;                                // done = 0, ep_len = 0 (a sampled source is in no rectangle)
+                S.epi[n] = ep_seq;
+                const int slot = atomicAdd(S.refill_count + a.parity, 1);
+                if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
+                else status |= RS_ST_REFILL_OVERFLOW;
+                sched = false;
+            }
+        }
+        if (!adopted) {
+            S.meta[n] = c.meta;
+            reinterpret_cast<int2 *>(S.det)[n] = o.det;
+            S.best[n] = c.best;
+            S.aflags[n] = o.af;
+        }
+        if (P.standardize) {
+            S.st_mean[n] = stm;
+            S.st_m2[n] = stq;
+            if (S.raw_count) S.raw_count[n] = raw;
         }
         rs::raise_status(S, n, status);
     }
@@ -561,13 +535,14 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     // ---- observation rows: the warp's 32 rows are one contiguous run of 352 floats in shared memory and in HBM --------------
     {
         const int nw = n0 + w0;                             // first environment of this warp
+        const float *sw = s_obs + w0 * RS_OBS_DIM;
         float *g = a.obs + (size_t)nw * RS_OBS_DIM;
         if (bulk_ok && nw + 32 <= a.n_env) {
             for (int i = lane; i < 32 * RS_OBS_DIM / 4; i += 32)
-                reinterpret_cast<float4 *>(g)[i] = reinterpret_cast<const float4 *>(rows)[i];
+                reinterpret_cast<float4 *>(g)[i] = reinterpret_cast<const float4 *>(sw)[i];
         } else {
-            const int nrows = min(32, a.n_env - nw);
-            for (int i = lane; i < nrows * RS_OBS_DIM; i += 32) g[i] = rows[i];
+            const int rows = min(32, a.n_env - nw);
+            for (int i = lane; i < rows * RS_OBS_DIM; i += 32) g[i] = sw[i];
         }
     }
 }
@@ -689,6 +664,13 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
         cudaError_t e = cudaMemsetAsync(st->reset_count, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return (int)e;
     }
+    if (flags & RS_F_ZERO_REFILL) {         // a new refill list starts with this step (the step kernel itself appends to it)
+        cudaError_t e = cudaMemsetAsync(st->refill_count + parity, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if ((flags & RS_F_PREFETCH) && (flags & RS_F_AUTO_RESET)) {
+        if (int rc = check_prefetch(cfg, st)) return rc;
+    }
     rs::Params P = rs::make_params(*cfg);
     rs::StepArgs a;
     a.actions = actions; a.obs = obs; a.reward = reward; a.team_reward = team_reward; a.final_obs = final_obs;
@@ -796,6 +778,8 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
         need = (a.n_env + kBlock / prepare_nl - 1) / (kBlock / prepare_nl);
         cap = 148;
     }
+    // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
+    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 148;
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
