@@ -565,8 +565,13 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
 // Reset: a persistent grid whose threads team up in groups of `nl` lanes per environment.  Few envs to reset (the
 // steady state: ~N/120 per step) -> a whole warp per env for low latency; a bulk reset (epoch end, synchronised
 // timeouts) -> one thread per env, which wastes no lanes on the sequential rejection sampling.
+// RS_RESET_MINB: CTAs per SM the register allocation of the reset / prepare kernel aims at.  rs_prepare shares the GPU with
+// the step kernels of other env batches for its whole (latency-bound) life: what it costs them is registers x time.
+#ifndef RS_RESET_MINB
+#define RS_RESET_MINB 1
+#endif
 template <bool kFast>
-__global__ void __launch_bounds__(kBlock) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
+__global__ void __launch_bounds__(kBlock, RS_RESET_MINB) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
                                                         const uint8_t *new_mask, int flags, const int32_t *list,
                                                         const int32_t *count, int prepare_nl) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -779,7 +784,7 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
         cap = 148;
     }
     // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
-    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 148;
+    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 16;
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;

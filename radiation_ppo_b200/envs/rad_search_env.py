@@ -213,7 +213,7 @@ class RadSearch:
         self.observation_space = Box(0, np.inf, shape=(L.OBS_DIM,), dtype=np.float32)
         self.background_radiation_bounds = (10, 51)
         self.radiation_intensity_bounds = (1e6, 10e6)
-        self.coord_noise = False
+        self.coord_noise = False                           # settable, like the reference's dataclass field (R:570-574)
         self.epoch_end = True                                                                          # R:421
         self.epoch_cnt = 0
         self.iter_count = 0
@@ -721,7 +721,21 @@ class RadSearch:
     # ------------------------------------------------------------------------------------------------------------
     # gym API
     # ------------------------------------------------------------------------------------------------------------
-    def _pack(self):
+    def _noisy(self, obs):
+        """R:570-574 `coord_noise`: N(0, 5) on the detector coordinates of the observation (not of the state), scaled like
+        them.  Drawn from `np_random` for one env (per agent, in agent order, as the reference does), from torch's
+        generator for a batch."""
+        if not self.coord_noise:
+            return obs
+        if self.num_envs == 1:
+            for i in range(self.number_agents):
+                obs[i][1:3] += self.np_random.normal(scale=5, size=2) * self.scale
+            return obs
+        out = obs.clone()
+        out[..., 1:3] += torch.randn_like(out[..., 1:3]) * (5.0 * self.scale)
+        return out
+
+    def _pack(self, only=None):
         A = self.number_agents
         if self.num_envs > 1:
             info = {
@@ -733,7 +747,7 @@ class RadSearch:
                 "ended": self.ended,
                 "final_observation": self.final_obs,
             }
-            return (self.obs, {"team_reward": self.team_reward, "individual_reward": self.reward},
+            return (self._noisy(self.obs), {"team_reward": self.team_reward, "individual_reward": self.reward},
                     self.done_flags != 0, info)
         obs = self.obs[0].double().cpu().numpy()
         rew = self.reward[0].double().cpu().numpy()
@@ -742,12 +756,20 @@ class RadSearch:
         inf = self.info_flags[0].cpu().numpy()
         oobc = (self._aflags[:, 0] & 0xFFFFFF).cpu().numpy()
         r2 = lambda v: round(float(v), 2)                                   # noqa: E731  rewards are 2-decimal values
+        ids = range(A) if only is None else only
+        # agents a dict action did not name were not stepped by the reference: their entries stay None (R:627-630)
+        pick = lambda d: {i: (d[i] if i in ids else None) for i in range(A)}   # noqa: E731
+        rewards = [r2(rew[i]) for i in ids]
+        if only is not None:                                                # team reward = max over the stepped agents R:661-665
+            team = None
+            for r in rewards:
+                team = r if not team else max(team, r)
         return (
-            {i: obs[i].copy() for i in range(A)},
-            {"team_reward": r2(team), "individual_reward": {i: r2(rew[i]) for i in range(A)}},
-            {i: bool(done[i]) for i in range(A)},
-            {i: {"out_of_bounds": bool(inf[i] & L.I_OOB), "out_of_bounds_count": int(oobc[i]),
-                 "blocked": bool(inf[i] & L.I_BLOCKED), "scale": self.scale} for i in range(A)},
+            pick(self._noisy({i: obs[i].copy() for i in range(A)})),
+            {"team_reward": r2(team) if team is not None else None, "individual_reward": pick({i: r2(rew[i]) for i in range(A)})},
+            pick({i: bool(done[i]) for i in range(A)}),
+            pick({i: {"out_of_bounds": bool(inf[i] & L.I_OOB), "out_of_bounds_count": int(oobc[i]),
+                      "blocked": bool(inf[i] & L.I_BLOCKED), "scale": self.scale} for i in range(A)}),
         )
 
     def reset(self):
@@ -779,16 +801,22 @@ class RadSearch:
         """R:443-728.  ``action``: int (applied to every agent; -1 = idle), dict {agent_id: action}, None (probe), or for
         ``num_envs > 1`` an integer tensor [N] / [N, A]."""
         A = self.number_agents
+        only = None
         if action is None:
             acts = None
         elif isinstance(action, torch.Tensor):
             acts = action
         elif isinstance(action, dict):
-            if sorted(action.keys()) != list(range(A)):
-                raise ValueError("the batched kernels need an action for every agent (reference dict keyed 0..A-1)")
+            if not action or any(i not in range(A) for i in action):
+                raise ValueError("action dict must be keyed by agent ids 0..number_agents-1")
             for a in action.values():
                 assert int(a) in range(A_SIZE)
-            acts = torch.tensor([[int(action[i]) for i in range(A)]] * self.num_envs, dtype=torch.int32)
+            # R:645-659 steps only the agents the dict names; the others are probed without moving (action -1, which the
+            # kernel treats like step(None) for that agent) and reported as None.  Difference to the reference: a named
+            # agent that moves onto the cell of an unnamed one counts as a collision here.
+            if len(action) < A:
+                only = sorted(action)
+            acts = torch.tensor([[int(action.get(i, -1)) for i in range(A)]] * self.num_envs, dtype=torch.int32)
         elif isinstance(action, (int, np.integer)):
             a = 8 if int(action) == -1 else int(action)                   # R:620-623
             assert a in range(A_SIZE)
@@ -798,7 +826,7 @@ class RadSearch:
         self.step_batch(acts)
         if acts is not None:
             self.iter_count += 1
-        return self._pack()
+        return self._pack(only)
 
     def refresh_environment(self, env_dict: Dict, id: int, num_obs: int = 0):
         """R:799-874: load scenario ``env_<id>`` of a saved test-environment dict into every env of this instance."""

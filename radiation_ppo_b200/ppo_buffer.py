@@ -93,11 +93,14 @@ def normalize_advantages_(adv: torch.Tensor, mean: torch.Tensor, std: torch.Tens
 
 
 class PPOBuffer:
-    """Reference-compatible single-trajectory buffer (P:220-502) with device storage.
+    """Reference-compatible single-trajectory buffer (P:220-502).
 
-    The `*_buf` fields are float32 CUDA tensors of length `max_size`; assigning numpy arrays / lists to them (as the
-    reference's tests do) is accepted.  `get()` returns the same dict of float32 torch tensors as the reference, on the
-    buffer's device."""
+    Like the reference's, the `*_buf` fields are float32 numpy arrays of length `max_size` on the host (its unit tests read
+    and assign them directly, unit_tests/test_PPO.py:315-660), `store` is a handful of array writes, and `get()` returns
+    CPU float32 torch tensors.  What runs on the GPU is the arithmetic: `GAE_advantage_and_rewardsToGO` sends the finished
+    trajectory through rs_gae (thread-per-column form, the reference's float64 operation order) and `get()` takes the
+    advantage statistics and the normalisation from rs_adv_stats / rs_adv_normalize.  One env stepping at a time is the
+    reference's own regime (BASELINE configs[0]); batches belong in BatchedPPOBuffer."""
 
     def __init__(self, observation_dimension: int, max_size: int, max_episode_length: int, number_agents: int,
                  gamma: float = 0.99, lam: float = 0.90, device=None) -> None:
@@ -111,7 +114,7 @@ class PPOBuffer:
         self.ptr = 0
         self.path_start_idx = 0
         self.episode_lengths_buffer: List[int] = []
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)   # noqa: E731
+        z = lambda *s: np.zeros(s, dtype=np.float32)   # noqa: E731
         self.obs_buf = z(*combined_shape(max_size, observation_dimension))
         self.act_buf = z(max_size)
         self.adv_buf = z(max_size)
@@ -130,21 +133,16 @@ class PPOBuffer:
         self.path_start_idx = 0
         self.episode_lengths_buffer = []
 
-    def _t(self, x, shape=None) -> torch.Tensor:
-        t = torch.as_tensor(np.asarray(x, dtype=np.float32) if not isinstance(x, torch.Tensor) else x)
-        t = t.to(device=self.device, dtype=torch.float32)
-        return t if shape is None else t.reshape(shape)
-
     def store(self, obs, act, rew, val, logp, src, full_observation=None, heatmap_stacks=None, terminal=False) -> None:
         """P:339-381."""
         assert self.ptr < self.max_size
         p = self.ptr
-        self.obs_buf[p, :] = self._t(obs, (self.observation_dimension,))
-        self.act_buf[p] = float(act)
-        self.rew_buf[p] = float(rew)
-        self.val_buf[p] = float(val)
-        self.source_tar[p] = self._t(src, (2,))
-        self.logp_buf[p] = float(logp)
+        self.obs_buf[p, :] = obs
+        self.act_buf[p] = act
+        self.rew_buf[p] = rew
+        self.val_buf[p] = val
+        self.source_tar[p] = np.asarray(src, dtype=np.float32).reshape(2)
+        self.logp_buf[p] = logp
         if heatmap_stacks:
             self.heatmap_buffer["actor"][p] = heatmap_stacks.actor
             self.heatmap_buffer["critic"][p] = heatmap_stacks.critic
@@ -153,23 +151,27 @@ class PPOBuffer:
     def store_episode_length(self, episode_length: int) -> None:      # P:383-389
         self.episode_lengths_buffer.append(episode_length)
 
+    def _dev(self, x) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+
     def GAE_advantage_and_rewardsToGO(self, last_state_value: float = 0.0) -> None:
-        """P:391-423: finish the trajectory [path_start_idx, ptr) with bootstrap `last_state_value`."""
+        """P:391-423: finish the trajectory [path_start_idx, ptr) with bootstrap `last_state_value` (carried to the device
+        as float32, like the buffer's own values; the reference appends it to float32 slices as a Python float)."""
         s, e = self.path_start_idx, self.ptr
         n = e - s
         if n > 0:
-            for name in ("rew_buf", "val_buf", "adv_buf", "ret_buf"):     # tests assign numpy arrays to these
+            for name in ("rew_buf", "val_buf", "adv_buf", "ret_buf"):     # the reference's tests assign lists / float64 arrays
                 v = getattr(self, name)
-                if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32):
-                    setattr(self, name, self._t(v).contiguous())
-            rew = self.rew_buf[s:e].reshape(n, 1)
-            val = self.val_buf[s:e].reshape(n, 1)
+                if not (isinstance(v, np.ndarray) and v.dtype == np.float32):
+                    setattr(self, name, np.array(v, dtype=np.float32))
             pe = torch.zeros(n, 1, dtype=torch.uint8, device=self.device)
             boot = torch.zeros(n, 1, dtype=torch.float32, device=self.device)
             boot[n - 1, 0] = float(last_state_value)
-            adv, ret = gae_advantages(rew, val, pe, boot, self.gamma, self.lam, variant=1)
-            self.adv_buf[s:e] = adv.view(-1)
-            self.ret_buf[s:e] = ret.view(-1)
+            adv, ret = gae_advantages(self._dev(self.rew_buf[s:e]).reshape(n, 1), self._dev(self.val_buf[s:e]).reshape(n, 1),
+                                      pe, boot, self.gamma, self.lam, variant=1)
+            both = torch.stack((adv.view(-1), ret.view(-1))).cpu().numpy()      # one device -> host copy
+            self.adv_buf[s:e] = both[0]
+            self.ret_buf[s:e] = both[1]
         self.path_start_idx = self.ptr
 
     def get(self) -> Dict[str, object]:
@@ -179,24 +181,23 @@ class PPOBuffer:
         number_episodes = len(episode_lengths)
         total_episode_length = sum(episode_lengths)
         assert number_episodes > 0, "0 completed episodes. Usually caused by having epochs shorter than an episode"
-        mean, std = advantage_statistics(self.adv_buf)
-        normalize_advantages_(self.adv_buf, mean.float().double(), std.float().double())
+        adv = self._dev(self.adv_buf)
+        mean, std = advantage_statistics(adv)                         # mpi_statistics_scalar P:445
+        normalize_advantages_(adv, mean.float().double(), std.float().double())
+        self.adv_buf = adv.cpu().numpy()
         self.quick_reset()
         # ep_form (P:456-486): one [len, D + 6] tensor of [obs | adv | ret | logp | act | source_tar] rows per recorded
         # episode, plus the unfinished tail of the buffer when the recorded lengths do not cover it
-        rows = torch.cat((self.obs_buf, self.adv_buf[:, None], self.ret_buf[:, None], self.logp_buf[:, None],
-                          self.act_buf[:, None], self.source_tar), dim=1)
+        rows = torch.as_tensor(np.hstack((self.obs_buf, self.adv_buf[:, None], self.ret_buf[:, None], self.logp_buf[:, None],
+                                          self.act_buf[:, None], self.source_tar)), dtype=torch.float32)
         sizes = list(episode_lengths)
         tail = rows.shape[0] - total_episode_length
         if tail:
             sizes.append(tail)
         episode_form: List[List[torch.Tensor]] = [[piece.clone()] for piece in torch.split(rows, sizes, dim=0)]
-        return dict(
-            obs=self.obs_buf.clone(), act=self.act_buf.clone(), ret=self.ret_buf.clone(), adv=self.adv_buf.clone(),
-            logp=self.logp_buf.clone(), loc_pred=self.obs_win_std.clone(),
-            ep_len=torch.as_tensor(float(total_episode_length), dtype=torch.float32, device=self.device),
-            ep_form=episode_form,
-        )
+        t = lambda x: torch.as_tensor(np.copy(x), dtype=torch.float32)          # noqa: E731
+        return dict(obs=t(self.obs_buf), act=t(self.act_buf), ret=t(self.ret_buf), adv=t(self.adv_buf), logp=t(self.logp_buf),
+                    loc_pred=t(self.obs_win_std), ep_len=t(total_episode_length), ep_form=episode_form)
 
 
 class BatchedPPOBuffer:

@@ -329,6 +329,32 @@ def test_prefetched_resets_match_oracle(graph):
     pu.compare_state(pu.GpuView(env), ob, A)
 
 
+def test_coord_noise_and_partial_action_dicts():
+    """R:570-574 `coord_noise` perturbs the reported coordinates only (state and rewards unchanged); R:645-659 a dict
+    action that names a subset of the agents steps only those and reports None for the others."""
+    kw = dict(obstruction_count=3, enforce_grid_boundaries=True, np_random=np.random.default_rng(5), seed=77)
+    a, b = rp.RadSearch(**kw), rp.RadSearch(**dict(kw, np_random=np.random.default_rng(5)))
+    b.coord_noise = True
+    for act in (2, 4, 6, 0, 3):
+        oa, ra, da, _ = a.step(act)
+        ob_, rb, db, _ = b.step(act)
+        assert ra == rb and da == db and a.agents[0].det_coords == b.agents[0].det_coords
+        assert oa[0][0] == ob_[0][0] and np.array_equal(oa[0][3:], ob_[0][3:])
+        d = (ob_[0][1:3] - oa[0][1:3]) / a.scale
+        assert np.all(d != 0) and np.all(np.abs(d) < 40)            # N(0, 5) on the coordinates
+    env = rp.RadSearch(obstruction_count=2, enforce_grid_boundaries=True, number_agents=3, seed=9)
+    before = [env.agents[i].det_coords for i in range(3)]
+    obs, rew, done, info = env.step({1: 4})
+    assert obs[0] is None and obs[2] is None and obs[1].shape == (11,)
+    assert rew["individual_reward"][0] is None and rew["individual_reward"][1] == rew["team_reward"]
+    assert done[0] is None and info[2] is None and info[1]["scale"] == env.scale
+    after = [env.agents[i].det_coords for i in range(3)]
+    assert after[0] == before[0] and after[2] == before[2]
+    assert after[1] != before[1] or info[1]["blocked"] or info[1]["out_of_bounds"]
+    with pytest.raises(ValueError):
+        env.step({5: 1})
+
+
 def test_prefetch_is_refused_for_episodes_shorter_than_a_block():
     """An env is listed for refill once per block of PREFETCH_PERIOD steps: with 2-step episodes the prefetch machinery is
     switched off (the results are those of the synchronous resets) instead of overrunning its lists."""

@@ -136,10 +136,10 @@ def test_ppobuffer_init_quick_reset_store():                      # unit_tests/t
     for i in range(2):
         buf.store(obs=obs, act=1, rew=-0.46, val=-0.26629042625427246, logp=-1.777620792388916, src=src,
                   full_observation={0: obs, 1: obs}, heatmap_stacks=None, terminal=False)
-        assert buf.obs_buf.shape == (2, 11) and np.array_equal(buf.obs_buf[i].cpu().numpy(), obs)
+        assert buf.obs_buf.shape == (2, 11) and np.array_equal(buf.obs_buf[i], obs)
         assert buf.act_buf.shape == (2,) and buf.act_buf[i].item() == 1
         assert buf.rew_buf[i].item() == pytest.approx(-0.46) and buf.val_buf[i].item() == pytest.approx(-0.26629042625427246)
-        assert buf.source_tar.shape == (2, 2) and np.array_equal(buf.source_tar[i].cpu().numpy(), src)
+        assert buf.source_tar.shape == (2, 2) and np.array_equal(buf.source_tar[i], src)
         assert buf.logp_buf[i].item() == pytest.approx(-1.777620792388916) and buf.ptr == i + 1
     with pytest.raises(AssertionError):
         buf.store(obs=obs, act=1, rew=0, val=0, logp=0, src=src)
@@ -184,7 +184,7 @@ def test_ppobuffer_get_matches_reference_semantics():             # P:425-502, u
             buf.GAE_advantage_and_rewardsToGO(0.0)
             buf.store_episode_length(5)
     buf.GAE_advantage_and_rewardsToGO(float(val[-1]))
-    adv_before = buf.adv_buf.cpu().numpy().copy()
+    adv_before = buf.adv_buf.copy()
     data = buf.get()
     assert buf.ptr == 0 and buf.path_start_idx == 0 and len(buf.episode_lengths_buffer) == 0
     assert set(data) == {"obs", "act", "ret", "adv", "logp", "loc_pred", "ep_len", "ep_form"}

@@ -1,11 +1,13 @@
 #!/bin/bash
 # Parity tests on the shipped library, then bench.py --quick for the shipped library and for every variant build under
 # radiation_ppo_b200/_C/var_*.so (made with `python -m radiation_ppo_b200.build -DNAME=VALUE -ovar_x.so`), then one ncu capture.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_variants.sh r02c'
+#   gpurun --timeout 1500 -- 'bash tools/gpu_variants.sh r02c [noncu] [notests]'
 tag=${1:-vX}
 mkdir -p gpurun_out
+if [ "$3" != "notests" ]; then
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/pytest_gpu_$tag.log
+fi
 echo "== shipped"; timeout 300 python bench.py --steps 20 --warmup 5 --quick 2>&1 | tail -1
 echo "== shipped, exact sampler"; timeout 300 python bench.py --steps 20 --warmup 5 --quick --exact-poisson 2>&1 | tail -1
 echo "== shipped, ring 1 (state stays in L2)"; timeout 300 python bench.py --steps 20 --warmup 5 --quick --ring 1 2>&1 | tail -1
