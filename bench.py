@@ -526,17 +526,20 @@ class GruPolicy:
             self.h.masked_fill_(mask[:, None], 0.0)
 
 
-def ppo_update(cx: Ctx, pol: GruPolicy, buf, data, opt, chunk: int = 16384, clip: float = 0.2):
-    """One PPO update over the epoch's rollout (clipped policy loss + value loss, P:1150-1281 in spirit): the GRU is re-run
-    over the T steps of every column with its state restarted where a path ended, gradients accumulated over column
-    chunks, averaged over ranks with ONE flattened all-reduce (dist.average_gradients = mpi_avg_grads), one Adam step."""
+def ppo_update(cx: Ctx, pol: GruPolicy, buf, data, opt, columns: int = 8192, chunk: int = 8192, clip: float = 0.2):
+    """One PPO update on a minibatch of `columns` trajectories x T steps of the epoch's rollout (clipped policy loss + value
+    loss, P:1150-1281 in spirit): the GRU is re-run over the T steps of those columns with its state restarted where a path
+    ended, the gradients are averaged over ranks with ONE flattened all-reduce (dist.average_gradients = mpi_avg_grads),
+    one Adam step.  Stock PyTorch, step by step: it is the consumer of the hot path, not part of it."""
     torch = cx.torch
     from radiation_ppo_b200 import dist as rdist
 
-    T, N, D = buf.T, buf.N, buf.D
-    obs = data["obs"].view(T, N, D)
-    act = data["act"].view(T, N).long()
-    adv, ret, logp_old = data["adv"].view(T, N), data["ret"].view(T, N), data["logp"].view(T, N)
+    T, N, D = buf.T, min(buf.N, columns), buf.D
+    data = {k: (v.view(buf.T, buf.N, *v.shape[1:])[:, :N] if k in ("obs", "act", "adv", "ret", "logp") else v) for k, v in data.items()}
+    data["end"] = data["end"][:, :N]
+    obs = data["obs"]
+    act = data["act"].long()
+    adv, ret, logp_old = data["adv"], data["ret"], data["logp"]
     end = data["end"]
     opt.zero_grad(set_to_none=True)
     total = 0.0
@@ -603,7 +606,7 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
     tot = cx.max_over_ranks([r["rollout_gae_ms"], r["rollout_gae_ms"] + r["get_ms"] + r["episode_stats_ms"] + r["update_ms"]])
     out = {"workload": f"{N} envs/GPU x T={T}, 5 obstructions, GRU(11->24) policy in the loop, count standardiser fused in the "
                        "step kernel, step kernel stores into the rollout buffer (no store copies), GAE, get(episodes=True), "
-                       "1 PPO update (BASELINE configs[2])",
+                       "1 PPO update (one Adam step on a minibatch of 8,192 trajectories x 480 steps) (BASELINE configs[2])",
            "rollout_env_steps_per_s": N * cx.world * T / (tot[0] / 1e3),
            "pipeline_env_steps_per_s": N * cx.world * T / (tot[1] / 1e3),
            "us_per_rollout_step": 1e3 * r["rollout_gae_ms"] / T, "stages_ms": r, "epochs_run": epochs,

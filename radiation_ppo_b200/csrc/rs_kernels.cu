@@ -778,10 +778,13 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
     rs::Params P = rs::make_params(*cfg);
     int need = (a.n_env + 3) / 4;                       // one warp per env is the widest teaming
     int cap = kResetGrid;
-    const int prepare_nl = 1;                           // rs_prepare: one thread per environment (throughput, not latency)
+#ifndef RS_PREPARE_NL
+#define RS_PREPARE_NL 1
+#endif
+    const int prepare_nl = RS_PREPARE_NL;               // rs_prepare: lanes per environment (1: throughput, not latency)
     if (a.prepare) {                                    // kept small: it shares the GPU with rs_step
         need = (a.n_env + kBlock / prepare_nl - 1) / (kBlock / prepare_nl);
-        cap = 148;
+        cap = 148 * (prepare_nl > 1 ? 4 : 1);
     }
     // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
     if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 16;

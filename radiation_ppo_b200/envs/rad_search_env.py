@@ -334,6 +334,8 @@ class RadSearch:
         contiguous, on this device) -- e.g. the rows of a rollout buffer, so that the kernel stores straight into them."""
         if not out:
             return (self.obs, self.reward, self.team_reward, self.done_flags, self.info_flags, self.ended, self.final_obs)
+        if isinstance(out, tuple):                      # already resolved by resolve_outputs()
+            return out
         unknown = set(out) - {k for k, _, _ in self._OUT_SPEC}
         if unknown:
             raise ValueError(f"unknown step outputs {sorted(unknown)}")
@@ -348,6 +350,11 @@ class RadSearch:
                 raise ValueError(f"out[{key!r}] must be a contiguous {dt} tensor of {own.numel()} elements on {own.device}")
             res.append(t)
         return tuple(res)
+
+    def resolve_outputs(self, out: Dict[str, torch.Tensor]) -> tuple:
+        """Validate an `out` mapping once; the returned tuple can be passed as `out=` to step_batch any number of times
+        (a rollout loop resolves its T rows up front instead of at every step)."""
+        return self._outputs(dict(out))
 
     def step_batch(self, actions: Optional[torch.Tensor], epoch_end: bool = False,
                    uniforms: Optional[torch.Tensor] = None, auto_reset: Optional[bool] = None,

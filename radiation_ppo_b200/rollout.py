@@ -52,7 +52,10 @@ class RolloutCollector:
             raise ValueError("buffer shape does not match the env batch")
         self.env, self.buf, self.policy, self.stats = env, buf, policy, stats
         self._first = True
-        self._src = None
+        # the rows of the (persistent) buffer every step writes: resolved once, not at every step
+        self._rows = [buf.policy_rows(t) for t in range(buf.T)]
+        self._outs = [buf.step_outputs(t) for t in range(buf.T)]
+        self._outs_resolved = [env.resolve_outputs(o) for o in self._outs]
 
     def collect(self, gae_variant: int = 0) -> None:
         env, buf, pol = self.env, self.buf, self.policy
@@ -69,14 +72,14 @@ class RolloutCollector:
         st = self.stats.fused_args() if self.stats is not None else (None,) * 5
         final_obs = env.final_obs.reshape(N, buf.D)
         for t in range(T):
-            rows = buf.policy_rows(t)
+            rows = self._rows[t]
             action, value, logp = pol.act(rows["obs"])
             # row t of the buffer <- action, value, log-probability, source coordinates (T:416-428), one launch
             L.check(lib.rs_rollout_pre(p(action), p(value), p(logp), p(env._src), p(rows["act"]), p(rows["val"]),
                                        p(rows["logp"]), p(rows["src"]), N, stream), "rs_rollout_pre")
             last = t == T - 1
-            outs = buf.step_outputs(t)
-            env.step_batch(action, epoch_end=last, out=outs)                         # obs -> row t+1, reward / ended -> row t
+            outs = self._outs[t]
+            env.step_batch(action, epoch_end=last, out=self._outs_resolved[t])       # obs -> row t+1, reward / ended -> row t
             # T:462-487 bootstrap where the trajectory was cut, T:509-511 recurrent state, T:361-391 episode statistics
             v_next = pol.value(final_obs)
             L.check(lib.rs_rollout_post(p(outs["reward"]), p(outs["ended"]), p(env.done_flags), p(env.info_flags), p(v_next),

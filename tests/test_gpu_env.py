@@ -329,6 +329,66 @@ def test_prefetched_resets_match_oracle(graph):
     pu.compare_state(pu.GpuView(env), ob, A)
 
 
+def test_full_size_batch_matches_oracle():
+    """BASELINE configs[4]'s batch (131,072 envs, 5 obstructions) through the prefetch + CUDA-graph path, 60 steps with
+    staggered episodes (~66 k resets): every output of every step and the full state against the oracle, Poisson counts
+    included (numpy-exact sampler on the shared Philox stream).  tests/full_size_soak.py is the same loop for T = 480."""
+    n, T, ML, A = 131072, 60, 120, 1
+    env, ob = make_pair(n, A, 5, True, seed=777, env_id0=0, max_ep_len=ML, auto_reset=True, prefetch=True, use_cuda_graph=True)
+    g = torch.Generator(device=env.device).manual_seed(1)
+    stagger = torch.randint(0, ML, (n,), generator=g, device=env.device, dtype=torch.int32)
+    env._meta.add_(stagger << 16)
+    ob.envs["ep_len"] = stagger.cpu().numpy()
+    rng = np.random.default_rng(1)
+    resets = 0
+    for t in range(1, T + 1):
+        acts = rng.integers(0, 8, size=(n, A))
+        env.step_batch(torch.as_tensor(acts, dtype=torch.int32, device=env.device))
+        ob.step(acts, env._ctr)
+        e, o = ob.envs, ob.outs
+        terminal, timeout = e["done"] == 1, e["ep_len"] == ML
+        want = terminal * 1 | timeout * 2 | ((terminal | timeout) * 4)
+        mask = (want & 4) != 0
+        final = o["obs"][:, :A].copy()
+        rew = o["reward"][:, :A].astype(np.float32).copy()
+        if mask.any():
+            ob.reset(mask=mask, new_obstacles=np.zeros(n))
+        v = pu.GpuView(env)
+        np.testing.assert_array_equal(v.ended, want)
+        np.testing.assert_array_equal(v.reward, rew)
+        pu.compare_obs(v.final_obs, final, sel=np.where(mask)[0])
+        pu.compare_obs(v.obs, np.where(mask[:, None, None], o["obs"][:, :A], final))
+        pu.compare_state(v, ob, A)
+        resets += int(mask.sum())
+    assert resets > n // 4 and int((env.status & ~2).sum()) == 0
+
+
+def test_step_block_equals_single_steps():
+    """RadSearch.step_block (PREFETCH_PERIOD steps + the refill rs_prepare as ONE graph launch) against the same steps taken
+    one by one: identical state, outputs and Philox counters, also when blocks and single steps are mixed."""
+    n, ML = 4096, 30
+    kw = dict(obstruction_count=5, enforce_grid_boundaries=True, num_envs=n, seed=123, steps_per_episode=ML, auto_reset=True,
+              prefetch=True, use_cuda_graph=True)
+    a, b = rp.RadSearch(**kw), rp.RadSearch(**kw)
+    P = a.PREFETCH_PERIOD
+    rng = np.random.default_rng(2)
+    for rnd in range(14):
+        acts = torch.as_tensor(rng.integers(0, 8, size=(P, n, 1)), dtype=torch.int32, device=a.device)
+        if rnd % 5 == 4:                                 # a block taken step by step on both (mixing the two paths)
+            for i in range(P):
+                a.step_batch(acts[i])
+        else:
+            a.step_block(acts)
+        for i in range(P):
+            b.step_batch(acts[i])
+        assert a._ctr == b._ctr
+        for name in ("obs", "reward", "done_flags", "info_flags", "ended", "final_obs", "_det", "_src", "_meta", "_best", "_epi"):
+            np.testing.assert_array_equal(getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy(), err_msg=f"{name} round {rnd}")
+    assert int(a._epi.sum()) > 2 * n
+    with pytest.raises(ValueError):
+        a.step_batch(acts[0]); a.step_block(acts)        # not at a block boundary
+
+
 def test_coord_noise_and_partial_action_dicts():
     """R:570-574 `coord_noise` perturbs the reported coordinates only (state and rewards unchanged); R:645-659 a dict
     action that names a subset of the agents steps only those and reports None for the others."""

@@ -338,3 +338,93 @@ def test_rollout_to_advantages_pipeline_matches_oracle():
     packed = data["packed"].cpu().numpy().reshape(N, T, 17)
     np.testing.assert_array_equal(packed[:, :, 12], r0.T)
     assert end_o.sum() > 4 * N
+
+
+def test_rollout_collector_zero_copy_epoch_matches_oracle():
+    """RolloutCollector (train.py:321-571 for a batched env): the step kernel stores observation t+1 / reward / path-end flags
+    straight into the buffer rows (step_batch(out=)), rs_rollout_pre / rs_rollout_post do the caller-side bookkeeping --
+    against the oracle env stepped the reference's way: every buffer row, the bootstrap rule (value of the next observation
+    where the trajectory was cut by the timeout or the epoch's last step, else 0), the episode statistics, then GAE."""
+    N, T, ML = 2048, 96, 24
+    env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, num_envs=N, seed=41, steps_per_episode=ML,
+                       auto_reset=True, prefetch=True)
+    ob = co.OracleBatch(N, co.default_config(obstruction_count=5, enforce=1, max_ep_len=ML), seed=41)
+    ob.reset()
+    d = env.device
+    rng = np.random.default_rng(8)
+    w = torch.as_tensor(rng.normal(size=11).astype(np.float32), device=d)
+    actions = rng.integers(0, 8, size=(2 * T, N)).astype(np.int32)
+
+    def value_fn(obs):
+        x = obs.reshape(-1, 11).clone()
+        x[:, 0] = torch.log1p(x[:, 0]) * 0.1
+        return torch.tanh(x @ w)
+
+    class Scripted:
+        def __init__(self):
+            self.t = 0
+            self.acts = torch.as_tensor(actions, device=d)
+            self.hidden_state = torch.ones(N, 3, device=d)            # restarted in place by rs_rollout_post
+        def act(self, obs):
+            a = self.acts[self.t]; self.t += 1
+            v = value_fn(obs)
+            return a, v, (-0.5 * v).contiguous()
+        def value(self, obs):
+            return value_fn(obs)
+        def reset_state(self, mask):
+            assert mask is None
+            self.hidden_state.fill_(1.0)
+
+    pol = Scripted()
+    buf = rp.BatchedPPOBuffer(11, T, N)
+    stats = rp.EpisodeStats(N, 1, d)
+    col = rp.RolloutCollector(env, buf, pol, stats)
+    ep_ret, ep_len = np.zeros(N), np.zeros(N, int)
+    for epoch in range(2):
+        first_obs = ob.outs["obs"][:, :1].astype(np.float32).copy()
+        col.collect(gae_variant=1)
+        obs_o = np.zeros((T, N, 11), np.float32); rew_o = np.zeros((T, N), np.float32)
+        end_o = np.zeros((T, N), np.uint8); boot_o = np.zeros((T, N), np.float32); src_o = np.zeros((T, N, 2), np.float32)
+        rets, lens, done_count, hid = [], [], 0, np.ones(N)
+        cur = first_obs
+        for t in range(T):
+            obs_o[t] = cur[:, 0]
+            src_o[t] = ob.envs["src"]
+            acts = actions[epoch * T + t][:, None]
+            last = t == T - 1
+            ob.step(acts, env._ctr - (T - 1 - t))                 # the Philox step counter the env used at that step
+            e = ob.envs
+            term, timeout = e["done"] == 1, e["ep_len"] == ML
+            pe = term | timeout | last
+            rew_o[t] = ob.outs["reward"][:, 0].astype(np.float32)
+            end_o[t] = pe
+            fin = torch.as_tensor(ob.outs["obs"][:, :1].astype(np.float32), device=d)
+            cut = np.full(N, True) if last else timeout
+            boot_o[t] = np.where(cut, value_fn(fin).cpu().numpy(), 0.0)
+            ep_ret += rew_o[t].astype(np.float64); ep_len += 1
+            over = term | timeout
+            rets += list(ep_ret[over]); lens += list(ep_len[over]); done_count += int(term.sum())
+            ep_ret[pe] = 0.0; ep_len[pe] = 0
+            if not last:
+                hid = np.where(pe, 0.0, hid)
+            if pe.any():
+                ob.reset(mask=pe, new_obstacles=np.full(N, last))
+            cur = ob.outs["obs"][:, :1].astype(np.float32).copy()
+        pu.compare_obs(buf.obs_buf.cpu().numpy().reshape(T * N, 1, 11), obs_o.reshape(T * N, 1, 11))
+        np.testing.assert_array_equal(buf.rew_buf.cpu().numpy(), rew_o)
+        np.testing.assert_array_equal(buf.end_buf.cpu().numpy() != 0, end_o != 0)
+        np.testing.assert_array_equal(buf.act_buf.cpu().numpy(), actions[epoch * T:(epoch + 1) * T].astype(np.float32))
+        np.testing.assert_array_equal(buf.source_tar.cpu().numpy(), src_o)
+        np.testing.assert_allclose(buf.boot_buf.cpu().numpy(), boot_o, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(buf.logp_buf.cpu().numpy(), -0.5 * buf.val_buf.cpu().numpy(), rtol=0, atol=0)
+        a0, r0 = co.gae(buf.rew_buf.cpu().numpy(), buf.val_buf.cpu().numpy(), (end_o != 0).astype(np.uint8), buf.boot_buf.cpu().numpy())
+        np.testing.assert_array_equal(buf.adv_buf.cpu().numpy(), a0)
+        np.testing.assert_array_equal(buf.ret_buf.cpu().numpy(), r0)
+        np.testing.assert_array_equal(pol.hidden_state[:, 0].cpu().numpy(), hid)
+        summ = stats.epoch_summary()
+        assert int(summ["Episodes"][0]) == len(rets) and int(summ["DoneCount"][0]) == done_count
+        np.testing.assert_allclose(float(summ["AverageEpRet"][0]), np.mean(rets), rtol=1e-9)
+        np.testing.assert_allclose(float(summ["EpLen"][0]), np.mean(lens), rtol=1e-12)
+        assert float(summ["MinEpRet"][0]) == min(rets) and float(summ["MaxEpRet"][0]) == max(rets)
+        buf.get()
+    assert int((env.status & ~2).sum()) == 0
