@@ -855,6 +855,8 @@ def main():
         "gpu_launches": head["launches"], "graph_launches": head["graph_launches"], "clocks": head["clocks"],
         "status_flags_raised": status,
     }
+    if "e2e" in legs:
+        line["e2e"] = e2e_leg(cx, envs, K, W)
     if "exact" in legs and fast:
         for e in envs:
             e._quiesce_prefetch()
@@ -867,8 +869,6 @@ def main():
                                  "ring": 2}
         line["exact_poisson_value"] = hx["value"]
         del envs_x
-    if "e2e" in legs:
-        line["e2e"] = e2e_leg(cx, envs, K, W)
     del envs
     torch.cuda.empty_cache()
     if "sweep" in legs and cx.world == 1:

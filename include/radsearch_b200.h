@@ -175,7 +175,8 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
  * variant: 0 auto; 1 thread-per-column recurrence in the reference's operation order (bit-exact vs scipy's lfilter), fed by
  * bulk-async tile copies when N % 128 == 0 and the arrays are 16-byte aligned, else by register-pipelined loads; 2 warp-
  * shuffle scan along T (small N; within 1e-5).  3 / 4 force the 8- / 16-deep register-pipelined form, 7 the 3-stage tile
- * ring, 8 / 9 / 11 the producer-warp form with 3 x 8, 6 x 4 and 6 x 8 rows in flight -- all bit-identical to variant 1. */
+ * ring, 10 the same ring over 64-column tiles, 8 / 11 the producer-warp form with 3 x 8 and 6 x 8 rows in flight
+ * -- all bit-identical to variant 1. */
 int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
            int32_t T, int32_t N, double gamma, double lam, double *stats, int32_t variant, void *stream);
 

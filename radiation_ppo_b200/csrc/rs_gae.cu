@@ -519,6 +519,8 @@ int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const fl
         }
         if (variant == 7)
             gae_tile_kernel<128, 8, 3, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 10)
+            gae_tile_kernel<64, 8, 3, 14><<<N / 64, 64, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 8)
             gae_tile_ws_kernel<8, 3, 7><<<grid, kColsBlock + 32, 9 * 3 * 8 * kColsBlock + 2 * 3 * 8, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 11) {

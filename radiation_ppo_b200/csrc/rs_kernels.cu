@@ -328,6 +328,19 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         if (a.actions) action = a.actions[n];
         if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
     }
+    // an episode that times out at this step is known now: its prefetched successor (adopted in the commit phase) is pulled
+    // into L2 while the step is computed
+    if (live && (a.flags & RS_F_PREFETCH) && a.actions && (meta >> 16) + 1 == P.max_ep_len) {
+        const char *r = reinterpret_cast<const char *>(S.nx_dsrc + (size_t)n * 4 * K);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_dsf + (size_t)n * 4 * K));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_obs + (size_t)n * RS_OBS_DIM));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_src + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_det + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_rad + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_best + n));
+    }
     // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
     const int hint = (af >> 25) & 31;
     double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
