@@ -237,8 +237,9 @@ typedef struct RsMapsConfig {
 } RsMapsConfig;
 
 typedef struct RsMapsState {     /* caller-owned device memory; X = dim_x, Y = dim_y, cell = x * Y + y              */
-    float *actor;                /* [N][A][6][X][Y] per buffer: prediction, own location, others, readings, visits, obstacles :1799-1823 */
-    float *critic;               /* [N][4][X][Y]    combined locations, readings, visits, obstacles (same in all A buffers) :1825-1832 */
+    float *actor;                /* [N][A][X][Y][6] per buffer, channel innermost (channels_last): prediction, own location,    */
+                                 /*                 others, readings, visits, obstacles                              :1799-1823 */
+    float *critic;               /* [N][X][Y][4]    combined locations, readings, visits, obstacles (same in all A buffers) :1825-1832 */
     uint16_t *log_cell;          /* [N][log_cap]    sample table of the IntensityEstimator: cell of reading i (0xffff = none) */
     float *log_val;              /* [N][log_cap]                                                value of reading i  */
     int32_t *log_len;            /* [N]                                                                             */

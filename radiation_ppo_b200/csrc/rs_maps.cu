@@ -13,10 +13,12 @@
 // One warp per environment.  Per call and environment the work is: the episode's sample table (<= (T+1)*A readings, 6
 // bytes each) staged into shared memory, per agent a compaction + rank selection among the samples of its cell, and
 // ~6*A*A scattered 4-byte STORES -- the location counts are recomputed from the agents' recorded cells and the visit
-// counter from the sample table, so no map is ever read back.  Bound by latency and by the scattered 32-byte-sector
-// traffic of those stores (per-cell chains instead of the table scan were tried: fewer instructions, one more dependent
-// load, slower); the dense stacks (29 KB per agent at 27x27) are never rewritten, the policy's convolutions read them
-// where they lie.
+// counter from the sample table, so no map is ever read back.  Bound by the random 32-byte-sector traffic of those stores
+// (every partially written sector is filled from DRAM first): the stacks are therefore stored CHANNEL-INNERMOST
+// ([X][Y][6], torch's channels_last), so that the 4-5 values a call writes for one cell of one buffer share one or two
+// sectors instead of one sector per channel plane (round 1: 117 sector fills per call and environment, now ~50).  The
+// dense stacks are never rewritten; the policy's convolutions read them where they lie (channels_last is cuDNN's
+// native layout).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -112,13 +114,17 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
     }
     __syncwarp();
 
+    // stacks are stored cell-major, channel innermost ([X][Y][6] / [X][Y][4]): the values one call writes for a cell of
+    // a buffer share a 32-byte sector or two instead of one sector per channel plane
     float *actor = S.actor + ((size_t)n * A + (lane < A ? lane : 0)) * 6 * XY;   // lane a' owns buffer a'
     float *critic = S.critic + (size_t)n * 4 * XY;
+#define ACT(ch, cell) actor[(size_t)(cell) * 6 + (ch)]
+#define CRI(ch, cell) critic[(size_t)(cell) * 4 + (ch)]
 
     // ---- source prediction map of buffer a' (PFGRU) M:564-568, 748-766: the old mark (a 1) goes, the new one is set ------
     if (pred_given) {
-        if (last_pred >= 0 && last_pred != my_pred) actor[last_pred] = 0.0f;
-        if (my_pred >= 0) actor[my_pred] = 1.0f;       // outside the map (the reference raises): old mark cleared, none set
+        if (last_pred >= 0 && last_pred != my_pred) ACT(0, last_pred) = 0.0f;
+        if (my_pred >= 0) ACT(0, my_pred) = 1.0f;      // outside the map (the reference raises): old mark cleared, none set
         S.last_pred[(size_t)n * A + lane] = my_pred;
     }
 
@@ -185,24 +191,26 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
         const int n_last = __popc(__ballot_sync(0xffffffffu, lane < A && last >= 0 && rec == last));
         if (lane < A) {
             if (lane == a) {                                                // own location map M:812-830
-                if (last >= 0 && last != cc) actor[XY + last] = 0.0f;
-                actor[XY + cc] = 1.0f;
+                if (last >= 0 && last != cc) ACT(1, last) = 0.0f;
+                ACT(1, cc) = 1.0f;
             } else {                                                        // others' locations M:832-848: agents != a'
-                if (last >= 0) actor[2 * XY + last] = (float)(n_last - (rec == last));
-                actor[2 * XY + cc] = (float)(n_cc - (rec == cc));
+                if (last >= 0) ACT(2, last) = (float)(n_last - (rec == last));
+                ACT(2, cc) = (float)(n_cc - (rec == cc));
             }
-            actor[3 * XY + cc] = z;                                         // readings map M:884
-            actor[4 * XY + cc] = vis;                                       // visit counts map M:906
-            if (has_obst) actor[5 * XY + cc] = obst;                        // obstacles map M:929-932
+            ACT(3, cc) = z;                                                 // readings map M:884
+            ACT(4, cc) = vis;                                               // visit counts map M:906
+            if (has_obst) ACT(5, cc) = obst;                                // obstacles map M:929-932
         }
         if (lane == 0) {                                                    // the critic's stack (same in every buffer)
-            if (last >= 0) critic[last] = (float)n_last;                    // combined locations M:786-810
-            critic[cc] = (float)n_cc;
-            critic[XY + cc] = z;
-            critic[2 * XY + cc] = vis;
-            if (has_obst) critic[3 * XY + cc] = obst;
+            if (last >= 0) CRI(0, last) = (float)n_last;                    // combined locations M:786-810
+            CRI(0, cc) = (float)n_cc;
+            CRI(1, cc) = z;
+            CRI(2, cc) = vis;
+            if (has_obst) CRI(3, cc) = obst;
         }
     }
+#undef ACT
+#undef CRI
     if (lane < A) S.last_cell[(size_t)n * A + lane] = rec;
     if (lane == 0) {
         S.log_len[n] = len;

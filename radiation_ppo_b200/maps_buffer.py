@@ -69,8 +69,12 @@ class BatchedMapsBuffer:
         self._cfg = cfg
         dev = self.device
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)     # noqa: E731
-        self.actor_maps = z(N, A, 6, X, Y)
-        self.critic_maps = z(N, 4, X, Y)
+        # stored channel-innermost (rs_maps.cu): the public tensors are channels-first VIEWS of that storage, i.e. torch's
+        # channels_last memory format -- what cuDNN convolutions take natively; .contiguous() gives the planar copy
+        self._actor_store = z(N, A, X, Y, 6)
+        self._critic_store = z(N, X, Y, 4)
+        self.actor_maps = self._actor_store.permute(0, 1, 4, 2, 3)       # [N, A, 6, X, Y]
+        self.critic_maps = self._critic_store.permute(0, 3, 1, 2)        # [N, 4, X, Y]
         self._log_cell, self._log_val, self._log_len = z(N, cap, dt=torch.int16), z(N, cap), z(N, dt=torch.int32)
         self._last_cell = torch.full((N, A), -1, dtype=torch.int32, device=dev)
         self._last_pred = torch.full((N, A), -1, dtype=torch.int32, device=dev)
@@ -81,7 +85,7 @@ class BatchedMapsBuffer:
         self._visit_lut = torch.tensor(np.asarray(lut, dtype=np.float64).astype(np.float32), device=dev)
         self.status = z(N, dt=torch.int32)
         self._st = L.RsMapsState(*[t.data_ptr() for t in (
-            self.actor_maps, self.critic_maps, self._log_cell, self._log_val, self._log_len,
+            self._actor_store, self._critic_store, self._log_cell, self._log_val, self._log_len,
             self._last_cell, self._last_pred, self._std, self._std_count, self._visit_lut, self.status)])
 
     def _stream(self):
