@@ -455,7 +455,8 @@ class GruPolicy:
     head (the shape of the reference's RAD-A2C core, algos/test_environment/core.py).  `act` / `value` run as captured CUDA
     graphs on static buffers; everything inside them is torch's own kernels (cuBLAS GEMMs, elementwise)."""
 
-    def __init__(self, cx: Ctx, N: int, obs_dim: int = 11, hidden: int = 24, n_act: int = 8, final_obs=None):
+    def __init__(self, cx: Ctx, N: int, obs_dim: int = 11, hidden: int = 24, n_act: int = 8, final_obs=None, obs_in=None,
+                 action_out=None):
         torch = cx.torch
         self.torch, self.N = torch, N
         torch.manual_seed(0)
@@ -463,9 +464,10 @@ class GruPolicy:
                                         "v": torch.nn.Linear(hidden, 1)}).to(cx.dev)
         self.h = torch.zeros(N, hidden, device=cx.dev)
         self.hidden_state = self.h                       # restarted in place by rs_rollout_post (RolloutCollector)
-        self.obs_in = torch.zeros(N, obs_dim, device=cx.dev)
+        # obs_in / action_out: the env's own observation and action buffers (graph mode: nothing is copied)
+        self.obs_in = torch.zeros(N, obs_dim, device=cx.dev) if obs_in is None else obs_in
         self.final_obs = final_obs
-        self.action = torch.zeros(N, dtype=torch.int32, device=cx.dev)
+        self.action = torch.zeros(N, dtype=torch.int32, device=cx.dev) if action_out is None else action_out
         self.val = torch.zeros(N, device=cx.dev)
         self.logp = torch.zeros(N, device=cx.dev)
         self.v_next = torch.zeros(N, device=cx.dev)
@@ -510,7 +512,8 @@ class GruPolicy:
         self.h.zero_()
 
     def act(self, obs):
-        self.obs_in.copy_(obs)
+        if obs.data_ptr() != self.obs_in.data_ptr():
+            self.obs_in.copy_(obs)
         self.g_act.replay()
         return self.action, self.val, self.logp
 
@@ -567,7 +570,8 @@ def ppo_update(cx: Ctx, pol: GruPolicy, buf, data, opt, columns: int = 8192, chu
     return total, (t0, t1)
 
 
-def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: int = 2, do_update: bool = True):
+def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: int = 2, do_update: bool = True,
+                 mode: str = "graph"):
     """BASELINE configs[2]: rollout (policy -> env step storing into the buffer -> bootstrap) x T, GAE, get(episodes=True),
     one PPO update; train.py:321-571 with ppo.py:746 / 1150-1281 as the consumer."""
     torch, rp = cx.torch, cx.rp
@@ -575,13 +579,17 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
 
     env = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=4, device=cx.dev,
                        env_id_offset=cx.rank * N, auto_reset=True, fast_poisson=fast, steps_per_episode=120,
-                       prefetch=True, use_cuda_graph=False, standardize=1)
+                       prefetch=True, use_cuda_graph=(mode == "graph"), standardize=1)
     buf = rp.BatchedPPOBuffer(11, T, N, device=cx.dev)
-    pol = GruPolicy(cx, N, final_obs=env.final_obs.view(N, 11))
+    if mode == "graph":
+        pol = GruPolicy(cx, N, final_obs=env.final_obs.view(N, 11), obs_in=env.obs.view(N, 11),
+                        action_out=env.action_buffer.view(N))
+    else:
+        pol = GruPolicy(cx, N, final_obs=env.final_obs.view(N, 11))
     if cx.world > 1:
         rdist.sync_params(pol.net)                                                   # train.py:250-256
     stats = rp.EpisodeStats(N, 1, cx.dev)
-    col = rp.RolloutCollector(env, buf, pol, stats)
+    col = rp.RolloutCollector(env, buf, pol, stats, mode=mode)
     opt = torch.optim.Adam(pol.net.parameters(), lr=3e-4)
     rec = []
     for ep in range(epochs):
@@ -604,8 +612,10 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
                     "n_episodes_packed": int(data["ep_len"].numel())})
     r = rec[-1]
     tot = cx.max_over_ranks([r["rollout_gae_ms"], r["rollout_gae_ms"] + r["get_ms"] + r["episode_stats_ms"] + r["update_ms"]])
-    out = {"workload": f"{N} envs/GPU x T={T}, 5 obstructions, GRU(11->24) policy in the loop, count standardiser fused in the "
-                       "step kernel, step kernel stores into the rollout buffer (no store copies), GAE, get(episodes=True), "
+    how = ("step kernel stores into the rollout buffer rows (no copies, stream launches)" if mode == "rows" else
+           "captured step graph, rs_rollout_pre / rs_rollout_post carry its outputs into the buffer rows")
+    out = {"mode": mode, "workload": f"{N} envs/GPU x T={T}, 5 obstructions, GRU(11->24) policy in the loop, count standardiser fused in the "
+                       f"step kernel, {how}, GAE, get(episodes=True), "
                        "1 PPO update (one Adam step on a minibatch of 8,192 trajectories x 480 steps) (BASELINE configs[2])",
            "rollout_env_steps_per_s": N * cx.world * T / (tot[0] / 1e3),
            "pipeline_env_steps_per_s": N * cx.world * T / (tot[1] / 1e3),
@@ -655,7 +665,26 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
         times["backend"] = "nccl"
         times["checked"] = True
         out["collectives_us"] = times
-    del env, buf, pol
+    del env, buf, pol, col
+    torch.cuda.empty_cache()
+    if mode == "graph" and cx.world == 1:
+        # the zero-copy variant of the same rollout (rs_step stores into the buffer rows; plain stream launches)
+        env = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=4, device=cx.dev,
+                           auto_reset=True, fast_poisson=fast, steps_per_episode=120, prefetch=True, standardize=1)
+        buf = rp.BatchedPPOBuffer(11, T, N, device=cx.dev)
+        pol = GruPolicy(cx, N, final_obs=env.final_obs.view(N, 11))
+        col = rp.RolloutCollector(env, buf, pol, rp.EpisodeStats(N, 1, cx.dev), mode="rows")
+        ms = []
+        for ep in range(2):
+            torch.cuda.synchronize()
+            a, b = cx.event(), cx.event()
+            a.record(); col.collect(); b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+            buf.get()
+        out["rows_mode"] = {"rollout_env_steps_per_s": N * T / (ms[-1] / 1e3), "us_per_rollout_step": 1e3 * ms[-1] / T,
+                            "how": "rs_step stores observation / reward / path-end flags straight into the buffer rows"}
+        del env, buf, pol, col
     return out
 
 

@@ -209,12 +209,17 @@ int rs_episode_table(const uint8_t *path_end, int32_t T, int32_t N, int32_t *ep_
  * episode statistics (nullable as a group): ep_return[n] += reward[n], ep_steps[n] += 1, acc[0..5] += {episodes over by a
  * terminal state or the timeout, sum / sum of squares of their returns, sum of their lengths, done flags, out-of-bounds
  * flags}, *ep_min / *ep_max = extreme returns, then return and length restart where a reset was scheduled (T:361-391,
- * 493-535).  All arrays device, [n] unless noted. */
+ * 493-535).  All arrays device, [n] unless noted.
+ * A caller whose env step stores into the rollout buffer's rows itself (rs_step's output pointers = the rows) passes NULL
+ * for obs_row / rew_row / end_row; one that replays a captured step graph with fixed output buffers has these two launches
+ * copy them: obs[n][obs_dim] -> obs_row (the observation of step t), reward -> rew_row, ended -> end_row. */
 int rs_rollout_pre(const int32_t *action, const float *val, const float *logp, const int32_t *src, float *act_row,
-                   float *val_row, float *logp_row, float *src_row, int32_t n, void *stream);
+                   float *val_row, float *logp_row, float *src_row, const float *obs, float *obs_row, int32_t obs_dim,
+                   int32_t n, void *stream);
 int rs_rollout_post(const float *reward, const uint8_t *ended, const uint8_t *done, const uint8_t *info, const float *v_next,
                     float *boot_row, float *hidden, int32_t hidden_dim, double *ep_return, int32_t *ep_steps, double *acc,
-                    double *ep_min, double *ep_max, int32_t n, int32_t last_step, void *stream);
+                    double *ep_min, double *ep_max, float *rew_row, uint8_t *end_row, int32_t n, int32_t last_step,
+                    void *stream);
 
 /* ---- RAD-TEAM map observation ---------------------------------------------------------------------
  * MapsBuffer.observation_to_map (algos/multiagent/NeuralNetworkCores/RADTEAM_core.py:532-616 with its helpers :101-182

@@ -111,9 +111,9 @@ def declare(lib, prefix="rs_"):
         lib.rs_episode_table.restype = i32
         lib.rs_episode_table.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
         lib.rs_rollout_pre.restype = i32
-        lib.rs_rollout_pre.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.rs_rollout_pre.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
         lib.rs_rollout_post.restype = i32
-        lib.rs_rollout_post.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp]
+        lib.rs_rollout_post.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
         lib.rs_sizeof_maps_config.restype = i32
         lib.rs_sizeof_maps_state.restype = i32
         lib.rs_last_error.restype = C.c_char_p

@@ -18,8 +18,12 @@ namespace {
 __global__ void __launch_bounds__(256) rollout_pre_kernel(const int32_t *__restrict__ action, const float *__restrict__ val,
                                                           const float *__restrict__ logp, const int32_t *__restrict__ src,
                                                           float *__restrict__ act_row, float *__restrict__ val_row,
-                                                          float *__restrict__ logp_row, float *__restrict__ src_row, int n) {
+                                                          float *__restrict__ logp_row, float *__restrict__ src_row,
+                                                          const float *__restrict__ obs, float *__restrict__ obs_row, int obs_dim,
+                                                          int n) {
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (obs_row)        // the observation the policy just saw -> row t (a caller whose env step writes into fixed buffers)
+        for (int j = i; j < n * obs_dim; j += gridDim.x * 256) obs_row[j] = obs[j];
     if (i >= n) return;
     act_row[i] = (float)action[i];
     val_row[i] = val[i];
@@ -54,11 +58,14 @@ __global__ void __launch_bounds__(256) rollout_post_kernel(const float *__restri
                                                            const float *__restrict__ v_next, float *__restrict__ boot_row,
                                                            float *__restrict__ hidden, int hidden_dim, double *__restrict__ ep_return,
                                                            int32_t *__restrict__ ep_steps, double *acc, double *ep_min,
-                                                           double *ep_max, int n, int last_step) {
+                                                           double *ep_max, float *__restrict__ rew_row, uint8_t *__restrict__ end_row,
+                                                           int n, int last_step) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};           // episodes, sum EpRet, sum EpRet^2, sum EpLen, DoneCount, OutOfBound
     if (i < n) {
         const int e = ended[i];
+        if (rew_row) rew_row[i] = reward[i];                 // (a caller whose env step writes into fixed buffers)
+        if (end_row) end_row[i] = (uint8_t)e;
         // T:462-487: a trajectory cut by the timeout, or by the epoch's last step, is bootstrapped with V(next observation)
         const bool cut = last_step ? true : (e & RS_E_TIMEOUT) != 0;
         boot_row[i] = cut ? v_next[i] : 0.0f;
@@ -95,25 +102,29 @@ __global__ void __launch_bounds__(256) rollout_post_kernel(const float *__restri
 extern "C" {
 
 int rs_rollout_pre(const int32_t *action, const float *val, const float *logp, const int32_t *src, float *act_row,
-                   float *val_row, float *logp_row, float *src_row, int32_t n, void *stream) {
+                   float *val_row, float *logp_row, float *src_row, const float *obs, float *obs_row, int32_t obs_dim,
+                   int32_t n, void *stream) {
     if (!action || !val || !logp || !act_row || !val_row || !logp_row) return rs_set_error("rs_rollout_pre: NULL buffer");
     if (src_row && !src) return rs_set_error("rs_rollout_pre: src_row without src");
+    if (obs_row && (!obs || obs_dim <= 0)) return rs_set_error("rs_rollout_pre: obs_row without obs");
     if (n <= 0) return rs_set_error("rs_rollout_pre: n must be positive");
     rollout_pre_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(action, val, logp, src, act_row, val_row,
-                                                                                     logp_row, src_row, n);
+                                                                                     logp_row, src_row, obs, obs_row, obs_dim, n);
     return (int)cudaGetLastError();
 }
 
 int rs_rollout_post(const float *reward, const uint8_t *ended, const uint8_t *done, const uint8_t *info, const float *v_next,
                     float *boot_row, float *hidden, int32_t hidden_dim, double *ep_return, int32_t *ep_steps, double *acc,
-                    double *ep_min, double *ep_max, int32_t n, int32_t last_step, void *stream) {
+                    double *ep_min, double *ep_max, float *rew_row, uint8_t *end_row, int32_t n, int32_t last_step,
+                    void *stream) {
     if (!ended || !v_next || !boot_row) return rs_set_error("rs_rollout_post: NULL buffer");
+    if (rew_row && !reward) return rs_set_error("rs_rollout_post: rew_row without reward");
     if (ep_return && (!reward || !done || !info || !ep_steps || !acc || !ep_min || !ep_max))
         return rs_set_error("rs_rollout_post: episode statistics need reward / done / info / ep_steps / acc / ep_min / ep_max");
     if (n <= 0 || (hidden && hidden_dim <= 0)) return rs_set_error("rs_rollout_post: bad sizes");
     rollout_post_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reward, ended, done, info, v_next, boot_row, hidden, hidden_dim, ep_return, ep_steps, ep_return ? acc : nullptr, ep_min,
-        ep_max, n, last_step);
+        ep_max, rew_row, end_row, n, last_step);
     return (int)cudaGetLastError();
 }
 

@@ -340,14 +340,16 @@ def test_rollout_to_advantages_pipeline_matches_oracle():
     assert end_o.sum() > 4 * N
 
 
-def test_rollout_collector_zero_copy_epoch_matches_oracle():
+@pytest.mark.parametrize("mode", ["rows", "graph"])
+def test_rollout_collector_zero_copy_epoch_matches_oracle(mode):
     """RolloutCollector (train.py:321-571 for a batched env): the step kernel stores observation t+1 / reward / path-end flags
-    straight into the buffer rows (step_batch(out=)), rs_rollout_pre / rs_rollout_post do the caller-side bookkeeping --
+    straight into the buffer rows (step_batch(out=); mode "graph": the captured step graph's fixed outputs are carried
+    into the rows by the bookkeeping launches), rs_rollout_pre / rs_rollout_post do the caller-side bookkeeping --
     against the oracle env stepped the reference's way: every buffer row, the bootstrap rule (value of the next observation
     where the trajectory was cut by the timeout or the epoch's last step, else 0), the episode statistics, then GAE."""
     N, T, ML = 2048, 96, 24
     env = rp.RadSearch(obstruction_count=5, enforce_grid_boundaries=True, num_envs=N, seed=41, steps_per_episode=ML,
-                       auto_reset=True, prefetch=True)
+                       auto_reset=True, prefetch=True, use_cuda_graph=(mode == "graph"))
     ob = co.OracleBatch(N, co.default_config(obstruction_count=5, enforce=1, max_ep_len=ML), seed=41)
     ob.reset()
     d = env.device
@@ -378,7 +380,7 @@ def test_rollout_collector_zero_copy_epoch_matches_oracle():
     pol = Scripted()
     buf = rp.BatchedPPOBuffer(11, T, N)
     stats = rp.EpisodeStats(N, 1, d)
-    col = rp.RolloutCollector(env, buf, pol, stats)
+    col = rp.RolloutCollector(env, buf, pol, stats, mode=mode)
     ep_ret, ep_len = np.zeros(N), np.zeros(N, int)
     for epoch in range(2):
         first_obs = ob.outs["obs"][:, :1].astype(np.float32).copy()
