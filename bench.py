@@ -610,6 +610,38 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
                     "grad_allreduce_us": 1e3 * g0.elapsed_time(g1), "loss": loss,
                     "episodes": float(summ["Episodes"][0]), "avg_ep_ret": float(summ["AverageEpRet"][0]),
                     "n_episodes_packed": int(data["ep_len"].numel())})
+    # where a rollout step's GPU time goes: each stage between its own event pair, median over 24 steps (one stage at a time,
+    # so the pieces do not overlap; the loop above runs them back to back)
+    stage_us = {}
+    if True:
+        import ctypes as C
+        L_, lib_ = cx.L, cx.lib
+        stream = C.c_void_p(torch.cuda.current_stream(cx.dev).cuda_stream)
+        pp = lambda t: None if t is None else C.c_void_p(t.data_ptr())      # noqa: E731
+        rows, outs = buf.policy_rows(0), buf.step_outputs(0)
+        env_obs, fin = env.obs.view(N, 11), env.final_obs.view(N, 11)
+
+        def timed(fn, n=24):
+            ts = []
+            for _ in range(n):
+                torch.cuda.synchronize()
+                a, b = cx.event(), cx.event()
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(1e3 * a.elapsed_time(b))
+            return median(ts)
+
+        stage_us["policy_act_us"] = timed(lambda: pol.act(env_obs if mode == "graph" else rows["obs"]))
+        stage_us["policy_value_us"] = timed(lambda: pol.value(fin))
+        stage_us["env_step_reset_us"] = timed(lambda: env.step_batch(pol.action))
+        stage_us["bookkeeping_pre_post_us"] = timed(lambda: (
+            L_.check(lib_.rs_rollout_pre(pp(pol.action), pp(pol.val), pp(pol.logp), pp(env._src), pp(rows["act"]), pp(rows["val"]),
+                                         pp(rows["logp"]), pp(rows["src"]), pp(env.obs), pp(rows["obs"]), 11, N, stream), "pre"),
+            L_.check(lib_.rs_rollout_post(pp(env.reward), pp(env.ended), pp(env.done_flags), pp(env.info_flags), pp(pol.v_next),
+                                          pp(rows["boot"]), pp(pol.h), 24, None, None, None, None, None, pp(outs["reward"]),
+                                          pp(outs["ended"]), N, 0, stream), "post")))
+        stage_us["note"] = ("GPU time per stage of one rollout step; the policy is stock PyTorch (GRUCell + heads + Gumbel-max "
+                            "sampling, replayed as CUDA graphs) and sets the pace of the rollout, not the env step")
     r = rec[-1]
     tot = cx.max_over_ranks([r["rollout_gae_ms"], r["rollout_gae_ms"] + r["get_ms"] + r["episode_stats_ms"] + r["update_ms"]])
     how = ("step kernel stores into the rollout buffer rows (no copies, stream launches)" if mode == "rows" else
@@ -619,7 +651,8 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
                        "1 PPO update (one Adam step on a minibatch of 8,192 trajectories x 480 steps) (BASELINE configs[2])",
            "rollout_env_steps_per_s": N * cx.world * T / (tot[0] / 1e3),
            "pipeline_env_steps_per_s": N * cx.world * T / (tot[1] / 1e3),
-           "us_per_rollout_step": 1e3 * r["rollout_gae_ms"] / T, "stages_ms": r, "epochs_run": epochs,
+           "us_per_rollout_step": 1e3 * r["rollout_gae_ms"] / T, "rollout_step_stages_us": stage_us, "stages_ms": r,
+           "epochs_run": epochs,
            "status_flags_raised": int((env.status & ~2).ne(0).sum().item())}
     # ---- SURVEY 8e collectives on their own: timed over 20 calls each, results asserted -----------------------------------
     if cx.world > 1:

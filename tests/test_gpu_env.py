@@ -193,6 +193,29 @@ def test_poisson_philox_distribution_ks_against_numpy():
             assert abs(c.var() / lam - 1) < 0.03, (lam, fast, c.var())
 
 
+def test_poisson_alias_table_ks_against_numpy():
+    """RS_F_FAST_POISSON with a blocked line of sight: the count is Poisson(bkg) for the integer background rate and comes
+    from the alias tables (rs_poisson_alias.h) -- KS, mean and variance against numpy for the ends and the middle of the
+    table's range, and for a rate outside it (PTRS fallback)."""
+    from scipy import stats
+
+    n = 40000
+    for bkg in (10, 23, 50, 77):
+        env = rp.RadSearch(obstruction_count=1, enforce_grid_boundaries=True, num_envs=n, seed=100 + bkg, fast_poisson=True)
+        env.load_scenarios(src=np.tile([500, 500], (n, 1)), det=np.tile([1900, 500], (n, 1)), intensity=np.full(n, 5_000_000),
+                           bkg=np.full(n, bkg), rects=np.tile([[1000, 300, 1300, 700]], (n, 1, 1)), num_obs=np.ones(n))
+        counts = []
+        for _ in range(3):
+            env.step_batch(None)
+            assert bool(((env.info_flags & L.I_LOS_BLOCKED) != 0).all())
+            counts.append(env.obs[:, 0, 0].cpu().numpy())
+        c = np.concatenate(counts)
+        ref = np.random.default_rng(bkg).poisson(bkg, 300000)
+        assert stats.ks_2samp(c, ref).pvalue > 1e-3, bkg
+        assert abs(c.mean() - bkg) < 5 * np.sqrt(bkg / len(c)) and abs(c.var() / bkg - 1) < 0.03, (bkg, c.mean(), c.var())
+        assert c.min() >= 0 and float(c.max()) < bkg + 12 * np.sqrt(bkg)
+
+
 def test_single_env_gym_api_matches_reference_shapes():
     env = rp.RadSearch(obstruction_count=3, enforce_grid_boundaries=True, np_random=np.random.default_rng(2))
     obs, rew, done, info = env.reset()

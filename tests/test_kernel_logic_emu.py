@@ -333,3 +333,19 @@ def test_emulated_standardizer_follows_the_callers_order(mode, A):
         if t % 2:
             em.prepare(flags=L.F_REFILL_LIST | (L.F_PARITY1 if p else 0))
     assert big > 0
+
+
+def test_division_through_the_reciprocal_equals_ieee_division():
+    """rs_step1.cuh::div_const (x * (1/d), one exact-residual correction) against `/` for the two launch-constant divisors of
+    the commit phase, and round2_fast (Python round(x, 2) with that division) against round2 and against Python itself."""
+    import ctypes as C
+    from tests.emu.harness import emu
+    e = emu()
+    rng = np.random.default_rng(0)
+    for d in (2000.0, 100.0, 1732.0, 3.0):
+        xs = np.concatenate([rng.uniform(-5000, 5000, 4_000_000), -0.5 * np.sqrt(rng.integers(1, 2 ** 24, 4_000_000).astype(np.float64)),
+                             rng.integers(-400, 400, 1_000_000).astype(np.float64), np.array([0.0, -0.0, np.inf, -np.inf, 1e-310, 1e300])])
+        assert e.emu_div_const_mismatches(xs.ctypes.data_as(C.c_void_p), len(xs), d) == 0, d
+    for x in np.concatenate([rng.uniform(-2, 1, 200_000), (rng.integers(-200, 100, 2000) + 0.5) / 100.0, [0.125, -0.125, 0.005, -0.005, 0.1]]):
+        a, b = e.emu_round2_fast(float(x)), e.emu_round2(float(x))
+        assert a == b == round(float(x), 2), x
