@@ -366,6 +366,8 @@ def step_kernel_time(cx: Ctx, envs, groups: int, fast: bool):
         e1.record()
         launch_reset(e)
         single.append((e0, e1))
+    for e in envs:
+        e.prefetch_all()            # the raw calls above bypassed the prefetch bookkeeping: next episodes of every env again
     torch.cuda.synchronize()
     t_b2b = [a.elapsed_time(b) / R for a, b in b2b]
     t_single = [a.elapsed_time(b) for a, b in single]

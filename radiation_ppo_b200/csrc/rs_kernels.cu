@@ -800,7 +800,7 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
         cap = 148 * (prepare_nl > 1 ? 4 : 1);
     }
     // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
-    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 16;
+    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 148;
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;

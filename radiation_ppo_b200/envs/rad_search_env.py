@@ -412,6 +412,17 @@ class RadSearch:
         self._pending = [False, False]
         self._blk_pos = 0
 
+    def prefetch_all(self) -> None:
+        """(Re)compute the next episode of EVERY env on the current stream (one rs_prepare launch over all envs).  Done
+        automatically after reset / load_scenarios; call it after driving the C entry points directly, or after anything
+        else that dropped the pending refill lists, so that the next resets adopt prefetched episodes again instead of
+        going through the reset kernel."""
+        if not self.prefetch:
+            return
+        self._quiesce_prefetch()
+        with torch.cuda.device(self.device):
+            self._launch_prepare(0, use_list=False)
+
     def _launch_step_sequence(self, a, p: int, epoch_end: bool, device_ctr: bool, first: bool, outs=None) -> None:
         """rs_step (which starts refill list p when `first`) + rs_reset(list) on the current stream; with the device
         step counter the reset kernel's last CTA advances it (RS_F_BUMP_CTR): two launches per step."""

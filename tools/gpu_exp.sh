@@ -1,12 +1,10 @@
 #!/bin/bash
-# ad-hoc measurement list (one line per experiment), see gpurun_out/exp_<tag>.log
 tag=${1:-x}
 mkdir -p gpurun_out
 {
-for v in "" radiation_ppo_b200/_C/var_*.so; do
-  echo "== lib=$v"; RADSEARCH_B200_LIB=${v:+$PWD/$v} python bench.py --steps 20 --warmup 5 --legs sweep 2>&1 | tail -1 | python -c "
+for legs in e2e e2e,exact e2e,sweep e2e,gae e2e,pipeline e2e,maps e2e,cpu; do
+  echo "== legs=$legs"; python bench.py --steps 20 --warmup 5 --legs $legs 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read())
-print('  headline value %.4g  ms/step %.4f  kernel_ms %.4f  single %.4f'%(d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['kernel_ms_single_launch']), ' sweep:', [(s['n_envs'], round(s['kernel_ms'],4)) for s in d['sweep']])"
+d=json.loads(sys.stdin.read()); e=d['e2e']; print('  e2e %.4g sync %.4g pipelined %.4g frac_of_link %.3f'%(e['value'], e['sync_value'], e['pipelined_value'], e['frac_of_link']))"
 done
 } 2>&1 | tee gpurun_out/exp_$tag.log
