@@ -602,7 +602,8 @@ class RadSearch:
         other's kernels (the copy engines and the SMs work concurrently)."""
         if self._host_stream is None:
             self._host_stream = torch.cuda.Stream(device=self.device)
-            self._host_stream.wait_stream(torch.cuda.current_stream(self.device))
+        # whatever the caller's stream did to this env before (reset, step_batch, load_scenarios) is ordered first
+        self._host_stream.wait_stream(torch.cuda.current_stream(self.device))
         h_act = hb.actions if actions is None else actions.reshape(self.num_envs, self.number_agents)
         with torch.cuda.stream(self._host_stream):
             if self.use_cuda_graph and self.auto_reset and not epoch_end:
