@@ -232,13 +232,23 @@ class Ctx:
         return self.torch.cuda.Event(enable_timing=True)
 
 
-def make_ring(cx: Ctx, N: int, R: int, fast: bool, episode_steps: int, graph: bool = True, prefetch: bool = True):
+def pick_period(K: int, episode_steps: int = 120) -> int:
+    """Steps per prefetch block (= per CUDA-graph launch) for windows of K steps: the largest divisor of K up to 12 that
+    leaves at least two blocks per window (K = 20 -> 10, 240 -> 12), so that a window is whole blocks."""
+    cands = [p for p in range(1, 13) if K % p == 0 and 2 * p <= episode_steps]
+    two = [p for p in cands if K // p >= 2]
+    return max(two or cands or [4])
+
+
+def make_ring(cx: Ctx, N: int, R: int, fast: bool, episode_steps: int, graph: bool = True, prefetch: bool = True,
+              period: int = 0):
     torch, rp = cx.torch, cx.rp
     envs = []
     for r in range(R):
         e = rp.RadSearch(obstruction_count=K_OBS, enforce_grid_boundaries=True, num_envs=N, seed=2, device=cx.dev,
                          env_id_offset=(cx.rank * R + r) * N, auto_reset=True, fast_poisson=fast,
-                         steps_per_episode=episode_steps, prefetch=prefetch, use_cuda_graph=graph and prefetch)
+                         steps_per_episode=episode_steps, prefetch=prefetch, use_cuda_graph=graph and prefetch,
+                         prefetch_period=period or None)
         # stagger the episodes: steady state of a training run (about 1/120 of the envs finish at every step)
         g = torch.Generator(device=cx.dev).manual_seed(1000 + cx.rank * R + r)
         e._meta.add_(torch.randint(0, min(episode_steps, 120), (N,), generator=g, device=cx.dev, dtype=torch.int32) << 16)
@@ -862,6 +872,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of CUDA-graph replay")
     ap.add_argument("--episode-steps", type=int, default=120, help="steps_per_episode (120 = the reference's; a huge value "
                     "shows the throughput without resets)")
+    ap.add_argument("--period", type=int, default=0, help="steps per prefetch block / graph launch (0 = pick_period(steps))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -876,7 +887,8 @@ def main():
     reps = args.reps if args.reps > 0 else max(10, min(50, int(2.0e6 / max(K * 20, 1))))
     graph, prefetch = not (args.no_graph or args.no_prefetch), not args.no_prefetch
 
-    envs = make_ring(cx, N, R, fast, args.episode_steps, graph, prefetch)
+    period = args.period or pick_period(K, args.episode_steps)
+    envs = make_ring(cx, N, R, fast, args.episode_steps, graph, prefetch, period)
     head = headline(cx, envs, K, W, reps, sample_clocks=True)
     k_mean, k_med, k_single = step_kernel_time(cx, envs, 120, fast)
     achieved = BYTES_PER_ENV_STEP * N / (k_mean / 1e3) / 1e9

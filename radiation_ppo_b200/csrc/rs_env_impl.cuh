@@ -732,19 +732,35 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     RS_SYNCWARP(sync_mask);
     const int nc = 4 * e.num_obs;
     if (new_obstacles) {
-        // corner-to-corner visibility rows (depend on the obstructions only): lane c owns row c
-        for (int c = lane; c < nc; c += nl) {
+        // corner-to-corner visibility (depends on the obstructions only).  The predicate is exact integer arithmetic and
+        // therefore symmetric: every unordered pair is tested once and sets both bits.  Two corners of the SAME sampled
+        // rectangle need no test: the sampler keeps the rectangles apart (R:985-992, is_valid R:788-791), so an edge is
+        // always free and a diagonal always crosses its own interior (an injected scenario may break that: tested there).
+        const bool own_known = !inject && !(status & RS_ST_REJECT_CAP);
+        for (int c = lane; c < nc; c += nl) w_vis[c] = 0u;
+        RS_SYNCWARP(sync_mask);
+        for (int c = 0; c + 1 < nc; c++) {
             const int4 rc = w_rects[c >> 2];
             const int cx = corner_x(rc, c & 3), cy = corner_y(rc, c & 3);
             uint32_t m = 0u;
-            for (int c2 = 0; c2 < nc; c2++) {
-                if (c2 == c) continue;
-                const int4 r2 = w_rects[c2 >> 2];
-                if (visible(e, cx, cy, corner_x(r2, c2 & 3), corner_y(r2, c2 & 3))) m |= 1u << c2;
+            for (int c2 = c + 1 + lane; c2 < nc; c2 += nl) {
+                bool v;
+                if (own_known && (c2 >> 2) == (c >> 2)) v = ((c ^ c2) & 1) != 0;      // neighbours along an edge
+                else {
+                    const int4 r2 = w_rects[c2 >> 2];
+                    v = visible(e, cx, cy, corner_x(r2, c2 & 3), corner_y(r2, c2 & 3));
+                }
+                if (v) {
+                    m |= 1u << c2;
+                    if (nl == 1) w_vis[c2] |= 1u << c;
+                    else atomicOr(&w_vis[c2], 1u << c);
+                }
             }
-            w_vis[c] = m;
-            S.vis[(size_t)c * N + n] = m;
+            if (nl == 1) w_vis[c] |= m;
+            else if (m) atomicOr(&w_vis[c], m);
         }
+        RS_SYNCWARP(sync_mask);
+        for (int c = lane; c < nc; c += nl) S.vis[(size_t)c * N + n] = w_vis[c];
         for (int k = lane; k < e.num_obs; k += nl) reinterpret_cast<int4 *>(S.rects)[(size_t)k * N + n] = w_rects[k];
     }
     int detx, dety;

@@ -583,22 +583,27 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
 #ifndef RS_RESET_MINB
 #define RS_RESET_MINB 1
 #endif
-template <bool kFast>
-__global__ void __launch_bounds__(kBlock, RS_RESET_MINB) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
-                                                        const uint8_t *new_mask, int flags, const int32_t *list,
-                                                        const int32_t *count, int prepare_nl) {
+#ifdef RS_RESET_MAXREG
+#define RS_RESET_BOUNDS(TB) __maxnreg__(RS_RESET_MAXREG)
+#else
+#define RS_RESET_BOUNDS(TB) __launch_bounds__(TB, RS_RESET_MINB)
+#endif
+template <bool kFast, int TB>
+__global__ void RS_RESET_BOUNDS(TB) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
+                                                    const uint8_t *new_mask, int flags, const int32_t *list,
+                                                    const int32_t *count, int prepare_nl) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int total = list ? *count : a.n_env;
     // rs_prepare runs off the critical path: one thread per env wastes no lanes; a reset the step is waiting for
     // teams up lanes for latency
     const int nl = a.prepare ? prepare_nl : (total > 32768 ? 1 : (total > 4096 ? 8 : 32));
-    const int G = kBlock / nl;                          // groups (environments in flight) per CTA
+    const int G = TB / nl;                              // groups (environments in flight) per CTA
     const int g = threadIdx.x / nl, lane = threadIdx.x % nl;
     const uint32_t sync_mask = nl == 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) & ~(nl - 1)));
     // scratch columns, element i of group g at [i * G + g]: rects [K] int4 | dsrc [4K] f64 | vis [4K] u32
     int4 *srects = reinterpret_cast<int4 *>(smem);
-    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * kBlock);
-    uint32_t *svis = reinterpret_cast<uint32_t *>(sdsrc + (size_t)4 * P.k_max * kBlock);
+    double *sdsrc = reinterpret_cast<double *>(srects + (size_t)P.k_max * TB);
+    uint32_t *svis = reinterpret_cast<uint32_t *>(sdsrc + (size_t)4 * P.k_max * TB);
     const int stride = gridDim.x * G;
     for (int i = blockIdx.x * G + g; i < total; i += stride) {
         int n = i;
@@ -652,8 +657,8 @@ int check_cfg(const RsConfig *cfg, const RsState *st, int32_t n_env) {
 int step_tile_envs(int n_agents) { return n_agents == 2 ? 64 : 32; }
 size_t query_smem(const RsConfig *cfg) { return (size_t)cfg->k_max * kBlock * sizeof(int4); }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-size_t reset_smem(const RsConfig *cfg) {
-    return (size_t)kBlock * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
+size_t reset_smem(const RsConfig *cfg, int tb = kBlock) {
+    return (size_t)tb * cfg->k_max * (sizeof(int4) + 4 * sizeof(double) + 4 * sizeof(uint32_t));
 }
 constexpr int kResetGrid = 148 * 8;      // persistent: 8 CTAs of 4 warps per SM
 
@@ -795,21 +800,30 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
 #define RS_PREPARE_NL 1
 #endif
     const int prepare_nl = RS_PREPARE_NL;               // rs_prepare: lanes per environment (1: throughput, not latency)
+#ifndef RS_PREPARE_TB
+#define RS_PREPARE_TB 128
+#endif
+    constexpr int kPrepTB = RS_PREPARE_TB;              // CTA size of rs_prepare
+    int tb = kBlock;
     if (a.prepare) {                                    // kept small: it shares the GPU with rs_step
-        need = (a.n_env + kBlock / prepare_nl - 1) / (kBlock / prepare_nl);
-        cap = 148 * (prepare_nl > 1 ? 4 : 1);
+        tb = kPrepTB;
+        need = (a.n_env + tb / prepare_nl - 1) / (tb / prepare_nl);
+        cap = 148 * (prepare_nl > 1 ? 4 : 1) * (kBlock / tb);
     }
     // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
     if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 148;
     const int grid = need < cap ? need : cap;
-    const size_t smem = reset_smem(cfg);
+    const size_t smem = reset_smem(cfg, tb);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    if (fast) reset_kernel<true><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);
-    else reset_kernel<false><<<grid, kBlock, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);
+#define RS_LAUNCH_RESET(FAST, TBV)                                                                                          \
+    do {                                                                                                                    \
+        if (smem > 48 * 1024)                                                                                               \
+            cudaFuncSetAttribute(reset_kernel<FAST, TBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        reset_kernel<FAST, TBV><<<grid, TBV, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);         \
+    } while (0)
+    if (a.prepare && kPrepTB != kBlock) { if (fast) RS_LAUNCH_RESET(true, kPrepTB); else RS_LAUNCH_RESET(false, kPrepTB); }
+    else { if (fast) RS_LAUNCH_RESET(true, kBlock); else RS_LAUNCH_RESET(false, kBlock); }
+#undef RS_LAUNCH_RESET
     return (int)cudaGetLastError();
 }
 

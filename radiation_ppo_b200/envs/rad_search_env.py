@@ -148,6 +148,7 @@ class RadSearch:
         prefetch: bool = False,
         use_cuda_graph: bool = False,
         standardize: Union[int, str] = 0,
+        prefetch_period: Optional[int] = None,
     ) -> None:
         if DEBUG:
             raise NotImplementedError("the reference's DEBUG hard-codes (R:373-378, 782-784) are not reproduced")
@@ -173,8 +174,12 @@ class RadSearch:
         self.auto_reset = bool(auto_reset)
         self.fast_poisson = bool(fast_poisson)
         self.env_id_offset = int(env_id_offset)
-        # prefetch lists every env at most once per block of PREFETCH_PERIOD steps: episodes must outlast a block
-        # (terminal episodes always do: >= 9 steps; timeouts only if steps_per_episode allows it)
+        if prefetch_period is not None:
+            if not 1 <= int(prefetch_period) <= 64:
+                raise ValueError("prefetch_period must be in 1..64")
+            self.PREFETCH_PERIOD = int(prefetch_period)      # this instance's block length (class default: 4)
+        # prefetch lists an env once per block of PREFETCH_PERIOD steps: timed-out episodes must outlast two blocks (a
+        # terminal episode lasts >= 9 steps; one that ends before its refill is back takes the synchronous reset)
         self.prefetch = bool(prefetch) and self.auto_reset and int(steps_per_episode) >= 2 * self.PREFETCH_PERIOD
         self.use_cuda_graph = bool(use_cuda_graph) and self.prefetch
         self.seed = int(seed) if seed is not None else int(self.np_random.integers(0, 2**63 - 1))
@@ -391,7 +396,8 @@ class RadSearch:
         return outs[:6]
 
     # ---- prefetch machinery -------------------------------------------------------------------------------------
-    # Steps are grouped in blocks of PREFETCH_PERIOD (4: one rs_prepare launch must finish within a block); the envs that adopt their prefetched episode during block b are
+    # Steps are grouped in blocks of PREFETCH_PERIOD (default 4, `prefetch_period=` per instance: one rs_prepare launch and
+    # one CUDA-graph launch per block; longer blocks amortise both); the envs that adopt their prefetched episode during block b are
     # appended to refill list b & 1, and one rs_prepare launch (one thread per env: throughput, not latency) drains that
     # list on a high-priority side stream while block b+1 runs.  An episode lasts >= 9 steps (source and detector
     # start >= 1000 apart, a step is <= 100.4, the goal radius is 110), so the next scenario is back in place in time;

@@ -386,14 +386,18 @@ def test_full_size_batch_matches_oracle():
     assert resets > n // 4 and int((env.status & ~2).sum()) == 0
 
 
-def test_step_block_equals_single_steps():
+@pytest.mark.parametrize("period", [None, 10])
+def test_step_block_equals_single_steps(period):
     """RadSearch.step_block (PREFETCH_PERIOD steps + the refill rs_prepare as ONE graph launch) against the same steps taken
-    one by one: identical state, outputs and Philox counters, also when blocks and single steps are mixed."""
+    one by one: identical state, outputs and Philox counters, also when blocks and single steps are mixed; with the
+    default block length and with `prefetch_period=10` (episodes that end before their refill is back take the
+    synchronous reset: same state) against an env that prefetches in blocks of 4."""
     n, ML = 4096, 30
     kw = dict(obstruction_count=5, enforce_grid_boundaries=True, num_envs=n, seed=123, steps_per_episode=ML, auto_reset=True,
               prefetch=True, use_cuda_graph=True)
-    a, b = rp.RadSearch(**kw), rp.RadSearch(**kw)
+    a, b = rp.RadSearch(**kw, prefetch_period=period), rp.RadSearch(**kw)
     P = a.PREFETCH_PERIOD
+    assert P == (period or 4) and b.PREFETCH_PERIOD == 4 and a.prefetch and a.use_cuda_graph
     rng = np.random.default_rng(2)
     for rnd in range(14):
         acts = torch.as_tensor(rng.integers(0, 8, size=(P, n, 1)), dtype=torch.int32, device=a.device)

@@ -9,12 +9,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--episode-steps", type=int, default=120)
 ap.add_argument("--ring", type=int, default=4)
 ap.add_argument("--blocks", type=int, default=16)
+ap.add_argument("--period", type=int, default=0, help="steps per prefetch block (0: the library's)")
+ap.add_argument("--rows", type=int, default=60)
 a = ap.parse_args()
 
 class A: pass
 args = A(); args.__dict__.update(gpus=1)
 cx = bench.Ctx(args)
-envs = bench.make_ring(cx, 131072, a.ring, True, a.episode_steps)
+envs = bench.make_ring(cx, 131072, a.ring, True, a.episode_steps, period=a.period)
 R, P = a.ring, envs[0].PREFETCH_PERIOD
 g = torch.Generator(device=cx.dev).manual_seed(7)
 acts = torch.randint(0, 8, (8, P, 131072, 1), generator=g, device=cx.dev, dtype=torch.int32)
@@ -32,22 +34,26 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     run(a.blocks, 40 * R)
     torch.cuda.synchronize()
-ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-ev.sort(key=lambda e: e.time_range.start)
-t0 = ev[0].time_range.start
+kev = [e for e in prof.profiler.kineto_results.events() if "CUDA" in str(e.device_type()) and e.duration_ns() > 0]
+kev.sort(key=lambda e: e.start_ns())
+t0 = kev[0].start_ns()
 tot = collections.defaultdict(lambda: [0, 0.0])
 rows = []
-for e in ev:
-    import re
-    m = re.search(r"(step1_kernel|step_kernel|reset_kernel|maps_\w+|gae_\w+|Memcpy \w+|Memset)", e.name)
-    name = m.group(1) if m else e.name[:28]
-    if name == "reset_kernel": name += f" grid{getattr(e, 'grid', '')}" 
-    tot[name][0] += 1; tot[name][1] += e.time_range.end - e.time_range.start
-    rows.append((e.time_range.start - t0, e.time_range.end - t0, name))
+import re
+sid = {}
+for e in kev:
+    m = re.search(r"(step1_kernel|step_kernel|reset_kernel|maps_\w+|gae_\w+|Memcpy \w+|Memset)", e.name())
+    name = m.group(1) if m else e.name()[:28]
+    b, d = (e.start_ns() - t0) / 1e3, e.duration_ns() / 1e3
+    if name == "reset_kernel":
+        name = "prepare" if d > 50 else "reset(stragglers)"
+    st = sid.setdefault(e.device_resource_id(), len(sid))
+    tot[name][0] += 1; tot[name][1] += d
+    rows.append((b, b + d, name, st))
 span = max(r[1] for r in rows)
-print(f"span {span:.1f} us for {a.blocks * P} steps = {span / (a.blocks * P):.2f} us/step")
+print(f"span {span:.1f} us for {a.blocks * P} steps = {span / (a.blocks * P):.2f} us/step  (period {P}, ring {R})")
 for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:30s} n={c:4d}  total {t:9.1f} us  mean {t / c:7.2f} us")
-print("first 60 kernels: start, end, name")
-for r in rows[:60]:
-    print(f"{r[0]:9.1f} {r[1]:9.1f}  {r[2]}")
+print(f"first {a.rows} kernels: start, end, stream, name")
+for r in rows[:a.rows]:
+    print(f"{r[0]:9.1f} {r[1]:9.1f}  s{r[3]}  {r[2]}")
