@@ -812,8 +812,13 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         for (int w = lane; w < nc; w += nl) {
             if (!((m >> w) & 1u)) continue;
             const int4 rw = w_rects[w >> 2];
-            const double nd = du + dist_int(ux - corner_x(rw, w & 3), uy - corner_y(rw, w & 3));
-            if (nd < w_dsrc[w]) w_dsrc[w] = nd;
+            const int dx = ux - corner_x(rw, w & 3), dy = uy - corner_y(rw, w & 3);
+            const double old = w_dsrc[w];
+            // |u - w| >= max(|dx|, |dy|), an integer: rounding is monotone, so a label this bound cannot beat stands
+            // (most relaxations end here, without the square root)
+            if (du + (double)max(abs(dx), abs(dy)) >= old) continue;
+            const double nd = du + dist_int(dx, dy);
+            if (nd < old) w_dsrc[w] = nd;
         }
         RS_SYNCWARP(sync_mask);
     }
@@ -823,6 +828,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     // prev_det_dist R:771-776 = shortest_path(e, det): the lanes evaluate one corner each, then everybody takes the min
     double *dsrc_out = (prepare ? S.nx_dsrc : S.dsrc) + (size_t)n * 4 * P.k_max;
     float *dsf_out = (prepare ? S.nx_dsf : S.dsf) + (size_t)n * 4 * P.k_max;     // lower bounds for the marking pass
+    double lane_best = inf;
     for (int c = lane; c < nc; c += nl) {
         const double ds = w_dsrc[c];
         dsrc_out[c] = ds;
@@ -830,7 +836,11 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const int4 r = w_rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         double cand = inf;
-        if (!direct && ds < inf && visible(e, detx, dety, cx, cy)) cand = ds + dist_int(detx - cx, dety - cy);
+        // a corner whose lower bound ds + max(|dx|, |dy|) does not beat this lane's best so far cannot be the minimum
+        if (!direct && ds + (double)max(abs(detx - cx), abs(dety - cy)) < lane_best && visible(e, detx, dety, cx, cy)) {
+            cand = ds + dist_int(detx - cx, dety - cy);
+            lane_best = fmin(lane_best, cand);
+        }
         w_dsrc[c] = cand;
     }
     RS_SYNCWARP(sync_mask);

@@ -473,11 +473,13 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         __syncwarp();
     }
     // ---- commit: reward, terminal, caller rules, state and scalar outputs (coalesced) --------------------------------------
-    bool sched = false;
+    bool sched = false, adopt = false;
+    uint32_t status = 0;
+    float raw = 0.0f;
+    rs::Commit1 c;
     if (live) {
-        uint32_t status = o.status;
-        float raw = 0.0f;
-        const rs::Commit1 c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw, status);
+        status = o.status;
+        c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw, status);
         if (a.reward) a.reward[n] = c.reward;
         if (a.team_reward) a.team_reward[n] = c.reward;                 // one agent: the team reward is its reward R:661-665
         if (a.done) a.done[n] = (uint8_t)c.done;
@@ -489,40 +491,54 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             for (int i = 0; i < RS_OBS_DIM; i++) a.final_obs[(size_t)n * RS_OBS_DIM + i] = row[i];
         }
         // RS_F_PREFETCH: an env whose next episode rs_prepare has already computed (same seed, env, episode number and
-        // obstructions: nx_seq carries the episode number) starts it right here -- a few copies by the thread that has the
-        // env in hand -- and never reaches the reset kernel; the others go to the reset work list as before
-        bool adopted = false;
-        if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
-            const uint32_t ep_seq = S.epi[n] + 1u;
-            if (*reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n) == ep_seq) {
-                __threadfence();
-                adopted = true;
-                const size_t r0 = (size_t)n * 4 * K;
-                for (int c4 = 0; c4 < num_obs; c4++) {                  // source-distance rows of the new episode
-                    reinterpret_cast<double2 *>(S.dsrc + r0)[2 * c4] = reinterpret_cast<const double2 *>(S.nx_dsrc + r0)[2 * c4];
-                    reinterpret_cast<double2 *>(S.dsrc + r0)[2 * c4 + 1] = reinterpret_cast<const double2 *>(S.nx_dsrc + r0)[2 * c4 + 1];
-                    reinterpret_cast<float4 *>(S.dsf + r0)[c4] = reinterpret_cast<const float4 *>(S.nx_dsf + r0)[c4];
-                }
-                const float *nxo = S.nx_obs + (size_t)n * RS_OBS_DIM;
-#pragma unroll
-                for (int i = 0; i < RS_OBS_DIM; i++) row[i] = nxo[i];
-                if (P.standardize) {                                    // first reading of the episode: z = 0
-                    stm = (double)row[0]; stq = 0.0; raw = row[0]; row[0] = 0.0f;
-                }
-                reinterpret_cast<int2 *>(S.src)[n] = reinterpret_cast<const int2 *>(S.nx_src)[n];
-                reinterpret_cast<int2 *>(S.rad)[n] = reinterpret_cast<const int2 *>(S.nx_rad)[n];
-                reinterpret_cast<int2 *>(S.det)[n] = reinterpret_cast<const int2 *>(S.nx_det)[n];
-                S.best[n] = S.nx_best[n];
-                S.aflags[n] = 0;
-                S.meta[n] = meta & 0xff;                                // done = 0, ep_len = 0 (a sampled source is in no rectangle)
-                S.epi[n] = ep_seq;
-                const int slot = atomicAdd(S.refill_count + a.parity, 1);
-                if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
-                else status |= RS_ST_REFILL_OVERFLOW;
-                sched = false;
-            }
+        // obstructions: nx_seq carries the episode number) starts it right here and never reaches the reset kernel; the
+        // others go to the reset work list as before
+        if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END))
+            adopt = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n) == S.epi[n] + 1u;
+    }
+    // The copies of an adopted episode are shared by the warp: one lane per table entry / observation value, so that they
+    // cost one round trip to memory instead of a chain of twenty by the one thread that owns the env
+    unsigned am = __ballot_sync(0xffffffffu, adopt);
+    if (am) {
+        __syncwarp();
+        __threadfence();                                                // the tag was read before the data it publishes
+        while (am) {
+            const int owner = __ffs(am) - 1;
+            am &= am - 1;
+            const int nn = n0 + w0 + owner;
+            const int nc = 4 * __shfl_sync(0xffffffffu, num_obs, owner);
+            const size_t r0 = (size_t)nn * 4 * K;
+            const bool t1 = lane < nc, t2 = lane < RS_OBS_DIM;
+            double ds = 0.0;
+            float df = 0.0f, ob = 0.0f;
+            if (t1) { ds = S.nx_dsrc[r0 + lane]; df = S.nx_dsf[r0 + lane]; }      // source-distance rows of the new episode
+            if (t2) ob = S.nx_obs[(size_t)nn * RS_OBS_DIM + lane];                 // its first observation
+            if (t1) { S.dsrc[r0 + lane] = ds; S.dsf[r0 + lane] = df; }
+            if (t2) s_obs[(w0 + owner) * RS_OBS_DIM + lane] = ob;                  // -> the env's staged row
         }
-        if (!adopted) {
+        __syncwarp();
+    }
+    if (live) {
+        if (adopt) {
+            const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
+            const int2 r1 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+            const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
+            const double b0 = S.nx_best[n];
+            if (P.standardize) {                                        // first reading of the episode: z = 0
+                stm = (double)row[0]; stq = 0.0; raw = row[0]; row[0] = 0.0f;
+            }
+            reinterpret_cast<int2 *>(S.src)[n] = s0;
+            reinterpret_cast<int2 *>(S.rad)[n] = r1;
+            reinterpret_cast<int2 *>(S.det)[n] = d0;
+            S.best[n] = b0;
+            S.aflags[n] = 0;
+            S.meta[n] = meta & 0xff;                                    // done = 0, ep_len = 0 (a sampled source is in no rectangle)
+            S.epi[n] = S.epi[n] + 1u;
+            const int slot = atomicAdd(S.refill_count + a.parity, 1);
+            if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
+            else status |= RS_ST_REFILL_OVERFLOW;
+            sched = false;
+        } else {
             S.meta[n] = c.meta;
             reinterpret_cast<int2 *>(S.det)[n] = o.det;
             S.best[n] = c.best;
@@ -583,13 +599,8 @@ __global__ void __launch_bounds__(kBlock) sp_query_kernel(rs::Params P, RsState 
 #ifndef RS_RESET_MINB
 #define RS_RESET_MINB 1
 #endif
-#ifdef RS_RESET_MAXREG
-#define RS_RESET_BOUNDS(TB) __maxnreg__(RS_RESET_MAXREG)
-#else
-#define RS_RESET_BOUNDS(TB) __launch_bounds__(TB, RS_RESET_MINB)
-#endif
-template <bool kFast, int TB>
-__global__ void RS_RESET_BOUNDS(TB) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
+template <bool kFast, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) reset_kernel(rs::Params P, RsState S, rs::ResetArgs a, const uint8_t *mask,
                                                     const uint8_t *new_mask, int flags, const int32_t *list,
                                                     const int32_t *count, int prepare_nl) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -800,29 +811,50 @@ static int launch_reset(const RsConfig *cfg, const RsState *st, const rs::ResetA
 #define RS_PREPARE_NL 1
 #endif
     const int prepare_nl = RS_PREPARE_NL;               // rs_prepare: lanes per environment (1: throughput, not latency)
-#ifndef RS_PREPARE_TB
-#define RS_PREPARE_TB 128
-#endif
-    constexpr int kPrepTB = RS_PREPARE_TB;              // CTA size of rs_prepare
     int tb = kBlock;
-    if (a.prepare) {                                    // kept small: it shares the GPU with rs_step
-        tb = kPrepTB;
+    if (a.prepare) {
+        // rs_prepare shares the GPU with the step kernels of the other env batches for its whole (latency-bound) life.  Its
+        // threads are packed into the largest CTAs the scratch columns allow (512 threads for k_max <= 6), i.e. onto as few
+        // SMs as possible: a few SMs given over to it cost the step kernels less than one fat CTA on every fourth SM
+        // (measured, 131 072 envs: 128 / 256 / 512 threads per CTA = 36.0 / 32.7 / 32.4 us per step)
+        const size_t per_thread = reset_smem(cfg, 1);
+        tb = 512 * per_thread <= 200 * 1024 ? 512 : (256 * per_thread <= 200 * 1024 ? 256 : 128);
+#ifdef RS_PREPARE_TB
+        tb = RS_PREPARE_TB;
+#endif
         need = (a.n_env + tb / prepare_nl - 1) / (tb / prepare_nl);
-        cap = 148 * (prepare_nl > 1 ? 4 : 1) * (kBlock / tb);
+        cap = 148 * (prepare_nl > 1 ? 4 : 1) * kBlock / tb;
     }
-    // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers
-    if (list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1) cap = 148;
+    // single-agent steps adopt prefetched episodes themselves (step1_kernel): their work list only holds the stragglers.
+    // That launch follows every step, mostly to find an empty list (CTA size, register cap and grid are build switches:
+    // 32-thread CTAs and grids of 16 / 37 measured within 2 % of this shape, a 72-register build 7 % slower)
+#ifndef RS_STRAG_TB
+#define RS_STRAG_TB 128
+#endif
+#ifndef RS_STRAG_MINB
+#define RS_STRAG_MINB 1
+#endif
+#ifndef RS_STRAG_CAP
+#define RS_STRAG_CAP 148
+#endif
+    const bool stragglers = list && (flags & RS_F_PREFETCH) && cfg->n_agents == 1 && !a.prepare;
+    if (stragglers) { tb = RS_STRAG_TB; cap = RS_STRAG_CAP; }
     const int grid = need < cap ? need : cap;
     const size_t smem = reset_smem(cfg, tb);
     const bool fast = (flags & RS_F_FAST_POISSON) && !a.uniforms;
-#define RS_LAUNCH_RESET(FAST, TBV)                                                                                          \
+#define RS_LAUNCH_RESET(FAST, TBV, MINB)                                                                                    \
     do {                                                                                                                    \
         if (smem > 48 * 1024)                                                                                               \
-            cudaFuncSetAttribute(reset_kernel<FAST, TBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        reset_kernel<FAST, TBV><<<grid, TBV, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);         \
+            cudaFuncSetAttribute(reset_kernel<FAST, TBV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        reset_kernel<FAST, TBV, MINB><<<grid, TBV, smem, s>>>(P, *st, a, mask, new_mask, flags, list, count, prepare_nl);   \
     } while (0)
-    if (a.prepare && kPrepTB != kBlock) { if (fast) RS_LAUNCH_RESET(true, kPrepTB); else RS_LAUNCH_RESET(false, kPrepTB); }
-    else { if (fast) RS_LAUNCH_RESET(true, kBlock); else RS_LAUNCH_RESET(false, kBlock); }
+#define RS_LAUNCH_RESET2(TBV, MINB) do { if (fast) RS_LAUNCH_RESET(true, TBV, MINB); else RS_LAUNCH_RESET(false, TBV, MINB); } while (0)
+    if (stragglers) RS_LAUNCH_RESET2(RS_STRAG_TB, RS_STRAG_MINB);
+    else if (a.prepare && tb == 512) RS_LAUNCH_RESET2(512, 1);
+    else if (a.prepare && tb == 256) RS_LAUNCH_RESET2(256, 2);
+    else if (tb == kBlock) RS_LAUNCH_RESET2(kBlock, RS_RESET_MINB);
+    else return fail("rs_prepare: unsupported RS_PREPARE_TB");
+#undef RS_LAUNCH_RESET2
 #undef RS_LAUNCH_RESET
     return (int)cudaGetLastError();
 }
