@@ -175,8 +175,10 @@ int rs_query_shortest_path(const RsConfig *cfg, const RsState *st, const int32_t
  * variant: 0 auto; 1 thread-per-column recurrence in the reference's operation order (bit-exact vs scipy's lfilter), fed by
  * bulk-async tile copies when N % 128 == 0 and the arrays are 16-byte aligned, else by register-pipelined loads; 2 warp-
  * shuffle scan along T (small N; within 1e-5).  3 / 4 force the 8- / 16-deep register-pipelined form, 7 the 3-stage tile
- * ring, 10 the same ring over 64-column tiles, 8 / 11 the producer-warp form with 3 x 8 and 6 x 8 rows in flight
- * -- all bit-identical to variant 1. */
+ * ring, 10 the same ring over 64-column tiles, 8 / 11 the producer-warp form with 3 x 8 and 6 x 8 rows in flight, 12 / 13
+ * that form over 64- / 224-column tiles, 14 / 15 the producer-warp form fed by tensor-map (2-D TMA) copies over 128- /
+ * 224-column tiles -- all bit-identical to variant 1.  Auto: N >= 75776 -> 7, N >= 32768 -> 13, N >= 16384 -> 14 (whole
+ * tiles), N < 16384 -> 2. */
 int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const float *boot, float *adv, float *ret,
            int32_t T, int32_t N, double gamma, double lam, double *stats, int32_t variant, void *stream);
 

@@ -6,6 +6,7 @@
 //   end   = path_end[t][n] || t == T-1
 //   nv,na,nr = end ? (boot, 0, boot) : (val[t+1], adv[t+1], ret[t+1])
 //   adv[t] = (rew + gamma*nv) - val + (gamma*lam)*na ;  ret[t] = rew + gamma*nr
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -118,6 +119,58 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t *mbar, uint32_t parity) {
         : "memory");
 }
 
+// U consecutive steps (t_hi, t_hi-1, ...) of one column, values already in registers.  A whole chunk runs as straight-line
+// code: the end-of-path restart is a select, not a branch, so the compiler overlaps the rows and only the one-operation
+// recurrences (a, g, the two sums) stay serial.  Same operations per element as variant 1: bit-identical.
+template <int U>
+__device__ __forceinline__ void gae_rows(const float (&rj)[U], const float (&vj)[U], const uint8_t (&ej)[U], const float (&bc)[U],
+                                         bool last_step_first, int t_hi, int N, size_t n, float *__restrict__ adv,
+                                         float *__restrict__ ret, double gamma, double gl, double &nv, double &na, double &nr,
+                                         double &s1, double &s2) {
+    if (t_hi - (U - 1) >= 0) {
+        float *pa = adv + (size_t)t_hi * N + n, *pr = ret + (size_t)t_hi * N + n;
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const bool e = ej[j] != 0 || (last_step_first && j == 0);
+            const double b = (double)bc[j];
+            nv = e ? b : nv; na = e ? 0.0 : na; nr = e ? b : nr;
+            const double rr = (double)rj[j], vv = (double)vj[j];
+            const double delta = (rr + gamma * nv) - vv;
+            const double a = delta + gl * na;
+            const double g = rr + gamma * nr;
+            const float af = (float)a;
+            __stcs(pa, af);
+            __stcs(pr, (float)g);
+            pa -= N; pr -= N;
+            s1 += (double)af;
+            s2 += (double)af * (double)af;
+            nv = vv; na = a; nr = g;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t_hi - j;
+            if (t >= 0) {
+                if (ej[j] || (last_step_first && j == 0)) {
+                    const double b = (double)bc[j];
+                    nv = b; na = 0.0; nr = b;
+                }
+                const double rr = (double)rj[j], vv = (double)vj[j];
+                const double delta = (rr + gamma * nv) - vv;
+                const double a = delta + gl * na;
+                const double g = rr + gamma * nr;
+                const float af = (float)a;
+                const size_t i = (size_t)t * N + n;
+                __stcs(adv + i, af);
+                __stcs(ret + i, (float)g);
+                s1 += (double)af;
+                s2 += (double)af * (double)af;
+                nv = vv; na = a; nr = g;
+            }
+        }
+    }
+}
+
 template <int C, int U, int S, int MINB>
 __global__ void __launch_bounds__(C, MINB) gae_tile_kernel(const float *__restrict__ rew, const float *__restrict__ val,
                                                                     const uint8_t *__restrict__ pe, const float *__restrict__ boot,
@@ -175,26 +228,12 @@ __global__ void __launch_bounds__(C, MINB) gae_tile_kernel(const float *__restri
                 if (t >= 0 && s_pe[sn][j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
             }
         }
+        {
+            float rj[U], vj[U];
+            uint8_t ej[U];
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int t = t_hi - j;
-            if (t >= 0) {
-                if (s_pe[st][j][tid] || t == T - 1) {
-                    const double b = (double)bc[j];
-                    nv = b; na = 0.0; nr = b;
-                }
-                const double rr = (double)s_rew[st][j][tid], vv = (double)s_val[st][j][tid];
-                const double delta = (rr + gamma * nv) - vv;
-                const double a = delta + gl * na;
-                const double g = rr + gamma * nr;
-                const float af = (float)a;
-                const size_t i = (size_t)t * N + n;
-                __stcs(adv + i, af);
-                __stcs(ret + i, (float)g);
-                s1 += (double)af;
-                s2 += (double)af * (double)af;
-                nv = vv; na = a; nr = g;
-            }
+            for (int j = 0; j < U; j++) { rj[j] = s_rew[st][j][tid]; vj[j] = s_val[st][j][tid]; ej[j] = s_pe[st][j][tid]; }
+            gae_rows<U>(rj, vj, ej, bc, c == 0, t_hi, N, (size_t)n, adv, ret, gamma, gl, nv, na, nr, s1, s2);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) bc[j] = bn[j];
@@ -217,51 +256,54 @@ __global__ void __launch_bounds__(C, MINB) gae_tile_kernel(const float *__restri
 // variant 8: variant 6/7 with a producer warp.  Warp 4 only refills stages (it waits on the stage's `empty` barrier, which
 // the 128 consumer threads arrive on when they are done reading it), so no CTA-wide barrier sits in the consumers' loop
 // and the four consumer warps drift apart by up to S chunks.
-template <int U, int S, int MINB>
-__global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(const float *__restrict__ rew, const float *__restrict__ val,
-                                                                           const uint8_t *__restrict__ pe, const float *__restrict__ boot,
-                                                                           float *__restrict__ adv, float *__restrict__ ret, int T, int N,
-                                                                           double gamma, double gl, double *stats) {
-    // dynamic shared memory (the 6-stage form needs 54 KB): [S][U][128] rew | val | path_end, then the barriers
+template <int C, int U, int S, int MINB>
+__global__ void __launch_bounds__(C + 32, MINB) gae_tile_ws_kernel(const float *__restrict__ rew, const float *__restrict__ val,
+                                                                  const uint8_t *__restrict__ pe, const float *__restrict__ boot,
+                                                                  float *__restrict__ adv, float *__restrict__ ret, int T, int N,
+                                                                  double gamma, double gl, double *stats) {
+    // dynamic shared memory: [S][U][C] rew | val | path_end, then the barriers.  C columns per CTA (C consumer threads + the
+    // producer warp); the last CTA may own fewer (a multiple of 32: N % 128 == 0), its spare threads only keep the barriers
     extern __shared__ __align__(128) unsigned char ws_smem[];
-    typedef float (*TileF)[U][kColsBlock];
-    typedef uint8_t (*TileB)[U][kColsBlock];
+    typedef float (*TileF)[U][C];
+    typedef uint8_t (*TileB)[U][C];
     TileF s_rew = reinterpret_cast<TileF>(ws_smem);
-    TileF s_val = reinterpret_cast<TileF>(ws_smem + sizeof(float) * S * U * kColsBlock);
-    TileB s_pe = reinterpret_cast<TileB>(ws_smem + 2 * sizeof(float) * S * U * kColsBlock);
-    uint64_t *full = reinterpret_cast<uint64_t *>(ws_smem + 9 * S * U * kColsBlock);
+    TileF s_val = reinterpret_cast<TileF>(ws_smem + sizeof(float) * S * U * C);
+    TileB s_pe = reinterpret_cast<TileB>(ws_smem + 2 * sizeof(float) * S * U * C);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ws_smem + 9 * S * U * C);
     uint64_t *empty = full + S;
     const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * kColsBlock, n = n0 + tid;
+    const int n0 = blockIdx.x * C, n = n0 + tid;
+    const int cols = min(C, N - n0);
     const int chunks = (T + U - 1) / U;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(full + s)), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(empty + s)), "r"(kColsBlock) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(empty + s)), "r"(C) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid >= kColsBlock) {                            // ---- producer warp: lane j moves row j of the tile --------------
-        const int lane = tid - kColsBlock;
+    if (tid >= C) {                                     // ---- producer warp: lane j moves row j of the tile --------------
+        const int lane = tid - C;
         for (int c = 0; c < chunks; c++) {
             const int st = c % S, t_hi = T - 1 - c * U, rows = min(U, t_hi + 1);
             if (c >= S) g_mbar_wait(empty + st, (uint32_t)(c / S - 1) & 1u);
             if (lane == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(full + st)),
-                             "r"((uint32_t)rows * (uint32_t)(kColsBlock * 9))
+                             "r"((uint32_t)rows * (uint32_t)(cols * 9))
                              : "memory");
             __syncwarp();
             if (lane < rows) {
                 const size_t g = (size_t)(t_hi - lane) * N + n0;
-                g_bulk_g2s(&s_rew[st][lane][0], rew + g, kColsBlock * 4, full + st);
-                g_bulk_g2s(&s_val[st][lane][0], val + g, kColsBlock * 4, full + st);
-                g_bulk_g2s(&s_pe[st][lane][0], pe + g, kColsBlock, full + st);
+                g_bulk_g2s(&s_rew[st][lane][0], rew + g, cols * 4, full + st);
+                g_bulk_g2s(&s_val[st][lane][0], val + g, cols * 4, full + st);
+                g_bulk_g2s(&s_pe[st][lane][0], pe + g, cols, full + st);
             }
         }
         return;
     }
+    const bool active = tid < cols;
     double nv = 0.0, na = 0.0, nr = 0.0, s1 = 0.0, s2 = 0.0;
     float bc[U], bn[U];
     g_mbar_wait(full + 0, 0);
@@ -269,7 +311,7 @@ __global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(cons
     for (int j = 0; j < U; j++) {
         const int t = T - 1 - j;
         bc[j] = 0.0f;
-        if (t >= 0 && (s_pe[0][j][tid] || t == T - 1)) bc[j] = __ldcs(boot + (size_t)t * N + n);
+        if (active && t >= 0 && (s_pe[0][j][tid] || t == T - 1)) bc[j] = __ldcs(boot + (size_t)t * N + n);
     }
     for (int c = 0; c < chunks; c++) {
         const int st = c % S, t_hi = T - 1 - c * U;
@@ -280,7 +322,7 @@ __global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(cons
             for (int j = 0; j < U; j++) {
                 const int t = t_hi - U - j;
                 bn[j] = 0.0f;
-                if (t >= 0 && s_pe[sn][j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
+                if (active && t >= 0 && s_pe[sn][j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
             }
         }
         float rj[U], vj[U];
@@ -288,27 +330,7 @@ __global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(cons
 #pragma unroll
         for (int j = 0; j < U; j++) { rj[j] = s_rew[st][j][tid]; vj[j] = s_val[st][j][tid]; ej[j] = s_pe[st][j][tid]; }
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(empty + st)) : "memory");   // stage read
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int t = t_hi - j;
-            if (t >= 0) {
-                if (ej[j] || t == T - 1) {
-                    const double b = (double)bc[j];
-                    nv = b; na = 0.0; nr = b;
-                }
-                const double rr = (double)rj[j], vv = (double)vj[j];
-                const double delta = (rr + gamma * nv) - vv;
-                const double a = delta + gl * na;
-                const double g = rr + gamma * nr;
-                const float af = (float)a;
-                const size_t i = (size_t)t * N + n;
-                __stcs(adv + i, af);
-                __stcs(ret + i, (float)g);
-                s1 += (double)af;
-                s2 += (double)af * (double)af;
-                nv = vv; na = a; nr = g;
-            }
-        }
+        if (active) gae_rows<U>(rj, vj, ej, bc, c == 0, t_hi, N, (size_t)n, adv, ret, gamma, gl, nv, na, nr, s1, s2);
 #pragma unroll
         for (int j = 0; j < U; j++) bc[j] = bn[j];
     }
@@ -318,11 +340,136 @@ __global__ void __launch_bounds__(kColsBlock + 32, MINB) gae_tile_ws_kernel(cons
             s1 += __shfl_down_sync(0xffffffffu, s1, o);
             s2 += __shfl_down_sync(0xffffffffu, s2, o);
         }
-        if ((threadIdx.x & 31) == 0) {
+        if ((threadIdx.x & 31) == 0 && active) {
             atomicAdd(stats, s1);
             atomicAdd(stats + 1, s2);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// variants 14 / 15: the producer-warp form fed by TENSOR-MAP copies.  One cp.async.bulk.tensor.2d request moves a whole
+// [U rows][C columns] box of an array, so a chunk costs the copy engine 3 requests instead of 3 U row copies (the row form
+// spends ~40-80 cycles of the SM's copy unit per request: at mid sizes that, not HBM, paces the kernel).  Rows of a box are
+// in ascending step order (row r of chunk c = step t_hi - (U-1) + r); rows below step 0 and columns beyond N are zero-
+// filled by the unit and still counted by the barrier, so every chunk expects the full box.  Same operation order per
+// column as variant 1: bit-identical.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void g_tmap_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     g_smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(g_smem_u32(mbar))
+                 : "memory");
+}
+
+template <int C, int U, int S, int MINB>
+__global__ void __launch_bounds__(C + 32, MINB) gae_tmap_kernel(const __grid_constant__ CUtensorMap tm_rew,
+                                                               const __grid_constant__ CUtensorMap tm_val,
+                                                               const __grid_constant__ CUtensorMap tm_pe,
+                                                               const float *__restrict__ boot, float *__restrict__ adv,
+                                                               float *__restrict__ ret, int T, int N, double gamma, double gl,
+                                                               double *stats) {
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    typedef float (*TileF)[U][C];
+    typedef uint8_t (*TileB)[U][C];
+    TileF s_rew = reinterpret_cast<TileF>(ws_smem);
+    TileF s_val = reinterpret_cast<TileF>(ws_smem + sizeof(float) * S * U * C);
+    TileB s_pe = reinterpret_cast<TileB>(ws_smem + 2 * sizeof(float) * S * U * C);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ws_smem + 9 * S * U * C);
+    uint64_t *empty = full + S;
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * C, n = n0 + tid;
+    const int chunks = (T + U - 1) / U;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(full + s)), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(empty + s)), "r"(C) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid >= C) {                                     // ---- producer warp: one lane, three requests per chunk -----------
+        if (tid == C) {
+            for (int c = 0; c < chunks; c++) {
+                const int st = c % S, y0 = T - 1 - c * U - (U - 1);
+                if (c >= S) g_mbar_wait(empty + st, (uint32_t)(c / S - 1) & 1u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(full + st)),
+                             "r"((uint32_t)(U * C * 9))
+                             : "memory");
+                g_tmap_2d(&s_rew[st][0][0], &tm_rew, n0, y0, full + st);
+                g_tmap_2d(&s_val[st][0][0], &tm_val, n0, y0, full + st);
+                g_tmap_2d(&s_pe[st][0][0], &tm_pe, n0, y0, full + st);
+            }
+        }
+        return;
+    }
+    const bool active = n < N;
+    double nv = 0.0, na = 0.0, nr = 0.0, s1 = 0.0, s2 = 0.0;
+    float bc[U], bn[U];
+    g_mbar_wait(full + 0, 0);
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int t = T - 1 - j;
+        bc[j] = 0.0f;
+        if (active && t >= 0 && (s_pe[0][U - 1 - j][tid] || t == T - 1)) bc[j] = __ldcs(boot + (size_t)t * N + n);
+    }
+    for (int c = 0; c < chunks; c++) {
+        const int st = c % S, t_hi = T - 1 - c * U;
+        if (c + 1 < chunks) {
+            const int sn = (c + 1) % S;
+            g_mbar_wait(full + sn, (uint32_t)((c + 1) / S) & 1u);
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const int t = t_hi - U - j;
+                bn[j] = 0.0f;
+                if (active && t >= 0 && s_pe[sn][U - 1 - j][tid]) bn[j] = __ldcs(boot + (size_t)t * N + n);
+            }
+        }
+        float rj[U], vj[U];
+        uint8_t ej[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            rj[j] = s_rew[st][U - 1 - j][tid]; vj[j] = s_val[st][U - 1 - j][tid]; ej[j] = s_pe[st][U - 1 - j][tid];
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(empty + st)) : "memory");   // stage read
+        if (active) gae_rows<U>(rj, vj, ej, bc, c == 0, t_hi, N, (size_t)n, adv, ret, gamma, gl, nv, na, nr, s1, s2);
+#pragma unroll
+        for (int j = 0; j < U; j++) bc[j] = bn[j];
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, o);
+            s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        }
+        if ((threadIdx.x & 31) == 0 && (s1 != 0.0 || s2 != 0.0)) {
+            atomicAdd(stats, s1);
+            atomicAdd(stats + 1, s2);
+        }
+    }
+}
+
+// tensor map of a row-major [T][N] array with [U][C] boxes; the driver entry point is looked up through the runtime, so
+// the library does not link against libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_tmap(CUtensorMap *tm, const void *base, bool bytes, int T, int N, int U, int C) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * (bytes ? 1 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)U};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -509,26 +656,52 @@ int rs_gae(const float *rew, const float *val, const uint8_t *path_end, const fl
         // would otherwise not all be resident in one wave (N = 131072: 886 threads per SM)
         const bool tile_ok = (N % kColsBlock) == 0 && ((reinterpret_cast<uintptr_t>(rew) | reinterpret_cast<uintptr_t>(val) |
                                                         reinterpret_cast<uintptr_t>(path_end)) & 15) == 0;
-        if (variant >= 7 && variant <= 11 && !tile_ok) return rs_set_error("rs_gae: the tile variants need N % 128 == 0 and 16-byte aligned arrays");
+        if (variant >= 7 && variant <= 15 && !tile_ok) return rs_set_error("rs_gae: the tile variants need N % 128 == 0 and 16-byte aligned arrays");
         // auto: the copy-engine variants whenever the tiles are whole and fill the GPU (measured on B200, T = 480:
         // N = 131072 -> 4.9 TB/s with the plain ring, N = 65536 -> 3.4 TB/s with the producer warp; register-pipelined
         // loads 3.9 / 2.7 TB/s)
         if (variant == 0 || variant == 1) {
             if (tile_ok && (long long)N >= 148LL * 128 * 4) variant = 7;
-            else if (tile_ok && N >= 16384) variant = 11;     // <= 4 CTAs per SM: twice the stages in flight per CTA
+            else if (tile_ok && N >= 32768) variant = 13;     // 224-column CTAs, 2 per SM: N / 224 CTAs spread evenly
+            else if (tile_ok && N >= 16384) variant = 14;     // 128-column CTAs fed by tensor-map copies
         }
         if (variant == 7)
             gae_tile_kernel<128, 8, 3, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 10)
             gae_tile_kernel<64, 8, 3, 14><<<N / 64, 64, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else if (variant == 8)
-            gae_tile_ws_kernel<8, 3, 7><<<grid, kColsBlock + 32, 9 * 3 * 8 * kColsBlock + 2 * 3 * 8, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
-        else if (variant == 11) {
-            // 6 stages of 8 rows (54 KB of tiles per CTA, 4 CTAs per SM): mid-size rollouts (N < 75776 columns) do not fill
-            // the SMs with CTAs, so each CTA keeps more bytes in flight instead
-            constexpr int smem11 = 9 * 6 * 8 * kColsBlock + 2 * 6 * 8;
-            cudaFuncSetAttribute(gae_tile_ws_kernel<8, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem11);
-            gae_tile_ws_kernel<8, 6, 4><<<grid, kColsBlock + 32, smem11, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+            gae_tile_ws_kernel<128, 8, 3, 5><<<grid, kColsBlock + 32, 9 * 3 * 8 * kColsBlock + 2 * 3 * 8, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
+        else if (variant == 11 || variant == 12 || variant == 13) {
+            // 6 stages of 8 rows: mid-size rollouts (N < 75776 columns) do not fill the SMs with CTAs, so each CTA keeps more
+            // bytes in flight instead.  11: 128 columns per CTA (54 KB of tiles, 4 CTAs per SM); 12: 64 columns (7 per SM);
+            // 13: 224 columns (95 KB, 2 per SM) -- the widths differ in how evenly N / width CTAs spread over 148 SMs
+            // (N = 65536: 512 CTAs = 3.46 per SM at width 128, 293 = 1.98 per SM at width 224)
+#define RS_GAE_WS(CW, MINB)                                                                                                \
+    do {                                                                                                                   \
+        constexpr int sm = 9 * 6 * 8 * CW + 2 * 6 * 8;                                                                     \
+        cudaFuncSetAttribute(gae_tile_ws_kernel<CW, 8, 6, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);         \
+        gae_tile_ws_kernel<CW, 8, 6, MINB><<<(N + CW - 1) / CW, CW + 32, sm, s>>>(rew, val, path_end, boot, adv, ret, T, N, \
+                                                                              gamma, gl, stats);                          \
+    } while (0)
+            if (variant == 11) RS_GAE_WS(128, 4);
+            else if (variant == 12) RS_GAE_WS(64, 7);
+            else RS_GAE_WS(224, 2);
+#undef RS_GAE_WS
+        } else if (variant == 14 || variant == 15) {
+            alignas(64) CUtensorMap tr, tv, tp;
+#define RS_GAE_TMAP(CW, MINB)                                                                                              \
+    do {                                                                                                                   \
+        if (!make_tmap(&tr, rew, false, T, N, 8, CW) || !make_tmap(&tv, val, false, T, N, 8, CW) ||                        \
+            !make_tmap(&tp, path_end, true, T, N, 8, CW))                                                                  \
+            return rs_set_error("rs_gae: cuTensorMapEncodeTiled failed");                                                  \
+        constexpr int sm = 9 * 6 * 8 * CW + 2 * 6 * 8;                                                                     \
+        cudaFuncSetAttribute(gae_tmap_kernel<CW, 8, 6, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);            \
+        gae_tmap_kernel<CW, 8, 6, MINB><<<(N + CW - 1) / CW, CW + 32, sm, s>>>(tr, tv, tp, boot, adv, ret, T, N, gamma, gl, \
+                                                                           stats);                                        \
+    } while (0)
+            if (variant == 14) RS_GAE_TMAP(128, 4);
+            else RS_GAE_TMAP(224, 2);
+#undef RS_GAE_TMAP
         } else if (variant == 3 || (variant != 4 && (long long)grid > 148LL * 4))
             gae_cols_kernel<8, 7><<<grid, kColsBlock, 0, s>>>(rew, val, path_end, boot, adv, ret, T, N, gamma, gl, stats);
         else

@@ -33,8 +33,8 @@ def test_gae_thread_per_column_is_bit_exact(T, N):
     np.testing.assert_allclose(st, [a0.astype(np.float64).sum(), (a0.astype(np.float64) ** 2).sum()], rtol=1e-12)
 
 
-@pytest.mark.parametrize("variant", [7, 8, 10, 11])
-@pytest.mark.parametrize("T,N", [(480, 1024), (96, 128), (481, 4096), (7, 256), (1, 128), (33, 384), (3, 128), (12, 128)])
+@pytest.mark.parametrize("variant", [7, 8, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("T,N", [(480, 1024), (96, 128), (481, 4096), (7, 256), (1, 128), (33, 384), (3, 128), (12, 128), (50, 1152)])
 def test_gae_copy_engine_tiles_are_bit_exact(T, N, variant):
     """variant 6 / 7: the per-column recurrence fed by bulk-async tile copies (N % 128 == 0); same operation order as
     variant 1, hence bit-identical to the reference recurrence, incl. T not a multiple of the tile height."""

@@ -23,7 +23,7 @@ for N in (1024, 16384, 32768, 65536, 131072):
     end = (torch.rand(T, N, generator=g, device=dev) < 0.01).to(torch.uint8); end[T - 1] = 1
     boot = torch.randn(T, N, generator=g, device=dev) * end
     adv, ret = torch.empty_like(rew), torch.empty_like(rew)
-    for v in (0, 3, 7, 8, 10, 11) if N % 128 == 0 and N >= 16384 else (0, 2, 3):
+    for v in (0, 7, 8, 11, 12, 13, 14, 15) if N % 128 == 0 and N >= 16384 else (0, 2, 3):
         ms = timeit(lambda: rp.gae_advantages(rew, val, end, boot, adv=adv, ret=ret, variant=v))
         out[f"N{N}_v{v}"] = f"{ms * 1e3:.0f} us  {17 * T * N / ms / 1e6:.0f} GB/s"
     del rew, val, end, boot, adv, ret
