@@ -7,6 +7,7 @@
 //   nv,na,nr = end ? (boot, 0, boot) : (val[t+1], adv[t+1], ret[t+1])
 //   adv[t] = (rew + gamma*nv) - val + (gamma*lam)*na ;  ret[t] = rew + gamma*nr
 #include <cuda.h>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -583,11 +584,18 @@ __global__ void __launch_bounds__(kScanBlock) gae_scan_kernel(const float *__res
     }
 }
 
-__global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict__ x, long long n, const double *center,
+// `head` = elements in front of the first 16-byte boundary (0..3; handled one by one like the tail)
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict__ x0, long long n0, int head, const double *center,
                                                         double *stats) {
     const double c = center ? *center : 0.0;
     double s1 = 0.0, s2 = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x < head) {
+        const double a = (double)x0[threadIdx.x] - c;
+        s1 += a; s2 += a * a;
+    }
+    const float *x = x0 + head;
+    const long long n = n0 - head;
     const long long n4 = n >> 2;
     const float4 *x4 = reinterpret_cast<const float4 *>(x);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -617,10 +625,13 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) adv_normalize_kernel(float *__restrict__ x, long long n, const double *mean,
+__global__ void __launch_bounds__(256) adv_normalize_kernel(float *__restrict__ x0, long long n0, int head, const double *mean,
                                                             const double *std) {
     const float m = (float)*mean, s = (float)*std;      // (adv_buf - adv_mean) / adv_std on a float32 buffer P:446
     const long long stride = (long long)gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x < head) x0[threadIdx.x] = __fdiv_rn(x0[threadIdx.x] - m, s);
+    float *x = x0 + head;
+    const long long n = n0 - head;
     const long long n4 = n >> 2;
     float4 *x4 = reinterpret_cast<float4 *>(x);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -715,7 +726,9 @@ int rs_adv_stats(const float *x, int64_t n, const double *center, double *stats,
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    adv_stats_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (long long)n, center, stats);
+    if (reinterpret_cast<uintptr_t>(x) & 3) return rs_set_error("rs_adv_stats: x is not 4-byte aligned");
+    const int head = (int)std::min<long long>(n, (long long)(((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) / 4));
+    adv_stats_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (long long)n, head, center, stats);
     return (int)cudaGetLastError();
 }
 
@@ -724,7 +737,9 @@ int rs_adv_normalize(float *x, int64_t n, const double *mean, const double *std,
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    adv_normalize_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (long long)n, mean, std);
+    if (reinterpret_cast<uintptr_t>(x) & 3) return rs_set_error("rs_adv_normalize: x is not 4-byte aligned");
+    const int head = (int)std::min<long long>(n, (long long)(((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) / 4));
+    adv_normalize_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (long long)n, head, mean, std);
     return (int)cudaGetLastError();
 }
 

@@ -735,7 +735,11 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 #endif
         if (K == 0) RS_LAUNCH_STEP1_K(0, RS_STEP1_OCC);
         else if (K <= 3) RS_LAUNCH_STEP1_K(3, RS_STEP1_OCC);
-        else if (K <= 5) RS_LAUNCH_STEP1_K(5, RS_STEP1_OCC);
+        else if (K <= 5) {
+            // up to 4 CTAs per SM there is room for 128 registers: no spills, 8 % faster per launch (65 536 envs: 26.6 -> 24.6 us)
+            if ((long long)n_env <= 148LL * 4 * TB && RS_STEP1_OCC > 4) RS_LAUNCH_STEP1_K(5, 4);
+            else RS_LAUNCH_STEP1_K(5, RS_STEP1_OCC);
+        }
         else RS_LAUNCH_STEP1_K(8, 5);
 #undef RS_LAUNCH_STEP1_K
 #undef RS_LAUNCH_STEP1

@@ -92,14 +92,18 @@ def test_gae_full_size_properties():
     np.testing.assert_array_equal(r1[:, sl].cpu().numpy(), r0)
 
 
-def test_advantage_normalisation_matches_reference_statistics():
+@pytest.mark.parametrize("offset", [0, 1, 3])
+def test_advantage_normalisation_matches_reference_statistics(offset):
+    """`offset`: a view that starts 4 / 12 bytes past a 16-byte boundary (the kernels read float4 behind a scalar head)."""
     d = dev()
-    x = torch.randn(480 * 1024 + 3, device=d) * 3 + 0.7
+    x = (torch.randn(480 * 1024 + 3 + offset, device=d) * 3 + 0.7)[offset:]
+    assert x.data_ptr() % 16 == 4 * offset
     mean, std = rp.advantage_statistics(x)
     xs = x.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(mean.item(), xs.mean(), rtol=1e-12)
     np.testing.assert_allclose(std.item(), xs.std(), rtol=1e-12)
-    y = x.clone()
+    y = torch.empty(x.numel() + offset, device=d)[offset:]
+    y.copy_(x)
     rp.normalize_advantages_(y, mean.float().double(), std.float().double())
     want = (x.cpu().numpy() - np.float32(xs.mean())) / np.float32(xs.std())        # float32 math as in P:446
     np.testing.assert_allclose(y.cpu().numpy(), want, rtol=2e-7, atol=1e-7)
