@@ -278,89 +278,34 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Single-agent step kernel (rs_step1.cuh): one thread per environment, warp-autonomous.  A CTA of TB threads owns TB
-// consecutive environments.  Thread 0 starts bulk-async copies (cp.async.bulk, one mbarrier) of the tile's rectangle rows
-// [k][TB] and of its block of the float source-distance table [TB][4K] into shared memory -- the two tables that lanes
-// read for each other's environments or index dynamically; every other state row goes straight from HBM into the
-// owning thread's registers with coalesced loads, and the unit's Philox block is computed while both are in flight.
-// After the one CTA barrier that publishes the mbarrier, warps never meet again: the front half (move, segment to the
-// source, shortest path, Poisson draw) is straight-line per-lane code, the ray casts are (unit, direction) items of the
-// warp, the reset work list is appended with one atomic per warp, state and scalar outputs leave as coalesced stores and
-// the observation rows through a shared-memory staging block as 16-byte stores.
+// Single-agent step (rs_step1.cuh): one thread per environment, warp-autonomous.  step1_tile is what a warp does for the
+// 32 consecutive environments [nw, nw + 32) once their rectangle rows and their block of the float source-distance
+// table are in shared memory and the scalar state rows in registers: the front half (move, segment to the source,
+// shortest path, Poisson draw) is straight-line per-lane code, the marked corners and the ray casts are (unit, corner) /
+// (unit, direction) items of the warp, the reset work list is appended with one atomic per warp, state and scalar outputs
+// leave as coalesced stores and the observation rows through a shared-memory staging block as 16-byte stores.  Two
+// kernels call it: step1_kernel (a CTA stages one tile of TB environments, every warp runs once) and step1p_kernel
+// (every warp walks several tiles and has the next one in flight while it computes).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool kFast, int KMAX, int TB, int kOcc>
-__global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__ rs::Params P,
-                                                          const __grid_constant__ RsState S,
-                                                          const __grid_constant__ rs::StepArgs a, int bulk_ok) {
-    constexpr int KS = KMAX > 0 ? KMAX : 1;
-    __shared__ __align__(16) int4 s_rects[KS * TB];
-    __shared__ __align__(16) float s_dsf[TB * 4 * KS];
-    __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
-    __shared__ uint8_t s_list[TB];
-    constexpr int kPairCap = 128;                           // (unit, corner) pairs of a warp: ~35 at 5 obstructions
-    __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
-    __shared__ __align__(8) uint64_t s_mbar;
-    const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
-    const int n0 = blockIdx.x * TB;
-    const int n = n0 + tid;
-    const bool live = n < a.n_env;
-    const int K = KMAX > 0 ? P.k_max : 0;
+constexpr int kPairCap = 128;                               // (unit, corner) pairs of a warp: ~35 at 5 obstructions
+struct WarpTile {
+    const int4 *rects;      // rectangle k of lane l at rects[k * RST + l]
+    const float *dsf;       // [32][4K] float source-distance rows
+    float *obs;             // [32][RS_OBS_DIM] staging block of the observation rows (scratch until the commit phase)
+    uint8_t *list;          // [32]
+    uint16_t *pairs;        // [kPairCap]
+};
+
+template <bool kFast, int KMAX, int RST>
+__device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S, const rs::StepArgs &a, const int K,
+                                           const int nw, const int lane, const bool live, const int2 src, const int2 rad,
+                                           const int2 det, const int meta, const int action, const int af,
+                                           const double best, double stm, double stq, const double ds_hint,
+                                           const uint64_t step_ctr, const uint32_t (&x)[4], const WarpTile t,
+                                           const int bulk_ok) {
+    const int n = nw + lane;
     const size_t N = (size_t)a.n_env;
-    const bool bulk = KMAX > 0 && bulk_ok && n0 + TB <= a.n_env;
-    if (bulk && tid == 0) {
-        mbar_init(&s_mbar, 1);
-        mbar_expect_tx(&s_mbar, (uint32_t)(2 * K * 16 * TB));
-        for (int k = 0; k < K; k++)
-            bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar);
-        bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar);
-    }
-    // scalar state rows: coalesced, straight into registers
-    int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
-    int meta = 0, action = -1, af = 0;
-    double best = 0.0, stm = 0.0, stq = 0.0;
-    if (live) {
-        src = reinterpret_cast<const int2 *>(S.src)[n];
-        rad = reinterpret_cast<const int2 *>(S.rad)[n];
-        det = reinterpret_cast<const int2 *>(S.det)[n];
-        meta = S.meta[n];
-        af = S.aflags[n];
-        best = S.best[n];
-        if (a.actions) action = a.actions[n];
-        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
-    }
-    // an episode that times out at this step is known now: its prefetched successor (adopted in the commit phase) is pulled
-    // into L2 while the step is computed
-    if (live && (a.flags & RS_F_PREFETCH) && a.actions && (meta >> 16) + 1 == P.max_ep_len) {
-        const char *r = reinterpret_cast<const char *>(S.nx_dsrc + (size_t)n * 4 * K);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_dsf + (size_t)n * 4 * K));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_obs + (size_t)n * RS_OBS_DIM));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_src + (size_t)n * 2));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_det + (size_t)n * 2));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_rad + (size_t)n * 2));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_best + n));
-    }
-    // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
     const int hint = (af >> 25) & 31;
-    double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
-    if (KMAX > 0 && live && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
-    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
-    uint32_t x[4] = {0u, 0u, 0u, 0u};
-    if (kFast)      // needs nothing from memory: runs while the tile is in flight
-        rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
-                          (uint32_t)(a.seed >> 32), x);
-    if (bulk) {
-        __syncthreads();                                    // the barrier object is initialised for everybody
-        mbar_wait(&s_mbar, 0);
-    } else if (KMAX > 0) {
-        if (live) {
-            for (int k = 0; k < K; k++) s_rects[k * TB + tid] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
-            for (int k = 0; k < K; k++)
-                reinterpret_cast<float4 *>(s_dsf)[tid * K + k] = reinterpret_cast<const float4 *>(S.dsf)[(size_t)n * K + k];
-        }
-        __syncwarp();
-    }
     // ---- take_action, segment to the source; for obstructed units the bound through last step's corner + marking pass -----
     const int num_obs = meta & 0xff;
     rs::Move1 mv;
@@ -369,9 +314,9 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     int besti = -1;
     uint32_t marked = 0u;
     if (live) {
-        mv = rs::unit1_move<KMAX>(P, s_rects + tid, TB, src, meta, action, det, af);
+        mv = rs::unit1_move<KMAX>(P, t.rects + lane, RST, src, meta, action, det, af);
         if (!mv.direct)
-            marked = rs::sp_hint_mark1<KMAX>(s_rects + tid, TB, num_obs, s_dsf + tid * 4 * K, mv.det.x, mv.det.y, hint, ds_hint,
+            marked = rs::sp_hint_mark1<KMAX>(t.rects + lane, RST, num_obs, t.dsf + lane * 4 * K, mv.det.x, mv.det.y, hint, ds_hint,
                                              best_sp, besti);
     }
     // ---- the marked corners of the warp as (unit, corner) pairs, one per lane: exact candidate + visibility ---------------
@@ -384,8 +329,8 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             if (lane >= s) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
-        uint16_t *pl = s_pairs + (w0 >> 5) * kPairCap;
-        double *res = reinterpret_cast<double *>(s_obs + w0 * RS_OBS_DIM);      // the warp's staging block, free until commit
+        uint16_t *pl = t.pairs;
+        double *res = reinterpret_cast<double *>(t.obs);      // the warp's staging block, free until commit
         {
             uint32_t m = marked;
             int pos = off;
@@ -406,8 +351,8 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             const int nob = __shfl_sync(0xffffffffu, num_obs, owner);
             const double bo = __shfl_sync(0xffffffffu, best_sp, owner);
             double ds = __longlong_as_double(0x7ff0000000000000LL);
-            if (valid) ds = S.dsrc[(size_t)(n0 + w0 + owner) * 4 * K + c];
-            const double v = rs::sp_pair1<KMAX>(s_rects + w0 + owner, TB, nob, px, py, c, ds, bo);
+            if (valid) ds = S.dsrc[(size_t)(nw + owner) * 4 * K + c];
+            const double v = rs::sp_pair1<KMAX>(t.rects + owner, RST, nob, px, py, c, ds, bo);
             if (valid) res[j] = v;
         }
         __syncwarp();
@@ -419,7 +364,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
                 m &= m - 1;
                 // pairs beyond the warp's list (never seen so far) are evaluated by their own thread
                 const double v = pos < kPairCap ? res[pos]
-                                                : rs::sp_pair1<KMAX>(s_rects + tid, TB, num_obs, mv.det.x, mv.det.y, c,
+                                                : rs::sp_pair1<KMAX>(t.rects + lane, RST, num_obs, mv.det.x, mv.det.y, c,
                                                                      S.dsrc[(size_t)n * 4 * K + c], best_sp);
                 if (v < best_sp) { best_sp = v; besti = c; }
                 pos++;
@@ -427,7 +372,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         }
         __syncwarp();
     }
-    float *row = s_obs + tid * RS_OBS_DIM;
+    float *row = t.obs + lane * RS_OBS_DIM;
 #pragma unroll
     for (int d = 0; d < 8; d++) row[3 + d] = 0.0f;
     rs::Unit1 o;
@@ -437,7 +382,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     // ---- obstruction_sensors: (unit, direction) items of the warp ---------------------------------------------------------
     const unsigned need = __ballot_sync(0xffffffffu, (o.uf & rs::UF_NEED_D) != 0);
     if (need) {
-        uint8_t *wl = s_list + w0;
+        uint8_t *wl = t.list;
         if ((need >> lane) & 1u) wl[__popc(need & ((1u << lane) - 1u))] = (uint8_t)lane;
         __syncwarp();
         const int cnt = __popc(need);
@@ -447,10 +392,10 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             const int owner = valid ? (int)wl[j] : 0;
             const int px = __shfl_sync(0xffffffffu, o.det.x, owner), py = __shfl_sync(0xffffffffu, o.det.y, owner);
             const int ufo = __shfl_sync(0xffffffffu, o.uf, owner), nob = __shfl_sync(0xffffffffu, meta, owner) & 0xff;
-            const int4 *col = s_rects + w0 + owner;
+            const int4 *col = t.rects + owner;
             unsigned long long hits = 0ull;
             int dmin = -1;
-            if (valid) dmin = rs::sense_dir1(col, TB, (ufo >> 16) & 0xff, px, py, d, hits);
+            if (valid) dmin = rs::sense_dir1(col, RST, (ufo >> 16) & 0xff, px, py, d, hits);
             float v = rs::sense_value(dmin);
             // the detector stands on an obstruction edge when more than three of its rays read exactly 1.0: R:1219-1226
             const unsigned zero = __ballot_sync(0xffffffffu, valid && dmin == 0);
@@ -461,14 +406,14 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
                 if (fix) {
                     float out[8];
                     uint32_t st = 0u;
-                    rs::correct_coords(px, py, col[rs::sense_correct_rect(col, TB, nob, hits) * TB], out, st);
+                    rs::correct_coords(px, py, col[rs::sense_correct_rect(col, RST, nob, hits) * RST], out, st);
                     v = out[0];
 #pragma unroll
                     for (int i = 1; i < 8; i++) v = d == i ? out[i] : v;
-                    if (d == 0) rs::raise_status(S, n0 + w0 + owner, st);
+                    if (d == 0) rs::raise_status(S, nw + owner, st);
                 }
             }
-            if (valid) s_obs[(w0 + owner) * RS_OBS_DIM + 3 + d] = v;
+            if (valid) t.obs[owner * RS_OBS_DIM + 3 + d] = v;
         }
         __syncwarp();
     }
@@ -505,7 +450,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         while (am) {
             const int owner = __ffs(am) - 1;
             am &= am - 1;
-            const int nn = n0 + w0 + owner;
+            const int nn = nw + owner;
             const int nc = 4 * __shfl_sync(0xffffffffu, num_obs, owner);
             const size_t r0 = (size_t)nn * 4 * K;
             const bool t1 = lane < nc, t2 = lane < RS_OBS_DIM;
@@ -514,7 +459,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             if (t1) { ds = S.nx_dsrc[r0 + lane]; df = S.nx_dsf[r0 + lane]; }      // source-distance rows of the new episode
             if (t2) ob = S.nx_obs[(size_t)nn * RS_OBS_DIM + lane];                 // its first observation
             if (t1) { S.dsrc[r0 + lane] = ds; S.dsf[r0 + lane] = df; }
-            if (t2) s_obs[(w0 + owner) * RS_OBS_DIM + lane] = ob;                  // -> the env's staged row
+            if (t2) t.obs[owner * RS_OBS_DIM + lane] = ob;                  // -> the env's staged row
         }
         __syncwarp();
     }
@@ -563,8 +508,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     __syncwarp();
     // ---- observation rows: the warp's 32 rows are one contiguous run of 352 floats in shared memory and in HBM --------------
     {
-        const int nw = n0 + w0;                             // first environment of this warp
-        const float *sw = s_obs + w0 * RS_OBS_DIM;
+        const float *sw = t.obs;
         float *g = a.obs + (size_t)nw * RS_OBS_DIM;
         if (bulk_ok && nw + 32 <= a.n_env) {
             for (int i = lane; i < 32 * RS_OBS_DIM / 4; i += 32)
@@ -573,6 +517,184 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
             const int rows = min(32, a.n_env - nw);
             for (int i = lane; i < rows * RS_OBS_DIM; i += 32) g[i] = sw[i];
         }
+    }
+}
+
+// an episode that times out at this step is known when its meta word arrives: its prefetched successor (adopted in the
+// commit phase) is pulled into L2 while the step is computed
+__device__ __forceinline__ void step1_successor_prefetch(const rs::Params &P, const RsState &S, const rs::StepArgs &a,
+                                                         const int K, const int n, const int meta) {
+    if ((a.flags & RS_F_PREFETCH) && a.actions && (meta >> 16) + 1 == P.max_ep_len) {
+        const char *r = reinterpret_cast<const char *>(S.nx_dsrc + (size_t)n * 4 * K);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_dsf + (size_t)n * 4 * K));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_obs + (size_t)n * RS_OBS_DIM));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_src + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_det + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_rad + (size_t)n * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_best + n));
+    }
+}
+
+// A CTA of TB threads owns TB consecutive environments.  Thread 0 starts bulk-async copies (cp.async.bulk, one mbarrier)
+// of the tile's rectangle rows [k][TB] and of its block of the float source-distance table [TB][4K] into shared memory --
+// the two tables that lanes read for each other's environments or index dynamically; every other state row goes straight
+// from HBM into the owning thread's registers with coalesced loads, and the unit's Philox block is computed while both
+// are in flight.  After the one CTA barrier that publishes the mbarrier, warps never meet again.
+template <bool kFast, int KMAX, int TB, int kOcc>
+__global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__ rs::Params P,
+                                                          const __grid_constant__ RsState S,
+                                                          const __grid_constant__ rs::StepArgs a, int bulk_ok) {
+    constexpr int KS = KMAX > 0 ? KMAX : 1;
+    __shared__ __align__(16) int4 s_rects[KS * TB];
+    __shared__ __align__(16) float s_dsf[TB * 4 * KS];
+    __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
+    __shared__ uint8_t s_list[TB];
+    __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
+    const int n0 = blockIdx.x * TB;
+    const int n = n0 + tid;
+    const bool live = n < a.n_env;
+    const int K = KMAX > 0 ? P.k_max : 0;
+    const size_t N = (size_t)a.n_env;
+    const bool bulk = KMAX > 0 && bulk_ok && n0 + TB <= a.n_env;
+    if (bulk && tid == 0) {
+        mbar_init(&s_mbar, 1);
+        mbar_expect_tx(&s_mbar, (uint32_t)(2 * K * 16 * TB));
+        for (int k = 0; k < K; k++)
+            bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar);
+        bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar);
+    }
+    // scalar state rows: coalesced, straight into registers
+    int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
+    int meta = 0, action = -1, af = 0;
+    double best = 0.0, stm = 0.0, stq = 0.0;
+    if (live) {
+        src = reinterpret_cast<const int2 *>(S.src)[n];
+        rad = reinterpret_cast<const int2 *>(S.rad)[n];
+        det = reinterpret_cast<const int2 *>(S.det)[n];
+        meta = S.meta[n];
+        af = S.aflags[n];
+        best = S.best[n];
+        if (a.actions) action = a.actions[n];
+        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
+    }
+    if (live) step1_successor_prefetch(P, S, a, K, n, meta);
+    // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
+    const int hint = (af >> 25) & 31;
+    double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
+    if (KMAX > 0 && live && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
+    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
+    uint32_t x[4] = {0u, 0u, 0u, 0u};
+    if (kFast)      // needs nothing from memory: runs while the tile is in flight
+        rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), x);
+    if (bulk) {
+        __syncthreads();                                    // the barrier object is initialised for everybody
+        mbar_wait(&s_mbar, 0);
+    } else if (KMAX > 0) {
+        if (live) {
+            for (int k = 0; k < K; k++) s_rects[k * TB + tid] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
+            for (int k = 0; k < K; k++)
+                reinterpret_cast<float4 *>(s_dsf)[tid * K + k] = reinterpret_cast<const float4 *>(S.dsf)[(size_t)n * K + k];
+        }
+        __syncwarp();
+    }
+    WarpTile t;
+    t.rects = s_rects + w0; t.dsf = s_dsf + w0 * 4 * K; t.obs = s_obs + w0 * RS_OBS_DIM; t.list = s_list + w0;
+    t.pairs = s_pairs + (w0 >> 5) * kPairCap;
+    step1_tile<kFast, KMAX, TB>(P, S, a, K, n0 + w0, lane, live, src, rad, det, meta, action, af, best, stm, stq, ds_hint,
+                                step_ctr, x, t, bulk_ok);
+}
+
+// The same step for large batches: every warp walks `tpw` tiles of 32 environments and has the next one in flight while it
+// computes the current one.  ALL state rows of a tile (rectangles, float source-distance block, source, intensities,
+// detector, meta, flags, running minimum, action) arrive by bulk-async copies into one of the warp's two shared-memory
+// stages, completing on the stage's mbarrier; lane 0 issues them for tile i+1 before the warp starts on tile i, so that
+// only a warp's first tile waits for HBM.  No CTA barrier anywhere: warps are independent from the first instruction on.
+// NW warps per CTA, two CTAs per SM (register cap 144: nothing spills); the grid is ceil(tiles / (NW * tpw)) CTAs, tile
+// (cta * tpw + j) * NW + warp for j = 0..tpw-1.  Needs n_env % 32 == 0 and 16-byte aligned rows (else step1_kernel).
+template <int KMAX>
+struct Stage1P {
+    static constexpr int KS = KMAX > 0 ? KMAX : 1;
+    int4 rects[KS * 32];
+    float dsf[32 * 4 * KS];
+    int2 src[32], rad[32], det[32];
+    double best[32];
+    int meta[32], af[32], action[32];
+};
+template <int KMAX>
+struct Warp1P {
+    Stage1P<KMAX> st[2];
+    float obs[32 * RS_OBS_DIM];
+    uint16_t pairs[kPairCap];
+    uint8_t list[32];
+    uint64_t mbar[2];
+};
+
+template <bool kFast, int KMAX, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) step1p_kernel(const __grid_constant__ rs::Params P,
+                                                             const __grid_constant__ RsState S,
+                                                             const __grid_constant__ rs::StepArgs a, const int tpw) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Warp1P<KMAX> &W = reinterpret_cast<Warp1P<KMAX> *>(s_dyn)[warp];
+    const int K = KMAX > 0 ? P.k_max : 0;
+    const size_t N = (size_t)a.n_env;
+    const int ntiles = a.n_env >> 5;
+    const int tile0 = blockIdx.x * tpw * NW + warp;
+    // lane 0: all rows of tile `tile` -> stage s
+    auto fetch = [&](int s, int tile) {
+        Stage1P<KMAX> &G = W.st[s];
+        const size_t n0 = (size_t)tile * 32;
+        mbar_expect_tx(&W.mbar[s], (uint32_t)(2 * K * 512 + 4 * 256 + (a.actions ? 3 : 2) * 128));
+        for (int k = 0; k < K; k++) bulk_g2s(G.rects + k * 32, S.rects + ((size_t)k * N + n0) * 4, 512, &W.mbar[s]);
+        if (KMAX > 0) bulk_g2s(G.dsf, S.dsf + n0 * 4 * K, (uint32_t)(512 * K), &W.mbar[s]);
+        bulk_g2s(G.src, S.src + n0 * 2, 256, &W.mbar[s]);
+        bulk_g2s(G.rad, S.rad + n0 * 2, 256, &W.mbar[s]);
+        bulk_g2s(G.det, S.det + n0 * 2, 256, &W.mbar[s]);
+        bulk_g2s(G.best, S.best + n0, 256, &W.mbar[s]);
+        bulk_g2s(G.meta, S.meta + n0, 128, &W.mbar[s]);
+        bulk_g2s(G.af, S.aflags + n0, 128, &W.mbar[s]);
+        if (a.actions) bulk_g2s(G.action, a.actions + n0, 128, &W.mbar[s]);
+    };
+    if (tile0 >= ntiles) return;
+    if (lane == 0) {
+        mbar_init(&W.mbar[0], 1);
+        mbar_init(&W.mbar[1], 1);
+        fetch(0, tile0);
+    }
+    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
+    __syncwarp();
+    for (int j = 0; j < tpw; j++) {
+        const int tile = tile0 + j * NW;
+        if (tile >= ntiles) break;
+        const int s = j & 1;
+        if (lane == 0 && j + 1 < tpw && tile + NW < ntiles) fetch(s ^ 1, tile + NW);     // stage s^1 was released by the
+        const int nw = tile * 32, n = nw + lane;                                           // __syncwarp that ended tile j-1
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+        if (kFast)      // needs nothing from memory: runs while the tile is in flight
+            rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
+                              (uint32_t)(a.seed >> 32), x);
+        mbar_wait(&W.mbar[s], (uint32_t)((j >> 1) & 1));
+        const Stage1P<KMAX> &G = W.st[s];
+        const int2 src = G.src[lane], rad = G.rad[lane], det = G.det[lane];
+        const int meta = G.meta[lane], af = G.af[lane], action = a.actions ? G.action[lane] : -1;
+        const double best = G.best[lane];
+        double stm = 0.0, stq = 0.0;
+        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
+        step1_successor_prefetch(P, S, a, K, n, meta);
+        // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
+        const int hint = (af >> 25) & 31;
+        double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
+        if (KMAX > 0 && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
+        WarpTile t;
+        t.rects = G.rects; t.dsf = G.dsf; t.obs = W.obs; t.list = W.list; t.pairs = W.pairs;
+        step1_tile<kFast, KMAX, 32>(P, S, a, K, nw, lane, true, src, rad, det, meta, action, af, best, stm, stq, ds_hint,
+                                    step_ctr, x, t, 1);
+        __syncwarp();
     }
 }
 
@@ -733,6 +855,34 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 #ifndef RS_STEP1_OCC
 #define RS_STEP1_OCC 7
 #endif
+        // large batches: the pipelined form (step1p_kernel), NW warps per CTA, two CTAs per SM, tpw tiles per warp so that
+        // the whole batch is one wave of 2 * 148 CTAs
+#ifndef RS_STEP1P_NW
+#define RS_STEP1P_NW 7
+#endif
+#ifndef RS_STEP1P_MIN_TILES
+#define RS_STEP1P_MIN_TILES 3072
+#endif
+        constexpr int NW = RS_STEP1P_NW;
+        const int ntiles = n_env / 32;
+        const bool rows_ok = bulk_ok && aligned16(st->src) && aligned16(st->det) && aligned16(st->meta) &&
+                             aligned16(st->aflags) && aligned16(actions) && n_env % 32 == 0;
+        if (rows_ok && K >= 1 && K <= 5 && ntiles >= RS_STEP1P_MIN_TILES) {
+            const int slots = 148 * 2 * NW;
+            int tpw = (ntiles + slots - 1) / slots;
+            if (tpw < 2) tpw = 2;
+            const int gridp = (ntiles + NW * tpw - 1) / (NW * tpw);
+#define RS_LAUNCH_STEP1P(FAST, KM)                                                                                        \
+    do {                                                                                                                  \
+        const int smem = NW * (int)sizeof(Warp1P<KM>);                                                                    \
+        cudaFuncSetAttribute(step1p_kernel<FAST, KM, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
+        step1p_kernel<FAST, KM, NW><<<gridp, NW * 32, smem, s>>>(P, *st, a, tpw);                                         \
+    } while (0)
+            if (K <= 3) { if (fast) RS_LAUNCH_STEP1P(true, 3); else RS_LAUNCH_STEP1P(false, 3); }
+            else { if (fast) RS_LAUNCH_STEP1P(true, 5); else RS_LAUNCH_STEP1P(false, 5); }
+#undef RS_LAUNCH_STEP1P
+            return (int)cudaGetLastError();
+        }
         if (K == 0) RS_LAUNCH_STEP1_K(0, RS_STEP1_OCC);
         else if (K <= 3) RS_LAUNCH_STEP1_K(3, RS_STEP1_OCC);
         else if (K <= 5) {

@@ -23,7 +23,15 @@
 #include "rs_step_tiled.cuh"
 #include "rs_poisson_alias.h"
 
+// Measurement switch (A/B builds only): bit set = keep that per-rectangle loop rolled instead of unrolling it over KMAX
+// (1 in_obstruction, 2 source segment, 4 visibility, 8 marking pass, 16 sensor candidates)
+#ifndef RS_S1_ROLL
+#define RS_S1_ROLL 0
+#endif
+
 namespace rs {
+
+constexpr int kS1Roll = RS_S1_ROLL;
 
 // x / d for a divisor d that is a launch constant, rd = 1 / d rounded to nearest: q0 = x * rd, then one correction with
 // the exact residual.  Equals the IEEE quotient (Markstein: a correctly rounded reciprocal and a faithful first quotient
@@ -48,19 +56,49 @@ __device__ __forceinline__ double round2_fast(double x) {
     return div_const(n, 100.0, 0.01);
 }
 
-// in_obstruction R:1148-1170 over the unit's rectangle column, unrolled
+// in_obstruction R:1148-1170 over the unit's rectangle column, unrolled and branch-free: the FIRST rectangle (index order)
+// whose closed set holds the point decides, so the rectangles are visited last to first and each overrides the later ones
 template <int KMAX>
 __device__ __forceinline__ bool in_obstruction1(const int4 *rects, int rstride, int num_obs, int px, int py) {
-    bool found = false, blocked = false;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-        if (k < num_obs) {
-            const int4 r = rects[k * rstride];
-            const bool closed = in_rect_closed(px, py, r);
-            if (!found && closed) { found = true; blocked = in_rect_open(px, py, r); }
-        }
+    bool blocked = false;
+#pragma unroll((kS1Roll & 1) ? 1 : (KMAX > 0 ? KMAX : 1))
+    for (int k = KMAX - 1; k >= 0; k--) {
+        const int4 r = rects[k * rstride];
+        const bool closed = (k < num_obs) & (r.x <= px) & (px <= r.z) & (r.y <= py) & (py <= r.w);
+        const bool open = (r.x < px) & (px < r.z) & (r.y < py) & (py < r.w);
+        blocked = closed ? open : blocked;
     }
     return blocked;
+}
+
+// A segment p -> q prepared for tests against many rectangles: everything that does not depend on the rectangle.
+// The cross product of corner (x, y) is (x - px) * dy - (y - py) * dx = x * dy - y * dx + t with t = py * dx - px * dy:
+// two multiply-adds per corner coordinate, no subtraction per rectangle (all values fit int32 for |coord| <= 16383).
+struct Seg1 {
+    int px, py, dx, dy, ndx, t, xlo, xhi, ylo, yhi;
+};
+__device__ __forceinline__ Seg1 make_seg1(int px, int py, int qx, int qy) {
+    Seg1 s;
+    s.px = px; s.py = py; s.dx = qx - px; s.dy = qy - py; s.ndx = -s.dx;
+    s.t = py * s.dx - px * s.dy;
+    s.xlo = min(px, qx); s.xhi = max(px, qx); s.ylo = min(py, qy); s.yhi = max(py, qy);
+    return s;
+}
+// seg_rect's bit 0 (the segment meets the OPEN rectangle) as a predicate: min / max of the four corner cross products
+// from the products of the two x and the two y coordinates, compared without forming the corner values
+__device__ __forceinline__ bool seg_open1(const Seg1 &s, int4 r) {
+    const int a = r.x * s.dy + s.t, b = r.z * s.dy + s.t;               // x part (+ t)
+    const int c = r.y * s.dx, d = r.w * s.dx;                          // y part
+    const bool mn_neg = min(a, b) < max(c, d), mx_pos = max(a, b) > min(c, d);
+    return (r.x < s.xhi) & (s.xlo < r.z) & (r.y < s.yhi) & (s.ylo < r.w) & mn_neg & mx_pos;
+}
+// seg_rect with both bits as predicates and the four cross products (order p0, p1, p2, p3 as seg_rect)
+__device__ __forceinline__ void seg_both1(const Seg1 &s, int4 r, bool &open, bool &closed, int cr[4]) {
+    const int a = r.x * s.dy + s.t, b = r.z * s.dy + s.t;
+    cr[0] = r.y * s.ndx + a; cr[1] = r.w * s.ndx + a; cr[2] = r.w * s.ndx + b; cr[3] = r.y * s.ndx + b;
+    const int mn = min(min(cr[0], cr[1]), min(cr[2], cr[3])), mx = max(max(cr[0], cr[1]), max(cr[2], cr[3]));
+    open = (r.x < s.xhi) & (s.xlo < r.z) & (r.y < s.yhi) & (s.ylo < r.w) & (mn < 0) & (mx > 0);
+    closed = (r.x <= s.xhi) & (s.xlo <= r.z) & (r.y <= s.yhi) & (s.ylo <= r.w) & (mn <= 0) & (mx >= 0);
 }
 
 // the near-corner clause of boundary_distance < 0.001 (see corner_grazes) as a call: it is needed for about one segment
@@ -72,42 +110,43 @@ __device__ __noinline__ bool graze_call(int px, int py, int qx, int qy, int4 r) 
     return corner_grazes(px, py, dx, dy, dx * dx + dy * dy, r, cr);
 }
 
-// source_segment() of rs_env_impl.cuh without the box pre-filter and the per-lane rectangle list: every rectangle, every lane
+// source_segment() of rs_env_impl.cuh without the box pre-filter and the per-lane rectangle list: every rectangle, every
+// lane, no branch but the (rare) near-corner call; rectangles past num_obs are computed and masked out.
 // src_in: the rectangles that hold the source strictly inside (meta bits 9..15, set by rs_load_scenarios; never in a
 // sampled scenario): there, a detector strictly inside the same rectangle meets no boundary.
 template <int KMAX>
 __device__ __forceinline__ void source_segment1(const int4 *rects, int rstride, int num_obs, int src_in, int px, int py, int sx,
                                                 int sy, bool &direct, bool &blocked) {
-    const int dx = sx - px, dy = sy - py;
-    const int l2 = dx * dx + dy * dy;
-    int acc = 0;                                            // bit 0: some open rectangle met, bit 1: some boundary within 0.001
-#pragma unroll
+    const Seg1 s = make_seg1(px, py, sx, sy);
+    const bool far = s.dx * s.dx + s.dy * s.dy > 1000000;
+    bool any_open = false, any_closed = false;
+#pragma unroll((kS1Roll & 2) ? 1 : (KMAX > 0 ? KMAX : 1))
     for (int k = 0; k < KMAX; k++) {
-        if (k < num_obs) {
-            const int4 r = rects[k * rstride];
-            int cr[4];
-            const int h = seg_rect(px, py, sx, sy, r, cr);
-            int b = h & 2;
-            if (src_in && ((src_in >> k) & 1) && in_rect_open(px, py, r)) b = 0;
-            // near-corner clause (|cross| <= 3, |pq| > 1000): guarded by one unsigned minimum over the four cross products
-            const unsigned g = min(min((unsigned)(cr[0] + 3), (unsigned)(cr[1] + 3)),
-                                   min((unsigned)(cr[2] + 3), (unsigned)(cr[3] + 3)));
-            if (g <= 6u && !b && l2 > 1000000 && graze_call(px, py, sx, sy, r)) b = 2;
-            acc |= (h & 1) | b;
-        }
+        const bool on = k < num_obs;
+        const int4 r = rects[k * rstride];
+        int cr[4];
+        bool open, closed;
+        seg_both1(s, r, open, closed, cr);
+        if (src_in) closed = closed & !(((src_in >> k) & 1) && in_rect_open(px, py, r));
+        // near-corner clause (|cross| <= 3, |pq| > 1000): guarded by one unsigned minimum over the four cross products
+        const unsigned g = min(min((unsigned)(cr[0] + 3), (unsigned)(cr[1] + 3)),
+                               min((unsigned)(cr[2] + 3), (unsigned)(cr[3] + 3)));
+        if (on & far & (g <= 6u) & !closed) closed = graze_call(px, py, sx, sy, r);
+        any_open |= on & open;
+        any_closed |= on & closed;
     }
-    direct = !(acc & 1);
-    blocked = (acc & 2) != 0;
+    direct = !any_open;
+    blocked = any_closed;
 }
 
-// visible() of rs_env_impl.cuh, unrolled and branch-free
+// visible() of rs_env_impl.cuh, unrolled and branch-free (rectangles past num_obs are computed and masked out)
 template <int KMAX>
 __device__ __forceinline__ bool visible1(const int4 *rects, int rstride, int num_obs, int px, int py, int qx, int qy) {
-    int hit = 0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++)
-        if (k < num_obs) hit |= seg_rect(px, py, qx, qy, rects[k * rstride]);      // every rectangle: no lane leaves early
-    return !(hit & 1);
+    const Seg1 s = make_seg1(px, py, qx, qy);
+    bool hit = false;
+#pragma unroll((kS1Roll & 4) ? 1 : (KMAX > 0 ? KMAX : 1))
+    for (int k = 0; k < KMAX; k++) hit |= (k < num_obs) & seg_open1(s, rects[k * rstride]);
+    return !hit;
 }
 
 // Marking pass of the pruned shortest path: the corners that may still improve on the upper bound `best`.  A corner c
@@ -120,21 +159,20 @@ template <int KMAX>
 __device__ __forceinline__ uint32_t mark1(const int4 *rects, int rstride, int num_obs, const float *dsf, int px, int py,
                                           float bf) {
     uint32_t mask = 0u;
-#pragma unroll
+#pragma unroll((kS1Roll & 8) ? 1 : (KMAX > 0 ? KMAX : 1))
     for (int k = 0; k < KMAX; k++) {
-        if (k < num_obs) {
-            const int4 r = rects[k * rstride];
-            const float4 d = *reinterpret_cast<const float4 *>(dsf + 4 * k);
-            const int ux0 = r.x - px, ux1 = r.z - px, uy0 = r.y - py, uy1 = r.w - py;
-            const int qx0 = ux0 * ux0, qx1 = ux1 * ux1, qy0 = uy0 * uy0, qy1 = uy1 * uy1;
-            const float t0 = __fsub_ru(bf, d.x), t1 = __fsub_ru(bf, d.y), t2 = __fsub_ru(bf, d.z), t3 = __fsub_ru(bf, d.w);
-            // corners p0 (x0,y0), p1 (x0,y1), p2 (x1,y1), p3 (x1,y0); tangent: u.x*u.y <= 0 at p0/p2, >= 0 at p1/p3
-            const bool m0 = ux0 * uy0 <= 0 && t0 > 0.0f && __int2float_rd(qx0 + qy0) < __fmul_ru(t0, t0);
-            const bool m1 = ux0 * uy1 >= 0 && t1 > 0.0f && __int2float_rd(qx0 + qy1) < __fmul_ru(t1, t1);
-            const bool m2 = ux1 * uy1 <= 0 && t2 > 0.0f && __int2float_rd(qx1 + qy1) < __fmul_ru(t2, t2);
-            const bool m3 = ux1 * uy0 >= 0 && t3 > 0.0f && __int2float_rd(qx1 + qy0) < __fmul_ru(t3, t3);
-            mask |= ((uint32_t)m0 | ((uint32_t)m1 << 1) | ((uint32_t)m2 << 2) | ((uint32_t)m3 << 3)) << (4 * k);
-        }
+        const int4 r = rects[k * rstride];
+        const float4 d = *reinterpret_cast<const float4 *>(dsf + 4 * k);
+        const int ux0 = r.x - px, ux1 = r.z - px, uy0 = r.y - py, uy1 = r.w - py;
+        const int qx0 = ux0 * ux0, qx1 = ux1 * ux1, qy0 = uy0 * uy0, qy1 = uy1 * uy1;
+        const float t0 = __fsub_ru(bf, d.x), t1 = __fsub_ru(bf, d.y), t2 = __fsub_ru(bf, d.z), t3 = __fsub_ru(bf, d.w);
+        // corners p0 (x0,y0), p1 (x0,y1), p2 (x1,y1), p3 (x1,y0); tangent: u.x*u.y <= 0 at p0/p2, >= 0 at p1/p3
+        const bool m0 = (ux0 * uy0 <= 0) & (t0 > 0.0f) & (__int2float_rd(qx0 + qy0) < __fmul_ru(t0, t0));
+        const bool m1 = (ux0 * uy1 >= 0) & (t1 > 0.0f) & (__int2float_rd(qx0 + qy1) < __fmul_ru(t1, t1));
+        const bool m2 = (ux1 * uy1 <= 0) & (t2 > 0.0f) & (__int2float_rd(qx1 + qy1) < __fmul_ru(t2, t2));
+        const bool m3 = (ux1 * uy0 >= 0) & (t3 > 0.0f) & (__int2float_rd(qx1 + qy0) < __fmul_ru(t3, t3));
+        const uint32_t m4 = (uint32_t)m0 | ((uint32_t)m1 << 1) | ((uint32_t)m2 << 2) | ((uint32_t)m3 << 3);
+        mask |= (k < num_obs ? m4 : 0u) << (4 * k);         // rectangles past num_obs: computed and masked out
     }
     return mask;
 }
@@ -262,12 +300,11 @@ __device__ __forceinline__ Move1 unit1_move(const Params &P, const int4 *rects, 
     if ((unsigned)(det.x + 16383) > 32766u || (unsigned)(det.y + 16383) > 32766u) status |= RS_ST_COORD_RANGE;
     source_segment1<KMAX>(rects, rstride, num_obs, (meta >> 9) & 0x7f, det.x, det.y, src.x, src.y, m.direct, m.blocked_raw);
     int cand = 0;                                                       // sensor candidates: a ray is at most 100 long
-#pragma unroll
+#pragma unroll((kS1Roll & 16) ? 1 : (KMAX > 0 ? KMAX : 1))
     for (int k = 0; k < KMAX; k++) {
-        if (k < num_obs) {
-            const int4 r = rects[k * rstride];
-            if (r.x - 100 <= det.x && det.x <= r.z + 100 && r.y - 100 <= det.y && det.y <= r.w + 100) cand |= 1 << k;
-        }
+        const int4 r = rects[k * rstride];
+        const bool near = (k < num_obs) & (r.x - 100 <= det.x) & (det.x <= r.z + 100) & (r.y - 100 <= det.y) & (det.y <= r.w + 100);
+        cand |= (int)near << k;
     }
     if (cand) uf |= UF_NEED_D | (cand << 16);
     const int ddx = det.x - src.x, ddy = det.y - src.y;

@@ -595,10 +595,11 @@ def test_results_do_not_depend_on_how_envs_are_sharded():
             np.testing.assert_array_equal(e._rects.cpu().numpy(), full._rects[:, lo:hi].cpu().numpy())
 
 
-@pytest.mark.parametrize("n", [4096, 76032, 76001])
+@pytest.mark.parametrize("n", [4096, 76032, 76001, 98464])
 def test_fast_sampler_kernel_variants_match_oracle_except_counts(n):
     """fast_poisson=True selects other instantiations of the step kernel (64-register, 8 CTAs per SM; 256-env tiles on 256
-    threads from 75776 envs up -- the ones bench.py times; 76001 envs end in a partial tile, staged without bulk copies).  Everything but the Poisson counts (KS-tested elsewhere) must
+    threads from 75776 envs up; 76001 envs end in a partial tile, staged without bulk copies; 98464 envs = 3077 tiles take the
+    pipelined step1p_kernel, the one bench.py times, with a last CTA that is not full).  Everything but the Poisson counts (KS-tested elsewhere) must
     still equal the oracle bit for bit: positions, flags, shortest paths, rewards, termination, resets, sensors."""
     ML, T = 60, 90
     env, ob = make_pair(n, 1, 5, True, seed=2024, max_ep_len=ML, auto_reset=True, fast_poisson=True, prefetch=True,

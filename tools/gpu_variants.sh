@@ -16,6 +16,6 @@ for v in radiation_ppo_b200/_C/var_*.so; do
   echo "== $v"; RADSEARCH_B200_LIB=$PWD/$v timeout 300 python bench.py --steps 20 --warmup 5 --quick 2>&1 | tail -1
 done
 if [ "$2" != "noncu" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:step1_kernel -s 9 -c 1 -f -o gpurun_out/prof_step_$tag \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step1 -s 9 -c 2 -f -o gpurun_out/prof_step_$tag \
     python bench.py --steps 20 --warmup 5 --quick > gpurun_out/ncu_step_$tag.log 2>&1; echo "ncu step rc=$?"
 fi
