@@ -283,9 +283,10 @@ __global__ void __launch_bounds__(TB, kOcc) step_kernel(const __grid_constant__ 
 // table are in shared memory and the scalar state rows in registers: the front half (move, segment to the source,
 // shortest path, Poisson draw) is straight-line per-lane code, the marked corners and the ray casts are (unit, corner) /
 // (unit, direction) items of the warp, the reset work list is appended with one atomic per warp, state and scalar outputs
-// leave as coalesced stores and the observation rows through a shared-memory staging block as 16-byte stores.  Two
-// kernels call it: step1_kernel (a CTA stages one tile of TB environments, every warp runs once) and step1p_kernel
-// (every warp walks several tiles and has the next one in flight while it computes).
+// leave as coalesced stores and the observation rows through a shared-memory staging block as 16-byte stores.
+// (A pipelined caller -- 14 warps per SM walking two tiles each with the next tile's rows in flight by bulk copies, no
+// spills -- was measured at 33.5 us against 32.1 us for step1_kernel below: a warp issues one instruction in ~8 cycles
+// whatever it waits for, so 28 resident warps that all wait at the start beat 14 that never do.  Removed.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPairCap = 128;                               // (unit, corner) pairs of a warp: ~35 at 5 obstructions
 struct WarpTile {
@@ -302,7 +303,7 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
                                            const int2 det, const int meta, const int action, const int af,
                                            const double best, double stm, double stq, const double ds_hint,
                                            const uint64_t step_ctr, const uint32_t (&x)[4], const WarpTile t,
-                                           const int bulk_ok) {
+                                           const int bulk_ok, uint64_t *dsf_bar) {
     const int n = nw + lane;
     const size_t N = (size_t)a.n_env;
     const int hint = (af >> 25) & 31;
@@ -313,8 +314,9 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     double best_sp = 0.0;
     int besti = -1;
     uint32_t marked = 0u;
+    if (live) mv = rs::unit1_move<KMAX>(P, t.rects + lane, RST, src, meta, action, det, af);
+    if (KMAX > 0 && dsf_bar) mbar_wait(dsf_bar, 0);         // the float table was requested after the rectangles had landed
     if (live) {
-        mv = rs::unit1_move<KMAX>(P, t.rects + lane, RST, src, meta, action, det, af);
         if (!mv.direct)
             marked = rs::sp_hint_mark1<KMAX>(t.rects + lane, RST, num_obs, t.dsf + lane * 4 * K, mv.det.x, mv.det.y, hint, ds_hint,
                                              best_sp, besti);
@@ -331,14 +333,17 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
         const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
         uint16_t *pl = t.pairs;
         double *res = reinterpret_cast<double *>(t.obs);      // the warp's staging block, free until commit
+        // the unit's corners, highest first, at list positions [off, off + fit); the loops below run as long as the unit with
+        // the most corners needs, so their bodies are kept to a few instructions
+        const int fit = max(0, min(cnt, kPairCap - off));
         {
             uint32_t m = marked;
-            int pos = off;
-            while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                if (pos < kPairCap) pl[pos] = (uint16_t)((lane << 5) | c);
-                pos++;
+            uint16_t *q = pl + off;
+            const int tag = lane << 5;
+            for (int i = 0; i < fit; i++) {
+                const int c = 31 - __clz(m);
+                m ^= 1u << c;
+                q[i] = (uint16_t)(tag | c);
             }
         }
         __syncwarp();
@@ -356,18 +361,25 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
             if (valid) res[j] = v;
         }
         __syncwarp();
-        {
+        {   // the unit's own pairs: keep the smallest (its list position; the corner is read back once)
+            const double *r = res + off;
+            int imin = -1;
+            for (int i = 0; i < fit; i++) {
+                const double v = r[i];
+                if (v < best_sp) { best_sp = v; imin = i; }
+            }
+            if (imin >= 0) besti = (int)pl[off + imin] & 31;
+        }
+        if (__any_sync(0xffffffffu, fit < cnt)) {           // pairs beyond the warp's list (never seen so far): by their own thread
             uint32_t m = marked;
-            int pos = off;
-            while (m) {                                     // the unit's own pairs: keep the smallest
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                // pairs beyond the warp's list (never seen so far) are evaluated by their own thread
-                const double v = pos < kPairCap ? res[pos]
-                                                : rs::sp_pair1<KMAX>(t.rects + lane, RST, num_obs, mv.det.x, mv.det.y, c,
-                                                                     S.dsrc[(size_t)n * 4 * K + c], best_sp);
-                if (v < best_sp) { best_sp = v; besti = c; }
-                pos++;
+            for (int i = 0; i < cnt; i++) {
+                const int c = 31 - __clz(m);
+                m ^= 1u << c;
+                if (i >= fit) {
+                    const double v = rs::sp_pair1<KMAX>(t.rects + lane, RST, num_obs, mv.det.x, mv.det.y, c,
+                                                        S.dsrc[(size_t)n * 4 * K + c], best_sp);
+                    if (v < best_sp) { best_sp = v; besti = c; }
+                }
             }
         }
         __syncwarp();
@@ -552,7 +564,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
     __shared__ uint8_t s_list[TB];
     __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
-    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ __align__(8) uint64_t s_mbar[2];
     const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
     const int n0 = blockIdx.x * TB;
     const int n = n0 + tid;
@@ -560,12 +572,22 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     const int K = KMAX > 0 ? P.k_max : 0;
     const size_t N = (size_t)a.n_env;
     const bool bulk = KMAX > 0 && bulk_ok && n0 + TB <= a.n_env;
+    // The rectangles are needed first (move, segment to the source); the float source-distance block only by the marking
+    // pass.  RS_STEP1_DSF_LATE: its copy is requested when the rectangles have landed, so that a launch whose CTAs all start
+    // together asks HBM for a third less before anybody can compute.
+#ifndef RS_STEP1_DSF_LATE
+#define RS_STEP1_DSF_LATE 1
+#endif
     if (bulk && tid == 0) {
-        mbar_init(&s_mbar, 1);
-        mbar_expect_tx(&s_mbar, (uint32_t)(2 * K * 16 * TB));
+        mbar_init(&s_mbar[0], 1);
+        mbar_init(&s_mbar[1], 1);
+        mbar_expect_tx(&s_mbar[0], (uint32_t)(K * 16 * TB));
         for (int k = 0; k < K; k++)
-            bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar);
-        bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar);
+            bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar[0]);
+        if (!RS_STEP1_DSF_LATE) {
+            mbar_expect_tx(&s_mbar[1], (uint32_t)(K * 16 * TB));
+            bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar[1]);
+        }
     }
     // scalar state rows: coalesced, straight into registers
     int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
@@ -592,8 +614,12 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
                           (uint32_t)(a.seed >> 32), x);
     if (bulk) {
-        __syncthreads();                                    // the barrier object is initialised for everybody
-        mbar_wait(&s_mbar, 0);
+        __syncthreads();                                    // the barrier objects are initialised for everybody
+        mbar_wait(&s_mbar[0], 0);
+        if (RS_STEP1_DSF_LATE && tid == 0) {
+            mbar_expect_tx(&s_mbar[1], (uint32_t)(K * 16 * TB));
+            bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar[1]);
+        }
     } else if (KMAX > 0) {
         if (live) {
             for (int k = 0; k < K; k++) s_rects[k * TB + tid] = reinterpret_cast<const int4 *>(S.rects)[(size_t)k * N + n];
@@ -606,96 +632,7 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     t.rects = s_rects + w0; t.dsf = s_dsf + w0 * 4 * K; t.obs = s_obs + w0 * RS_OBS_DIM; t.list = s_list + w0;
     t.pairs = s_pairs + (w0 >> 5) * kPairCap;
     step1_tile<kFast, KMAX, TB>(P, S, a, K, n0 + w0, lane, live, src, rad, det, meta, action, af, best, stm, stq, ds_hint,
-                                step_ctr, x, t, bulk_ok);
-}
-
-// The same step for large batches: every warp walks `tpw` tiles of 32 environments and has the next one in flight while it
-// computes the current one.  ALL state rows of a tile (rectangles, float source-distance block, source, intensities,
-// detector, meta, flags, running minimum, action) arrive by bulk-async copies into one of the warp's two shared-memory
-// stages, completing on the stage's mbarrier; lane 0 issues them for tile i+1 before the warp starts on tile i, so that
-// only a warp's first tile waits for HBM.  No CTA barrier anywhere: warps are independent from the first instruction on.
-// NW warps per CTA, two CTAs per SM (register cap 144: nothing spills); the grid is ceil(tiles / (NW * tpw)) CTAs, tile
-// (cta * tpw + j) * NW + warp for j = 0..tpw-1.  Needs n_env % 32 == 0 and 16-byte aligned rows (else step1_kernel).
-template <int KMAX>
-struct Stage1P {
-    static constexpr int KS = KMAX > 0 ? KMAX : 1;
-    int4 rects[KS * 32];
-    float dsf[32 * 4 * KS];
-    int2 src[32], rad[32], det[32];
-    double best[32];
-    int meta[32], af[32], action[32];
-};
-template <int KMAX>
-struct Warp1P {
-    Stage1P<KMAX> st[2];
-    float obs[32 * RS_OBS_DIM];
-    uint16_t pairs[kPairCap];
-    uint8_t list[32];
-    uint64_t mbar[2];
-};
-
-template <bool kFast, int KMAX, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) step1p_kernel(const __grid_constant__ rs::Params P,
-                                                             const __grid_constant__ RsState S,
-                                                             const __grid_constant__ rs::StepArgs a, const int tpw) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Warp1P<KMAX> &W = reinterpret_cast<Warp1P<KMAX> *>(s_dyn)[warp];
-    const int K = KMAX > 0 ? P.k_max : 0;
-    const size_t N = (size_t)a.n_env;
-    const int ntiles = a.n_env >> 5;
-    const int tile0 = blockIdx.x * tpw * NW + warp;
-    // lane 0: all rows of tile `tile` -> stage s
-    auto fetch = [&](int s, int tile) {
-        Stage1P<KMAX> &G = W.st[s];
-        const size_t n0 = (size_t)tile * 32;
-        mbar_expect_tx(&W.mbar[s], (uint32_t)(2 * K * 512 + 4 * 256 + (a.actions ? 3 : 2) * 128));
-        for (int k = 0; k < K; k++) bulk_g2s(G.rects + k * 32, S.rects + ((size_t)k * N + n0) * 4, 512, &W.mbar[s]);
-        if (KMAX > 0) bulk_g2s(G.dsf, S.dsf + n0 * 4 * K, (uint32_t)(512 * K), &W.mbar[s]);
-        bulk_g2s(G.src, S.src + n0 * 2, 256, &W.mbar[s]);
-        bulk_g2s(G.rad, S.rad + n0 * 2, 256, &W.mbar[s]);
-        bulk_g2s(G.det, S.det + n0 * 2, 256, &W.mbar[s]);
-        bulk_g2s(G.best, S.best + n0, 256, &W.mbar[s]);
-        bulk_g2s(G.meta, S.meta + n0, 128, &W.mbar[s]);
-        bulk_g2s(G.af, S.aflags + n0, 128, &W.mbar[s]);
-        if (a.actions) bulk_g2s(G.action, a.actions + n0, 128, &W.mbar[s]);
-    };
-    if (tile0 >= ntiles) return;
-    if (lane == 0) {
-        mbar_init(&W.mbar[0], 1);
-        mbar_init(&W.mbar[1], 1);
-        fetch(0, tile0);
-    }
-    const uint64_t step_ctr = (a.flags & RS_F_DEVICE_CTR) ? *S.ctr_dev : a.step_ctr;
-    __syncwarp();
-    for (int j = 0; j < tpw; j++) {
-        const int tile = tile0 + j * NW;
-        if (tile >= ntiles) break;
-        const int s = j & 1;
-        if (lane == 0 && j + 1 < tpw && tile + NW < ntiles) fetch(s ^ 1, tile + NW);     // stage s^1 was released by the
-        const int nw = tile * 32, n = nw + lane;                                           // __syncwarp that ended tile j-1
-        uint32_t x[4] = {0u, 0u, 0u, 0u};
-        if (kFast)      // needs nothing from memory: runs while the tile is in flight
-            rs::philox4x32_10(a.env_id0 + (uint32_t)n, 0u, (uint32_t)step_ctr, (uint32_t)(step_ctr >> 32), (uint32_t)a.seed,
-                              (uint32_t)(a.seed >> 32), x);
-        mbar_wait(&W.mbar[s], (uint32_t)((j >> 1) & 1));
-        const Stage1P<KMAX> &G = W.st[s];
-        const int2 src = G.src[lane], rad = G.rad[lane], det = G.det[lane];
-        const int meta = G.meta[lane], af = G.af[lane], action = a.actions ? G.action[lane] : -1;
-        const double best = G.best[lane];
-        double stm = 0.0, stq = 0.0;
-        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
-        step1_successor_prefetch(P, S, a, K, n, meta);
-        // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
-        const int hint = (af >> 25) & 31;
-        double ds_hint = __longlong_as_double(0x7ff0000000000000LL);
-        if (KMAX > 0 && hint < 4 * (meta & 0xff)) ds_hint = S.dsrc[(size_t)n * 4 * K + hint];
-        WarpTile t;
-        t.rects = G.rects; t.dsf = G.dsf; t.obs = W.obs; t.list = W.list; t.pairs = W.pairs;
-        step1_tile<kFast, KMAX, 32>(P, S, a, K, nw, lane, true, src, rad, det, meta, action, af, best, stm, stq, ds_hint,
-                                    step_ctr, x, t, 1);
-        __syncwarp();
-    }
+                                step_ctr, x, t, bulk_ok, bulk ? &s_mbar[1] : nullptr);
 }
 
 // end of a captured step: advance the device step counter and empty the reset list for the next replay
@@ -855,34 +792,6 @@ int rs_step(const RsConfig *cfg, const RsState *st, const int32_t *actions, floa
 #ifndef RS_STEP1_OCC
 #define RS_STEP1_OCC 7
 #endif
-        // large batches: the pipelined form (step1p_kernel), NW warps per CTA, two CTAs per SM, tpw tiles per warp so that
-        // the whole batch is one wave of 2 * 148 CTAs
-#ifndef RS_STEP1P_NW
-#define RS_STEP1P_NW 7
-#endif
-#ifndef RS_STEP1P_MIN_TILES
-#define RS_STEP1P_MIN_TILES 3072
-#endif
-        constexpr int NW = RS_STEP1P_NW;
-        const int ntiles = n_env / 32;
-        const bool rows_ok = bulk_ok && aligned16(st->src) && aligned16(st->det) && aligned16(st->meta) &&
-                             aligned16(st->aflags) && aligned16(actions) && n_env % 32 == 0;
-        if (rows_ok && K >= 1 && K <= 5 && ntiles >= RS_STEP1P_MIN_TILES) {
-            const int slots = 148 * 2 * NW;
-            int tpw = (ntiles + slots - 1) / slots;
-            if (tpw < 2) tpw = 2;
-            const int gridp = (ntiles + NW * tpw - 1) / (NW * tpw);
-#define RS_LAUNCH_STEP1P(FAST, KM)                                                                                        \
-    do {                                                                                                                  \
-        const int smem = NW * (int)sizeof(Warp1P<KM>);                                                                    \
-        cudaFuncSetAttribute(step1p_kernel<FAST, KM, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
-        step1p_kernel<FAST, KM, NW><<<gridp, NW * 32, smem, s>>>(P, *st, a, tpw);                                         \
-    } while (0)
-            if (K <= 3) { if (fast) RS_LAUNCH_STEP1P(true, 3); else RS_LAUNCH_STEP1P(false, 3); }
-            else { if (fast) RS_LAUNCH_STEP1P(true, 5); else RS_LAUNCH_STEP1P(false, 5); }
-#undef RS_LAUNCH_STEP1P
-            return (int)cudaGetLastError();
-        }
         if (K == 0) RS_LAUNCH_STEP1_K(0, RS_STEP1_OCC);
         else if (K <= 3) RS_LAUNCH_STEP1_K(3, RS_STEP1_OCC);
         else if (K <= 5) {
