@@ -295,13 +295,15 @@ struct WarpTile {
     float *obs;             // [32][RS_OBS_DIM] staging block of the observation rows (scratch until the commit phase)
     uint8_t *list;          // [32]
     uint16_t *pairs;        // [kPairCap]
+    const int2 *rad;        // [32] intensity, background: first needed by the measurement
+    const double *best;     // [32] running minimum of the shortest path: first needed by the commit phase
 };
 
 template <bool kFast, int KMAX, int RST>
 __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S, const rs::StepArgs &a, const int K,
-                                           const int nw, const int lane, const bool live, const int2 src, const int2 rad,
+                                           const int nw, const int lane, const bool live, const int2 src,
                                            const int2 det, const int meta, const int action, const int af,
-                                           const double best, double stm, double stq, const double ds_hint,
+                                           const double ds_hint,
                                            const uint64_t step_ctr, const uint32_t (&x)[4], const WarpTile t,
                                            const int bulk_ok, uint64_t *dsf_bar) {
     const int n = nw + lane;
@@ -389,8 +391,14 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     for (int d = 0; d < 8; d++) row[3 + d] = 0.0f;
     rs::Unit1 o;
     o.det = det; o.af = af; o.uf = 0; o.sp = 0.0; o.blocked_los = false; o.count = 0.0f; o.status = 0u;
-    if (live) o = rs::unit1_measure<kFast>(P, a, mv, n, rad, best_sp, besti >= 0 ? besti : hint, step_ctr, x);
+    if (live) o = rs::unit1_measure<kFast>(P, a, mv, n, t.rad[lane], best_sp, besti >= 0 ? besti : hint, step_ctr, x);
     __syncwarp();
+#ifndef RS_S1_RESYNC
+#define RS_S1_RESYNC 1
+#endif
+    // the CTA's warps enter the back half together: they drift apart over the pair phase, and warps at different places of
+    // the 46 KB of hot code miss the instruction cache (measured: 85 % of the no-instruction stalls sat behind this point)
+    if (RS_S1_RESYNC && RST > 32) __syncthreads();
     // ---- obstruction_sensors: (unit, direction) items of the warp ---------------------------------------------------------
     const unsigned need = __ballot_sync(0xffffffffu, (o.uf & rs::UF_NEED_D) != 0);
     if (need) {
@@ -431,12 +439,14 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     }
     // ---- commit: reward, terminal, caller rules, state and scalar outputs (coalesced) --------------------------------------
     bool sched = false, adopt = false;
-    uint32_t status = 0;
+    uint32_t status = 0, epi_n = 0u;
     float raw = 0.0f;
+    double stm = 0.0, stq = 0.0;
     rs::Commit1 c;
     if (live) {
         status = o.status;
-        c = rs::unit1_commit(P, a, o, meta, action, best, row, P.standardize ? &stm : nullptr, &stq, &raw, status);
+        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }    // (L2-prefetched when the step started)
+        c = rs::unit1_commit(P, a, o, meta, action, t.best[lane], row, P.standardize ? &stm : nullptr, &stq, &raw, status);
         if (a.reward) a.reward[n] = c.reward;
         if (a.team_reward) a.team_reward[n] = c.reward;                 // one agent: the team reward is its reward R:661-665
         if (a.done) a.done[n] = (uint8_t)c.done;
@@ -450,15 +460,19 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
         // RS_F_PREFETCH: an env whose next episode rs_prepare has already computed (same seed, env, episode number and
         // obstructions: nx_seq carries the episode number) starts it right here and never reaches the reset kernel; the
         // others go to the reset work list as before
-        if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END))
-            adopt = *reinterpret_cast<volatile const uint32_t *>(S.nx_seq + n) == S.epi[n] + 1u;
+        if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
+            // acquire: the tag is read before the rows it publishes (rs_prepare stores them, fences, then stores the tag)
+            uint32_t tag;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(S.nx_seq + n) : "memory");
+            epi_n = S.epi[n];
+            adopt = tag == epi_n + 1u;
+        }
     }
     // The copies of an adopted episode are shared by the warp: one lane per table entry / observation value, so that they
     // cost one round trip to memory instead of a chain of twenty by the one thread that owns the env
     unsigned am = __ballot_sync(0xffffffffu, adopt);
     if (am) {
         __syncwarp();
-        __threadfence();                                                // the tag was read before the data it publishes
         while (am) {
             const int owner = __ffs(am) - 1;
             am &= am - 1;
@@ -490,7 +504,7 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
             S.best[n] = b0;
             S.aflags[n] = 0;
             S.meta[n] = meta & 0xff;                                    // done = 0, ep_len = 0 (a sampled source is in no rectangle)
-            S.epi[n] = S.epi[n] + 1u;
+            S.epi[n] = epi_n + 1u;
             const int slot = atomicAdd(S.refill_count + a.parity, 1);
             if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
             else status |= RS_ST_REFILL_OVERFLOW;
@@ -546,6 +560,12 @@ __device__ __forceinline__ void step1_successor_prefetch(const rs::Params &P, co
         asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_det + (size_t)n * 2));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_rad + (size_t)n * 2));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_best + n));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.nx_seq + n));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.epi + n));
+    }
+    if (P.standardize) {                                    // read by the commit phase
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.st_mean + n));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.st_m2 + n));
     }
 }
 
@@ -564,6 +584,8 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     __shared__ __align__(16) float s_obs[TB * RS_OBS_DIM];
     __shared__ uint8_t s_list[TB];
     __shared__ uint16_t s_pairs[(TB / 32) * kPairCap];
+    __shared__ __align__(16) int2 s_rad[TB];
+    __shared__ __align__(16) double s_best[TB];
     __shared__ __align__(8) uint64_t s_mbar[2];
     const int tid = threadIdx.x, lane = tid & 31, w0 = tid & ~31;
     const int n0 = blockIdx.x * TB;
@@ -580,28 +602,32 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
 #endif
     if (bulk && tid == 0) {
         mbar_init(&s_mbar[0], 1);
-        mbar_init(&s_mbar[1], 1);
+        mbar_init(&s_mbar[1], 2);                           // two arrivals: the late rows here, the float table below
         mbar_expect_tx(&s_mbar[0], (uint32_t)(K * 16 * TB));
         for (int k = 0; k < K; k++)
             bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar[0]);
+        // rows that are first needed late in the step wait in shared memory instead of in (spilled) registers
+        mbar_expect_tx(&s_mbar[1], (uint32_t)(16 * TB));
+        bulk_g2s(s_rad, S.rad + (size_t)n0 * 2, TB * 8, &s_mbar[1]);
+        bulk_g2s(s_best, S.best + n0, TB * 8, &s_mbar[1]);
         if (!RS_STEP1_DSF_LATE) {
             mbar_expect_tx(&s_mbar[1], (uint32_t)(K * 16 * TB));
             bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar[1]);
         }
     }
     // scalar state rows: coalesced, straight into registers
-    int2 src = make_int2(0, 0), rad = make_int2(1, 10), det = make_int2(0, 0);
+    int2 src = make_int2(0, 0), det = make_int2(0, 0);
     int meta = 0, action = -1, af = 0;
-    double best = 0.0, stm = 0.0, stq = 0.0;
     if (live) {
         src = reinterpret_cast<const int2 *>(S.src)[n];
-        rad = reinterpret_cast<const int2 *>(S.rad)[n];
         det = reinterpret_cast<const int2 *>(S.det)[n];
         meta = S.meta[n];
         af = S.aflags[n];
-        best = S.best[n];
         if (a.actions) action = a.actions[n];
-        if (P.standardize) { stm = S.st_mean[n]; stq = S.st_m2[n]; }
+    }
+    if (!bulk) {
+        s_rad[tid] = live ? reinterpret_cast<const int2 *>(S.rad)[n] : make_int2(1, 10);
+        s_best[tid] = live ? S.best[n] : 0.0;
     }
     if (live) step1_successor_prefetch(P, S, a, K, n, meta);
     // the source distance of the corner that was optimal at the previous step: requested now, used after the segment test
@@ -630,9 +656,9 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
     }
     WarpTile t;
     t.rects = s_rects + w0; t.dsf = s_dsf + w0 * 4 * K; t.obs = s_obs + w0 * RS_OBS_DIM; t.list = s_list + w0;
-    t.pairs = s_pairs + (w0 >> 5) * kPairCap;
-    step1_tile<kFast, KMAX, TB>(P, S, a, K, n0 + w0, lane, live, src, rad, det, meta, action, af, best, stm, stq, ds_hint,
-                                step_ctr, x, t, bulk_ok, bulk ? &s_mbar[1] : nullptr);
+    t.pairs = s_pairs + (w0 >> 5) * kPairCap; t.rad = s_rad + w0; t.best = s_best + w0;
+    step1_tile<kFast, KMAX, TB>(P, S, a, K, n0 + w0, lane, live, src, det, meta, action, af, ds_hint, step_ctr, x, t, bulk_ok,
+                                bulk ? &s_mbar[1] : nullptr);
 }
 
 // end of a captured step: advance the device step counter and empty the reset list for the next replay

@@ -23,10 +23,11 @@
 #include "rs_step_tiled.cuh"
 #include "rs_poisson_alias.h"
 
-// Measurement switch (A/B builds only): bit set = keep that per-rectangle loop rolled instead of unrolling it over KMAX
-// (1 in_obstruction, 2 source segment, 4 visibility, 8 marking pass, 16 sensor candidates)
+// RS_S1_ROLL: bit set = that per-rectangle loop stays a loop instead of being unrolled over KMAX (1 in_obstruction, 2 source
+// segment, 4 visibility, 8 marking pass, 16 sensor candidates).  The bodies are branch-free either way; rolled, the kernel's
+// hot code is ~9 KB smaller (46 KB of hot instruction lines against a 32 KB instruction cache) and measures 2-4 % faster.
 #ifndef RS_S1_ROLL
-#define RS_S1_ROLL 0
+#define RS_S1_ROLL 31
 #endif
 
 namespace rs {
