@@ -649,6 +649,7 @@ def pipeline_leg(cx: Ctx, fast: bool, N: int = 65536, T: int = T_EPOCH, epochs: 
                     "grad_allreduce_us": 1e3 * g0.elapsed_time(g1), "loss": loss,
                     "episodes": float(summ["Episodes"][0]), "avg_ep_ret": float(summ["AverageEpRet"][0]),
                     "n_episodes_packed": int(data["ep_len"].numel())})
+        del data                                          # the epoch's packed rows go back to the allocator before the next epoch
     # where a rollout step's GPU time goes: each stage between its own event pair, median over 24 steps (one stage at a time,
     # so the pieces do not overlap; the loop above runs them back to back)
     stage_us = {}
