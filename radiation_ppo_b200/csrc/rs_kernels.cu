@@ -309,6 +309,17 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     const int n = nw + lane;
     const size_t N = (size_t)a.n_env;
     const int hint = (af >> 25) & 31;
+    // An episode that reaches its step limit at this step is scheduled for reset whatever happens: whether its prefetched
+    // successor is ready (nx_seq == episode number + 1) is read NOW, while the step waits for its tile anyway, instead of as
+    // the first link of a chain of dependent loads in the commit phase.  0: not known, 1: not ready, 2: ready.
+    // acquire: the tag is read before the rows it publishes (rs_prepare stores them, fences, then stores the tag)
+    int pre_adopt = 0;
+    if (live && (a.flags & RS_F_PREFETCH) && (a.flags & RS_F_AUTO_RESET) && !(a.flags & RS_F_EPOCH_END) && a.actions &&
+        (meta >> 16) + 1 == P.max_ep_len) {
+        uint32_t tag;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(S.nx_seq + n) : "memory");
+        pre_adopt = tag == S.epi[n] + 1u ? 2 : 1;
+    }
     // ---- take_action, segment to the source; for obstructed units the bound through last step's corner + marking pass -----
     const int num_obs = meta & 0xff;
     rs::Move1 mv;
@@ -439,7 +450,7 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     }
     // ---- commit: reward, terminal, caller rules, state and scalar outputs (coalesced) --------------------------------------
     bool sched = false, adopt = false;
-    uint32_t status = 0, epi_n = 0u;
+    uint32_t status = 0;
     float raw = 0.0f;
     double stm = 0.0, stq = 0.0;
     rs::Commit1 c;
@@ -461,12 +472,27 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
         // obstructions: nx_seq carries the episode number) starts it right here and never reaches the reset kernel; the
         // others go to the reset work list as before
         if (sched && (a.flags & RS_F_PREFETCH) && !(a.flags & RS_F_EPOCH_END)) {
-            // acquire: the tag is read before the rows it publishes (rs_prepare stores them, fences, then stores the tag)
-            uint32_t tag;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(S.nx_seq + n) : "memory");
-            epi_n = S.epi[n];
-            adopt = tag == epi_n + 1u;
+            if (pre_adopt) adopt = pre_adopt == 2;
+            else {                                                      // ended before its step limit: the tag is read here
+                uint32_t tag;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(S.nx_seq + n) : "memory");
+                adopt = tag == S.epi[n] + 1u;
+            }
         }
+    }
+    // Everything an adopting env reads is requested before anything is stored (one round trip to memory: the rows were
+    // pulled into L2 when the step started), and its slot in the refill list is taken at the same time
+    int2 s0 = make_int2(0, 0), r1 = s0, d0 = s0;
+    double b0 = 0.0;
+    uint32_t epi_n = 0u;
+    int slot = 0;
+    if (adopt) {
+        s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
+        r1 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
+        d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
+        b0 = S.nx_best[n];
+        epi_n = S.epi[n];
+        slot = atomicAdd(S.refill_count + a.parity, 1);
     }
     // The copies of an adopted episode are shared by the warp: one lane per table entry / observation value, so that they
     // cost one round trip to memory instead of a chain of twenty by the one thread that owns the env
@@ -491,10 +517,6 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
     }
     if (live) {
         if (adopt) {
-            const int2 s0 = reinterpret_cast<const int2 *>(S.nx_src)[n];
-            const int2 r1 = reinterpret_cast<const int2 *>(S.nx_rad)[n];
-            const int2 d0 = reinterpret_cast<const int2 *>(S.nx_det)[n];
-            const double b0 = S.nx_best[n];
             if (P.standardize) {                                        // first reading of the episode: z = 0
                 stm = (double)row[0]; stq = 0.0; raw = row[0]; row[0] = 0.0f;
             }
@@ -505,7 +527,6 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
             S.aflags[n] = 0;
             S.meta[n] = meta & 0xff;                                    // done = 0, ep_len = 0 (a sampled source is in no rectangle)
             S.epi[n] = epi_n + 1u;
-            const int slot = atomicAdd(S.refill_count + a.parity, 1);
             if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
             else status |= RS_ST_REFILL_OVERFLOW;
             sched = false;

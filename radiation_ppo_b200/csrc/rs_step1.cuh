@@ -267,6 +267,8 @@ __device__ __forceinline__ long long count_exact1(const StepArgs &a, int n, uint
     return ok ? k : count_exact_retry(a, n, step_ctr, lam, status);
 }
 
+constexpr int UF1_IDLE = 512;   // unit flag of this kernel (next to UF_* of rs_step_tiled.cuh): the action was 8 (idle)
+
 // What take_action and the segment to the source leave in registers.
 struct Move1 {
     int2 det;            // position after take_action
@@ -287,6 +289,7 @@ __device__ __forceinline__ Move1 unit1_move(const Params &P, const int4 *rects, 
     const int num_obs = meta & 0xff;
     int uf = 0;
     uint32_t status = 0;
+    if (action == 8) uf |= UF1_IDLE;                                    // all the commit phase needs to know of the action
     if (action >= 0) {
         const int tx = det.x + step_dx(action), ty = det.y + step_dy(action);
         bool roll = false;
@@ -481,7 +484,7 @@ __device__ __forceinline__ Commit1 unit1_commit(const Params &P, const StepArgs 
         info |= RS_I_MOVED;
         if (sp < 110) { reward = 0.1; done = 1; }
         else if (sp < best) { reward = 0.1; best = sp; }
-        else if (action == 8) reward = div_const(-1.0 * sp, P.max_dist, P.inv_max_dist);
+        else if (o.uf & UF1_IDLE) reward = div_const(-1.0 * sp, P.max_dist, P.inv_max_dist);
         else reward = div_const(-0.5 * sp, P.max_dist, P.inv_max_dist);
     } else {
         reward = div_const(-0.5 * sp, P.max_dist, P.inv_max_dist);      // R:549, 567
