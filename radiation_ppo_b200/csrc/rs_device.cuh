@@ -300,6 +300,42 @@ __device__ __forceinline__ int seg_rect(int px, int py, int qx, int qy, int4 r) 
     return seg_rect(px, py, qx, qy, r, cr);
 }
 
+// A segment p -> q prepared for tests against many rectangles: everything that does not depend on the rectangle.
+// The cross product of corner (x, y) is (x - px) * dy - (y - py) * dx = x * dy - y * dx + t with t = py * dx - px * dy:
+// two multiply-adds per corner coordinate, no subtraction per rectangle (all values fit int32 for |coord| <= 16383).
+struct Seg1 {
+    int px, py, dx, dy, ndx, t, xlo, xhi, ylo, yhi;
+};
+__device__ __forceinline__ Seg1 make_seg1(int px, int py, int qx, int qy) {
+    Seg1 s;
+    s.px = px; s.py = py; s.dx = qx - px; s.dy = qy - py; s.ndx = -s.dx;
+    s.t = py * s.dx - px * s.dy;
+    s.xlo = min(px, qx); s.xhi = max(px, qx); s.ylo = min(py, qy); s.yhi = max(py, qy);
+    return s;
+}
+// seg_rect's bit 0 (the segment meets the OPEN rectangle) as a predicate: min / max of the four corner cross products
+// from the products of the two x and the two y coordinates, compared without forming the corner values
+__device__ __forceinline__ bool seg_open1(const Seg1 &s, int4 r) {
+    const int a = r.x * s.dy + s.t, b = r.z * s.dy + s.t;               // x part (+ t)
+    const int c = r.y * s.dx, d = r.w * s.dx;                          // y part
+    const bool mn_neg = min(a, b) < max(c, d), mx_pos = max(a, b) > min(c, d);
+    return (r.x < s.xhi) & (s.xlo < r.z) & (r.y < s.yhi) & (s.ylo < r.w) & mn_neg & mx_pos;
+}
+// the same without the box comparison, for callers that have already filtered the rectangles by the segment's box
+__device__ __forceinline__ bool seg_cross_open1(const Seg1 &s, int4 r) {
+    const int a = r.x * s.dy + s.t, b = r.z * s.dy + s.t;
+    const int c = r.y * s.dx, d = r.w * s.dx;
+    return (min(a, b) < max(c, d)) & (max(a, b) > min(c, d));
+}
+// seg_rect with both bits as predicates and the four cross products (order p0, p1, p2, p3 as seg_rect)
+__device__ __forceinline__ void seg_both1(const Seg1 &s, int4 r, bool &open, bool &closed, int cr[4]) {
+    const int a = r.x * s.dy + s.t, b = r.z * s.dy + s.t;
+    cr[0] = r.y * s.ndx + a; cr[1] = r.w * s.ndx + a; cr[2] = r.w * s.ndx + b; cr[3] = r.y * s.ndx + b;
+    const int mn = min(min(cr[0], cr[1]), min(cr[2], cr[3])), mx = max(max(cr[0], cr[1]), max(cr[2], cr[3]));
+    open = (r.x < s.xhi) & (s.xlo < r.z) & (r.y < s.yhi) & (s.ylo < r.w) & (mn < 0) & (mx > 0);
+    closed = (r.x <= s.xhi) & (s.xlo <= r.z) & (r.y <= s.yhi) & (s.ylo <= r.w) & (mn <= 0) & (mx >= 0);
+}
+
 // a rectangle corner whose projection lies inside pq within 0.001 of it: cross^2 * 1e6 < |pq|^2 (so |cross| <= 3 on
 // this lattice, and |pq| > 1000); cr[] from seg_rect
 __device__ __forceinline__ bool corner_grazes(int px, int py, int dx, int dy, int l2, int4 r, const int cr[4]) {

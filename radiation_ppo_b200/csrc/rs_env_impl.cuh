@@ -52,17 +52,17 @@ struct EnvView {
 __device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx, int qy) {
     // the open segment can only meet an open rectangle whose box overlaps the segment's box; each lane walks its own
     // (short) list of such rectangles so that the warp stays converged
-    const int xlo = min(px, qx), xhi = max(px, qx), ylo = min(py, qy), yhi = max(py, qy);
+    const Seg1 s = make_seg1(px, py, qx, qy);
     uint32_t m = 0u;
     for (int k = 0; k < e.num_obs; k++) {
         const int4 r = e.rects[k];
-        if (r.x < xhi && xlo < r.z && r.y < yhi && ylo < r.w) m |= 1u << k;
+        if (r.x < s.xhi && s.xlo < r.z && r.y < s.yhi && s.ylo < r.w) m |= 1u << k;
     }
     bool hit = false;
     while (m) {
         const int k = __ffs(m) - 1;
         m &= m - 1;
-        hit = hit || (seg_rect(px, py, qx, qy, e.rects[k]) & 1);
+        hit = hit || seg_cross_open1(s, e.rects[k]);
     }
     return !hit;
 }
@@ -97,9 +97,10 @@ __device__ __forceinline__ double shortest_path(const EnvView &e, int px, int py
 // One pass over the rectangles for the segment detector -> source: `direct` = mutually visible (shortest path is the
 // segment), `blocked` = boundary_distance < 0.001 for some rectangle (R:1139-1141, without the isclose clause).
 __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py, bool &direct, bool &blocked) {
-    const int dx = e.sx - px, dy = e.sy - py;
+    const Seg1 s = make_seg1(px, py, e.sx, e.sy);
+    const int dx = s.dx, dy = s.dy;
     const int l2 = dx * dx + dy * dy;
-    const int xlo = min(px, e.sx) - 1, xhi = max(px, e.sx) + 1, ylo = min(py, e.sy) - 1, yhi = max(py, e.sy) + 1;
+    const int xlo = s.xlo - 1, xhi = s.xhi + 1, ylo = s.ylo - 1, yhi = s.yhi + 1;
     bool vis_ok = true, blk = false;
     uint32_t m = 0u;
     for (int k = 0; k < e.num_obs; k++) {
@@ -111,9 +112,10 @@ __device__ __forceinline__ void source_segment(const EnvView &e, int px, int py,
         m &= m - 1;
         const int4 r = e.rects[k];
         int cr[4];
-        const int h = seg_rect(px, py, e.sx, e.sy, r, cr);
-        vis_ok = vis_ok && !(h & 1);
-        bool b = (h & 2) && !(in_rect_open(px, py, r) && in_rect_open(e.sx, e.sy, r));
+        bool open, closed;
+        seg_both1(s, r, open, closed, cr);
+        vis_ok = vis_ok && !open;
+        bool b = closed && !(in_rect_open(px, py, r) && in_rect_open(e.sx, e.sy, r));
         // near-corner clause: only for |pq| > 1000
         if (!b && l2 > 1000000) b = corner_grazes(px, py, dx, dy, l2, r, cr);
         blk = blk || b;

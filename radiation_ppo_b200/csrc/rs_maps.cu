@@ -24,33 +24,12 @@
 
 #include "../../include/radsearch_b200.h"
 #include "rs_error.h"
+#include "rs_rcp.cuh"
 
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kBlock = 32 * kWarpsPerBlock;
-
-// x / k for a small positive integer k through its correctly rounded reciprocal (a compile-time table) and one exact
-// residual correction: q0 = x * (1/k), r = x - q0 * k (one FMA, exact), q = q0 + r * (1/k).  Markstein's theorem makes q the
-// correctly rounded quotient (the IEEE division's result) for every finite x when the reciprocal is correctly rounded and
-// the divisor's significand is not all ones -- true of every integer below 2^53 - 1.  The standardiser divides by the
-// reading count twice per agent and call; the two IEEE divisions were a sixth of the kernel's instructions.
-constexpr int kRcpN = 4096;
-struct RcpTable {
-    double v[kRcpN];
-    constexpr RcpTable() : v() {
-        for (int i = 1; i < kRcpN; i++) v[i] = 1.0 / (double)i;
-    }
-};
-__constant__ RcpTable g_rcp = RcpTable();
-
-__device__ __forceinline__ double div_count(double x, int k) {
-    if (k <= 0 || k >= kRcpN || !(fabs(x) < __longlong_as_double(0x7ff0000000000000LL))) return x / (double)k;
-    const double d = (double)k, rd = g_rcp.v[k];
-    const double q0 = __dmul_rn(x, rd);
-    const double r = __fma_rn(-q0, d, x);
-    return __fma_rn(r, rd, q0);
-}
 
 __device__ __forceinline__ int cell_of(const RsMapsConfig &c, double vx, double vy) {
     // int(v * resolution_accuracy) M:704-713, then numpy indexing: negative indices wrap once

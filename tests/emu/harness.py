@@ -25,6 +25,7 @@ def build_emu(force=False):
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_step1.cuh"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_poisson_alias.h"),
             os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_device.cuh"),
+            os.path.join(ROOT, "radiation_ppo_b200", "csrc", "rs_rcp.cuh"),
             os.path.join(ROOT, "include", "radsearch_b200.h")]
     if force or not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I" + HERE, "-o", EMU_LIB,
@@ -41,6 +42,8 @@ def emu():
         _emu = L.declare(C.CDLL(build_emu()), prefix="emu_")
         _emu.emu_step1.restype = _emu.emu_step.restype
         _emu.emu_step1.argtypes = _emu.emu_step.argtypes
+        _emu.emu_div_count_mismatches.restype = C.c_longlong
+        _emu.emu_div_count_mismatches.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong]
         _emu.emu_div_const_mismatches.restype = C.c_longlong
         _emu.emu_div_const_mismatches.argtypes = [C.c_void_p, C.c_longlong, C.c_double]
         _emu.emu_round2_fast.restype = _emu.emu_round2.restype = C.c_double

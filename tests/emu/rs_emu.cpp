@@ -3,6 +3,7 @@
 // tests/test_kernel_logic_emu.py to compare the kernel logic with the oracle where no GPU exists.
 #define RS_HOST_EMU 1
 #include "../../radiation_ppo_b200/csrc/rs_step1.cuh"
+#include "../../radiation_ppo_b200/csrc/rs_rcp.cuh"
 
 #include <vector>
 
@@ -184,6 +185,28 @@ long long emu_div_const_mismatches(const double *x, long long n, double d) {
         bad += !(q == w || (q != q && w != w));
     }
     return bad;
+}
+// x / k through the reciprocal table (rs_rcp.cuh::div_count) against the IEEE quotient: number of mismatches over x[] x k[]
+long long emu_div_count_mismatches(const double *x, long long n, const int *k, long long nk) {
+    long long bad = 0;
+    for (long long j = 0; j < nk; j++)
+        for (long long i = 0; i < n; i++) {
+            const double q = div_count(x[i], k[j]), w = x[i] / (double)k[j];
+            bad += !(q == w || (q != q && w != w));
+        }
+    return bad;
+}
+// the prepared-segment predicates of rs_device.cuh (seg_open1 | seg_both1's closed bit << 1 | disagreement with seg_cross_open1 << 2)
+int emu_seg_prepared(int px, int py, int qx, int qy, int x0, int y0, int x1, int y1) {
+    const rs::Seg1 s = rs::make_seg1(px, py, qx, qy);
+    const int4 r = make_int4(x0, y0, x1, y1);
+    int cr[4];
+    bool open, closed;
+    rs::seg_both1(s, r, open, closed, cr);
+    const bool o1 = rs::seg_open1(s, r);
+    const bool box = r.x < s.xhi && s.xlo < r.z && r.y < s.yhi && s.ylo < r.w;
+    const bool o2 = box && rs::seg_cross_open1(s, r);
+    return (int)o1 | ((int)closed << 1) | ((int)(o1 != open || o1 != o2) << 2);
 }
 double emu_round2_fast(double x) { return rs::round2_fast(x); }
 double emu_round2(double x) { return rs::round2(x); }

@@ -349,3 +349,49 @@ def test_division_through_the_reciprocal_equals_ieee_division():
     for x in np.concatenate([rng.uniform(-2, 1, 200_000), (rng.integers(-200, 100, 2000) + 0.5) / 100.0, [0.125, -0.125, 0.005, -0.005, 0.1]]):
         a, b = e.emu_round2_fast(float(x)), e.emu_round2(float(x))
         assert a == b == round(float(x), 2), x
+
+
+def test_division_by_the_reading_count_through_the_reciprocal_table_equals_ieee_division():
+    """rs_rcp.cuh::div_count (the map standardiser's x / count: table reciprocal + one exact-residual correction) against `/`
+    for every divisor of the table and operands of the magnitudes the standardiser sees (count differences and squared
+    distances), plus zeros, tiny, huge and non-finite values."""
+    import ctypes as C
+    from tests.emu.harness import emu
+    e = emu()
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.normal(0, 1, 1500) * 10.0 ** rng.integers(-12, 12, 1500), rng.integers(-10**7, 10**7, 500) / 3.0,
+                         rng.integers(0, 10**6, 500).astype(np.float64),
+                         np.array([0.0, -0.0, 1.0, -1.0, 5e-324, 2.2e-308, 1.7e308, -1.7e308, np.inf, -np.inf, np.nan])])
+    ks = np.concatenate([np.arange(1, 4096), np.array([0, -3, 4096, 5000, 2**30])]).astype(np.int32)
+    bad = e.emu_div_count_mismatches(xs.ctypes.data_as(C.c_void_p), len(xs), ks.ctypes.data_as(C.c_void_p), len(ks))
+    assert bad == 0
+
+
+def test_prepared_segment_predicates_are_exact():
+    """rs_device.cuh::seg_open1 / seg_both1 / seg_cross_open1 (segment prepared once, corner cross products by multiply-adds,
+    min / max compared without forming the corner values) against exact rational clipping, like seg_rect above."""
+    from tests.emu.harness import emu
+    lib = emu()
+    rng = np.random.default_rng(12)
+    n_checked = 0
+    for it in range(9000):
+        if it < 6000:
+            x0, y0 = (int(v) for v in rng.integers(-40, 40, 2))
+            x1, y1 = x0 + int(rng.integers(1, 30)), y0 + int(rng.integers(1, 30))
+            pool_x = [x0, x1, x0 - 1, x1 + 1, x0 + 1, x1 - 1, int(rng.integers(-60, 60)), int(rng.integers(-60, 60))]
+            pool_y = [y0, y1, y0 - 1, y1 + 1, y0 + 1, y1 - 1, int(rng.integers(-60, 60)), int(rng.integers(-60, 60))]
+            px, qx = (int(v) for v in rng.choice(pool_x, 2))
+            py, qy = (int(v) for v in rng.choice(pool_y, 2))
+        else:                                                           # arena scale, up to the coordinate limit
+            x0, y0 = (int(v) for v in rng.integers(-16000, 15000, 2))
+            x1, y1 = x0 + int(rng.integers(200, 1300)), y0 + int(rng.integers(200, 1300))
+            px, py, qx, qy = (int(v) for v in rng.integers(-16383, 16384, 4))
+            if it % 3 == 0:
+                px, py = x0, int(rng.integers(y0, y1 + 1))
+        if (px, py) == (qx, qy):
+            continue
+        got = lib.emu_seg_prepared(px, py, qx, qy, x0, y0, x1, y1)
+        want = int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, False)) | (int(_clip_exact(px, py, qx, qy, x0, y0, x1, y1, True)) << 1)
+        assert got == want, (px, py, qx, qy, x0, y0, x1, y1, got, want)
+        n_checked += 1
+    assert n_checked > 8000
