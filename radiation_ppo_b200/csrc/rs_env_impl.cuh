@@ -811,16 +811,28 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const int ux = corner_x(ru, u & 3), uy = corner_y(ru, u & 3);
         const uint32_t m = w_vis[u] & ~fin;
         RS_SYNCWARP(sync_mask);
-        for (int w = lane; w < nc; w += nl) {
-            if (!((m >> w) & 1u)) continue;
+        auto relax = [&](int w) {
             const int4 rw = w_rects[w >> 2];
             const int dx = ux - corner_x(rw, w & 3), dy = uy - corner_y(rw, w & 3);
             const double old = w_dsrc[w];
             // |u - w| >= max(|dx|, |dy|), an integer: rounding is monotone, so a label this bound cannot beat stands
             // (most relaxations end here, without the square root)
-            if (du + (double)max(abs(dx), abs(dy)) >= old) continue;
+            if (du + (double)max(abs(dx), abs(dy)) >= old) return;
             const double nd = du + dist_int(dx, dy);
             if (nd < old) w_dsrc[w] = nd;
+        };
+        if (nl == 1) {
+            // one thread per environment: the thread walks ITS corner's open neighbours only (the lanes of a warp are at
+            // different corners of different scenes, so a loop over all corners runs as long as the union of their masks)
+            uint32_t mm = m;
+            while (mm) {
+                const int w = __ffs(mm) - 1;
+                mm &= mm - 1;
+                relax(w);
+            }
+        } else {
+            for (int w = lane; w < nc; w += nl)
+                if ((m >> w) & 1u) relax(w);
         }
         RS_SYNCWARP(sync_mask);
     }
