@@ -97,7 +97,7 @@ typedef struct RsState {
     int32_t *meta;               /* [N]       num_obs | done<<8 | (rectangles holding the source strictly inside)<<9 | ep_len<<16 */
     int32_t *det;                /* [A][N][2] detector x,y                                                      */
     double *best;                /* [A][N]    Agent.prev_det_dist (running minimum of the shortest-path length)  */
-    int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24                       */
+    int32_t *aflags;             /* [A][N]    out_of_bounds_count | obstacle_blocking<<24 | search seed corner<<25 */
     double *dsrc;                /* [N][4K]   shortest-path length source -> obstruction corner c (inf if none), env-major */
                                  /*           (a unit gathers its own row on demand)                                          */
     uint32_t *vis;               /* [4K][N]   corner-to-corner visibility bit masks                              */
@@ -108,7 +108,7 @@ typedef struct RsState {
     /* prefetched next episode (optional, RS_F_PREFETCH; NULL otherwise) */
     int32_t *nx_src;             /* [N][2]                                                                        */
     int32_t *nx_det;             /* [N][2]    all agents start at the same point (R:771-773)                       */
-    int32_t *nx_rad;             /* [N][2]                                                                        */
+    int32_t *nx_rad;             /* [N][2]    intensity, background | (corner of the initial shortest path << 8)   */
     double *nx_best;             /* [N]                                                                           */
     double *nx_dsrc;             /* [N][4K]   source-distance row of the prefetched episode                            */
     float *nx_obs;               /* [N][A][11] first observation of the prefetched episode                        */

@@ -701,10 +701,10 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
                     for (int i = 0; i < RS_OBS_DIM; i++) dst[ag * RS_OBS_DIM + i] = row[i];
                     reinterpret_cast<int2 *>(S.det)[ia] = d0;
                     S.best[ia] = b0;
-                    S.aflags[ia] = 0;
+                    S.aflags[ia] = (r0.y >> 8) << 25;                     // the prefetched episode's search seed
                 }
                 reinterpret_cast<int2 *>(S.src)[n] = s0;
-                reinterpret_cast<int2 *>(S.rad)[n] = r0;
+                reinterpret_cast<int2 *>(S.rad)[n] = make_int2(r0.x, r0.y & 0xff);
                 S.meta[n] = meta & 0xff;                                  // done = 0, ep_len = 0
                 S.epi[n] = ep_seq;
                 // an env is listed once per block of steps (episodes outlast a block: RadSearch refuses prefetch
@@ -858,14 +858,19 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         w_dsrc[c] = cand;
     }
     RS_SYNCWARP(sync_mask);
+    // the first step's seed for the pruned search: the corner the initial shortest path goes through (aflags bits 25..29)
     double sp = direct ? euc : inf;
+    int hint0 = 0;
     if (!direct)
-        for (int c = 0; c < nc; c++) sp = fmin(sp, w_dsrc[c]);
+        for (int c = 0; c < nc; c++) {
+            const double d = w_dsrc[c];
+            if (d < sp) { sp = d; hint0 = c; }
+        }
     const bool blocked_los = blocked_raw && !isclose_quirk(euc, sp);
     if (lane == 0) {
         if (prepare) {
             reinterpret_cast<int2 *>(S.nx_src)[n] = make_int2(e.sx, e.sy);
-            reinterpret_cast<int2 *>(S.nx_rad)[n] = make_int2(e.intensity, e.bkg);
+            reinterpret_cast<int2 *>(S.nx_rad)[n] = make_int2(e.intensity, e.bkg | (hint0 << 8));    // bkg < 256 R:779
             reinterpret_cast<int2 *>(S.nx_det)[n] = make_int2(detx, dety);
             S.nx_best[n] = sp;
         } else {
@@ -892,7 +897,7 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
             if (!prepare) {
                 reinterpret_cast<int2 *>(S.det)[ia] = make_int2(detx, dety);
                 S.best[ia] = sp;
-                S.aflags[ia] = 0;                                        // Agent.reset R:289-300
+                S.aflags[ia] = hint0 << 25;                              // Agent.reset R:289-300 (+ the search seed)
                 if (P.standardize) {                                     // stat_buffers[id].reset(); .update(obs[0])
                     S.st_mean[ia] = (double)row[0];                      // T:509, 548: first reading, z = 0
                     S.st_m2[ia] = 0.0;

@@ -521,10 +521,10 @@ __device__ __forceinline__ void step1_tile(const rs::Params &P, const RsState &S
                 stm = (double)row[0]; stq = 0.0; raw = row[0]; row[0] = 0.0f;
             }
             reinterpret_cast<int2 *>(S.src)[n] = s0;
-            reinterpret_cast<int2 *>(S.rad)[n] = r1;
+            reinterpret_cast<int2 *>(S.rad)[n] = make_int2(r1.x, r1.y & 0xff);
             reinterpret_cast<int2 *>(S.det)[n] = d0;
             S.best[n] = b0;
-            S.aflags[n] = 0;
+            S.aflags[n] = (r1.y >> 8) << 25;                            // the new episode's search seed (rs_prepare)
             S.meta[n] = meta & 0xff;                                    // done = 0, ep_len = 0 (a sampled source is in no rectangle)
             S.epi[n] = epi_n + 1u;
             if (slot < a.n_env) S.refill_list[(size_t)a.parity * N + slot] = n;
