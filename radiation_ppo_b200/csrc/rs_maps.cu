@@ -151,21 +151,29 @@ __global__ void __launch_bounds__(kBlock) maps_update_kernel(const __grid_consta
         }
         __syncwarp();
         const int k1 = (m - 1) >> 1, k2 = m >> 1;
-        float r1 = -1.0f, r2 = -1.0f;                                       // readings are >= 0
-        for (int i = lane; i < m; i += 32) {
-            const float v = scratch[i];
-            int rank = 0;
-            for (int j = 0; j < m; j++) {
-                const float u = scratch[j];
-                rank += (u < v) || (u == v && j < i);
+        float r1, r2;                                                       // readings are >= 0
+        if (m == 0) {                                                       // (only when the sample table is full: RS_MS_LOG_FULL)
+            r1 = r2 = -1.0f;
+        } else if (m <= 2) {
+            // a cell the agent has visited once or twice (most calls: agents keep moving): the median is the sample or the
+            // mean of the two -- no rank selection (m is the same on every lane: it comes from ballots)
+            const float s0 = scratch[0], s1 = scratch[m - 1];
+            r1 = fminf(s0, s1);
+            r2 = fmaxf(s0, s1);
+        } else {
+            uint32_t b1 = 0u, b2 = 0u;                                      // the selected values as bit patterns (>= 0: ordered)
+            for (int i = lane; i < m; i += 32) {
+                const float v = scratch[i];
+                int rank = 0;
+                for (int j = 0; j < m; j++) {
+                    const float u = scratch[j];
+                    rank += (u < v) || (u == v && j < i);
+                }
+                if (rank == k1) b1 = __float_as_uint(v);
+                if (rank == k2) b2 = __float_as_uint(v);
             }
-            if (rank == k1) r1 = v;
-            if (rank == k2) r2 = v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, o));
-            r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+            r1 = __uint_as_float(__reduce_max_sync(0xffffffffu, b1));       // exactly one lane holds each rank
+            r2 = __uint_as_float(__reduce_max_sync(0xffffffffu, b2));
         }
         __syncwarp();                                                       // scratch is reused by the next agent
         const double est = ((double)r1 + (double)r2) / 2.0;                 // statistics.median
