@@ -69,6 +69,15 @@ __device__ __forceinline__ bool visible(const EnvView &e, int px, int py, int qx
 
 __device__ __forceinline__ double dist_int(int dx, int dy) { return sqrt((double)(dx * dx + dy * dy)); }
 
+// Corner i of rectangle r (order p0 (x0,y0), p1 (x0,y1), p2 (x1,y1), p3 (x1,y0)) is hidden from p by its OWN rectangle iff p
+// lies strictly on the inner side of both edges that meet there: the segment then runs through the open rectangle just
+// before it reaches the corner.  visible() returns false for exactly these, so callers skip the test.
+__device__ __forceinline__ bool corner_hidden_by_own_rect(int4 r, int i, int px, int py) {
+    const bool in_x = (i < 2) ? px > r.x : px < r.z;
+    const bool in_y = (i == 0 || i == 3) ? py > r.y : py < r.w;
+    return in_x && in_y;
+}
+
 // the same test as a real function: the step kernel calls it from three places (hint, pair, fall-back walk) and its
 // instruction footprint, not its call overhead, is what costs there (the kernel is instruction-fetch limited)
 __device__ __noinline__ bool visible_call(const int4 *rects, int stride, int num_obs, int px, int py, int qx, int qy) {
@@ -780,7 +789,8 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
     for (int c = lane; c < nc; c += nl) {
         const int4 r = w_rects[c >> 2];
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
-        w_dsrc[c] = visible(e, e.sx, e.sy, cx, cy) ? dist_int(cx - e.sx, cy - e.sy) : inf;
+        w_dsrc[c] = (!corner_hidden_by_own_rect(r, c & 3, e.sx, e.sy) && visible(e, e.sx, e.sy, cx, cy))
+                        ? dist_int(cx - e.sx, cy - e.sy) : inf;
     }
     RS_SYNCWARP(sync_mask);
     uint32_t fin = 0;
@@ -800,9 +810,12 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         } else
 #endif
         {
-            for (int c = 0; c < nc; c++) {                               // every lane scans: uniform result
+            uint32_t rem = (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u)) & ~fin;     // unsettled corners only, lowest index
+            while (rem) {                                                           // first: every lane scans, uniform result
+                const int c = __ffs(rem) - 1;
+                rem &= rem - 1;
                 const double d = w_dsrc[c];
-                if (!((fin >> c) & 1) && d < du) { du = d; u = c; }
+                if (d < du) { du = d; u = c; }
             }
         }
         if (u < 0) break;
@@ -851,7 +864,8 @@ __device__ __forceinline__ void reset_env(const Params &P, const RsState &S, con
         const int cx = corner_x(r, c & 3), cy = corner_y(r, c & 3);
         double cand = inf;
         // a corner whose lower bound ds + max(|dx|, |dy|) does not beat this lane's best so far cannot be the minimum
-        if (!direct && ds + (double)max(abs(detx - cx), abs(dety - cy)) < lane_best && visible(e, detx, dety, cx, cy)) {
+        if (!direct && ds + (double)max(abs(detx - cx), abs(dety - cy)) < lane_best &&
+            !corner_hidden_by_own_rect(r, c & 3, detx, dety) && visible(e, detx, dety, cx, cy)) {
             cand = ds + dist_int(detx - cx, dety - cy);
             lane_best = fmin(lane_best, cand);
         }
