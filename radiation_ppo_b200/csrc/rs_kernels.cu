@@ -627,11 +627,10 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         mbar_expect_tx(&s_mbar[0], (uint32_t)(K * 16 * TB));
         for (int k = 0; k < K; k++)
             bulk_g2s(s_rects + k * TB, S.rects + ((size_t)k * N + n0) * 4, TB * 16, &s_mbar[0]);
-        // rows that are first needed late in the step wait in shared memory instead of in (spilled) registers
-        mbar_expect_tx(&s_mbar[1], (uint32_t)(16 * TB));
-        bulk_g2s(s_rad, S.rad + (size_t)n0 * 2, TB * 8, &s_mbar[1]);
-        bulk_g2s(s_best, S.best + n0, TB * 8, &s_mbar[1]);
         if (!RS_STEP1_DSF_LATE) {
+            mbar_expect_tx(&s_mbar[1], (uint32_t)(16 * TB));
+            bulk_g2s(s_rad, S.rad + (size_t)n0 * 2, TB * 8, &s_mbar[1]);
+            bulk_g2s(s_best, S.best + n0, TB * 8, &s_mbar[1]);
             mbar_expect_tx(&s_mbar[1], (uint32_t)(K * 16 * TB));
             bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar[1]);
         }
@@ -666,6 +665,11 @@ __global__ void __launch_bounds__(TB, kOcc) step1_kernel(const __grid_constant__
         if (RS_STEP1_DSF_LATE && tid == 0) {
             mbar_expect_tx(&s_mbar[1], (uint32_t)(K * 16 * TB));
             bulk_g2s(s_dsf, S.dsf + (size_t)n0 * 4 * K, (uint32_t)(TB * 16 * K), &s_mbar[1]);
+            // rows that are first needed late in the step (intensities, running minimum) wait in shared memory instead of
+            // in (spilled) registers; like the float table they are asked for once the rectangles are here
+            mbar_expect_tx(&s_mbar[1], (uint32_t)(16 * TB));
+            bulk_g2s(s_rad, S.rad + (size_t)n0 * 2, TB * 8, &s_mbar[1]);
+            bulk_g2s(s_best, S.best + n0, TB * 8, &s_mbar[1]);
         }
     } else if (KMAX > 0) {
         if (live) {
